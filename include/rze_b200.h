@@ -1,0 +1,143 @@
+/*
+ * rze_b200.h — C ABI of the B200-native per-frame vertex-deformation path
+ * (vertex-morph accumulation fused with BDEF1/2/4/SDEF linear-blend skinning of
+ * positions + normals against a per-frame bone-matrix palette).
+ *
+ * This is the drop-in boundary for the deform stage of AmyangXYZ/reze-engine.
+ * Each entry point names the reference interface it replaces (file:line under
+ * the reference's engine/src/).  Plain pointers and sizes only; every input is
+ * caller-owned and copied before the call returns; outputs are library-owned.
+ * A rz_ctx is NOT thread-safe: one host thread drives it (the reference is
+ * single-threaded: one rAF callback, engine.ts:1671-1681).
+ *
+ * All functions return 0 (RZ_OK) on success or a negative rz_status; the text of
+ * the last failure is available from rz_last_error().  The reference convention
+ * "fatal => throw new Error" (engine.ts:161,167,1828) maps to: the N-API / ctypes
+ * shim raises when status != 0.
+ */
+#ifndef RZE_B200_H
+#define RZE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RZE_B200_ABI_VERSION 1
+
+typedef struct rz_ctx rz_ctx;
+
+typedef enum rz_status {
+  RZ_OK = 0,
+  RZ_ERR_INVALID_ARG = -1,
+  RZ_ERR_NO_DEVICE = -2,   /* no CUDA device / sm_100 kernel image not loadable: never a CPU fallback */
+  RZ_ERR_CUDA = -3,
+  RZ_ERR_OOM = -4,
+  RZ_ERR_STATE = -5        /* call order violated (e.g. deform before load_mesh / set_palettes) */
+} rz_status;
+
+/* rz_config.flags */
+#define RZ_FLAG_SDEF        0x1u  /* evaluate SDEF vertices spherically; default (0) = BDEF2, exactly as the
+                                     reference treats them (pmx-loader.ts:141-155) */
+#define RZ_FLAG_NO_NORMALS  0x2u  /* positions only — the reference's depth-only blend (engine.ts:692-715) */
+#define RZ_FLAG_BOUNDS      0x4u  /* also produce one AABB per instance (fused consumer) */
+
+typedef struct rz_config {
+  uint32_t struct_size;    /* sizeof(rz_config), for forward compatibility */
+  int32_t  device;         /* CUDA device ordinal this context owns (one process per GPU) */
+  uint32_t max_instances;  /* K: independent character instances resident on this device (>=1) */
+  uint32_t flags;          /* RZ_FLAG_* */
+  void*    stream;         /* optional cudaStream_t to launch on (e.g. the caller's current stream);
+                              NULL = the context creates its own non-blocking stream */
+  uint32_t tune_instances_per_group; /* 0 = auto; kernel tuning knob (instances sharing one vertex pass) */
+  uint32_t tune_store_mode;          /* 0 = auto; 1 = direct register stores; 2 = smem-staged bulk (TMA) stores */
+  uint32_t tune_threads;             /* 0 = auto; 256 or 512 threads per CTA */
+  uint32_t tune_chunks;              /* 0 = auto; vertex chunks per instance group (work-item granularity) */
+  uint32_t tune_ctas_per_sm;         /* 0 = auto; persistent CTAs per SM */
+  uint32_t tune_reserved[3];
+} rz_config;
+
+typedef struct rz_stats {
+  /* EngineStats of the reference (engine.ts:16-20): same three fields, same units */
+  double fps;               /* frames per second over the last second of rz_deform calls */
+  double frameTime;         /* ms, mean device time of the last <=60 rz_deform calls */
+  double gpuMemory;         /* MB of device memory held by this context */
+  /* additions */
+  double vertsPerSec;       /* skinned vertices per second, last rz_deform */
+  double algorithmicBytes;  /* compulsory DRAM bytes of the last rz_deform */
+  double achievedGBs;       /* algorithmicBytes / device time */
+  double lastDeformMs;      /* device time of the last rz_deform (CUDA events on the ctx stream) */
+  uint64_t frames;          /* rz_deform calls so far */
+  uint64_t kernelLaunches;  /* kernels launched by this context so far */
+  uint32_t vertexCount, boneCount, instanceCount, paletteCount;
+  uint32_t morphCount, morphNnz, sdefCount, activeMorphs;
+  uint32_t instancesPerGroup, storeMode, ctas, threads; /* launch shape actually used */
+  uint32_t smemBytes, reserved0;
+} rz_stats;
+
+/* ---- lifecycle: replaces Engine.init() (engine.ts:157-185) / dispose() (engine.ts:1692-1701) ---- */
+int32_t rz_create(const rz_config* cfg, rz_ctx** out);
+int32_t rz_destroy(rz_ctx* ctx);
+uint32_t rz_abi_version(void);
+
+/* ---- static tables: replaces setupModelBuffers (engine.ts:1728-1832) ----
+ * vtx8    : V x [x,y,z,nx,ny,nz,u,v] f32, exactly Model.getVertices() (model.ts:196-200)
+ * joints  : V x 4 u16, weights: V x 4 u8 (UNORM8), exactly Model.getSkinning() (model.ts:47-50)
+ * invBind : B x 16 f32 column-major, exactly Model.getBoneInverseBindMatrices() (model.ts:321-323)
+ * joints >= B are rejected (the reference's loader guarantees joints < B, pmx-loader.ts:865-876). */
+int32_t rz_load_mesh(rz_ctx* ctx, const float* vtx8, const uint16_t* joints, const uint8_t* weights,
+                     uint32_t V, const float* invBind, uint32_t B);
+
+/* Vertex morphs, morph-major CSR in PMX order (layout documented by pmx-loader.ts:483-488):
+ * morph m owns entries morphOffsets[m] .. morphOffsets[m+1]-1 of (vertIdx, delta3).  M may be 0. */
+int32_t rz_load_morphs(rz_ctx* ctx, const uint32_t* morphOffsets /* M+1 */, const uint32_t* vertIdx /* nnz */,
+                       const float* delta3 /* 3*nnz */, uint32_t M);
+
+/* SDEF records the reference steps over (pmx-loader.ts:153-155): per SDEF vertex C, R0, R1.
+ * Only used when RZ_FLAG_SDEF is set; the vertex must carry exactly two influences. */
+int32_t rz_load_sdef(rz_ctx* ctx, const uint32_t* vertIdx /* n */, const float* c_r0_r1 /* 9*n */, uint32_t n);
+
+/* ---- per frame: replaces queue.writeBuffer(worldMatrixBuffer) + computeSkinMatrices
+ * (engine.ts:2383-2402, shader engine.ts:920-929) ----
+ * world : P x B x 16 f32 column-major, exactly Model.getBoneWorldMatrices() (model.ts:317-319), P palettes.
+ * instToPalette : K entries < P, or NULL for identity (then P must be >= K).
+ * skin = world * invBind is evaluated on the device. */
+int32_t rz_set_palettes(rz_ctx* ctx, const float* world, uint32_t P, const uint32_t* instToPalette, uint32_t K);
+/* same, `world` / `instToPalette` are device pointers on this context's device (zero-copy producers) */
+int32_t rz_set_palettes_device(rz_ctx* ctx, const float* d_world, uint32_t P, const uint32_t* d_instToPalette, uint32_t K);
+/* pinned host staging the caller may fill directly and pass to rz_set_palettes (saves one host copy);
+ * valid until the next call that asks for a larger size or rz_destroy */
+int32_t rz_palette_staging(rz_ctx* ctx, size_t bytes, void** host_ptr);
+
+/* Per-instance weights of the active morphs: w[k*M_active + a] scales morph activeIds[a] for instance k.
+ * K must match the instance count in use; M_active = 0 disables morphing. */
+int32_t rz_set_morph_weights(rz_ctx* ctx, const float* w, const uint32_t* activeIds, uint32_t M_active, uint32_t K);
+
+/* ---- the deform pass: replaces the vertex-shader blend (engine.ts:245-276; 431-463; 692-715) ----
+ * Deforms instances [firstInstance, firstInstance+count) asynchronously on the context's stream. */
+int32_t rz_deform(rz_ctx* ctx, uint32_t firstInstance, uint32_t count);
+int32_t rz_sync(rz_ctx* ctx);
+
+/* ---- results (the reference feeds the rasteriser; nothing is stored, engine.ts:270-274) ----
+ * Device layout per instance k: pos plane V x 3 f32 at  base + k*instanceStride,
+ *                               nrm plane V x 3 f32 at  base + k*instanceStride + normalOffset.  */
+int32_t rz_output_device_ptr(rz_ctx* ctx, void** base, size_t* instanceStride, size_t* normalOffset);
+int32_t rz_read_instance(rz_ctx* ctx, uint32_t inst, float* pos3 /* 3V or NULL */, float* nrm3 /* 3V or NULL */);
+int32_t rz_read_bounds(rz_ctx* ctx, uint32_t firstInstance, uint32_t count, float* minmax6 /* 6*count */);
+/* bit-exact integer view of the tables the kernel consumes, mapped back to caller order (parity tests) */
+int32_t rz_read_skinning(rz_ctx* ctx, uint16_t* joints /* 4V */, uint8_t* weights /* 4V */);
+/* device-computed skin matrices of palette p as 3x4 row-major (12 floats per bone) */
+int32_t rz_read_skin_matrices(rz_ctx* ctx, uint32_t palette, float* skin3x4 /* 12*B */);
+
+/* ---- stats: replaces Engine.getStats() (engine.ts:1664-1666) ---- */
+int32_t rz_get_stats(rz_ctx* ctx, rz_stats* out);
+
+/* Last error text for ctx (or for the calling thread when ctx == NULL, e.g. after a failed rz_create). */
+const char* rz_last_error(rz_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RZE_B200_H */

@@ -1,0 +1,259 @@
+"""ctypes binding of the C ABI in `include/rze_b200.h` (librze_b200.so).
+
+This is the Python stand-in for the N-API addon a Node host would use (the same
+marshalling): numpy arrays in, status codes turned into
+exceptions like the reference's `throw new Error(...)` (engine.ts:161,167,1828).
+There is no fallback: if the shared library is missing or no CUDA device can run
+it, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "librze_b200.so")
+
+RZ_FLAG_SDEF = 0x1
+RZ_FLAG_NO_NORMALS = 0x2
+RZ_FLAG_BOUNDS = 0x4
+
+EXPORTS = [
+    "rz_create", "rz_destroy", "rz_abi_version", "rz_load_mesh", "rz_load_morphs", "rz_load_sdef",
+    "rz_set_palettes", "rz_set_palettes_device", "rz_palette_staging", "rz_set_morph_weights", "rz_deform",
+    "rz_sync", "rz_output_device_ptr", "rz_read_instance", "rz_read_bounds", "rz_read_skinning",
+    "rz_read_skin_matrices", "rz_get_stats", "rz_last_error",
+]
+
+
+class RzError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"rze_b200 status {status}: {message}")
+        self.status = status
+
+
+class RzConfig(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("device", C.c_int32), ("max_instances", C.c_uint32), ("flags", C.c_uint32),
+        ("stream", C.c_void_p),
+        ("tune_instances_per_group", C.c_uint32), ("tune_store_mode", C.c_uint32), ("tune_threads", C.c_uint32),
+        ("tune_chunks", C.c_uint32), ("tune_ctas_per_sm", C.c_uint32), ("tune_reserved", C.c_uint32 * 3),
+    ]
+
+
+class RzStats(C.Structure):
+    _fields_ = [
+        ("fps", C.c_double), ("frameTime", C.c_double), ("gpuMemory", C.c_double),
+        ("vertsPerSec", C.c_double), ("algorithmicBytes", C.c_double), ("achievedGBs", C.c_double),
+        ("lastDeformMs", C.c_double), ("frames", C.c_uint64), ("kernelLaunches", C.c_uint64),
+        ("vertexCount", C.c_uint32), ("boneCount", C.c_uint32), ("instanceCount", C.c_uint32), ("paletteCount", C.c_uint32),
+        ("morphCount", C.c_uint32), ("morphNnz", C.c_uint32), ("sdefCount", C.c_uint32), ("activeMorphs", C.c_uint32),
+        ("instancesPerGroup", C.c_uint32), ("storeMode", C.c_uint32), ("ctas", C.c_uint32), ("threads", C.c_uint32),
+        ("smemBytes", C.c_uint32), ("reserved0", C.c_uint32),
+    ]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved0"}
+
+
+_lib = None
+
+
+def load_library(path: Optional[str] = None) -> C.CDLL:
+    """dlopen librze_b200.so and declare every prototype.  Raises if the library was not built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise RzError(-2, f"{p} not found: build it with `python -m reze_engine_b200.build` (there is no CPU fallback)")
+    lib = C.CDLL(p)
+    vp, u32, i32, sz = C.c_void_p, C.c_uint32, C.c_int32, C.c_size_t
+    P = C.POINTER
+    lib.rz_create.argtypes = [P(RzConfig), P(vp)]
+    lib.rz_destroy.argtypes = [vp]
+    lib.rz_abi_version.restype = u32
+    lib.rz_load_mesh.argtypes = [vp, vp, vp, vp, u32, vp, u32]
+    lib.rz_load_morphs.argtypes = [vp, vp, vp, vp, u32]
+    lib.rz_load_sdef.argtypes = [vp, vp, vp, u32]
+    lib.rz_set_palettes.argtypes = [vp, vp, u32, vp, u32]
+    lib.rz_set_palettes_device.argtypes = [vp, vp, u32, vp, u32]
+    lib.rz_palette_staging.argtypes = [vp, sz, P(vp)]
+    lib.rz_set_morph_weights.argtypes = [vp, vp, vp, u32, u32]
+    lib.rz_deform.argtypes = [vp, u32, u32]
+    lib.rz_sync.argtypes = [vp]
+    lib.rz_output_device_ptr.argtypes = [vp, P(vp), P(sz), P(sz)]
+    lib.rz_read_instance.argtypes = [vp, u32, vp, vp]
+    lib.rz_read_bounds.argtypes = [vp, u32, u32, vp]
+    lib.rz_read_skinning.argtypes = [vp, vp, vp]
+    lib.rz_read_skin_matrices.argtypes = [vp, u32, vp]
+    lib.rz_get_stats.argtypes = [vp, P(RzStats)]
+    lib.rz_last_error.argtypes = [vp]
+    lib.rz_last_error.restype = C.c_char_p
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if name not in ("rz_abi_version", "rz_last_error"):
+            fn.restype = i32
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _arr(a, dtype) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class DeformContext:
+    """One rz_ctx: one GPU, one mesh, K instances."""
+
+    def __init__(self, max_instances: int = 1, device: int = 0, flags: int = 0, stream: int = 0,
+                 instances_per_group: int = 0, store_mode: int = 0, threads: int = 0, chunks: int = 0, ctas_per_sm: int = 0):
+        self.lib = load_library()
+        cfg = RzConfig()
+        cfg.struct_size = C.sizeof(RzConfig)
+        cfg.device = device
+        cfg.max_instances = max_instances
+        cfg.flags = flags
+        cfg.stream = stream or None
+        cfg.tune_instances_per_group = instances_per_group
+        cfg.tune_store_mode = store_mode
+        cfg.tune_threads = threads
+        cfg.tune_chunks = chunks
+        cfg.tune_ctas_per_sm = ctas_per_sm
+        h = C.c_void_p()
+        st = self.lib.rz_create(C.byref(cfg), C.byref(h))
+        if st != 0:
+            raise RzError(st, (self.lib.rz_last_error(None) or b"").decode())
+        self.h = h
+        self.max_instances = max_instances
+        self.flags = flags
+        self.V = 0
+        self.B = 0
+        self._stage = None
+
+    # -- plumbing
+    def _check(self, st: int):
+        if st != 0:
+            raise RzError(st, (self.lib.rz_last_error(self.h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rz_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- static tables
+    def load_mesh(self, vtx8, joints, weights, invBind):
+        vtx8 = _arr(vtx8, np.float32).reshape(-1)
+        joints = _arr(joints, np.uint16).reshape(-1)
+        weights = _arr(weights, np.uint8).reshape(-1)
+        invBind = _arr(invBind, np.float32).reshape(-1)
+        V, B = vtx8.size // 8, invBind.size // 16
+        if joints.size != V * 4 or weights.size != V * 4:
+            raise ValueError("joints/weights must hold 4 entries per vertex")
+        self._check(self.lib.rz_load_mesh(self.h, _ptr(vtx8), _ptr(joints), _ptr(weights), V, _ptr(invBind), B))
+        self.V, self.B = V, B
+
+    def load_morphs(self, offsets, vertIdx, delta3):
+        offsets = _arr(offsets, np.uint32).reshape(-1)
+        vertIdx = _arr(vertIdx, np.uint32).reshape(-1)
+        delta3 = _arr(delta3, np.float32).reshape(-1)
+        M = max(offsets.size - 1, 0)
+        self._check(self.lib.rz_load_morphs(self.h, _ptr(offsets) if M else None, _ptr(vertIdx) if vertIdx.size else None,
+                                            _ptr(delta3) if delta3.size else None, M))
+
+    def load_sdef(self, vertIdx, c_r0_r1):
+        vertIdx = _arr(vertIdx, np.uint32).reshape(-1)
+        vec = _arr(c_r0_r1, np.float32).reshape(-1)
+        self._check(self.lib.rz_load_sdef(self.h, _ptr(vertIdx) if vertIdx.size else None, _ptr(vec) if vec.size else None, vertIdx.size))
+
+    # -- per frame
+    def palette_staging(self, P: int) -> np.ndarray:
+        """Pinned host buffer shaped [P, B, 16] the caller may fill and hand to set_palettes."""
+        nbytes = P * self.B * 64
+        p = C.c_void_p()
+        self._check(self.lib.rz_palette_staging(self.h, nbytes, C.byref(p)))
+        buf = (C.c_float * (P * self.B * 16)).from_address(p.value)
+        return np.frombuffer(buf, dtype=np.float32).reshape(P, self.B, 16)
+
+    def set_palettes(self, world, inst_to_palette=None, K: Optional[int] = None):
+        world = np.asarray(world)
+        if world.dtype != np.float32 or not world.flags.c_contiguous:
+            world = _arr(world, np.float32)
+        P = world.size // (self.B * 16)
+        i2p = None if inst_to_palette is None else _arr(inst_to_palette, np.uint32).reshape(-1)
+        if K is None:
+            K = P if i2p is None else i2p.size
+        self._check(self.lib.rz_set_palettes(self.h, _ptr(world), P, _ptr(i2p), K))
+        self.K = K
+
+    def set_palettes_device(self, d_world_ptr: int, P: int, d_inst_to_palette_ptr: int = 0, K: Optional[int] = None):
+        K = P if K is None else K
+        self._check(self.lib.rz_set_palettes_device(self.h, C.c_void_p(d_world_ptr), P,
+                                                    C.c_void_p(d_inst_to_palette_ptr) if d_inst_to_palette_ptr else None, K))
+        self.K = K
+
+    def set_morph_weights(self, w, active_ids, K: Optional[int] = None):
+        ids = _arr(active_ids, np.uint32).reshape(-1)
+        w = _arr(w, np.float32)
+        Mact = ids.size
+        if K is None:
+            K = w.size // max(Mact, 1) if Mact else self.max_instances
+        self._check(self.lib.rz_set_morph_weights(self.h, _ptr(w) if Mact else None, _ptr(ids) if Mact else None, Mact, K))
+
+    def deform(self, first: int = 0, count: Optional[int] = None):
+        self._check(self.lib.rz_deform(self.h, first, self.K - first if count is None else count))
+
+    def sync(self):
+        self._check(self.lib.rz_sync(self.h))
+
+    # -- results
+    def output_device_ptr(self) -> Tuple[int, int, int]:
+        base, stride, noff = C.c_void_p(), C.c_size_t(), C.c_size_t()
+        self._check(self.lib.rz_output_device_ptr(self.h, C.byref(base), C.byref(stride), C.byref(noff)))
+        return base.value, stride.value, noff.value
+
+    def read_instance(self, inst: int, normals: bool = True):
+        pos = np.empty((self.V, 3), dtype=np.float32)
+        nrm = np.empty((self.V, 3), dtype=np.float32) if normals and not (self.flags & RZ_FLAG_NO_NORMALS) else None
+        self._check(self.lib.rz_read_instance(self.h, inst, _ptr(pos), _ptr(nrm)))
+        return pos, nrm
+
+    def read_bounds(self, first: int, count: int) -> np.ndarray:
+        out = np.empty((count, 6), dtype=np.float32)
+        self._check(self.lib.rz_read_bounds(self.h, first, count, _ptr(out)))
+        return out
+
+    def read_skinning(self):
+        j = np.zeros(self.V * 4, dtype=np.uint16)
+        w = np.zeros(self.V * 4, dtype=np.uint8)
+        self._check(self.lib.rz_read_skinning(self.h, _ptr(j), _ptr(w)))
+        return j, w
+
+    def read_skin_matrices(self, palette: int) -> np.ndarray:
+        out = np.empty((self.B, 12), dtype=np.float32)
+        self._check(self.lib.rz_read_skin_matrices(self.h, palette, _ptr(out)))
+        return out
+
+    def stats(self) -> dict:
+        s = RzStats()
+        self._check(self.lib.rz_get_stats(self.h, C.byref(s)))
+        return s.asdict()

@@ -1,0 +1,45 @@
+// aux_kernels.cuh — small per-frame helper kernels (included by rze_b200.cu only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rz {
+
+// ------------------------------------------------------------------ skin = world * invBind
+// Replaces the reference's only compute shader (engine.ts:920-929).  One thread per (palette, bone);
+// keeps rows 0..2 of the column-major product (row 3 never reaches the blend's outputs, engine.ts:260-272).
+__global__ void skin_matrices_kernel(const float4* __restrict__ world, const float4* __restrict__ invBind,
+                                     float4* __restrict__ skin, uint32_t P, uint32_t B) {
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P * B) return;
+  const uint32_t b = idx % B;
+  const float4 w0 = world[(size_t)idx * 4], w1 = world[(size_t)idx * 4 + 1], w2 = world[(size_t)idx * 4 + 2],
+               w3 = world[(size_t)idx * 4 + 3];                      // columns of world
+  float r[3][4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float4 ib = __ldg(invBind + (size_t)b * 4 + c);            // column c of invBind
+    r[0][c] = fmaf(w3.x, ib.w, fmaf(w2.x, ib.z, fmaf(w1.x, ib.y, w0.x * ib.x)));
+    r[1][c] = fmaf(w3.y, ib.w, fmaf(w2.y, ib.z, fmaf(w1.y, ib.y, w0.y * ib.x)));
+    r[2][c] = fmaf(w3.z, ib.w, fmaf(w2.z, ib.z, fmaf(w1.z, ib.y, w0.z * ib.x)));
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) skin[(size_t)idx * 3 + k] = make_float4(r[k][0], r[k][1], r[k][2], r[k][3]);
+}
+
+// dense per-instance morph weights: dense[k][m] = 0, dense[k][activeIds[a]] += w[k][a]
+__global__ void morph_weights_kernel(const float* __restrict__ w, const uint32_t* __restrict__ ids, float* __restrict__ dense,
+                                     uint32_t K, uint32_t Mact, uint32_t Mpad) {
+  const uint32_t k = blockIdx.x;
+  if (k >= K) return;
+  for (uint32_t m = threadIdx.x; m < Mpad; m += blockDim.x) dense[(size_t)k * Mpad + m] = 0.f;
+  __syncthreads();
+  for (uint32_t a = threadIdx.x; a < Mact; a += blockDim.x) atomicAdd(&dense[(size_t)k * Mpad + ids[a]], w[(size_t)k * Mact + a]);
+}
+
+__global__ void bounds_reset_kernel(int* b, uint32_t n6) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n6) b[i] = (i % 6) < 3 ? 0x7F7FFFFF : (int)(0x7F7FFFFF ^ 0x7FFFFFFF) | (int)0x80000000;
+}
+
+}  // namespace rz

@@ -1,0 +1,812 @@
+// rze_b200.cu — C ABI (include/rze_b200.h) over the sm_100a deform kernels.
+//
+// Host side of the deform stage: table preprocessing that replaces setupModelBuffers
+// (engine.ts:1728-1832), the per-frame palette upload (engine.ts:2383-2389) + skin-matrix
+// pass (engine.ts:2393-2402), and the launch logic for the fused deform kernel.
+// There is no CPU implementation behind this ABI: without a CUDA device that can run the
+// sm_100a image, rz_create fails with RZ_ERR_NO_DEVICE.
+#include "../../include/rze_b200.h"
+#include "deform_kernel.cuh"
+#include "aux_kernels.cuh"
+#include "kernel_table.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace rz;
+
+// the ctypes / N-API mirrors of these structs rely on the layout
+static_assert(sizeof(rz_config) == 56, "rz_config layout changed: update capi.py / napi shim");
+static_assert(sizeof(rz_stats) == 128, "rz_stats layout changed: update capi.py / napi shim");
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+struct rz_ctx_impl {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool ownStream = false;
+  uint32_t flags = 0, maxK = 1;
+  uint32_t tuneI = 0, tuneStore = 0, tuneThreads = 0, tuneChunks = 0, tuneCtas = 0;
+  int numSM = 0, maxSmemOptin = 0;
+  std::string err;
+
+  // host copies of the caller's tables (caller order)
+  uint32_t V = 0, B = 0;
+  std::vector<float> h_vtx8;
+  std::vector<uint16_t> h_joints;
+  std::vector<uint8_t> h_weights;
+  std::vector<float> h_invBind;
+  uint32_t M = 0;
+  std::vector<uint32_t> h_moff, h_mvert;
+  std::vector<float> h_mdelta;
+  std::vector<uint32_t> h_sdefVert;
+  std::vector<float> h_sdefVec;
+  bool tablesDirty = true;
+
+  // device tables (processing order)
+  uint32_t Vp = 0, nTiles = 0;
+  std::vector<uint32_t> procToVertex;   // processing index -> caller vertex id (or ~0u for padding)
+  DevBuf d_rec0, d_rec1, d_joints, d_mrange, d_ments, d_sdefIdx, d_sdefTab, d_invBind;
+  uint32_t morphNnz = 0, sdefActive = 0;
+
+  // per-frame
+  uint32_t P = 0, K = 0;
+  DevBuf d_world, d_skin, d_inst2pal, d_mwIn, d_mwIds, d_mwDense, d_out, d_bounds, d_counter;
+  bool haveInst2pal = false, palettesSet = false;
+  uint32_t Mact = 0, Mpad = 4;
+  void* h_stage = nullptr;
+  size_t h_stageBytes = 0;
+  void* h_small = nullptr;      // pinned scratch for index / weight uploads
+  size_t h_smallBytes = 0;
+  size_t instStrideF = 0, nrmOffF = 0;
+
+  // stats
+  cudaEvent_t evStart = nullptr, evStop = nullptr;
+  bool evPending = false;
+  double lastMs = 0, lastAlgBytes = 0;
+  uint64_t lastVerts = 0;
+  std::vector<double> msRing;
+  std::vector<double> frameStamps;
+  uint64_t frames = 0, launches = 0;
+  size_t devBytes = 0;
+  uint32_t usedI = 0, usedStore = 0, usedCtas = 0, usedThreads = 0, usedSmem = 0;
+};
+
+int fail(rz_ctx_impl* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  g_last_error = buf;
+  return code;
+}
+
+#define CU_TRY(c, expr)                                                                              \
+  do {                                                                                               \
+    cudaError_t e_ = (expr);                                                                         \
+    if (e_ != cudaSuccess)                                                                           \
+      return fail((c), e_ == cudaErrorMemoryAllocation ? RZ_ERR_OOM : RZ_ERR_CUDA, "%s: %s (%s:%d)", #expr, \
+                  cudaGetErrorString(e_), __FILE__, __LINE__);                                       \
+  } while (0)
+
+int dev_reserve(rz_ctx_impl* c, DevBuf& b, size_t bytes) {
+  if (bytes <= b.bytes && b.p) return RZ_OK;
+  if (b.p) {
+    cudaFree(b.p);
+    c->devBytes -= b.bytes;
+    b.p = nullptr;
+    b.bytes = 0;
+  }
+  if (bytes == 0) bytes = 16;
+  cudaError_t e = cudaMalloc(&b.p, bytes);
+  if (e != cudaSuccess) {
+    b.p = nullptr;
+    return fail(c, e == cudaErrorMemoryAllocation ? RZ_ERR_OOM : RZ_ERR_CUDA, "cudaMalloc(%zu bytes): %s", bytes,
+                cudaGetErrorString(e));
+  }
+  b.bytes = bytes;
+  c->devBytes += bytes;
+  return RZ_OK;
+}
+
+void dev_free(rz_ctx_impl* c, DevBuf& b) {
+  if (b.p) {
+    cudaFree(b.p);
+    c->devBytes -= b.bytes;
+  }
+  b.p = nullptr;
+  b.bytes = 0;
+}
+
+int pinned_reserve(rz_ctx_impl* c, void*& p, size_t& have, size_t bytes) {
+  if (bytes <= have && p) return RZ_OK;
+  if (p) cudaFreeHost(p);
+  p = nullptr;
+  have = 0;
+  CU_TRY(c, cudaMallocHost(&p, std::max<size_t>(bytes, 4096)));
+  have = std::max<size_t>(bytes, 4096);
+  return RZ_OK;
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+KernelEntry lookup_kernel(int feat, int I, int NT, bool staged) {
+  switch (feat) {
+#define RZ_CASE(f) case f: return lookup_feat_##f(I, NT, staged);
+    RZ_FEAT_LIST(RZ_CASE)
+#undef RZ_CASE
+    default: break;
+  }
+  KernelEntry none{nullptr, 0, 0, false, feat};
+  return none;
+}
+
+// smallest compiled feature set that covers `need` (GPAL / NONRM must match exactly: they change data paths)
+int resolve_feat(int need) {
+  static const int compiled[] = {
+#define RZ_V(f) f,
+      RZ_FEAT_LIST(RZ_V)
+#undef RZ_V
+  };
+  int best = -1, bestBits = 99;
+  const int exact = FEAT_GPAL | FEAT_NONRM;
+  for (int cnd : compiled) {
+    if ((cnd & need) != need) continue;
+    if ((cnd & exact) != (need & exact)) continue;
+    const int bits = __builtin_popcount((unsigned)cnd);
+    if (bits < bestBits) { bestBits = bits; best = cnd; }
+  }
+  return best;
+}
+
+size_t smem_needed(int I, int NT, bool staged, int feat, uint32_t B, uint32_t Mpad) {
+  size_t s = 16;
+  if (!(feat & FEAT_GPAL)) s += (size_t)I * B * 48;
+  if (feat & FEAT_MORPH) s += (size_t)I * Mpad * 4;
+  if (staged) s += (size_t)2 * I * ((feat & FEAT_NONRM) ? 1 : 2) * NT * 12;
+  return s;
+}
+
+// ---- table preprocessing ------------------------------------------------------------------------
+// Tile = 256 consecutive vertices.  Inside a tile, which WARP evaluates a vertex is chosen by class
+// (SDEF, morphed, influence count) while its LANE stays slot % 32, so that (a) warps are homogeneous
+// and (b) staging writes of one warp hit 32 distinct banks (3*slot mod 32 is a bijection on lanes).
+int rebuild_tables(rz_ctx_impl* c) {
+  const uint32_t V = c->V, B = c->B;
+  const uint32_t nTiles = (V + kTile - 1) / kTile;
+  const uint32_t Vp = nTiles * kTile;
+  c->nTiles = nTiles;
+  c->Vp = Vp;
+
+  // vertex-major morph CSR (caller vertex order)
+  std::vector<uint32_t> mcount(V, 0), mstart(V + 1, 0);
+  const uint32_t nnz = c->M ? c->h_moff[c->M] : 0;
+  for (uint32_t e = 0; e < nnz; ++e) mcount[c->h_mvert[e]]++;
+  for (uint32_t v = 0; v < V; ++v) mstart[v + 1] = mstart[v] + mcount[v];
+  std::vector<float4> ments(std::max<uint32_t>(nnz, 1));
+  {
+    std::vector<uint32_t> fill(mstart.begin(), mstart.end() - 1);
+    for (uint32_t m = 0; m < c->M; ++m)
+      for (uint32_t e = c->h_moff[m]; e < c->h_moff[m + 1]; ++e) {
+        const uint32_t v = c->h_mvert[e];
+        float4 r;
+        r.x = c->h_mdelta[(size_t)e * 3]; r.y = c->h_mdelta[(size_t)e * 3 + 1]; r.z = c->h_mdelta[(size_t)e * 3 + 2];
+        memcpy(&r.w, &m, 4);
+        ments[fill[v]++] = r;
+      }
+  }
+  c->morphNnz = nnz;
+
+  // SDEF table (only when enabled)
+  std::vector<int32_t> sdefOf(V, -1);
+  std::vector<float4> sdefTab;
+  c->sdefActive = 0;
+  if (c->flags & RZ_FLAG_SDEF) {
+    for (size_t n = 0; n < c->h_sdefVert.size(); ++n) {
+      const uint32_t v = c->h_sdefVert[n];
+      const uint8_t* w = &c->h_weights[(size_t)v * 4];
+      if (w[2] != 0 || w[3] != 0) continue;   // not a two-influence vertex: stays linear
+      const float* s = &c->h_sdefVec[n * 9];
+      // weights exactly as the kernel derives them
+      float w0 = (float)w[0] / 255.0f, w1 = (float)w[1] / 255.0f;
+      const float ws = w0 + w1 + 0.f + 0.f;
+      if (ws > 0.0001f) { const float inv = 1.0f / ws; w0 *= inv; w1 *= inv; } else { w0 = 1.f; w1 = 0.f; }
+      float C[3] = {s[0], s[1], s[2]}, c0[3], c1[3];
+      for (int k = 0; k < 3; ++k) {
+        const float R0 = s[3 + k], R1 = s[6 + k];
+        const float rw = w0 * R0 + w1 * R1;
+        const float r0 = C[k] + R0 - rw, r1 = C[k] + R1 - rw;
+        c0[k] = (C[k] + r0) * 0.5f;
+        c1[k] = (C[k] + r1) * 0.5f;
+      }
+      sdefOf[v] = (int32_t)(sdefTab.size() / 3);
+      sdefTab.push_back(make_float4(C[0], C[1], C[2], c0[0]));
+      sdefTab.push_back(make_float4(c0[1], c0[2], c1[0], c1[1]));
+      sdefTab.push_back(make_float4(c1[2], 0.f, 0.f, 0.f));
+      c->sdefActive++;
+    }
+  }
+
+  std::vector<float4> rec0(Vp), rec1(Vp);
+  std::vector<uint2> jrec(Vp), mrange(Vp);
+  std::vector<uint32_t> sdefIdx(Vp, 0);
+  c->procToVertex.assign(Vp, ~0u);
+
+  auto ninf_of = [&](uint32_t v) -> uint32_t {
+    const uint8_t* w = &c->h_weights[(size_t)v * 4];
+    if ((uint32_t)w[0] + w[1] + w[2] + w[3] == 0) return 1;   // shader rule: sum <= 1e-4 -> (1,0,0,0)
+    uint32_t n = 1;
+    for (uint32_t k = 0; k < 4; ++k) if (w[k]) n = k + 1;
+    return n;
+  };
+  auto key_of = [&](uint32_t v) -> uint32_t {
+    return (sdefOf[v] >= 0 ? 1u << 16 : 0u) | (mcount[v] ? 1u << 15 : 0u) | (ninf_of(v) << 8) | std::min<uint32_t>(mcount[v], 255u);
+  };
+
+  for (uint32_t t = 0; t < nTiles; ++t) {
+    const uint32_t base = t * kTile;
+    for (uint32_t lane = 0; lane < 32; ++lane) {
+      uint32_t slots[kTile / 32];
+      uint32_t n = 0;
+      for (uint32_t w = 0; w < kTile / 32; ++w) {
+        const uint32_t s = w * 32 + lane;
+        if (base + s < V) slots[n++] = s;
+      }
+      std::stable_sort(slots, slots + n, [&](uint32_t a, uint32_t b) { return key_of(base + a) < key_of(base + b); });
+      for (uint32_t w = 0; w < kTile / 32; ++w) {
+        const uint32_t p = base + w * 32 + lane;
+        if (w < n) {
+          const uint32_t s = slots[w], v = base + s;
+          const float* x = &c->h_vtx8[(size_t)v * 8];
+          uint32_t wb;
+          memcpy(&wb, &c->h_weights[(size_t)v * 4], 4);
+          uint32_t meta = s | (ninf_of(v) << kMetaNinfShift) | kMetaValid;
+          if (mcount[v]) meta |= kMetaMorph;
+          if (sdefOf[v] >= 0) { meta |= kMetaSdef; sdefIdx[p] = (uint32_t)sdefOf[v]; }
+          float wbf, metaf;
+          memcpy(&wbf, &wb, 4);
+          memcpy(&metaf, &meta, 4);
+          rec0[p] = make_float4(x[0], x[1], x[2], wbf);
+          rec1[p] = make_float4(x[3], x[4], x[5], metaf);
+          const uint16_t* j = &c->h_joints[(size_t)v * 4];
+          jrec[p] = make_uint2((uint32_t)j[0] | ((uint32_t)j[1] << 16), (uint32_t)j[2] | ((uint32_t)j[3] << 16));
+          mrange[p] = make_uint2(mstart[v], mcount[v]);
+          c->procToVertex[p] = v;
+        } else {
+          // padding: a harmless rigid vertex on bone 0, parked on the first free slot of this lane column
+          const uint32_t s = w * 32 + lane;
+          const uint32_t wb = 255u, meta = s | (1u << kMetaNinfShift);
+          float wbf, metaf;
+          memcpy(&wbf, &wb, 4);
+          memcpy(&metaf, &meta, 4);
+          rec0[p] = make_float4(0.f, 0.f, 0.f, wbf);
+          rec1[p] = make_float4(0.f, 0.f, 0.f, metaf);
+          jrec[p] = make_uint2(0u, 0u);
+          mrange[p] = make_uint2(0u, 0u);
+        }
+      }
+    }
+  }
+
+  int rc;
+  if ((rc = dev_reserve(c, c->d_rec0, (size_t)Vp * 16))) return rc;
+  if ((rc = dev_reserve(c, c->d_rec1, (size_t)Vp * 16))) return rc;
+  if ((rc = dev_reserve(c, c->d_joints, (size_t)Vp * 8))) return rc;
+  if ((rc = dev_reserve(c, c->d_mrange, (size_t)Vp * 8))) return rc;
+  if ((rc = dev_reserve(c, c->d_ments, ments.size() * 16))) return rc;
+  if ((rc = dev_reserve(c, c->d_sdefIdx, (size_t)Vp * 4))) return rc;
+  if ((rc = dev_reserve(c, c->d_sdefTab, std::max<size_t>(sdefTab.size(), 3) * 16))) return rc;
+  if ((rc = dev_reserve(c, c->d_invBind, (size_t)B * 64))) return rc;
+  CU_TRY(c, cudaMemcpyAsync(c->d_rec0.p, rec0.data(), (size_t)Vp * 16, cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(c->d_rec1.p, rec1.data(), (size_t)Vp * 16, cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(c->d_joints.p, jrec.data(), (size_t)Vp * 8, cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(c->d_mrange.p, mrange.data(), (size_t)Vp * 8, cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(c->d_ments.p, ments.data(), ments.size() * 16, cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(c->d_sdefIdx.p, sdefIdx.data(), (size_t)Vp * 4, cudaMemcpyHostToDevice, c->stream));
+  if (!sdefTab.empty())
+    CU_TRY(c, cudaMemcpyAsync(c->d_sdefTab.p, sdefTab.data(), sdefTab.size() * 16, cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(c->d_invBind.p, c->h_invBind.data(), (size_t)B * 64, cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));   // the std::vectors above go out of scope
+
+  // output planes: pos plane then normal plane, both 16-byte aligned (TMA bulk stores)
+  const bool nrm = !(c->flags & RZ_FLAG_NO_NORMALS);
+  c->nrmOffF = align_up((size_t)V * 3, 4);
+  c->instStrideF = nrm ? 2 * c->nrmOffF : c->nrmOffF;
+  if ((rc = dev_reserve(c, c->d_out, (size_t)c->maxK * c->instStrideF * 4))) return rc;
+  if (c->flags & RZ_FLAG_BOUNDS)
+    if ((rc = dev_reserve(c, c->d_bounds, (size_t)c->maxK * 24))) return rc;
+  if ((rc = dev_reserve(c, c->d_counter, 16))) return rc;
+  c->tablesDirty = false;
+  return RZ_OK;
+}
+
+int ensure_dense_weights(rz_ctx_impl* c) {
+  // dense [maxK][Mpad] table; zero when no weights were set
+  const uint32_t Mpad = (uint32_t)align_up(std::max<uint32_t>(c->M, 1), 4);
+  if (Mpad != c->Mpad || !c->d_mwDense.p) {
+    c->Mpad = Mpad;
+    int rc;
+    if ((rc = dev_reserve(c, c->d_mwDense, (size_t)c->maxK * Mpad * 4))) return rc;
+    CU_TRY(c, cudaMemsetAsync(c->d_mwDense.p, 0, (size_t)c->maxK * Mpad * 4, c->stream));
+    c->Mact = 0;
+  }
+  return RZ_OK;
+}
+
+}  // namespace
+
+struct rz_ctx : rz_ctx_impl {};
+
+extern "C" {
+
+uint32_t rz_abi_version(void) { return RZE_B200_ABI_VERSION; }
+
+const char* rz_last_error(rz_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+int32_t rz_create(const rz_config* cfg, rz_ctx** out) {
+  if (!cfg || !out) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_create: null argument");
+  if (cfg->struct_size < offsetof(rz_config, tune_instances_per_group))
+    return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_create: struct_size %u too small", cfg->struct_size);
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, RZ_ERR_NO_DEVICE, "no CUDA device (%s); this library has no CPU path", cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev)
+    return fail(nullptr, RZ_ERR_INVALID_ARG, "device %d out of range (have %d)", cfg->device, ndev);
+  if (cfg->max_instances == 0) return fail(nullptr, RZ_ERR_INVALID_ARG, "max_instances must be >= 1");
+  CU_TRY(nullptr, cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CU_TRY(nullptr, cudaGetDeviceProperties(&prop, cfg->device));
+  {
+    // the fat binary only holds sm_100a SASS: make sure it is loadable here, loudly
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(&skin_matrices_kernel));
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(nullptr, RZ_ERR_NO_DEVICE, "device %d (%s, sm_%d%d) cannot run the sm_100a kernels: %s", cfg->device,
+                  prop.name, prop.major, prop.minor, cudaGetErrorString(e));
+    }
+  }
+  rz_ctx* c = new rz_ctx();
+  c->device = cfg->device;
+  c->flags = cfg->flags;
+  c->maxK = cfg->max_instances;
+  c->numSM = prop.multiProcessorCount;
+  cudaDeviceGetAttribute(&c->maxSmemOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
+  if (cfg->struct_size >= sizeof(rz_config)) {
+    c->tuneI = cfg->tune_instances_per_group;
+    c->tuneStore = cfg->tune_store_mode;
+    c->tuneThreads = cfg->tune_threads;
+    c->tuneChunks = cfg->tune_chunks;
+    c->tuneCtas = cfg->tune_ctas_per_sm;
+  }
+  if (cfg->stream) {
+    c->stream = reinterpret_cast<cudaStream_t>(cfg->stream);
+  } else {
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; return fail(nullptr, RZ_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    c->ownStream = true;
+  }
+  cudaEventCreate(&c->evStart);
+  cudaEventCreate(&c->evStop);
+  *out = c;
+  return RZ_OK;
+}
+
+int32_t rz_destroy(rz_ctx* c) {
+  if (!c) return RZ_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  DevBuf* bufs[] = {&c->d_rec0, &c->d_rec1, &c->d_joints, &c->d_mrange, &c->d_ments, &c->d_sdefIdx, &c->d_sdefTab,
+                    &c->d_invBind, &c->d_world, &c->d_skin, &c->d_inst2pal, &c->d_mwIn, &c->d_mwIds, &c->d_mwDense,
+                    &c->d_out, &c->d_bounds, &c->d_counter};
+  for (DevBuf* b : bufs) dev_free(c, *b);
+  if (c->h_stage) cudaFreeHost(c->h_stage);
+  if (c->h_small) cudaFreeHost(c->h_small);
+  if (c->evStart) cudaEventDestroy(c->evStart);
+  if (c->evStop) cudaEventDestroy(c->evStop);
+  if (c->ownStream) cudaStreamDestroy(c->stream);
+  delete c;
+  return RZ_OK;
+}
+
+int32_t rz_load_mesh(rz_ctx* c, const float* vtx8, const uint16_t* joints, const uint8_t* weights, uint32_t V,
+                     const float* invBind, uint32_t B) {
+  if (!c) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_load_mesh: null ctx");
+  if (!vtx8 || !joints || !weights || !invBind) return fail(c, RZ_ERR_INVALID_ARG, "rz_load_mesh: null table");
+  if (V == 0 || B == 0) return fail(c, RZ_ERR_INVALID_ARG, "rz_load_mesh: V and B must be > 0 (the reference throws 'Model has no bones')");
+  if (B > 65536) return fail(c, RZ_ERR_INVALID_ARG, "rz_load_mesh: B=%u exceeds the u16 joint range", B);
+  for (size_t i = 0; i < (size_t)V * 4; ++i)
+    if (joints[i] >= B) return fail(c, RZ_ERR_INVALID_ARG, "rz_load_mesh: joint %u of vertex %zu >= bone count %u", joints[i], i / 4, B);
+  CU_TRY(c, cudaSetDevice(c->device));
+  c->V = V;
+  c->B = B;
+  c->h_vtx8.assign(vtx8, vtx8 + (size_t)V * 8);
+  c->h_joints.assign(joints, joints + (size_t)V * 4);
+  c->h_weights.assign(weights, weights + (size_t)V * 4);
+  c->h_invBind.assign(invBind, invBind + (size_t)B * 16);
+  c->M = 0;
+  c->h_moff.clear(); c->h_mvert.clear(); c->h_mdelta.clear();
+  c->h_sdefVert.clear(); c->h_sdefVec.clear();
+  c->palettesSet = false;
+  c->Mact = 0;
+  c->Mpad = 0;
+  c->tablesDirty = true;
+  return rebuild_tables(c);
+}
+
+int32_t rz_load_morphs(rz_ctx* c, const uint32_t* off, const uint32_t* vertIdx, const float* delta3, uint32_t M) {
+  if (!c) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_load_morphs: null ctx");
+  if (c->V == 0) return fail(c, RZ_ERR_STATE, "rz_load_morphs before rz_load_mesh");
+  if (M && (!off || off[0] != 0)) return fail(c, RZ_ERR_INVALID_ARG, "rz_load_morphs: morphOffsets[0] must be 0");
+  const uint32_t nnz = M ? off[M] : 0;
+  if (nnz && (!vertIdx || !delta3)) return fail(c, RZ_ERR_INVALID_ARG, "rz_load_morphs: null entries");
+  for (uint32_t m = 0; m < M; ++m)
+    if (off[m + 1] < off[m]) return fail(c, RZ_ERR_INVALID_ARG, "rz_load_morphs: offsets not monotone at %u", m);
+  for (uint32_t e = 0; e < nnz; ++e)
+    if (vertIdx[e] >= c->V) return fail(c, RZ_ERR_INVALID_ARG, "rz_load_morphs: vertex index %u >= V=%u", vertIdx[e], c->V);
+  CU_TRY(c, cudaSetDevice(c->device));
+  c->M = M;
+  if (M) c->h_moff.assign(off, off + M + 1); else c->h_moff.clear();
+  c->h_mvert.assign(vertIdx, vertIdx + nnz);
+  c->h_mdelta.assign(delta3, delta3 + (size_t)nnz * 3);
+  c->Mact = 0;
+  c->Mpad = 0;   // forces the dense table to be rebuilt
+  c->tablesDirty = true;
+  return rebuild_tables(c);
+}
+
+int32_t rz_load_sdef(rz_ctx* c, const uint32_t* vertIdx, const float* vec9, uint32_t n) {
+  if (!c) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_load_sdef: null ctx");
+  if (c->V == 0) return fail(c, RZ_ERR_STATE, "rz_load_sdef before rz_load_mesh");
+  if (n && (!vertIdx || !vec9)) return fail(c, RZ_ERR_INVALID_ARG, "rz_load_sdef: null table");
+  for (uint32_t i = 0; i < n; ++i)
+    if (vertIdx[i] >= c->V) return fail(c, RZ_ERR_INVALID_ARG, "rz_load_sdef: vertex index %u >= V=%u", vertIdx[i], c->V);
+  CU_TRY(c, cudaSetDevice(c->device));
+  c->h_sdefVert.assign(vertIdx, vertIdx + n);
+  c->h_sdefVec.assign(vec9, vec9 + (size_t)n * 9);
+  c->tablesDirty = true;
+  return rebuild_tables(c);
+}
+
+static int set_palettes_common(rz_ctx* c, const float* d_world, uint32_t P, uint32_t K) {
+  int rc;
+  if ((rc = dev_reserve(c, c->d_skin, (size_t)P * c->B * 48))) return rc;
+  const uint32_t n = P * c->B;
+  skin_matrices_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(reinterpret_cast<const float4*>(d_world),
+                                                              reinterpret_cast<const float4*>(c->d_invBind.p),
+                                                              reinterpret_cast<float4*>(c->d_skin.p), P, c->B);
+  CU_TRY(c, cudaGetLastError());
+  c->launches++;
+  c->P = P;
+  c->K = K;
+  c->palettesSet = true;
+  return RZ_OK;
+}
+
+int32_t rz_palette_staging(rz_ctx* c, size_t bytes, void** host_ptr) {
+  if (!c || !host_ptr) return fail(c, RZ_ERR_INVALID_ARG, "rz_palette_staging: null argument");
+  CU_TRY(c, cudaSetDevice(c->device));
+  if (bytes > c->h_stageBytes) CU_TRY(c, cudaStreamSynchronize(c->stream));
+  int rc = pinned_reserve(c, c->h_stage, c->h_stageBytes, bytes);
+  if (rc) return rc;
+  *host_ptr = c->h_stage;
+  return RZ_OK;
+}
+
+int32_t rz_set_palettes(rz_ctx* c, const float* world, uint32_t P, const uint32_t* inst2pal, uint32_t K) {
+  if (!c) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_set_palettes: null ctx");
+  if (c->V == 0) return fail(c, RZ_ERR_STATE, "rz_set_palettes before rz_load_mesh");
+  if (!world || P == 0 || K == 0) return fail(c, RZ_ERR_INVALID_ARG, "rz_set_palettes: world/P/K must be non-zero");
+  if (K > c->maxK) return fail(c, RZ_ERR_INVALID_ARG, "rz_set_palettes: K=%u exceeds max_instances=%u", K, c->maxK);
+  if (!inst2pal && P < K) return fail(c, RZ_ERR_INVALID_ARG, "rz_set_palettes: identity mapping needs P >= K (P=%u K=%u)", P, K);
+  if (inst2pal)
+    for (uint32_t k = 0; k < K; ++k)
+      if (inst2pal[k] >= P) return fail(c, RZ_ERR_INVALID_ARG, "rz_set_palettes: instToPalette[%u]=%u >= P=%u", k, inst2pal[k], P);
+  CU_TRY(c, cudaSetDevice(c->device));
+  const size_t bytes = (size_t)P * c->B * 64;
+  int rc;
+  if ((rc = dev_reserve(c, c->d_world, bytes))) return rc;
+  const char* src = reinterpret_cast<const char*>(world);
+  const bool inStage = c->h_stage && src >= (char*)c->h_stage && src + bytes <= (char*)c->h_stage + c->h_stageBytes;
+  if (!inStage) {
+    // the staging buffer may still be the source of the previous frame's copy
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    if ((rc = pinned_reserve(c, c->h_stage, c->h_stageBytes, bytes))) return rc;
+    memcpy(c->h_stage, world, bytes);
+    src = reinterpret_cast<const char*>(c->h_stage);
+  }
+  CU_TRY(c, cudaMemcpyAsync(c->d_world.p, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  if (inst2pal) {
+    if ((rc = dev_reserve(c, c->d_inst2pal, (size_t)c->maxK * 4))) return rc;
+    if (!inStage || true) {
+      if ((rc = pinned_reserve(c, c->h_small, c->h_smallBytes, (size_t)c->maxK * 4))) return rc;
+    }
+    memcpy(c->h_small, inst2pal, (size_t)K * 4);
+    CU_TRY(c, cudaMemcpyAsync(c->d_inst2pal.p, c->h_small, (size_t)K * 4, cudaMemcpyHostToDevice, c->stream));
+  }
+  c->haveInst2pal = inst2pal != nullptr;
+  return set_palettes_common(c, reinterpret_cast<const float*>(c->d_world.p), P, K);
+}
+
+int32_t rz_set_palettes_device(rz_ctx* c, const float* d_world, uint32_t P, const uint32_t* d_inst2pal, uint32_t K) {
+  if (!c) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_set_palettes_device: null ctx");
+  if (c->V == 0) return fail(c, RZ_ERR_STATE, "rz_set_palettes_device before rz_load_mesh");
+  if (!d_world || P == 0 || K == 0) return fail(c, RZ_ERR_INVALID_ARG, "rz_set_palettes_device: world/P/K must be non-zero");
+  if (K > c->maxK) return fail(c, RZ_ERR_INVALID_ARG, "rz_set_palettes_device: K=%u exceeds max_instances=%u", K, c->maxK);
+  if (!d_inst2pal && P < K) return fail(c, RZ_ERR_INVALID_ARG, "rz_set_palettes_device: identity mapping needs P >= K");
+  CU_TRY(c, cudaSetDevice(c->device));
+  int rc;
+  if (d_inst2pal) {
+    if ((rc = dev_reserve(c, c->d_inst2pal, (size_t)c->maxK * 4))) return rc;
+    CU_TRY(c, cudaMemcpyAsync(c->d_inst2pal.p, d_inst2pal, (size_t)K * 4, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  c->haveInst2pal = d_inst2pal != nullptr;
+  return set_palettes_common(c, d_world, P, K);
+}
+
+int32_t rz_set_morph_weights(rz_ctx* c, const float* w, const uint32_t* ids, uint32_t Mact, uint32_t K) {
+  if (!c) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_set_morph_weights: null ctx");
+  if (c->V == 0) return fail(c, RZ_ERR_STATE, "rz_set_morph_weights before rz_load_mesh");
+  if (K == 0 || K > c->maxK) return fail(c, RZ_ERR_INVALID_ARG, "rz_set_morph_weights: K=%u out of range (max %u)", K, c->maxK);
+  if (Mact && (!w || !ids)) return fail(c, RZ_ERR_INVALID_ARG, "rz_set_morph_weights: null weights/ids");
+  for (uint32_t a = 0; a < Mact; ++a)
+    if (ids[a] >= c->M) return fail(c, RZ_ERR_INVALID_ARG, "rz_set_morph_weights: morph id %u >= M=%u", ids[a], c->M);
+  CU_TRY(c, cudaSetDevice(c->device));
+  int rc;
+  if ((rc = ensure_dense_weights(c))) return rc;
+  if (Mact == 0) {
+    CU_TRY(c, cudaMemsetAsync(c->d_mwDense.p, 0, (size_t)c->maxK * c->Mpad * 4, c->stream));
+    c->Mact = 0;
+    return RZ_OK;
+  }
+  const size_t wBytes = (size_t)K * Mact * 4, idBytes = (size_t)Mact * 4;
+  if ((rc = dev_reserve(c, c->d_mwIn, wBytes))) return rc;
+  if ((rc = dev_reserve(c, c->d_mwIds, idBytes))) return rc;
+  CU_TRY(c, cudaStreamSynchronize(c->stream));   // pinned scratch reuse
+  if ((rc = pinned_reserve(c, c->h_small, c->h_smallBytes, std::max(wBytes + idBytes, (size_t)c->maxK * 4)))) return rc;
+  memcpy(c->h_small, w, wBytes);
+  memcpy((char*)c->h_small + wBytes, ids, idBytes);
+  CU_TRY(c, cudaMemcpyAsync(c->d_mwIn.p, c->h_small, wBytes, cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(c->d_mwIds.p, (char*)c->h_small + wBytes, idBytes, cudaMemcpyHostToDevice, c->stream));
+  morph_weights_kernel<<<K, 128, 0, c->stream>>>(reinterpret_cast<const float*>(c->d_mwIn.p),
+                                                 reinterpret_cast<const uint32_t*>(c->d_mwIds.p),
+                                                 reinterpret_cast<float*>(c->d_mwDense.p), K, Mact, c->Mpad);
+  CU_TRY(c, cudaGetLastError());
+  c->launches++;
+  c->Mact = Mact;
+  return RZ_OK;
+}
+
+int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
+  if (!c) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_deform: null ctx");
+  if (c->V == 0) return fail(c, RZ_ERR_STATE, "rz_deform before rz_load_mesh");
+  if (!c->palettesSet) return fail(c, RZ_ERR_STATE, "rz_deform before rz_set_palettes");
+  if (count == 0 || first >= c->K || count > c->K - first)
+    return fail(c, RZ_ERR_INVALID_ARG, "rz_deform: instance range [%u,+%u) outside K=%u", first, count, c->K);
+  CU_TRY(c, cudaSetDevice(c->device));
+  int rc;
+  if (c->tablesDirty && (rc = rebuild_tables(c))) return rc;
+
+  int need = 0;
+  if (c->M && c->morphNnz && c->Mact) need |= FEAT_MORPH;
+  if ((c->flags & RZ_FLAG_SDEF) && c->sdefActive) need |= FEAT_SDEF;
+  if (c->flags & RZ_FLAG_BOUNDS) need |= FEAT_BOUNDS;
+  if (c->flags & RZ_FLAG_NO_NORMALS) need |= FEAT_NONRM;
+  if ((rc = ensure_dense_weights(c))) return rc;
+  const uint32_t Mpad = c->Mpad;
+
+  // ---- pick the launch shape
+  const size_t smemMax = (size_t)c->maxSmemOptin;
+  if (smem_needed(1, 256, false, need, c->B, Mpad) > smemMax) need |= FEAT_GPAL;   // palette does not fit: gather from global
+  const int feat = resolve_feat(need);
+  if (feat < 0) return fail(c, RZ_ERR_INVALID_ARG, "rz_deform: feature combination 0x%x is not built", need);
+  const bool plain = feat == 0;
+  KernelEntry ke{nullptr, 0, 0, false, feat};
+  {
+    int wantI = c->tuneI ? (int)c->tuneI : 4;
+    while (wantI > 1 && (uint32_t)wantI > count) wantI >>= 1;
+    if (!plain && wantI > 4) wantI = 4;
+    const int wantStore = c->tuneStore ? (int)c->tuneStore : 2;
+    const int wantNT = c->tuneThreads ? (int)c->tuneThreads : 512;
+    // candidates in preference order; the first that is compiled and fits in shared memory wins
+    for (int I = wantI; I >= 1 && !ke.fn; I >>= 1) {
+      const int nts[2] = {wantNT, wantNT == 512 ? 256 : 512};
+      const bool sts[2] = {wantStore == 2, wantStore != 2};
+      for (int a = 0; a < 2 && !ke.fn; ++a)
+        for (int b = 0; b < 2 && !ke.fn; ++b) {
+          KernelEntry e = lookup_kernel(feat, I, nts[b], sts[a]);
+          if (e.fn && smem_needed(I, nts[b], sts[a], feat, c->B, Mpad) <= smemMax) ke = e;
+        }
+    }
+    if (!ke.fn) return fail(c, RZ_ERR_INVALID_ARG, "rz_deform: no kernel shape fits B=%u (smem limit %zu)", c->B, smemMax);
+  }
+  const size_t smem = smem_needed(ke.I, ke.NT, ke.staged, feat, c->B, Mpad);
+  CU_TRY(c, cudaFuncSetAttribute(ke.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CU_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ke.fn, ke.NT, smem));
+  if (occ < 1) return fail(c, RZ_ERR_CUDA, "rz_deform: kernel does not fit on an SM (smem %zu)", smem);
+  if (c->tuneCtas && (int)c->tuneCtas < occ) occ = (int)c->tuneCtas;
+
+  DeformParams prm;
+  memset(&prm, 0, sizeof prm);
+  prm.rec0 = reinterpret_cast<const float4*>(c->d_rec0.p);
+  prm.rec1 = reinterpret_cast<const float4*>(c->d_rec1.p);
+  prm.joints = reinterpret_cast<const uint2*>(c->d_joints.p);
+  prm.mrange = reinterpret_cast<const uint2*>(c->d_mrange.p);
+  prm.ments = reinterpret_cast<const float4*>(c->d_ments.p);
+  prm.sdefIdx = reinterpret_cast<const uint32_t*>(c->d_sdefIdx.p);
+  prm.sdefTab = reinterpret_cast<const float4*>(c->d_sdefTab.p);
+  prm.skin = reinterpret_cast<const float*>(c->d_skin.p);
+  prm.inst2pal = c->haveInst2pal ? reinterpret_cast<const uint32_t*>(c->d_inst2pal.p) : nullptr;
+  prm.mweights = reinterpret_cast<const float*>(c->d_mwDense.p);
+  prm.out = reinterpret_cast<float*>(c->d_out.p);
+  prm.bounds = reinterpret_cast<float*>(c->d_bounds.p);
+  prm.instStrideF = c->instStrideF;
+  prm.nrmOffF = c->nrmOffF;
+  prm.V = c->V; prm.B = c->B; prm.nTiles = c->nTiles; prm.K0 = first; prm.Kcount = count; prm.Mpad = Mpad;
+  prm.nGroups = (count + ke.I - 1) / ke.I;
+  const uint32_t tilesPerPass = ke.NT / kTile;
+  const uint32_t nPasses = (c->nTiles + tilesPerPass - 1) / tilesPerPass;
+  uint32_t grid = (uint32_t)(c->numSM * occ);
+  uint32_t nChunks = c->tuneChunks ? c->tuneChunks : (grid * 8 + prm.nGroups - 1) / prm.nGroups;
+  nChunks = std::max(1u, std::min(nChunks, nPasses));
+  const uint32_t passesPerChunk = (nPasses + nChunks - 1) / nChunks;
+  prm.tilesPerChunk = passesPerChunk * tilesPerPass;
+  prm.nChunks = (c->nTiles + prm.tilesPerChunk - 1) / prm.tilesPerChunk;
+  prm.counter = reinterpret_cast<uint32_t*>(c->d_counter.p);
+  const uint32_t nItems = prm.nGroups * prm.nChunks;
+  grid = std::min(grid, nItems);
+
+  CU_TRY(c, cudaEventRecord(c->evStart, c->stream));
+  CU_TRY(c, cudaMemsetAsync(c->d_counter.p, 0, 4, c->stream));
+  if (feat & FEAT_BOUNDS) {
+    bounds_reset_kernel<<<(count * 6 + 127) / 128, 128, 0, c->stream>>>(reinterpret_cast<int*>(c->d_bounds.p) + (size_t)first * 6, count * 6);
+    c->launches++;
+  }
+  void* args[] = {&prm};
+  CU_TRY(c, cudaLaunchKernel(ke.fn, dim3(grid), dim3(ke.NT), args, smem, c->stream));
+  CU_TRY(c, cudaEventRecord(c->evStop, c->stream));
+  c->launches++;
+  c->evPending = true;
+  c->frames++;
+  c->usedI = ke.I; c->usedStore = ke.staged ? 2 : 1; c->usedCtas = grid; c->usedThreads = ke.NT; c->usedSmem = (uint32_t)smem;
+  c->lastVerts = (uint64_t)count * c->V;
+  // compulsory DRAM bytes: outputs + mesh + palettes + invBind + morph entries/weights + sdef records
+  const double planes = (feat & FEAT_NONRM) ? 1.0 : 2.0;
+  c->lastAlgBytes = (double)count * c->V * 12.0 * planes + (double)c->V * 36.0 + (double)c->P * c->B * 64.0 + (double)c->B * 64.0 +
+                    ((feat & FEAT_MORPH) ? (double)c->morphNnz * 16.0 + (double)count * c->Mact * 4.0 : 0.0) +
+                    ((feat & FEAT_SDEF) ? (double)c->sdefActive * 36.0 : 0.0);
+  const double now = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  c->frameStamps.push_back(now);
+  while (!c->frameStamps.empty() && now - c->frameStamps.front() > 1.0) c->frameStamps.erase(c->frameStamps.begin());
+  return RZ_OK;
+}
+
+int32_t rz_sync(rz_ctx* c) {
+  if (!c) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_sync: null ctx");
+  CU_TRY(c, cudaSetDevice(c->device));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return RZ_OK;
+}
+
+int32_t rz_output_device_ptr(rz_ctx* c, void** base, size_t* stride, size_t* nrmOff) {
+  if (!c || !base) return fail(c, RZ_ERR_INVALID_ARG, "rz_output_device_ptr: null argument");
+  if (c->V == 0) return fail(c, RZ_ERR_STATE, "rz_output_device_ptr before rz_load_mesh");
+  *base = c->d_out.p;
+  if (stride) *stride = c->instStrideF * 4;
+  if (nrmOff) *nrmOff = (c->flags & RZ_FLAG_NO_NORMALS) ? 0 : c->nrmOffF * 4;
+  return RZ_OK;
+}
+
+int32_t rz_read_instance(rz_ctx* c, uint32_t inst, float* pos3, float* nrm3) {
+  if (!c) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_read_instance: null ctx");
+  if (c->V == 0) return fail(c, RZ_ERR_STATE, "rz_read_instance before rz_load_mesh");
+  if (inst >= c->maxK) return fail(c, RZ_ERR_INVALID_ARG, "rz_read_instance: instance %u >= max_instances %u", inst, c->maxK);
+  if (nrm3 && (c->flags & RZ_FLAG_NO_NORMALS)) return fail(c, RZ_ERR_STATE, "rz_read_instance: context was created with RZ_FLAG_NO_NORMALS");
+  CU_TRY(c, cudaSetDevice(c->device));
+  const float* src = reinterpret_cast<const float*>(c->d_out.p) + (size_t)inst * c->instStrideF;
+  if (pos3) CU_TRY(c, cudaMemcpyAsync(pos3, src, (size_t)c->V * 12, cudaMemcpyDeviceToHost, c->stream));
+  if (nrm3) CU_TRY(c, cudaMemcpyAsync(nrm3, src + c->nrmOffF, (size_t)c->V * 12, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return RZ_OK;
+}
+
+int32_t rz_read_bounds(rz_ctx* c, uint32_t first, uint32_t count, float* minmax6) {
+  if (!c || !minmax6) return fail(c, RZ_ERR_INVALID_ARG, "rz_read_bounds: null argument");
+  if (!(c->flags & RZ_FLAG_BOUNDS) || !c->d_bounds.p) return fail(c, RZ_ERR_STATE, "rz_read_bounds: context was created without RZ_FLAG_BOUNDS");
+  if (first >= c->maxK || count > c->maxK - first) return fail(c, RZ_ERR_INVALID_ARG, "rz_read_bounds: range outside max_instances");
+  CU_TRY(c, cudaSetDevice(c->device));
+  std::vector<int> tmp((size_t)count * 6);
+  CU_TRY(c, cudaMemcpyAsync(tmp.data(), reinterpret_cast<const int*>(c->d_bounds.p) + (size_t)first * 6, tmp.size() * 4,
+                            cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  for (size_t i = 0; i < tmp.size(); ++i) {
+    int v = tmp[i];
+    if (v < 0) v ^= 0x7FFFFFFF;
+    memcpy(&minmax6[i], &v, 4);
+  }
+  return RZ_OK;
+}
+
+int32_t rz_read_skinning(rz_ctx* c, uint16_t* joints, uint8_t* weights) {
+  if (!c) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_read_skinning: null ctx");
+  if (c->V == 0) return fail(c, RZ_ERR_STATE, "rz_read_skinning before rz_load_mesh");
+  CU_TRY(c, cudaSetDevice(c->device));
+  std::vector<float4> rec0(c->Vp);
+  std::vector<uint2> jrec(c->Vp);
+  CU_TRY(c, cudaMemcpyAsync(rec0.data(), c->d_rec0.p, (size_t)c->Vp * 16, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(jrec.data(), c->d_joints.p, (size_t)c->Vp * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  for (uint32_t p = 0; p < c->Vp; ++p) {
+    const uint32_t v = c->procToVertex[p];
+    if (v == ~0u) continue;
+    if (joints) {
+      joints[(size_t)v * 4] = (uint16_t)(jrec[p].x & 0xFFFF); joints[(size_t)v * 4 + 1] = (uint16_t)(jrec[p].x >> 16);
+      joints[(size_t)v * 4 + 2] = (uint16_t)(jrec[p].y & 0xFFFF); joints[(size_t)v * 4 + 3] = (uint16_t)(jrec[p].y >> 16);
+    }
+    if (weights) memcpy(&weights[(size_t)v * 4], &rec0[p].w, 4);
+  }
+  return RZ_OK;
+}
+
+int32_t rz_read_skin_matrices(rz_ctx* c, uint32_t palette, float* skin3x4) {
+  if (!c || !skin3x4) return fail(c, RZ_ERR_INVALID_ARG, "rz_read_skin_matrices: null argument");
+  if (!c->palettesSet) return fail(c, RZ_ERR_STATE, "rz_read_skin_matrices before rz_set_palettes");
+  if (palette >= c->P) return fail(c, RZ_ERR_INVALID_ARG, "rz_read_skin_matrices: palette %u >= P=%u", palette, c->P);
+  CU_TRY(c, cudaSetDevice(c->device));
+  CU_TRY(c, cudaMemcpyAsync(skin3x4, reinterpret_cast<const float*>(c->d_skin.p) + (size_t)palette * c->B * 12, (size_t)c->B * 48,
+                            cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return RZ_OK;
+}
+
+int32_t rz_get_stats(rz_ctx* c, rz_stats* out) {
+  if (!c || !out) return fail(c, RZ_ERR_INVALID_ARG, "rz_get_stats: null argument");
+  CU_TRY(c, cudaSetDevice(c->device));
+  if (c->evPending) {
+    CU_TRY(c, cudaEventSynchronize(c->evStop));
+    float ms = 0.f;
+    CU_TRY(c, cudaEventElapsedTime(&ms, c->evStart, c->evStop));
+    c->lastMs = ms;
+    c->msRing.push_back(ms);
+    if (c->msRing.size() > 60) c->msRing.erase(c->msRing.begin());   // 60-sample window like engine.ts:2423-2445
+    c->evPending = false;
+  }
+  memset(out, 0, sizeof *out);
+  double sum = 0;
+  for (double m : c->msRing) sum += m;
+  out->frameTime = c->msRing.empty() ? 0.0 : sum / (double)c->msRing.size();
+  out->fps = (double)c->frameStamps.size();
+  out->gpuMemory = (double)c->devBytes / (1024.0 * 1024.0);
+  out->lastDeformMs = c->lastMs;
+  out->algorithmicBytes = c->lastAlgBytes;
+  if (c->lastMs > 0) {
+    out->vertsPerSec = (double)c->lastVerts / (c->lastMs * 1e-3);
+    out->achievedGBs = c->lastAlgBytes / (c->lastMs * 1e-3) / 1e9;
+  }
+  out->frames = c->frames;
+  out->kernelLaunches = c->launches;
+  out->vertexCount = c->V; out->boneCount = c->B; out->instanceCount = c->K; out->paletteCount = c->P;
+  out->morphCount = c->M; out->morphNnz = c->morphNnz; out->sdefCount = c->sdefActive; out->activeMorphs = c->Mact;
+  out->instancesPerGroup = c->usedI; out->storeMode = c->usedStore; out->ctas = c->usedCtas; out->threads = c->usedThreads;
+  out->smemBytes = c->usedSmem;
+  return RZ_OK;
+}
+
+}  // extern "C"

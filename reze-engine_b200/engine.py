@@ -1,0 +1,311 @@
+"""Engine facade: the reference's public API surface over the B200 deform path.
+
+Keeps the method names and call order of `engine/src/engine.ts`
+(`new Engine(canvas, options)` -> `init()` -> `loadModel(path)` ->
+`loadAnimation(url)` -> `runRenderLoop(cb)` -> `playAnimation(opts)`;
+`rotateBones(names, quats, durationMs)`, `stopAnimation()`, `getStats()`,
+`dispose()`; engine.ts:145-157, 1419-1425, 1593, 1664-1725).  What it drives is
+only the stage this repo replaces: pose evaluation on the host (as the reference
+does, model.ts) -> palette upload + skin matrices + fused morph/skin kernel on the
+GPU (replacing engine.ts:2375-2402 and the vertex-shader blend engine.ts:245-276).
+Rasterisation, camera, bloom, physics are out of scope.
+
+Differences a caller sees, all forced by leaving the browser:
+* no canvas: the first constructor argument is accepted and ignored;
+* `init/loadModel/loadAnimation` are plain (synchronous) methods;
+* time is injected: `clock` (ms) replaces `performance.now()` (model.ts:160,249)
+  and `window.setTimeout` (engine.ts:1547,1587,1657) is an internal timer queue
+  pumped by `render()`; `ManualClock` gives reproducible playback;
+* `instances=K` deforms a crowd of K independent copies of the model; every
+  reference method addresses instance 0 unless `instance=` is given.
+"""
+from __future__ import annotations
+
+import heapq
+import itertools
+import time
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Sequence, Union
+
+import numpy as np
+
+from . import capi
+from .math3d import Quat, Vec3
+from .model import Model
+from .pmx import PmxLoader
+from .vmd import VMDKeyFrame, VMDLoader
+
+
+@dataclass
+class EngineStats:
+    """engine.ts:16-20 plus deform-stage counters."""
+    fps: float = 0.0
+    frameTime: float = 0.0   # ms
+    gpuMemory: float = 0.0   # MB
+    vertsPerSec: float = 0.0
+    achievedGBs: float = 0.0
+    algorithmicBytes: float = 0.0
+
+
+class ManualClock:
+    """Deterministic clock in milliseconds for tests and offline playback."""
+
+    def __init__(self, start_ms: float = 0.0):
+        self.now_ms = float(start_ms)
+
+    def __call__(self) -> float:
+        return self.now_ms
+
+    def advance(self, ms: float) -> float:
+        self.now_ms += ms
+        return self.now_ms
+
+
+class Engine:
+    def __init__(self, canvas=None, options: Optional[dict] = None, *, instances: int = 1, device: int = 0,
+                 clock: Optional[Callable[[], float]] = None, sdef: bool = False, bounds: bool = False, stream: int = 0):
+        o = options or {}
+        # EngineOptions (engine.ts:8-14): kept so existing call sites construct unchanged; they only
+        # parameterise passes this repo does not replace.
+        self.ambient = o.get("ambient", 1.0)
+        self.bloomIntensity = o.get("bloomIntensity", 0.12)
+        self.rimLightIntensity = o.get("rimLightIntensity", 0.45)
+        self.cameraDistance = o.get("cameraDistance", 26.6)
+        self.cameraTarget = o.get("cameraTarget", Vec3(0, 12.5, 0))
+        self.instances = int(instances)
+        self.device = device
+        self.clock = clock or (lambda: time.perf_counter() * 1000.0)
+        self._flags = (capi.RZ_FLAG_SDEF if sdef else 0) | (capi.RZ_FLAG_BOUNDS if bounds else 0)
+        self._stream = stream
+        self.ctx: Optional[capi.DeformContext] = None
+        self.currentModel: Optional[Model] = None
+        self.models: List[Model] = []
+        self.animationFrames: List[VMDKeyFrame] = []
+        self.hasAnimation = False
+        self.playingAnimation = False
+        self._timers: list = []
+        self._timer_ids = itertools.count(1)
+        self._cancelled: set = set()
+        self._animationTimeouts: List[int] = []
+        self._breathingTimeout: Optional[int] = None
+        self._breathingBase: Dict[str, Quat] = {}
+        self._loop_running = False
+        self._renderLoopCallback = None
+        self._stats = EngineStats()
+        self._morph_ids = np.zeros(0, np.uint32)
+
+    # ---- lifecycle ---------------------------------------------------------------------------
+    def init(self):
+        """engine.ts:157-185: acquire the device.  Raises if no sm_100 GPU / library (no fallback)."""
+        self.ctx = capi.DeformContext(max_instances=self.instances, device=self.device, flags=self._flags, stream=self._stream)
+        return self
+
+    def dispose(self):
+        """engine.ts:1692-1701."""
+        self.stopRenderLoop()
+        self.stopAnimation()
+        self._stopBreathing()
+        if self.ctx:
+            self.ctx.close()
+            self.ctx = None
+
+    # ---- timers (window.setTimeout stand-in) ------------------------------------------------
+    def _setTimeout(self, fn: Callable[[], None], delayMs: float) -> int:
+        tid = next(self._timer_ids)
+        heapq.heappush(self._timers, (self.clock() + max(0.0, delayMs), tid, fn))
+        return tid
+
+    def _clearTimeout(self, tid: Optional[int]):
+        if tid is not None:
+            self._cancelled.add(tid)
+
+    def _pumpTimers(self):
+        now = self.clock()
+        while self._timers and self._timers[0][0] <= now:
+            _, tid, fn = heapq.heappop(self._timers)
+            if tid in self._cancelled:
+                self._cancelled.discard(tid)
+                continue
+            fn()
+
+    # ---- assets ------------------------------------------------------------------------------
+    def loadModel(self, path: Union[str, Model]):
+        """engine.ts:1704-1721 -> setupModelBuffers (engine.ts:1728-1832): parse, then upload the static
+        tables through the C ABI.  Instances share the mesh; each gets its own skeleton runtime."""
+        if self.ctx is None:
+            raise RuntimeError("Engine.init() must be called before loadModel")
+        model = path if isinstance(path, Model) else PmxLoader.load(path, clock=self.clock)
+        model.clock = self.clock
+        self.currentModel = model
+        self.models = [model]
+        for _ in range(1, self.instances):
+            self.models.append(Model(model.vertexData, model.indexData, model.textures, model.materials, model.skeleton,
+                                     model.skinning, morphs=model.morphs, sdef=model.sdef, clock=self.clock))
+        sk = model.getSkinning()
+        self.ctx.load_mesh(model.getVertices(), sk.joints, sk.weights, model.getBoneInverseBindMatrices())
+        if model.morphs.count:
+            self.ctx.load_morphs(model.morphs.offsets, model.morphs.vertexIndex, model.morphs.delta)
+        if model.sdef.vertexIndex.size:
+            self.ctx.load_sdef(model.sdef.vertexIndex, model.sdef.c_r0_r1)
+        self._world_stage = self.ctx.palette_staging(self.instances)
+        return model
+
+    def loadAnimation(self, url: str):
+        """engine.ts:1419-1423."""
+        self.animationFrames = VMDLoader.load(url)
+        self.hasAnimation = True
+
+    # ---- bone API ----------------------------------------------------------------------------
+    def rotateBones(self, bones: Sequence[str], rotations: Sequence[Quat], durationMs: Optional[float] = None,
+                    instance: Optional[int] = 0):
+        """engine.ts:1723-1725 -> model.ts:246-315.  instance=None addresses every instance."""
+        targets = self.models if instance is None else self.models[instance:instance + 1]
+        for m in targets:
+            m.rotateBones(bones, rotations, durationMs)
+
+    def setMorphWeights(self, weights, morph_names_or_ids: Sequence[Union[str, int]]):
+        """New: per-instance weights [K, len(ids)] of the named vertex morphs."""
+        names = self.currentModel.morphs.names
+        ids = [names.index(x) if isinstance(x, str) else int(x) for x in morph_names_or_ids]
+        w = np.ascontiguousarray(weights, dtype=np.float32).reshape(self.instances, len(ids))
+        self.ctx.set_morph_weights(w, np.asarray(ids, np.uint32), K=self.instances)
+
+    # ---- animation playback (engine.ts:1425-1662) ----------------------------------------------
+    def playAnimation(self, options: Optional[dict] = None, instance: Optional[int] = 0):
+        if not self.animationFrames:
+            return
+        self.stopAnimation()
+        self._stopBreathing()
+        self.playingAnimation = True
+        opts = options or {}
+        bb = opts.get("breathBones")
+        enableBreath = bb is not None
+        breathBones: List[str] = []
+        breathRanges: Optional[Dict[str, float]] = None
+        if enableBreath and bb:
+            if isinstance(bb, dict):
+                breathBones, breathRanges = list(bb.keys()), dict(bb)
+            else:
+                breathBones = list(bb)
+        breathDuration = opts.get("breathDuration", 4000)
+
+        byBone: Dict[str, list] = {}
+        for kf in self.animationFrames:
+            for bf in kf.boneFrames:
+                byBone.setdefault(bf.boneName, []).append((kf.time, bf.rotation))
+        for v in byBone.values():
+            v.sort(key=lambda tr: tr[0])
+
+        rot = lambda names, quats, dur: self.rotateBones(names, quats, dur, instance=instance)
+        if self.currentModel:
+            t0 = [(n, v[0][1]) for n, v in byBone.items() if v and v[0][0] == 0]
+            have0 = {n for n, _ in t0}
+            if t0:
+                rot([n for n, _ in t0], [q for _, q in t0], 0)
+            reset = [b.name for b in self.currentModel.getSkeleton().bones if b.name not in have0]
+            if reset:
+                rot(reset, [Quat(0, 0, 0, 1)] * len(reset), 0)
+        for name, keys in byBone.items():
+            for i, (t, q) in enumerate(keys):
+                if t == 0:
+                    continue
+                prev = keys[i - 1] if i > 0 else None
+                durationMs = t * 1000 if i == 0 else (t - prev[0]) * 1000
+                delayMs = prev[0] * 1000 if prev is not None else 0
+                if delayMs <= 0:
+                    rot([name], [q], durationMs)
+                else:
+                    self._animationTimeouts.append(
+                        self._setTimeout(lambda n=name, qq=q, d=durationMs: rot([n], [qq], d), delayMs))
+        if enableBreath and self.currentModel:
+            maxTime = max((kf.time for kf in self.animationFrames), default=0)
+            last: Dict[str, Quat] = {}
+            for b in breathBones:
+                keys = byBone.get(b)
+                if keys:
+                    for (t, q) in reversed(keys):
+                        if t <= maxTime:
+                            last[b] = q
+                            break
+            self._breathingTimeout = self._setTimeout(
+                lambda: self._startBreathing(breathBones, last, breathRanges, breathDuration, instance), maxTime * 1000 + 200)
+
+    def stopAnimation(self):
+        for t in self._animationTimeouts:
+            self._clearTimeout(t)
+        self._animationTimeouts = []
+        self.playingAnimation = False
+
+    def _stopBreathing(self):
+        self._clearTimeout(self._breathingTimeout)
+        self._breathingTimeout = None
+        self._breathingBase.clear()
+
+    def _startBreathing(self, bones, baseRotations, ranges, durationMs, instance):
+        """engine.ts:1609-1662."""
+        if not self.currentModel:
+            return
+        for b in bones:
+            if b in baseRotations:
+                self._breathingBase[b] = baseRotations[b]
+        half = durationMs / 2
+
+        def animate(inhale: bool):
+            names, quats = [], []
+            for b in bones:
+                base = self._breathingBase.get(b)
+                if base is None:
+                    continue
+                r = (ranges or {}).get(b, 0.02)
+                names.append(b)
+                quats.append(base.multiply(Quat.fromEuler(r if inhale else -r, 0, 0)))
+            if names:
+                self.rotateBones(names, quats, half, instance=instance)
+            self._breathingTimeout = self._setTimeout(lambda: animate(not inhale), half)
+
+        animate(False)
+
+    # ---- frame ---------------------------------------------------------------------------------
+    def render(self):
+        """One frame of the replaced stage (engine.ts:2124 -> updateModelPose 2375-2391 -> draws)."""
+        if self.ctx is None or self.currentModel is None:
+            return
+        self._pumpTimers()
+        B = len(self.currentModel.skeleton.bones)
+        for k, m in enumerate(self.models):
+            m.evaluatePose()
+            self._world_stage[k] = m.getBoneWorldMatrices().reshape(B, 16)
+        self.ctx.set_palettes(self._world_stage, K=self.instances)
+        self.ctx.deform()
+
+    def runRenderLoop(self, callback: Optional[Callable[[], None]] = None, frames: Optional[int] = None,
+                      frame_ms: Optional[float] = None):
+        """engine.ts:1668-1682.  rAF does not exist here: runs `frames` frames (or until stopRenderLoop()
+        is called from the callback); `frame_ms` advances a ManualClock between frames."""
+        self._renderLoopCallback = callback
+        self._loop_running = True
+        n = 0
+        while self._loop_running and (frames is None or n < frames):
+            self.render()
+            if self._renderLoopCallback:
+                self._renderLoopCallback()
+            if frame_ms is not None and hasattr(self.clock, "advance"):
+                self.clock.advance(frame_ms)
+            n += 1
+        self._loop_running = False
+
+    def stopRenderLoop(self):
+        self._loop_running = False
+        self._renderLoopCallback = None
+
+    def getStats(self) -> EngineStats:
+        """engine.ts:1664-1666."""
+        if self.ctx:
+            s = self.ctx.stats()
+            self._stats = EngineStats(s["fps"], s["frameTime"], s["gpuMemory"], s["vertsPerSec"], s["achievedGBs"], s["algorithmicBytes"])
+        return EngineStats(**self._stats.__dict__)
+
+    # ---- results (the reference hands these straight to the rasteriser) ---------------------------
+    def readSkinned(self, instance: int = 0):
+        """Skinned positions and normals of one instance, [V,3] float32 each."""
+        return self.ctx.read_instance(instance)

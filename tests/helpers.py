@@ -1,0 +1,238 @@
+"""Test helpers: a tiny PMX 2.0 / VMD writer (our own data, exercising every weight type and
+the morph table), error metrics, and independent numpy restatements used as cross-checks."""
+from __future__ import annotations
+
+import struct
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+REF_ROOT = "/root/reference"
+
+
+def rel_err(out: np.ndarray, ref: np.ndarray) -> float:
+    """SURVEY 8c tolerance metric: max_v |out-ref|_inf / max(|ref|_inf, 1)."""
+    out = np.asarray(out, np.float64)
+    ref = np.asarray(ref, np.float64)
+    return float(np.abs(out - ref).max() / max(np.abs(ref).max(), 1.0))
+
+
+class PmxWriter:
+    def __init__(self, encoding=0, vertex_index_size=2, bone_index_size=2, morph_index_size=1, extra_vec4=0):
+        self.b = bytearray()
+        self.enc = encoding
+        self.vs, self.bs, self.ms, self.xv = vertex_index_size, bone_index_size, morph_index_size, extra_vec4
+
+    def text(self, s: str):
+        raw = s.encode("utf-16-le" if self.enc == 0 else "utf-8")
+        self.b += struct.pack("<i", len(raw)) + raw
+
+    def idx(self, v: int, size: int, signed=True):
+        fmt = {1: "b" if signed else "B", 2: "h" if signed else "H", 4: "i"}[size]
+        self.b += struct.pack("<" + fmt, v)
+
+    def header(self):
+        self.b += b"PMX " + struct.pack("<f", 2.0) + bytes([8, self.enc, self.xv, self.vs, 1, 1, self.bs, self.ms, 1])
+        for s in ("model", "model_en", "comment", "comment_en"):
+            self.text(s)
+
+    def vertices(self, verts: Sequence[dict]):
+        self.b += struct.pack("<i", len(verts))
+        for v in verts:
+            self.b += struct.pack("<8f", *v["pos"], *v["nrm"], *v["uv"])
+            self.b += b"\x00" * (16 * self.xv)
+            t = v["type"]
+            self.b += bytes([t])
+            if t == 0:
+                self.idx(v["bones"][0], self.bs)
+            elif t in (1, 3):
+                self.idx(v["bones"][0], self.bs)
+                self.idx(v["bones"][1], self.bs)
+                self.b += struct.pack("<f", v["w"][0])
+                if t == 3:
+                    self.b += struct.pack("<9f", *v["sdef"])
+            elif t in (2, 4):
+                for k in range(4):
+                    self.idx(v["bones"][k], self.bs)
+                self.b += struct.pack("<4f", *v["w"])
+            self.b += struct.pack("<f", 1.0)
+
+    def indices(self, idx: Sequence[int]):
+        self.b += struct.pack("<i", len(idx))
+        for i in idx:
+            self.idx(i, self.vs, signed=False)
+
+    def textures(self, names: Sequence[str]):
+        self.b += struct.pack("<i", len(names))
+        for n in names:
+            self.text(n)
+
+    def materials(self, n: int, vcount: int):
+        self.b += struct.pack("<i", n)
+        for i in range(n):
+            self.text(f"mat{i}")
+            self.text("")
+            self.b += struct.pack("<4f3ff3f", 1, 1, 1, 1, 0, 0, 0, 5.0, 0.5, 0.5, 0.5)
+            self.b += bytes([0x10]) + struct.pack("<4ff", 0, 0, 0, 1, 1.0)
+            self.idx(-1, 1)
+            self.idx(-1, 1)
+            self.b += bytes([0, 1, 0])
+            self.text("")
+            self.b += struct.pack("<i", vcount)
+
+    def bones(self, bones: Sequence[dict]):
+        self.b += struct.pack("<i", len(bones))
+        for bn in bones:
+            self.text(bn["name"])
+            self.text("")
+            self.b += struct.pack("<3f", *bn["pos"])
+            self.idx(bn["parent"], self.bs)
+            self.b += struct.pack("<i", 0)
+            flags = 0x0001 if bn.get("tail_bone") else 0
+            if bn.get("append_rotate"):
+                flags |= 0x0100
+            if bn.get("append_move"):
+                flags |= 0x0200
+            if bn.get("axis"):
+                flags |= 0x0400
+            if bn.get("local_axis"):
+                flags |= 0x0800
+            if bn.get("ik"):
+                flags |= 0x0020
+            self.b += struct.pack("<H", flags)
+            if flags & 1:
+                self.idx(0, self.bs)
+            else:
+                self.b += struct.pack("<3f", 0, 1, 0)
+            if flags & 0x0300:
+                self.idx(bn["append_parent"], self.bs)
+                self.b += struct.pack("<f", bn["append_ratio"])
+            if flags & 0x0400:
+                self.b += struct.pack("<3f", 1, 0, 0)
+            if flags & 0x0800:
+                self.b += struct.pack("<6f", 1, 0, 0, 0, 0, 1)
+            if flags & 0x0020:
+                self.idx(0, self.bs)
+                self.b += struct.pack("<ifi", 10, 1.0, 2)
+                self.idx(0, self.bs)
+                self.b += bytes([1]) + struct.pack("<6f", *([0.0] * 6))
+                self.idx(0, self.bs)
+                self.b += bytes([0])
+
+    def morphs(self, morphs: Sequence[dict]):
+        self.b += struct.pack("<i", len(morphs))
+        for m in morphs:
+            self.text(m["name"])
+            self.text("")
+            self.b += bytes([1, m["type"]]) + struct.pack("<i", len(m["items"]))
+            for it in m["items"]:
+                if m["type"] == 1:
+                    self.idx(it[0], self.vs, signed=False)
+                    self.b += struct.pack("<3f", *it[1])
+                elif m["type"] == 0:
+                    self.idx(it[0], self.ms)
+                    self.b += struct.pack("<f", it[1])
+                elif m["type"] == 2:
+                    self.idx(it[0], self.bs)
+                    self.b += struct.pack("<7f", *([0.0] * 7))
+                elif m["type"] == 3:
+                    self.idx(it[0], self.vs, signed=False)
+                    self.b += struct.pack("<4f", *([0.0] * 4))
+
+    def tail(self):
+        self.b += struct.pack("<iii", 0, 0, 0)  # display frames, rigid bodies, joints
+
+    def bytes(self) -> bytes:
+        return bytes(self.b)
+
+
+def write_vmd(keys: Sequence[tuple], morph_keys: Sequence[tuple] = ()) -> bytes:
+    """keys: (boneName, frame, (x,y,z,w)); morph_keys: (name, frame, weight)."""
+    b = bytearray(b"Vocaloid Motion Data 0002".ljust(30, b"\x00"))
+    b += b"model".ljust(20, b"\x00")
+    b += struct.pack("<I", len(keys))
+    for name, frame, q in keys:
+        b += name.encode("shift_jis").ljust(15, b"\x00")[:15]
+        b += struct.pack("<I3f4f", frame, 0, 0, 0, *q)
+        b += bytes(64)
+    b += struct.pack("<I", len(morph_keys))
+    for name, frame, w in morph_keys:
+        b += name.encode("shift_jis").ljust(15, b"\x00")[:15] + struct.pack("<If", frame, w)
+    b += struct.pack("<III", 0, 0, 0)
+    return bytes(b)
+
+
+def random_pmx(rng, V=300, B=12, n_morph=3, with_sdef=True, **kw):
+    """Synthetic PMX bytes covering BDEF1/2/4/SDEF/QDEF, append bones, IK block, all morph kinds."""
+    w = PmxWriter(**kw)
+    w.header()
+    verts = []
+    for i in range(V):
+        t = int(rng.choice([0, 1, 2, 3, 4] if with_sdef else [0, 1, 2, 4]))
+        bones = [int(x) for x in rng.integers(-1, B, 4)]
+        if t in (2, 4):
+            ws = rng.dirichlet(np.ones(4)).astype(np.float32)
+            if rng.random() < 0.15:
+                ws[int(rng.integers(0, 4))] = 0.0
+            if rng.random() < 0.05:
+                ws[:] = 0.0
+        else:
+            ws = np.array([rng.uniform(-0.1, 1.1), 0, 0, 0], np.float32)
+        p = rng.normal(size=3) * 3
+        n = rng.normal(size=3)
+        n /= np.linalg.norm(n)
+        v = dict(pos=[float(x) for x in p], nrm=[float(x) for x in n], uv=[float(x) for x in rng.random(2)], type=t, bones=bones,
+                 w=[float(x) for x in ws])
+        if t == 3:
+            c = p + rng.normal(size=3) * 0.1
+            d = rng.normal(size=3) * 0.2
+            v["sdef"] = [float(x) for x in np.concatenate([c, c + d, c - d])]
+        verts.append(v)
+    w.vertices(verts)
+    w.indices([int(x) for x in rng.integers(0, V, 3 * 10)])
+    w.textures(["a.png"])
+    w.materials(1, 30)
+    bones = []
+    pos = np.zeros((B, 3))
+    for i in range(B):
+        parent = -1 if i == 0 else int(rng.integers(0, i))
+        pos[i] = (pos[parent] if parent >= 0 else 0) + rng.normal(size=3)
+        bn = dict(name=f"骨{i}", pos=[float(x) for x in pos[i]], parent=parent, tail_bone=bool(i % 2), ik=(i == 3),
+                  axis=(i == 4), local_axis=(i == 5))
+        if i >= 2 and i % 3 == 0:
+            bn.update(append_rotate=True, append_parent=int(rng.integers(0, i)), append_ratio=float(rng.choice([-1.0, 0.25, 0.5, 1.5])))
+        bones.append(bn)
+    w.bones(bones)
+    morphs = []
+    for m in range(n_morph):
+        n = int(rng.integers(1, max(2, V // 5)))
+        vi = rng.choice(V, size=n, replace=False)
+        morphs.append(dict(name=f"m{m}", type=1, items=[(int(v), [float(x) for x in rng.normal(0, 0.05, 3)]) for v in vi]))
+    if n_morph >= 2:
+        morphs.append(dict(name="grp", type=0, items=[(0, 0.5), (1, -1.0)]))
+        morphs.append(dict(name="bonem", type=2, items=[(0, None)]))
+        morphs.append(dict(name="uvm", type=3, items=[(0, None), (1, None)]))
+    w.morphs(morphs)
+    w.tail()
+    return w.bytes(), verts, bones, morphs
+
+
+def numpy_blend_f64(vtx8, joints, weights, skin16):
+    """Independent dense restatement of engine.ts:253-272 in f64 (cross-check of the C oracle)."""
+    vtx8 = np.asarray(vtx8, np.float64).reshape(-1, 8)
+    V = vtx8.shape[0]
+    J = np.asarray(joints).reshape(V, 4)
+    W = np.asarray(weights, np.float64).reshape(V, 4) / 255.0
+    s = W.sum(axis=1, keepdims=True)
+    Wn = np.where(s > 1e-4, W / np.where(s > 1e-4, s, 1), np.array([1.0, 0, 0, 0]))
+    M = np.asarray(skin16, np.float64).reshape(-1, 4, 4).transpose(0, 2, 1)     # [B,row,col]
+    p4 = np.concatenate([vtx8[:, :3], np.ones((V, 1))], axis=1)
+    pos = np.zeros((V, 3))
+    nrm = np.zeros((V, 3))
+    for i in range(4):
+        Mi = M[J[:, i]]
+        pos += np.einsum("vrc,vc->vr", Mi[:, :3, :], p4) * Wn[:, i:i + 1]
+        nrm += np.einsum("vrc,vc->vr", Mi[:, :3, :3], vtx8[:, 3:6]) * Wn[:, i:i + 1]
+    ln = np.linalg.norm(nrm, axis=1, keepdims=True)
+    nrm = np.where(ln > 0, nrm / np.where(ln > 0, ln, 1), 0)
+    return pos, nrm

@@ -1,0 +1,355 @@
+"""GPU parity (-m gpu): the CUDA path through the C ABI vs the CPU oracle on the same inputs.
+
+Tolerance (SURVEY 8c / BASELINE.json): floats  max_v |out-ref|_inf / max(|ref|_inf, 1) <= 1e-5 against the f32
+oracle; integer tables bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import random_pmx, rel_err, write_vmd
+from reze_engine_b200 import Engine, PmxLoader, Quat, VMDLoader, capi, crowd, synth
+from reze_engine_b200.engine import ManualClock
+from reze_engine_b200.model import Bone
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+LOCAL = os.path.join(os.path.dirname(__file__), "golden", "_local")
+
+
+def oracle_instance(orc, wl, world_p, morphW=None, sdef=False):
+    skin = orc.skin_matrices(world_p, wl.invBind)
+    morph = (wl.morphs.offsets, wl.morphs.vertexIndex, wl.morphs.delta) if morphW is not None else None
+    sd = (wl.sdef.vertexIndex, wl.sdef.c_r0_r1) if sdef else None
+    return orc.deform(wl.vtx8, wl.joints, wl.weights, skin, morph=morph, morphW=morphW, sdef=sd)
+
+
+def check_all(orc, ctx, wl, world, i2p, K, morphW=None, sdef=False, instances=None):
+    for k in (range(K) if instances is None else instances):
+        p = k if i2p is None else int(i2p[k])
+        rp, rn = oracle_instance(orc, wl, world[p], None if morphW is None else morphW[k], sdef)
+        gp, gn = ctx.read_instance(k)
+        assert rel_err(gp, rp) <= TOL, (k, rel_err(gp, rp))
+        assert rel_err(gn, rn) <= TOL, (k, rel_err(gn, rn))
+
+
+@pytest.fixture(scope="module")
+def wl_small():
+    return synth.make_workload(5000, 64, M=8, sdef=True)
+
+
+SHAPES = [(I, nt, st) for I in (1, 2, 4, 8) for nt in (256, 512) for st in (1, 2)]
+
+
+@pytest.mark.parametrize("I,nt,st", SHAPES)
+def test_every_launch_shape_matches_oracle(rzlib, orc, wl_small, I, nt, st):
+    wl = wl_small
+    K, P = 11, 4                                    # partial last group for every I; shared palettes
+    world = synth.make_palettes(wl.bones, P, np.random.default_rng(1))
+    i2p = (np.arange(K) * 3) % P
+    with capi.DeformContext(max_instances=K, instances_per_group=I, threads=nt, store_mode=st) as ctx:
+        ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
+        ctx.set_palettes(world, i2p)
+        ctx.deform()
+        s = ctx.stats()
+        assert (s["instancesPerGroup"], s["threads"], s["storeMode"]) == (I, nt, st)
+        check_all(orc, ctx, wl, world, i2p, K)
+        # instances that share a palette are bit-identical
+        a, b = ctx.read_instance(0), ctx.read_instance(4)
+        assert i2p[0] == i2p[4] and np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+@pytest.mark.parametrize("V", [1, 31, 255, 256, 257, 1001, 1022])
+def test_ragged_vertex_counts(rzlib, orc, V):
+    wl = synth.make_workload(V, 16, seed=100 + V)
+    world = synth.make_palettes(wl.bones, 3, np.random.default_rng(2))
+    for st in (1, 2):
+        with capi.DeformContext(max_instances=3, store_mode=st) as ctx:
+            ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
+            ctx.set_palettes(world)
+            ctx.deform()
+            check_all(orc, ctx, wl, world, None, 3)
+
+
+def test_integer_tables_bit_exact_and_skin_matrices(rzlib, orc, wl_small):
+    wl = wl_small
+    world = synth.make_palettes(wl.bones, 2, np.random.default_rng(3))
+    with capi.DeformContext(max_instances=2) as ctx:
+        ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
+        j, w = ctx.read_skinning()
+        assert np.array_equal(j, wl.joints.reshape(-1)) and np.array_equal(w, wl.weights.reshape(-1))
+        ctx.set_palettes(world)
+        got = ctx.read_skin_matrices(1)                       # [B,12] rows
+        ref = orc.skin_matrices(world[1], wl.invBind).reshape(-1, 4, 4).transpose(0, 2, 1)[:, :3, :].reshape(-1, 12)
+        assert rel_err(got, ref) <= 1e-6
+
+
+def test_tpose_identity(rzlib, wl_small):
+    wl = wl_small
+    ident = np.tile(np.array([0, 0, 0, 1], np.float32), (1, wl.B, 1))
+    world = crowd.world_matrices_batch(wl.bones, ident)
+    with capi.DeformContext(max_instances=1) as ctx:
+        ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
+        ctx.set_palettes(world)
+        ctx.deform()
+        p, n = ctx.read_instance(0)
+        assert rel_err(p, wl.vtx8[:, :3]) <= 1e-6 and rel_err(n, wl.vtx8[:, 3:6]) <= 1e-6
+
+
+def test_morphs(rzlib, orc, wl_small):
+    wl = wl_small
+    K = 6
+    rng = np.random.default_rng(4)
+    world = synth.make_palettes(wl.bones, K, rng)
+    active = np.array([5, 0, 3], np.uint32)
+    w = rng.uniform(0, 1, (K, 3)).astype(np.float32)
+    dense = np.zeros((K, wl.morphs.count), np.float32)
+    dense[:, active] = w
+    for I, st in ((1, 1), (4, 2), (2, 1)):
+        with capi.DeformContext(max_instances=K, instances_per_group=I, store_mode=st) as ctx:
+            ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
+            ctx.load_morphs(wl.morphs.offsets, wl.morphs.vertexIndex, wl.morphs.delta)
+            ctx.set_palettes(world)
+            ctx.deform()                                    # no weights yet: the pinned (M = 0) path
+            check_all(orc, ctx, wl, world, None, K)
+            ctx.set_morph_weights(w, active, K=K)
+            ctx.deform()
+            assert ctx.stats()["activeMorphs"] == 3
+            check_all(orc, ctx, wl, world, None, K, morphW=dense)
+            ctx.set_morph_weights(None, [], K=K)            # back to zero weights
+            ctx.deform()
+            check_all(orc, ctx, wl, world, None, K)
+
+
+def test_sdef_on_and_compat_off(rzlib, orc, wl_small):
+    wl = wl_small
+    K = 5
+    rng = np.random.default_rng(5)
+    world = synth.make_palettes(wl.bones, K, rng)
+    dense = rng.uniform(0, 1, (K, wl.morphs.count)).astype(np.float32)
+    with capi.DeformContext(max_instances=K, flags=capi.RZ_FLAG_SDEF) as ctx:
+        ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
+        ctx.load_sdef(wl.sdef.vertexIndex, wl.sdef.c_r0_r1)
+        ctx.set_palettes(world)
+        ctx.deform()
+        assert ctx.stats()["sdefCount"] == wl.sdef.vertexIndex.size
+        check_all(orc, ctx, wl, world, None, K, sdef=True)
+        ctx.load_morphs(wl.morphs.offsets, wl.morphs.vertexIndex, wl.morphs.delta)
+        ctx.set_morph_weights(dense, np.arange(wl.morphs.count), K=K)
+        ctx.deform()
+        check_all(orc, ctx, wl, world, None, K, morphW=dense, sdef=True)
+    with capi.DeformContext(max_instances=K) as ctx:          # compat mode: SDEF records ignored => BDEF2 (reference behaviour)
+        ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
+        ctx.load_sdef(wl.sdef.vertexIndex, wl.sdef.c_r0_r1)
+        ctx.set_palettes(world)
+        ctx.deform()
+        check_all(orc, ctx, wl, world, None, K, sdef=False)
+
+
+def test_bounds_and_positions_only(rzlib, orc, wl_small):
+    wl = wl_small
+    K = 9
+    world = synth.make_palettes(wl.bones, K, np.random.default_rng(6))
+    with capi.DeformContext(max_instances=K, flags=capi.RZ_FLAG_BOUNDS) as ctx:
+        ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
+        ctx.set_palettes(world)
+        ctx.deform()
+        bb = ctx.read_bounds(0, K)
+        for k in range(K):
+            p, _ = ctx.read_instance(k)
+            assert np.array_equal(bb[k, :3], p.min(axis=0)) and np.array_equal(bb[k, 3:], p.max(axis=0))
+        check_all(orc, ctx, wl, world, None, K)
+    with capi.DeformContext(max_instances=K, flags=capi.RZ_FLAG_NO_NORMALS) as ctx:
+        ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
+        ctx.set_palettes(world)
+        ctx.deform()
+        for k in range(K):
+            rp, _ = oracle_instance(orc, wl, world[k])
+            gp, gn = ctx.read_instance(k)
+            assert gn is None and rel_err(gp, rp) <= TOL
+
+
+def test_sub_range_deform_and_device_palettes(rzlib, orc, wl_small):
+    import torch
+    wl = wl_small
+    K = 8
+    world = synth.make_palettes(wl.bones, K, np.random.default_rng(8))
+    dw = torch.from_numpy(world).cuda()
+    with capi.DeformContext(max_instances=K, stream=torch.cuda.current_stream().cuda_stream) as ctx:
+        ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
+        ctx.set_palettes_device(dw.data_ptr(), K)
+        ctx.deform(2, 3)
+        ctx.sync()
+        check_all(orc, ctx, wl, world, None, K, instances=[2, 3, 4])
+        base, stride, noff = ctx.output_device_ptr()
+        assert stride % 16 == 0 and noff % 16 == 0 and noff >= wl.V * 12
+
+
+def test_huge_bone_count_uses_global_palette_path(rzlib, orc):
+    wl = synth.make_workload(3000, 6000, seed=77)
+    world = synth.make_palettes(wl.bones, 2, np.random.default_rng(9))
+    with capi.DeformContext(max_instances=2) as ctx:
+        ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
+        ctx.set_palettes(world)
+        ctx.deform()
+        check_all(orc, ctx, wl, world, None, 2)
+
+
+def test_weight_edge_cases(rzlib, orc):
+    wl = synth.make_workload(600, 10, seed=5)
+    W = wl.weights.copy()
+    W[0] = [0, 0, 0, 0]            # sum <= 1e-4 -> (1,0,0,0) (engine.ts:257-258)
+    W[1] = [128, 0, 127, 0]        # zero weight in the middle
+    W[2] = [10, 20, 30, 40]        # sum != 255 is renormalised by the shader rule
+    W[3] = [0, 0, 0, 255]
+    wl.weights = W
+    world = synth.make_palettes(wl.bones, 1, np.random.default_rng(10))
+    with capi.DeformContext(max_instances=1) as ctx:
+        ctx.load_mesh(wl.vtx8, wl.joints, W, wl.invBind)
+        ctx.set_palettes(world)
+        ctx.deform()
+        check_all(orc, ctx, wl, world, None, 1)
+
+
+def test_error_paths(rzlib, wl_small):
+    wl = wl_small
+    with capi.DeformContext(max_instances=2) as ctx:
+        with pytest.raises(capi.RzError) as e:
+            ctx.lib.rz_deform(ctx.h, 0, 1) and None
+            ctx._check(ctx.lib.rz_deform(ctx.h, 0, 1))
+        assert e.value.status == -5
+        bad = wl.joints.copy()
+        bad[7, 2] = wl.B
+        with pytest.raises(capi.RzError) as e:
+            ctx.load_mesh(wl.vtx8, bad, wl.weights, wl.invBind)
+        assert e.value.status == -1 and "joint" in str(e.value)
+        ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
+        with pytest.raises(capi.RzError):
+            ctx.set_palettes(np.zeros((3, wl.B, 16), np.float32))          # K=3 > max_instances
+        with pytest.raises(capi.RzError):
+            ctx.set_palettes(np.zeros((1, wl.B, 16), np.float32), [0, 1])  # palette index out of range
+        with pytest.raises(capi.RzError):
+            ctx.load_morphs([0, 1], [wl.V], [0, 0, 0])
+
+
+def test_engine_facade_drives_the_path(rzlib, orc, tmp_path):
+    rng = np.random.default_rng(12)
+    data, *_ = random_pmx(rng, V=700, B=12)
+    pmx_path = tmp_path / "m.pmx"
+    pmx_path.write_bytes(data)
+    q1 = Quat(0, 0.3, 0, 0.95).normalize()
+    vmd_path = tmp_path / "a.vmd"
+    vmd_path.write_bytes(write_vmd([("骨1", 0, (0, 0, 0, 1)), ("骨1", 30, q1.toArray()), ("骨6", 15, (0.2, 0, 0, 0.98))]))
+    clock = ManualClock()
+    eng = Engine(None, {"ambient": 1.0, "bloomIntensity": 0.1}, instances=2, clock=clock, sdef=True).init()
+    model = eng.loadModel(str(pmx_path))
+    eng.loadAnimation(str(vmd_path))
+    eng.runRenderLoop(frames=1)                        # T pose frame
+    p, n = eng.readSkinned(0)
+    assert rel_err(p, model.getVertices().reshape(-1, 8)[:, :3]) <= 1e-6
+    eng.playAnimation()
+    eng.rotateBones(["骨2"], [Quat(0, 0, 0.4, 0.9)], 0, instance=1)      # instance 1 diverges
+    eng.setMorphWeights(np.array([[0.7], [0.2]], np.float32), ["m0"])
+    frames = []
+    eng.runRenderLoop(lambda: frames.append(clock()), frames=4, frame_ms=250.0)
+    assert frames == [0.0, 250.0, 500.0, 750.0]
+    st = eng.getStats()
+    assert st.frameTime > 0 and st.gpuMemory > 0
+    for k in range(2):
+        m = eng.models[k]
+        skin = orc.skin_matrices(m.getBoneWorldMatrices(), m.getBoneInverseBindMatrices())
+        dense = np.zeros(m.morphs.count, np.float32)
+        dense[0] = [0.7, 0.2][k]
+        rp, rn = orc.deform(m.getVertices(), m.skinning.joints, m.skinning.weights, skin,
+                            morph=(m.morphs.offsets, m.morphs.vertexIndex, m.morphs.delta), morphW=dense,
+                            sdef=(m.sdef.vertexIndex, m.sdef.c_r0_r1))
+        gp, gn = eng.readSkinned(k)
+        assert rel_err(gp, rp) <= TOL and rel_err(gn, rn) <= TOL
+    a, b = eng.readSkinned(0)[0], eng.readSkinned(1)[0]
+    assert not np.array_equal(a, b)
+    eng.dispose()
+
+
+def _load_local(name):
+    path = os.path.join(LOCAL, name)
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/_local not generated (needs the reference assets; see make_fixtures.py)")
+    return np.load(path, allow_pickle=False)
+
+
+def _bones_from(z):
+    bones = []
+    for i in range(len(z["parents"])):
+        ap = int(z["appendParent"][i])
+        ar = float(z["appendRatio"][i])
+        bones.append(Bone(name=str(z["names"][i]), parentIndex=int(z["parents"][i]), bindTranslation=[float(x) for x in z["bindTranslation"][i]],
+                          appendParentIndex=None if ap < 0 and not bool(z["appendRotate"][i]) and not bool(z["appendMove"][i]) else ap,
+                          appendRatio=None if np.isnan(ar) else ar, appendRotate=bool(z["appendRotate"][i]), appendMove=bool(z["appendMove"][i])))
+    return bones
+
+
+@pytest.mark.parametrize("key", ["serqet", "serqet2"])
+def test_real_model_poses(rzlib, orc, key):
+    """BASELINE configs 0/1: the shipped PMX in T pose, the tutorial pose (canvas4.tsx:16-17: 腰 = (0,0.3,0,1), 首 = id)
+    and the end pose of pool.vmd, skinned on the GPU vs the oracle; integer tables bit-exact."""
+    from reze_engine_b200.model import Model, Skeleton, Skinning
+    z = _load_local(f"{key}.npz")
+    bones = _bones_from(z)
+    clock = ManualClock()
+    model = Model(z["vtx8"], np.zeros(0, np.uint32), [], [], Skeleton(bones, z["invBind"]), Skinning(z["joints"], z["weights"]), clock=clock)
+    V, B = model.vertexCount, len(bones)
+    vmd = _load_local("pool_vmd.npz")
+    poses = []
+    model.evaluatePose()
+    poses.append(model.getBoneWorldMatrices().copy())
+    model.rotateBones(["腰", "首"], [Quat(0, 0.3, 0, 1), Quat(0, 0, 0, 1)], 0)
+    model.evaluatePose()
+    poses.append(model.getBoneWorldMatrices().copy())
+    last = {}
+    for nm, row in zip(vmd["names"], vmd["data"]):
+        last[str(nm)] = Quat(*row[1:5])
+    model.rotateBones(list(last.keys()), list(last.values()), 0)
+    model.evaluatePose()
+    poses.append(model.getBoneWorldMatrices().copy())
+    world = np.stack(poses).reshape(3, B, 16)
+    with capi.DeformContext(max_instances=3) as ctx:
+        ctx.load_mesh(z["vtx8"], z["joints"], z["weights"], z["invBind"])
+        j, w = ctx.read_skinning()
+        assert np.array_equal(j, z["joints"]) and np.array_equal(w, z["weights"])
+        ctx.set_palettes(world)
+        ctx.deform()
+        vt = z["vtx8"].reshape(-1, 8)
+        p0, n0 = ctx.read_instance(0)
+        assert rel_err(p0, vt[:, :3]) <= 1e-6
+        for k in range(3):
+            skin = orc.skin_matrices(world[k], z["invBind"])
+            rp, rn = orc.deform(z["vtx8"], z["joints"], z["weights"], skin)
+            gp, gn = ctx.read_instance(k)
+            assert rel_err(gp, rp) <= TOL and rel_err(gn, rn) <= TOL
+        assert rel_err(ctx.read_instance(1)[0], p0) > 1e-3        # the pose really moved vertices
+
+
+def test_headline_size_properties(rzlib, orc):
+    """BASELINE headline shape (V=100k, B=512) at a K that keeps the test short: oracle on sampled instances,
+    idempotence, and bit-identical outputs for instances sharing a palette."""
+    import zlib
+    wl = synth.make_workload(100_000, 512)
+    K, P = 256, 64
+    world = synth.make_palettes(wl.bones, P, np.random.default_rng(21))
+    i2p = (np.arange(K) * 7) % P
+    with capi.DeformContext(max_instances=K) as ctx:
+        ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
+        ctx.set_palettes(world, i2p)
+        ctx.deform()
+        check_all(orc, ctx, wl, world, i2p, K, instances=[0, 101, 255])
+        crc1 = [zlib.crc32(ctx.read_instance(k)[0].tobytes()) for k in (3, 67, 131, 200)]
+        ctx.deform()
+        crc2 = [zlib.crc32(ctx.read_instance(k)[0].tobytes()) for k in (3, 67, 131, 200)]
+        assert crc1 == crc2                                           # idempotent
+        same = [k for k in range(K) if i2p[k] == i2p[3]]
+        assert len(same) >= 4
+        ref = ctx.read_instance(3)
+        for k in same[1:4]:
+            got = ctx.read_instance(k)
+            assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])

@@ -1,0 +1,176 @@
+"""Host logic (no GPU): pose runtime, tween/timer semantics of the facade, oracle cross-checks,
+and the C-ABI library surface (loads, exports every declared symbol, fails loudly without a device)."""
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+from helpers import numpy_blend_f64, random_pmx, rel_err, write_vmd
+from reze_engine_b200 import Engine, Model, PmxLoader, Quat, VMDLoader, crowd, synth
+from reze_engine_b200.engine import ManualClock
+from reze_engine_b200.math3d import Mat4, easeInOut
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_math_conventions():
+    # column-major, v' = M v, translation in 12..14 (math.ts:303-320, 472-477)
+    t = Mat4.identity().translateInPlace(1, 2, 3)
+    r = Mat4.fromQuat(*Quat.fromEuler(0, math.pi / 2, 0).toArray())
+    m = t.multiply(r)
+    assert np.allclose(m.values[12:15], [1, 2, 3])
+    q = m.toQuat()
+    assert abs(abs(q.y) - math.sin(math.pi / 4)) < 1e-6
+    assert easeInOut(0) == 0 and easeInOut(1) == 1 and easeInOut(0.25) == 0.125 and easeInOut(0.75) == 0.875
+    a, b = Quat(0, 0, 0, 1), Quat(0, math.sin(0.4), 0, math.cos(0.4))
+    h = Quat.slerp(a, b, 0.5)
+    assert abs(h.y - math.sin(0.2)) < 1e-12
+    n = Quat.slerp(a, Quat(0, -math.sin(0.4), 0, -math.cos(0.4)), 0.5)      # shortest arc flips b
+    assert abs(n.y - math.sin(0.2)) < 1e-12
+    c = Quat.slerp(a, Quat(0, 1e-3, 0, 1).normalize(), 0.5)                  # lerp branch above 0.9995
+    assert abs(c.length() - 1) < 1e-12
+
+
+def test_tpose_world_is_bind_and_skin_is_identity(orc):
+    wl = synth.make_workload(500, 40)
+    m = wl.model(clock=ManualClock())
+    m.evaluatePose()
+    skin = orc.skin_matrices(m.getBoneWorldMatrices(), wl.invBind)
+    assert np.array_equal(skin, np.tile(np.eye(4, dtype=np.float32).reshape(-1), (40, 1)))   # exactly identity
+    pos, nrm = orc.deform(wl.vtx8, wl.joints, wl.weights, skin)
+    assert rel_err(pos, wl.vtx8[:, :3]) < 1e-6
+
+
+def test_rotate_bones_tween_semantics():
+    clock = ManualClock()
+    wl = synth.make_workload(64, 8)
+    m = wl.model(clock=clock)
+    target = Quat(0, 0.6, 0, 1)
+    m.rotateBones(["bone3", "nope"], [target, target], 1000)
+    clock.advance(250)
+    m.evaluatePose()
+    e = easeInOut(0.25)
+    want = Quat.slerp(Quat(0, 0, 0, 1), target.normalize(), e)
+    got = m.localRotations[12:16]
+    assert np.allclose(got, np.float32([want.x, want.y, want.z, want.w]))
+    # retarget mid-tween: start becomes the interpolated value *now* (model.ts:275-301)
+    m.rotateBones(["bone3"], [Quat(0.5, 0, 0, 1)], 500)
+    assert np.allclose(m._startQuat[12:16], np.float32([want.x, want.y, want.z, want.w]), atol=1e-7)
+    clock.advance(500)
+    m.evaluatePose()
+    assert m._active[3] == 0
+    assert np.allclose(m.localRotations[12:16], np.float32(Quat(0.5, 0, 0, 1).normalize().toArray()))
+    # duration 0 writes immediately and cancels
+    m.rotateBones(["bone2"], [Quat(0, 0, 1, 0)], 0)
+    assert m.localRotations[8:12].tolist() == [0, 0, 1, 0]
+
+
+def test_append_rotation_and_batch_evaluator_bit_exact():
+    rng = np.random.default_rng(5)
+    data, *_ = random_pmx(rng, V=50, B=12)
+    m = PmxLoader.loadFromBuffer(data, clock=ManualClock())
+    B = len(m.skeleton.bones)
+    assert any(b.appendRotate for b in m.skeleton.bones)
+    qa, qb = synth.make_pose_keys(B, rng)
+    lr = crowd.tween_pose_batch(qa, qb, np.array([0.0, 0.3, 0.77, 1.0]))
+    batch = crowd.world_matrices_batch(m.skeleton.bones, lr)
+    for p in range(4):
+        m.localRotations[:] = lr[p].reshape(-1)
+        m.computeWorldMatrices()
+        assert np.array_equal(m.worldMatrices.view(np.uint32), batch[p].reshape(-1).view(np.uint32))
+    # a negative ratio conjugates the append parent's rotation (model.ts:372-377)
+    b = next(b for b in m.skeleton.bones if b.appendRotate and b.appendRatio == -1.0) if any(
+        bb.appendRotate and bb.appendRatio == -1.0 for bb in m.skeleton.bones) else None
+    if b is not None:
+        assert max(-1.0, min(1.0, b.appendRatio)) == -1.0
+
+
+def test_play_animation_schedules_like_the_reference():
+    clock = ManualClock()
+    rng = np.random.default_rng(2)
+    data, *_ = random_pmx(rng, V=30, B=6, n_morph=0, with_sdef=False)
+    eng = Engine(None, {"ambient": 1.0}, clock=clock)
+    model = PmxLoader.loadFromBuffer(data, clock=clock)
+    eng.currentModel, eng.models = model, [model]          # no GPU here: drive the host side only
+    q1, q2 = Quat(0, 0.3, 0, 0.95).normalize(), Quat(0.2, 0, 0, 0.98).normalize()
+    vmd = write_vmd([("骨1", 0, (0, 0, 0, 1)), ("骨1", 30, q1.toArray()), ("骨1", 45, q2.toArray()), ("骨2", 15, q1.toArray())])
+    eng.animationFrames = VMDLoader.loadFromBuffer(vmd)
+    model.rotateBones(["骨4"], [q2], 0)
+    eng.playAnimation({"breathBones": {"骨1": 0.05}, "breathDuration": 1000})
+    assert model.localRotations[16:20].tolist() == [0, 0, 0, 1]          # bones without a t=0 key are reset
+    assert model._active[1] == 1 and model._durationMs[1] == 1000        # key 0 -> 30 frames tween starts now
+    assert model._active[2] == 1 and model._durationMs[2] == 500         # first key at t>0: duration = t
+    clock.advance(1000); eng._pumpTimers(); model.evaluatePose()
+    assert np.allclose(model.localRotations[4:8], np.float32(q1.toArray()), atol=1e-6)
+    assert model._active[1] == 1 and model._durationMs[1] == 500         # 30 -> 45 frames, scheduled at t=1s
+    clock.advance(500); eng._pumpTimers(); model.evaluatePose()
+    assert np.allclose(model.localRotations[4:8], np.float32(q2.toArray()), atol=1e-6)
+    clock.advance(200); eng._pumpTimers()                                 # maxTime + 200 ms: breathing starts (exhale first)
+    assert model._active[1] == 1 and model._durationMs[1] == 500
+    want = q2.multiply(Quat.fromEuler(-0.05, 0, 0))
+    assert np.allclose(model._targetQuat[4:8], np.float32(want.normalize().toArray()), atol=1e-6)
+    eng.stopAnimation()
+    assert not eng.playingAnimation
+
+
+def test_oracle_against_independent_numpy_restatement(orc):
+    wl = synth.make_workload(3000, 48)
+    world = synth.make_palettes(wl.bones, 2, np.random.default_rng(4))[1]
+    skin64 = orc.skin_matrices(world, wl.invBind, np.float64)
+    p64, n64 = orc.deform(wl.vtx8, wl.joints, wl.weights, skin64, dtype=np.float64)
+    pn, nn = numpy_blend_f64(wl.vtx8, wl.joints, wl.weights, skin64)
+    assert rel_err(p64, pn) < 1e-12 and rel_err(n64, nn) < 1e-12
+    p32, n32 = orc.deform(wl.vtx8, wl.joints, wl.weights, orc.skin_matrices(world, wl.invBind))
+    assert rel_err(p32, p64) < 2e-6 and rel_err(n32, n64) < 2e-6        # f32 oracle vs f64 oracle (reported in DESIGN.md)
+
+
+def test_oracle_morph_and_sdef_reduce_to_pinned_path(orc):
+    wl = synth.make_workload(2000, 32, M=6, sdef=True)
+    world = synth.make_palettes(wl.bones, 1, np.random.default_rng(9))[0]
+    skin = orc.skin_matrices(world, wl.invBind)
+    base = orc.deform(wl.vtx8, wl.joints, wl.weights, skin)
+    morph = (wl.morphs.offsets, wl.morphs.vertexIndex, wl.morphs.delta)
+    zero = orc.deform(wl.vtx8, wl.joints, wl.weights, skin, morph=morph, morphW=np.zeros(6, np.float32))
+    assert np.array_equal(zero[0], base[0]) and np.array_equal(zero[1], base[1])      # M = 0 equals the pinned path
+    # SDEF with both bones carrying the same rigid transform equals the linear blend up to rounding
+    same = np.tile(world[5], (wl.B, 1))
+    inv0 = np.tile(np.eye(4, dtype=np.float32).reshape(-1), (wl.B, 1))
+    sk = orc.skin_matrices(same, inv0)
+    lin = orc.deform(wl.vtx8, wl.joints, wl.weights, sk)
+    sd = orc.deform(wl.vtx8, wl.joints, wl.weights, sk, sdef=(wl.sdef.vertexIndex, wl.sdef.c_r0_r1))
+    assert rel_err(sd[0], lin[0]) < 5e-6 and rel_err(sd[1], lin[1]) < 5e-6
+
+
+def test_capi_exports_every_declared_symbol(rzlib):
+    from reze_engine_b200 import capi
+    hdr = open(os.path.join(ROOT, "include", "rze_b200.h")).read()
+    declared = set(re.findall(r"\b(rz_[a-z_]+)\s*\(", hdr))
+    assert declared == set(capi.EXPORTS)
+    for name in declared:
+        assert hasattr(rzlib, name), name
+    assert rzlib.rz_abi_version() == 1
+    import ctypes as C
+    assert C.sizeof(capi.RzConfig) == 56 and C.sizeof(capi.RzStats) == 128
+
+
+def test_no_device_fails_loudly_never_falls_back(rzlib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from reze_engine_b200 import capi
+    with pytest.raises(capi.RzError) as ei:
+        capi.DeformContext(max_instances=1)
+    assert ei.value.status == -2 and "no CPU path" in str(ei.value)
+    with pytest.raises(capi.RzError):
+        Engine(None).init()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "reze-engine_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f), encoding="utf-8").read()
+                assert "oracle" not in src.lower().replace("oracle convention", ""), f

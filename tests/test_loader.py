@@ -1,0 +1,172 @@
+"""Loader parity: PMX/VMD host code vs the reference's own fixture and vs the C oracle.
+
+Pins the integer outputs ("bone-index outputs bit-exact"): the reference's dump
+web/app/tutorial/model.json of 塞尔凯特.pmx must be reproduced exactly.  The reference assets
+carry a no-redistribution notice, so only SHA-256 digests of the arrays are committed
+(tests/golden/digests.json, written by tests/golden/make_fixtures.py); the comparison against
+model.json itself runs wherever /root/reference is mounted.
+"""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import REF_ROOT, random_pmx, write_vmd
+from reze_engine_b200 import PmxLoader, VMDLoader
+from reze_engine_b200 import pmx as pmxmod
+
+HAVE_REF = os.path.exists(os.path.join(REF_ROOT, "web/app/tutorial/model.json"))
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "digests.json")
+
+
+def _sha(a: np.ndarray) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def model_digests(m) -> dict:
+    return {
+        "V": int(m.vertexCount), "B": len(m.skeleton.bones),
+        "vertices": _sha(m.vertexData), "joints": _sha(m.skinning.joints), "weights": _sha(m.skinning.weights),
+        "indices": _sha(m.indexData), "invBind": _sha(m.skeleton.inverseBindMatrices),
+        "parents": _sha(np.asarray([b.parentIndex for b in m.skeleton.bones], np.int32)),
+        "bindTranslation": _sha(np.asarray([b.bindTranslation for b in m.skeleton.bones], np.float64)),
+        "morphCount": int(m.morphs.count), "morphNnz": int(m.morphs.vertexIndex.size),
+    }
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference tree not mounted")
+def test_pmx_loader_reproduces_model_json_exactly():
+    m = PmxLoader.load(os.path.join(REF_ROOT, "web/public/models/塞尔凯特/塞尔凯特.pmx"))
+    ref = json.load(open(os.path.join(REF_ROOT, "web/app/tutorial/model.json")))
+    v = np.asarray(ref["vertices"], dtype=np.float32)
+    assert np.array_equal(v.view(np.uint32), m.vertexData.view(np.uint32))
+    assert np.array_equal(np.asarray(ref["skinning"]["joints"], np.uint16), m.skinning.joints)
+    assert np.array_equal(np.asarray(ref["skinning"]["weights"], np.uint8), m.skinning.weights)
+    assert np.array_equal(np.asarray(ref["indices"], np.uint32), m.indexData)
+    assert len(ref["bones"]) == len(m.skeleton.bones) == 471
+    for b, rb in zip(m.skeleton.bones, ref["bones"]):
+        assert b.name == rb["name"] and b.parentIndex == rb["parentIndex"]
+        assert b.bindTranslation == rb["bindTranslation"]          # f64 differences of f32 reads, exact
+        assert b.appendRotate == rb["appendRotate"] and b.appendMove == rb["appendMove"]
+        assert b.appendParentIndex == rb.get("appendParentIndex") and b.appendRatio == rb.get("appendRatio")
+    # invariants the reference's loader guarantees (pmx-loader.ts:865-876, 892-938)
+    assert (m.skinning.weights.reshape(-1, 4).astype(int).sum(axis=1) == 255).all()
+    assert (m.skinning.joints < 471).all()
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference tree not mounted")
+def test_committed_digests_match_reference_assets():
+    want = json.load(open(GOLDEN))
+    for key, rel in (("serqet", "web/public/models/塞尔凯特/塞尔凯特.pmx"), ("serqet2", "web/public/models/塞尔凯特2/塞尔凯特2.pmx")):
+        assert model_digests(PmxLoader.load(os.path.join(REF_ROOT, rel))) == want[key]
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference tree not mounted")
+def test_vmd_clips():
+    for name, nkeys, times in (("pool", 68, [0.0, 1.5]), ("boom", 49, [0.0, 1.0, 1.3])):
+        kfs = VMDLoader.load(os.path.join(REF_ROOT, f"web/public/animations/{name}.vmd"))
+        assert [k.time for k in kfs] == times
+        assert sum(len(k.boneFrames) for k in kfs) == nkeys
+
+
+def test_quantisers_match_oracle(orc):
+    rng = np.random.default_rng(7)
+    specials = [0.0, 1.0, 0.5, -0.2, 1.3, float("nan"), 0.499999, 0.5019608, 1 / 255 * 0.5]
+    for w in specials + list(rng.uniform(-0.2, 1.2, 400)):
+        w = float(np.float32(w))
+        w0 = pmxmod._js_max(0, pmxmod._js_min(255, pmxmod._js_round(w * 255)))
+        w1 = pmxmod._js_max(0, pmxmod._js_min(255, 255 - w0))
+        assert [pmxmod._to_u8(w0), pmxmod._to_u8(w1)] == orc.quantize_bdef2(w).tolist()
+    for _ in range(600):
+        wf = rng.dirichlet(np.ones(4)).astype(np.float32) * rng.choice([1.0, 0.7, 1.4])
+        if rng.random() < 0.2:
+            wf[int(rng.integers(0, 4))] = 0
+        if rng.random() < 0.03:
+            wf[int(rng.integers(0, 4))] = np.nan
+        got = pmxmod.quantize_bdef4([float(x) for x in wf])
+        assert got == orc.quantize_bdef4(wf).tolist()
+        # (the reference's BDEF4 rounding can leave 254..256 here; toModel's renormalise pass fixes it)
+
+
+def test_finalize_skinning_matches_oracle(orc):
+    rng = np.random.default_rng(11)
+    V, B = 4000, 37
+    J = rng.integers(0, 60, (V, 4)).astype(np.uint16)          # many out-of-range joints
+    W = rng.integers(0, 256, (V, 4)).astype(np.uint8)
+    W[rng.random(V) < 0.3] = [255, 0, 0, 0]
+    W[rng.random(V) < 0.05] = 0
+    j1, w1 = J.reshape(-1).copy(), W.reshape(-1).copy()
+    pmxmod.finalize_skinning(j1, w1, B)
+    j2, w2 = orc.finalize_skinning(J, W, B)
+    assert np.array_equal(j1, j2) and np.array_equal(w1, w2)
+    assert (j1 < B).all()
+    s = w1.reshape(-1, 4).astype(int).sum(axis=1)
+    assert (s == 255).mean() > 0.99          # the reference's own fix-ups leave rare non-255 rows; we match them
+
+
+def test_synthetic_pmx_roundtrip_all_weight_types(orc):
+    rng = np.random.default_rng(3)
+    for kw in (dict(), dict(encoding=1, vertex_index_size=1, bone_index_size=1), dict(vertex_index_size=4, bone_index_size=4, extra_vec4=2)):
+        V = 200 if kw.get("vertex_index_size") == 1 else 300
+        data, verts, bones, morphs = random_pmx(rng, V=V, B=12, **kw)
+        m = PmxLoader.loadFromBuffer(data)
+        assert m.vertexCount == V and len(m.skeleton.bones) == 12
+        # expected skinning: oracle quantisers + oracle toModel
+        J = np.zeros((V, 4), np.uint16)
+        W = np.zeros((V, 4), np.uint8)
+        sdef_idx = []
+        for i, v in enumerate(verts):
+            W[i, 0] = 255
+            b = [x if x >= 0 else 0 for x in v["bones"]]
+            if v["type"] == 0:
+                J[i, 0] = b[0]
+            elif v["type"] in (1, 3):
+                J[i, :2] = b[:2]
+                W[i, :2] = orc.quantize_bdef2(np.float32(v["w"][0]))
+                if v["type"] == 3:
+                    sdef_idx.append(i)
+            else:
+                J[i] = b
+                W[i] = orc.quantize_bdef4(np.asarray(v["w"], np.float32))
+        j2, w2 = orc.finalize_skinning(J, W, 12)
+        assert np.array_equal(m.skinning.joints, j2) and np.array_equal(m.skinning.weights, w2)
+        assert m.sdef.vertexIndex.tolist() == sdef_idx
+        for n, i in enumerate(sdef_idx):
+            assert np.allclose(m.sdef.c_r0_r1[n], np.asarray(verts[i]["sdef"], np.float32))
+        # inverse bind vs oracle
+        ib = orc.inverse_bind([b.parentIndex for b in m.skeleton.bones], [b.bindTranslation for b in m.skeleton.bones])
+        assert np.array_equal(ib.view(np.uint32), m.skeleton.inverseBindMatrices.view(np.uint32))
+        # morphs: vertex morphs kept verbatim, group morph expanded, other kinds empty but slot-preserving
+        assert m.morphs.count == len(morphs)
+        for k, mm in enumerate(morphs):
+            lo, hi = int(m.morphs.offsets[k]), int(m.morphs.offsets[k + 1])
+            if mm["type"] == 1:
+                assert m.morphs.vertexIndex[lo:hi].tolist() == [it[0] for it in mm["items"]]
+                assert np.allclose(m.morphs.delta[lo:hi], np.asarray([it[1] for it in mm["items"]], np.float32))
+            elif mm["type"] == 0:
+                exp = sum(len(morphs[it[0]]["items"]) for it in mm["items"])
+                assert hi - lo == exp
+            else:
+                assert hi == lo
+        assert m.skeleton.bones[3].appendRotate and m.skeleton.bones[3].appendParentIndex is not None
+
+
+def test_pmx_rejects_garbage():
+    with pytest.raises(pmxmod.PmxFormatError):
+        PmxLoader.loadFromBuffer(b"PMD \x00\x00\x00\x00")
+    data, *_ = random_pmx(np.random.default_rng(1), V=20, B=4)
+    with pytest.raises(pmxmod.PmxFormatError):
+        PmxLoader.loadFromBuffer(data[:200])
+
+
+def test_vmd_writer_roundtrip():
+    keys = [("センター", 0, (0, 0, 0, 1)), ("首", 30, (0, 0.3, 0, 0.95)), ("センター", 45, (0.1, 0, 0, 0.99)), ("首", 0, (0, 0, 0, 1))]
+    ld = VMDLoader(write_vmd(keys, [("まばたき", 10, 0.5)]))
+    kfs = ld.parse()
+    assert [k.time for k in kfs] == [0.0, 1.0, 1.5]
+    assert [bf.boneName for bf in kfs[0].boneFrames] == ["センター", "首"]
+    assert ld.morphFrames[0].morphName == "まばたき" and ld.morphFrames[0].weight == 0.5
+    with pytest.raises(ValueError):
+        VMDLoader.loadFromBuffer(b"not a vmd" + bytes(60))
