@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py — skinned vertices / second of the fused morph+skin deform path on B200.
+
+Contract (driver): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line from rank 0.
+For N > 1 it is launched under torchrun (one rank per GPU); instances are sharded by rank with no
+collective on the data path (weak scaling: every GPU deforms the same K instances-per-GPU).
+
+A "step" = one frame of the hot path for every instance on the GPU:
+    skin-matrix pass over the resident world palettes + the fused deform kernel.
+`value`  : device-timed, inputs already resident in HBM.
+`e2e`    : same frame through the C ABI with HOST buffers: palettes copied from pinned host memory
+           (rz_set_palettes), deform, one instance read back (rz_read_instance) — inside the timed region.
+`roofline`: algorithmic bytes of one deform launch / its mean CUDA-event duration vs the measured HBM peak.
+`cpu_baseline`: the CPU oracle (a port of the reference arithmetic; the reference itself is TypeScript+WGSL
+           and cannot run here) on a bounded sample, all host cores.
+`--impl reference` times that CPU port alone with the same metric/config (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HEADLINE = dict(V=100_000, B=512, K=4096)
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_inputs(V, B, K, P, seed=None):
+    from reze_engine_b200 import synth
+    t = time.time()
+    wl = synth.make_workload(V, B) if seed is None else synth.make_workload(V, B, seed=seed)
+    world = synth.make_palettes(wl.bones, P, np.random.default_rng(synth.SEED + 1))
+    log(f"[bench] synthetic workload V={V} B={B} P={P}: {time.time() - t:.1f}s")
+    return wl, world
+
+
+def cpu_reference_rate(wl, world, K, target_s, threads):
+    """Times the CPU oracle on a bounded sample of the workload: the first Ks instances (palette k mod P) on
+    `threads` host threads, sized to last about `target_s` seconds.  Each thread overwrites one output slot
+    (no first-touch page faults on a K-instance buffer in the timing)."""
+    from oracle import oracle as orc
+    orc.build()
+    P = world.shape[0]
+    i2p = (np.arange(K) % P).astype(np.uint32)
+    ring = np.zeros((threads, 2 * ((wl.V * 3 + 3) // 4 * 4)), np.float32)
+    probe = min(2 * threads, K)
+    orc.deform_instances(wl.vtx8, wl.joints, wl.weights, world, wl.invBind, i2p, probe, nthreads=threads, out=ring, ring=True)
+    t = time.perf_counter()
+    orc.deform_instances(wl.vtx8, wl.joints, wl.weights, world, wl.invBind, i2p, probe, nthreads=threads, out=ring, ring=True)
+    rate = probe / max(time.perf_counter() - t, 1e-4)           # instances / s
+    Ks = int(min(K, max(threads, int(target_s * rate) // threads * threads)))
+    t = time.perf_counter()
+    orc.deform_instances(wl.vtx8, wl.joints, wl.weights, world, wl.invBind, i2p, Ks, nthreads=threads, out=ring, ring=True)
+    dt = time.perf_counter() - t
+    return (Ks * wl.V) / dt, Ks, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    V, B, K = args.verts, args.bones, args.instances
+    threads = os.cpu_count() or 1
+    Pc = min(K, max(threads * 4, 64))
+    wl, world = make_inputs(V, B, K, Pc)
+    rates, samples = [], None
+    for i in range(args.warmup + args.steps):
+        rate, Ks, dt = cpu_reference_rate(wl, world, K, args.cpu_seconds / max(args.steps, 1), threads)
+        if i >= args.warmup:
+            rates.append(rate)
+            samples = (Ks, dt)
+    val = float(np.mean(rates))
+    sample = f"{samples[0]} of {K} instances x {V} verts per step ({samples[1]:.2f}s), {threads} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "skinned_vertices_per_sec", "value": val, "unit": "verts/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": samples[1] * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(V, B, K), "V": V, "B": B, "K_per_gpu": K, "M": 0},
+        "cpu_baseline": {"value": val, "unit": "verts/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "verts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def workload_name(V, B, K):
+    return f"headline crowd: V={V} verts x K={K} instances per GPU, B={B} bones, M=0 morphs, one palette per instance (staggered phase)"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--verts", type=int, default=HEADLINE["V"])
+    ap.add_argument("--bones", type=int, default=HEADLINE["B"])
+    ap.add_argument("--instances", type=int, default=HEADLINE["K"], help="instances per GPU")
+    ap.add_argument("--palettes", type=int, default=0, help="distinct palettes (0 = one per instance)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--ipg", type=int, default=0)
+    ap.add_argument("--store", type=int, default=0)
+    ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--chunks", type=int, default=0)
+    ap.add_argument("--ctas", type=int, default=0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from reze_engine_b200 import capi
+
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the deform path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world_size > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    V, B, K = args.verts, args.bones, args.instances
+    P = args.palettes or K
+    wl, world = make_inputs(V, B, K, P)
+    i2p = None if P >= K else (np.arange(K) % P).astype(np.uint32)
+
+    stream = torch.cuda.current_stream()
+    ctx = capi.DeformContext(max_instances=K, device=local_rank, stream=stream.cuda_stream, instances_per_group=args.ipg,
+                             store_mode=args.store, threads=args.threads, chunks=args.chunks, ctas_per_sm=args.ctas)
+    ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
+    d_world = torch.from_numpy(world).cuda()
+    d_i2p = torch.from_numpy(i2p.astype(np.int64)).to(torch.int32).cuda() if i2p is not None else None
+    stage = ctx.palette_staging(P)
+    stage[:] = world
+    torch.cuda.synchronize()
+
+    def step_resident():
+        ctx.set_palettes_device(d_world.data_ptr(), P, d_i2p.data_ptr() if d_i2p is not None else 0, K)
+        ctx.deform()
+
+    def barrier():
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: resident inputs, device-timed ---------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    launches0 = ctx.stats()["kernelLaunches"]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for s in range(args.steps):
+        ctx.set_palettes_device(d_world.data_ptr(), P, d_i2p.data_ptr() if d_i2p is not None else 0, K)
+        ev[s][0].record()
+        ctx.deform()
+        ev[s][1].record()
+    t1.record()
+    barrier()
+    clocks = sampler.stop()
+    total_ms = t0.elapsed_time(t1)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    st = ctx.stats()
+    launches = int(st["kernelLaunches"] - launches0)
+    if world_size > 1:
+        tt = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms = float(tt.item())
+    ms_per_step = total_ms / args.steps
+    value = world_size * K * V / (ms_per_step * 1e-3)
+
+    # ---- e2e: host palettes -> H2D -> deform -> one instance back to the host, per step -------------------------
+    for _ in range(2):
+        ctx.set_palettes(stage, i2p, K=K)
+        ctx.deform()
+        ctx.read_instance(0)
+    barrier()
+    wall0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    esteps = max(3, min(args.steps, 10))
+    for s in range(esteps):
+        ctx.set_palettes(stage, i2p, K=K)
+        ctx.deform()
+        ctx.read_instance(s % K)
+    e1.record()
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - wall0) * 1e3) / esteps
+    if world_size > 1:
+        tt = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tt.item())
+    e2e_value = world_size * K * V / (e2e_ms * 1e-3)
+    h2d = P * B * 64 + (K * 4 if i2p is not None else 0)
+    d2h = V * 24
+
+    # trivial result gather (the only collective): one small record per GPU
+    if world_size > 1:
+        rec = torch.tensor([float(K * V), kernel_ms, float(launches)], device="cuda", dtype=torch.float64)
+        allrec = [torch.zeros_like(rec) for _ in range(world_size)]
+        dist.all_gather(allrec, rec)
+        per_gpu = [[float(x) for x in r.tolist()] for r in allrec]
+        launches = int(sum(r[2] for r in per_gpu))
+    else:
+        per_gpu = None
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        alg = st["algorithmicBytes"]
+        achieved = alg / (kernel_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        out = {
+            "metric": "skinned_vertices_per_sec", "value": value, "unit": "verts/s", "n_gpus": world_size, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(V, B, K), "V": V, "B": B, "K_per_gpu": K, "P_per_gpu": P, "M": 0,
+                       "parallelism": f"instances sharded over {world_size} GPU(s), no data-path collective",
+                       "l2": "no flush needed: each step writes K*V*24 B = %.2f GB >> 126 MB L2" % (K * V * 24 / 1e9),
+                       "kernel": {"instances_per_group": st["instancesPerGroup"], "threads": st["threads"],
+                                  "store_mode": {1: "direct st.global.cs", 2: "smem-staged TMA bulk store"}.get(st["storeMode"]),
+                                  "ctas": st["ctas"], "smem_bytes": st["smemBytes"]}},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "verts/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "path": "rz_set_palettes(pinned host) + rz_deform + rz_read_instance"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": peak_src, "kernel": "rz::deform_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg},
+        }
+        if per_gpu:
+            out["per_gpu"] = per_gpu
+        if not args.no_cpu and world_size == 1:
+            threads = os.cpu_count() or 1
+            rate, Ks, dt = cpu_reference_rate(wl, world, K, args.cpu_seconds, threads)
+            out["cpu_baseline"] = {"value": rate, "unit": "verts/s", "cores": threads, "kind": "port",
+                                   "sample": f"{Ks} of {K} instances x {V} verts in {dt:.2f}s on {threads} threads (oracle/rz_oracle.c)"}
+        print(json.dumps(out), flush=True)
+    ctx.close()
+    if world_size > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -94,7 +94,7 @@ def deform(vtx8, joints, weights, skin16, morph=None, morphW=None, sdef=None, dt
 
 
 def deform_instances(vtx8, joints, weights, world, invBind, inst2pal, K, morph=None, morphW=None, sdef=None, nthreads=1,
-                     out: Optional[np.ndarray] = None):
+                     out: Optional[np.ndarray] = None, ring: bool = False):
     """K instances, f32, multi-threaded (CPU baseline).  Returns out [K, 2, Vpad4*3] f32 view helpers."""
     vtx8 = np.ascontiguousarray(vtx8, np.float32).reshape(-1, 8)
     V = vtx8.shape[0]
@@ -120,10 +120,10 @@ def deform_instances(vtx8, joints, weights, world, invBind, inst2pal, K, morph=N
     nrmOff = (V * 3 + 3) // 4 * 4
     stride = 2 * nrmOff
     if out is None:
-        out = np.empty((K, stride), np.float32)
+        out = np.empty((max(nthreads, 1) if ring else K, stride), np.float32)
     lib().orc_deform_instances(_p(vtx8), _p(joints), _p(weights), C.c_uint32(V), C.c_uint32(B), _p(world), _p(invBind), _p(i2p),
                                C.c_uint32(K), _p(vs), _p(vm), _p(vd), _p(mw), C.c_uint32(M), _p(so), _p(sv), _p(out),
-                               C.c_size_t(stride), C.c_size_t(nrmOff), C.c_uint32(nthreads))
+                               C.c_size_t(stride), C.c_size_t(nrmOff), C.c_uint32(nthreads), C.c_int32(1 if ring else 0))
     return out, nrmOff
 
 

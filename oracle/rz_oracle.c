@@ -185,6 +185,7 @@ typedef struct {
   const int32_t* sdefOf; const float* sdefVec9;
   float* out; size_t instStrideF, nrmOffF;
   uint32_t k0, k1;
+  int32_t ringSlot; /* >= 0: every instance of this worker is written to this slot (timing runs) */
 } orc_job;
 
 static void* orc_worker(void* arg) {
@@ -193,7 +194,7 @@ static void* orc_worker(void* arg) {
   for (uint32_t k = j->k0; k < j->k1; ++k) {
     const uint32_t p = j->inst2pal ? j->inst2pal[k] : k;
     orc_skin_matrices_f32(j->world + (size_t)p * j->B * 16, j->invBind, j->B, skin);
-    float* pos = j->out + (size_t)k * j->instStrideF;
+    float* pos = j->out + (size_t)(j->ringSlot >= 0 ? (uint32_t)j->ringSlot : k) * j->instStrideF;
     orc_deform_range_f32(j->vtx8, j->joints, j->weights, 0, j->V, skin, j->vmStart, j->vmMorph, j->vmDelta,
                          j->morphW ? j->morphW + (size_t)k * j->M : NULL, j->sdefOf, j->sdefVec9, pos, pos + j->nrmOffF);
   }
@@ -201,12 +202,14 @@ static void* orc_worker(void* arg) {
   return NULL;
 }
 
-/* out layout identical to the product's: per instance pos plane then normal plane */
+/* out layout identical to the product's: per instance pos plane then normal plane.
+ * ring != 0: `out` holds only `nthreads` instance slots, worker t overwrites slot t (CPU-baseline timing without
+ * first-touch page faults on a K-instance buffer). */
 void orc_deform_instances(const float* vtx8, const uint16_t* joints, const uint8_t* weights, uint32_t V, uint32_t B,
                           const float* world, const float* invBind, const uint32_t* inst2pal, uint32_t K,
                           const uint32_t* vmStart, const uint32_t* vmMorph, const float* vmDelta, const float* morphW, uint32_t M,
                           const int32_t* sdefOf, const float* sdefVec9,
-                          float* out, size_t instStrideF, size_t nrmOffF, uint32_t nthreads) {
+                          float* out, size_t instStrideF, size_t nrmOffF, uint32_t nthreads, int32_t ring) {
   if (nthreads < 1) nthreads = 1;
   if (nthreads > K) nthreads = K;
   pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * nthreads);
@@ -214,7 +217,7 @@ void orc_deform_instances(const float* vtx8, const uint16_t* joints, const uint8
   for (uint32_t t = 0; t < nthreads; ++t) {
     orc_job j = {vtx8, joints, weights, V, B, K, world, invBind, inst2pal, vmStart, vmMorph, vmDelta, morphW, M,
                  sdefOf, sdefVec9, out, instStrideF, nrmOffF, (uint32_t)((uint64_t)K * t / nthreads),
-                 (uint32_t)((uint64_t)K * (t + 1) / nthreads)};
+                 (uint32_t)((uint64_t)K * (t + 1) / nthreads), ring ? (int32_t)t : -1};
     jobs[t] = j;
     if (nthreads == 1) orc_worker(&jobs[t]);
     else pthread_create(&th[t], NULL, orc_worker, &jobs[t]);

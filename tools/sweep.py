@@ -1,0 +1,69 @@
+"""Launch-shape sweep of the deform kernel on the headline workload (GPU box).  Writes gpurun_out/sweep.jsonl."""
+import argparse
+import itertools
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+from reze_engine_b200 import capi, synth  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--verts", type=int, default=100_000)
+    ap.add_argument("--bones", type=int, default=512)
+    ap.add_argument("--instances", type=int, default=2048)
+    ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--ipg", default="1,2,4,8")
+    ap.add_argument("--threads", default="256,512")
+    ap.add_argument("--store", default="1,2")
+    ap.add_argument("--ctas", default="0")
+    ap.add_argument("--chunks", default="0")
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.jsonl"))
+    a = ap.parse_args()
+    os.makedirs(os.path.dirname(a.out), exist_ok=True)
+    V, B, K = a.verts, a.bones, a.instances
+    wl = synth.make_workload(V, B)
+    P = min(K, 1024)
+    world = synth.make_palettes(wl.bones, P, np.random.default_rng(1))
+    dw = torch.from_numpy(world).cuda()
+    i2p = torch.arange(K, dtype=torch.int32, device="cuda") % P
+    stream = torch.cuda.current_stream()
+    rows = []
+    L = lambda s: [int(x) for x in s.split(",")]
+    for I, nt, st, ctas, chunks in itertools.product(L(a.ipg), L(a.threads), L(a.store), L(a.ctas), L(a.chunks)):
+        try:
+            ctx = capi.DeformContext(max_instances=K, stream=stream.cuda_stream, instances_per_group=I, threads=nt, store_mode=st,
+                                     ctas_per_sm=ctas, chunks=chunks)
+            ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
+            ctx.set_palettes_device(dw.data_ptr(), P, i2p.data_ptr(), K)
+            for _ in range(2):
+                ctx.deform()
+            torch.cuda.synchronize()
+            ms = []
+            for _ in range(a.iters):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); ctx.deform(); e1.record()
+                torch.cuda.synchronize()
+                ms.append(e0.elapsed_time(e1))
+            s = ctx.stats()
+            ctx.close()
+            med = float(np.median(ms))
+            row = dict(I=s["instancesPerGroup"], threads=s["threads"], store=s["storeMode"], ctas=s["ctas"], smem=s["smemBytes"], req=[I, nt, st, ctas, chunks],
+                       ms=med, ms_min=float(min(ms)), gverts=K * V / med / 1e6, gbs=s["algorithmicBytes"] / med / 1e6)
+        except Exception as e:  # noqa: BLE001
+            row = dict(req=[I, nt, st, ctas, chunks], error=str(e))
+        rows.append(row)
+        print(json.dumps(row), flush=True)
+        with open(a.out, "a") as f:
+            f.write(json.dumps(row) + "\n")
+
+
+if __name__ == "__main__":
+    main()
