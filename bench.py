@@ -48,51 +48,56 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle-reason sampling DURING the timed region (B200_PROFILING.md clocks line).
+    NVML polled every ~2 ms from a thread (the timed region is tens of ms: `nvidia-smi -lms` is too coarse)."""
 
     def __init__(self, index: int):
         self.index = index
-        self.proc = None
-        self.lines = []
+        self.samples = []
+        self.stop_flag = False
+        self.thread = None
+        self.err = None
+
+    def _loop(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self.stop_flag:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                except Exception:
+                    pw = float("nan")
+                self.samples.append((sm, mx, pw, int(get_reasons(h))))
+                time.sleep(0.002)
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
+        time.sleep(0.01)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons, pw = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"nvml unavailable: {self.err}"]}
+        bits = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        reasons = set()
+        for s in self.samples:
+            for b, n in bits.items():
+                if s[3] & b:
                     reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+        sm = [s[0] for s in self.samples]
+        return {"sm_mhz": float(np.median(sm)), "sm_min_mhz": float(min(sm)), "sm_max_mhz": float(self.samples[0][1]),
+                "power_w_max": float(np.nanmax([s[2] for s in self.samples])), "samples": len(sm), "reasons": sorted(reasons)}
 
 
 def make_inputs(V, B, K, P, seed=None):
@@ -197,7 +202,9 @@ def main():
     wl, world = make_inputs(V, B, K, P)
     i2p = None if P >= K else (np.arange(K) % P).astype(np.uint32)
 
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: the library launches on it and torch.cuda.Event times it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     ctx = capi.DeformContext(max_instances=K, device=local_rank, stream=stream.cuda_stream, instances_per_group=args.ipg,
                              store_mode=args.store, threads=args.threads, chunks=args.chunks, ctas_per_sm=args.ctas)
     ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)

@@ -175,8 +175,10 @@ def test_sub_range_deform_and_device_palettes(rzlib, orc, wl_small):
     wl = wl_small
     K = 8
     world = synth.make_palettes(wl.bones, K, np.random.default_rng(8))
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     dw = torch.from_numpy(world).cuda()
-    with capi.DeformContext(max_instances=K, stream=torch.cuda.current_stream().cuda_stream) as ctx:
+    with capi.DeformContext(max_instances=K, stream=stream.cuda_stream) as ctx:
         ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
         ctx.set_palettes_device(dw.data_ptr(), K)
         ctx.deform(2, 3)

@@ -34,7 +34,8 @@ def main():
     world = synth.make_palettes(wl.bones, P, np.random.default_rng(1))
     dw = torch.from_numpy(world).cuda()
     i2p = torch.arange(K, dtype=torch.int32, device="cuda") % P
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     rows = []
     L = lambda s: [int(x) for x in s.split(",")]
     for I, nt, st, ctas, chunks in itertools.product(L(a.ipg), L(a.threads), L(a.store), L(a.ctas), L(a.chunks)):
