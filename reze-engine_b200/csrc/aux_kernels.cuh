@@ -9,7 +9,7 @@ namespace rz {
 // Replaces the reference's only compute shader (engine.ts:920-929).  One thread per (palette, bone);
 // keeps rows 0..2 of the column-major product (row 3 never reaches the blend's outputs, engine.ts:260-272).
 __global__ void skin_matrices_kernel(const float4* __restrict__ world, const float4* __restrict__ invBind,
-                                     float4* __restrict__ skin, uint32_t P, uint32_t B) {
+                                     float4* __restrict__ skin, const uint32_t* __restrict__ bonePos, uint32_t P, uint32_t B) {
   const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= P * B) return;
   const uint32_t b = idx % B;
@@ -23,8 +23,11 @@ __global__ void skin_matrices_kernel(const float4* __restrict__ world, const flo
     r[1][c] = fmaf(w3.y, ib.w, fmaf(w2.y, ib.z, fmaf(w1.y, ib.y, w0.y * ib.x)));
     r[2][c] = fmaf(w3.z, ib.w, fmaf(w2.z, ib.z, fmaf(w1.z, ib.y, w0.z * ib.x)));
   }
-#pragma unroll
-  for (int k = 0; k < 3; ++k) skin[(size_t)idx * 3 + k] = make_float4(r[k][0], r[k][1], r[k][2], r[k][3]);
+  const size_t row = (size_t)(idx - b) + __ldg(bonePos + b);         // bank-aware palette permutation (rze_b200.cu rebuild_tables)
+  // pair layout (deform_kernel.cuh kRowF4): rows 0/1 interleaved, row 2 as is
+  skin[row * 3 + 0] = make_float4(r[0][0], r[1][0], r[0][1], r[1][1]);
+  skin[row * 3 + 1] = make_float4(r[0][2], r[1][2], r[0][3], r[1][3]);
+  skin[row * 3 + 2] = make_float4(r[2][0], r[2][1], r[2][2], r[2][3]);
 }
 
 // dense per-instance morph weights: dense[k][m] = 0, dense[k][activeIds[a]] += w[k][a]

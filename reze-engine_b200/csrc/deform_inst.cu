@@ -12,29 +12,25 @@ namespace rz {
 #define RZ_CAT2(a, b) a##b
 #define RZ_CAT(a, b) RZ_CAT2(a, b)
 
-template <int I, int NT, bool ST>
+template <int I, int NT, int MINB>
 static KernelEntry entry() {
   KernelEntry e;
-  e.fn = reinterpret_cast<const void*>(&deform_kernel<I, NT, ST, RZ_FEAT>);
-  e.I = I; e.NT = NT; e.staged = ST; e.feat = RZ_FEAT;
+  e.fn = reinterpret_cast<const void*>(&deform_kernel<I, NT, MINB, RZ_FEAT>);
+  e.I = I; e.NT = NT; e.MINB = MINB; e.feat = RZ_FEAT;
   return e;
 }
 
-// FEAT == 0 (the plain BDEF path) gets every launch shape; feature sets get a reduced list.
-KernelEntry RZ_CAT(lookup_feat_, RZ_FEAT)(int I, int NT, bool staged) {
-#define RZ_TRY(i, nt, st) if (I == i && NT == nt && staged == st) return entry<i, nt, st>();
+// MINB <= 0 matches the first compiled entry with the requested I and NT
+KernelEntry RZ_CAT(lookup_feat_, RZ_FEAT)(int I, int NT, int MINB) {
+#define RZ_TRY(i, nt, mb) if (I == i && NT == nt && (MINB <= 0 || MINB == mb)) return entry<i, nt, mb>();
 #if RZ_FEAT == 0
-  RZ_TRY(1, 256, false) RZ_TRY(2, 256, false) RZ_TRY(4, 256, false) RZ_TRY(8, 256, false)
-  RZ_TRY(1, 512, false) RZ_TRY(2, 512, false) RZ_TRY(4, 512, false) RZ_TRY(8, 512, false)
-  RZ_TRY(1, 256, true)  RZ_TRY(2, 256, true)  RZ_TRY(4, 256, true)  RZ_TRY(8, 256, true)
-  RZ_TRY(1, 512, true)  RZ_TRY(2, 512, true)  RZ_TRY(4, 512, true)  RZ_TRY(8, 512, true)
+  RZ_SHAPES_FULL(RZ_TRY)
 #else
-  RZ_TRY(1, 256, false) RZ_TRY(2, 256, false) RZ_TRY(4, 256, false)
-  RZ_TRY(1, 512, true)  RZ_TRY(2, 512, true)  RZ_TRY(4, 512, true)
+  RZ_SHAPES_LITE(RZ_TRY)
 #endif
 #undef RZ_TRY
   KernelEntry none;
-  none.fn = nullptr; none.I = 0; none.NT = 0; none.staged = false; none.feat = RZ_FEAT;
+  none.fn = nullptr; none.I = 0; none.NT = 0; none.MINB = 0; none.feat = RZ_FEAT;
   return none;
 }
 

@@ -1,30 +1,37 @@
-// deform_kernel.cuh — the fused morph + BDEF1/2/4/SDEF skinning kernel for sm_100a.
+// deform_kernel.cuh — the fused morph + BDEF1/2/4/SDEF skinning kernel for sm_100a (v2).
 //
 // Replaces the per-vertex blend the reference runs inside three WGSL vertex shaders
 // (engine.ts:245-276 main, 431-463 outline, 692-715 depth-only) and materialises the
 // skinned stream once per frame for K independent character instances.
 //
-// Work decomposition (B200: 148 SMs, 227 KB smem, HBM-bound on the 24 B/vertex write):
-//   work item = (group of I instances) x (chunk of vertex tiles); persistent CTAs pull
-//   items from an atomic counter.  Per item the I bone palettes (B x 48 B each, 3x4
-//   row-major skin matrices) are staged into shared memory with one cp.async.bulk
-//   (TMA bulk copy, mbarrier complete_tx) per instance; each thread then keeps ONE
-//   vertex (pos, normal, 4 joints, 4 weights = 40 B, float4-vectorised, L2-resident)
-//   in registers and evaluates it for the I instances, so the static mesh is read once
-//   per I outputs.  Results are written either directly (st.global.cs) or staged in
-//   shared memory in final layout and drained with cp.async.bulk shared->global
-//   (TMA bulk store, double-buffered, evict-first), which keeps the LSU free for the
-//   palette gathers.  No tensor cores: the work is a gather of 3x4 mat-vecs.
+// Work decomposition (B200: 148 SMs, 227 KB smem/SM, HBM-bound on the 24 B/vertex write):
+//   work item = (group of I instances) x (chunk of vertex tiles); persistent CTAs pull items from
+//   an atomic counter.  Per item the I bone palettes (B x 48 B each, 3x4 row-major skin matrices)
+//   are staged into shared memory with one cp.async.bulk (TMA bulk copy, mbarrier complete_tx) per
+//   instance.  NT compute threads each keep ONE vertex (pos, normal, 4 joints, 4 pre-normalised
+//   weights: 52 B, float4-vectorised, L2-resident, prefetched one pass ahead) in registers and
+//   evaluate it for the I instances, so the static mesh is read once per I outputs.
+//   Results go to a double-buffered shared-memory staging area laid out exactly like the output
+//   planes; a dedicated STORE WARP drains each buffer with cp.async.bulk shared->global (TMA bulk
+//   store, L2 evict-first).  Compute warps and the store warp are coupled only through full/empty
+//   mbarriers (no CTA-wide barrier inside an item), so warps of different cost (1..4 influences)
+//   run up to two steps apart.  The palette gather is the SM-side bottleneck (48 B per influence
+//   through the 128 B/clk shared-memory pipe), so the influence loop is specialised per warp on the
+//   warp-maximum influence count (warps are class-sorted at load time) and never branches per lane.
+//   No tensor cores: the work is a gather of 3x4 mat-vecs.
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 namespace rz {
 
 constexpr int kTile = 256;          // vertices per preprocessing tile (permutation unit)
-constexpr int kRowF4 = 3;           // float4 per bone (3x4 row-major)
+constexpr int kRowF4 = 3;           // float4 per bone.  PAIR LAYOUT of the 3x4 skin matrix m[row][col] (48 B):
+                                    //   A = (m00,m10,m01,m11)  B = (m02,m12,m03,m13)  C = (m20,m21,m22,m23)
+                                    // rows 0/1 are interleaved so that (x,y) of a transformed point come out of one FFMA2
 
-// meta word (rec1.w) layout
+// meta word layout
 constexpr uint32_t kMetaSlotMask = 0x3FFu;   // bits 0-9  : slot inside the tile
 constexpr int      kMetaNinfShift = 10;      // bits 10-12: 1 + index of last non-zero weight
 constexpr uint32_t kMetaValid = 1u << 13;
@@ -34,9 +41,10 @@ constexpr uint32_t kMetaSdef  = 1u << 15;
 enum : int { FEAT_MORPH = 1, FEAT_SDEF = 2, FEAT_BOUNDS = 4, FEAT_GPAL = 8, FEAT_NONRM = 16 };
 
 struct DeformParams {
-  const float4* __restrict__ rec0;     // [Vp] px,py,pz, weights(u8x4 bits)
-  const float4* __restrict__ rec1;     // [Vp] nx,ny,nz, meta bits
-  const uint2*  __restrict__ joints;   // [Vp] 4 x u16
+  const float4* __restrict__ rec0;     // [Vp] px,py,pz, w0      (weights already normalised like engine.ts:255-258)
+  const float4* __restrict__ rec1;     // [Vp] nx,ny,nz, w1
+  const float4* __restrict__ rec2;     // [Vp] w2, w3, joints01 bits, joints23 bits
+  const uint32_t* __restrict__ meta;   // [Vp] slot | ninf | flags
   const uint2*  __restrict__ mrange;   // [Vp] (first entry, count) into ments
   const float4* __restrict__ ments;    // [nnz] dx,dy,dz, morph id bits
   const uint32_t* __restrict__ sdefIdx;// [Vp] index into sdefTab (valid when kMetaSdef)
@@ -57,16 +65,19 @@ struct DeformParams {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
 __device__ __forceinline__ void fence_mbar_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAIT_%=:\n\t"
@@ -74,7 +85,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t}"
-      ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+      ::"r"(bar), "r"(parity) : "memory");
 }
 __device__ __forceinline__ uint64_t policy_evict_first() {
   uint64_t p;
@@ -87,18 +98,19 @@ __device__ __forceinline__ uint64_t policy_evict_last() {
   return p;
 }
 // global -> shared bulk copy (TMA, 1-D), completion on an mbarrier
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-      ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+      ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
 }
 // shared -> global bulk store (TMA, 1-D), tracked by bulk groups
-__device__ __forceinline__ void bulk_s2g(void* dst, const void* src_smem, uint32_t bytes, uint64_t pol) {
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes, uint64_t pol) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
-               ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes), "l"(pol) : "memory");
+               ::"l"(dst), "r"(src_smem), "r"(bytes), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -108,16 +120,36 @@ __device__ __forceinline__ float4 ldg_el(const float4* p, uint64_t pol) {   // r
                : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
   return r;
 }
-__device__ __forceinline__ uint2 ldg_el(const uint2* p, uint64_t pol) {
-  uint2 r;
-  asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(pol));
+__device__ __forceinline__ uint32_t ldg_el(const uint32_t* p, uint64_t pol) {
+  uint32_t r;
+  asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
   return r;
+}
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a));
+  return r;
+}
+__device__ __forceinline__ float lds32(uint32_t a) {
+  float r;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(a));
+  return r;
+}
+__device__ __forceinline__ void sts3(uint32_t a, float x, float y, float z) {
+  asm volatile("st.shared.f32 [%0], %1;\n\tst.shared.f32 [%0+4], %2;\n\tst.shared.f32 [%0+8], %3;" ::"r"(a), "f"(x), "f"(y), "f"(z) : "memory");
 }
 __device__ __forceinline__ void st_cs(float* p, float v) { asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
 
-__device__ __forceinline__ float4 f4_scale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
-__device__ __forceinline__ float4 f4_fma(float4 a, float s, float4 c) {
-  return make_float4(fmaf(a.x, s, c.x), fmaf(a.y, s, c.y), fmaf(a.z, s, c.z), fmaf(a.w, s, c.w));
+// Blackwell packed FP32 (FFMA2 / FMUL2: two fp32 lanes per instruction).  The blend of 3x4 matrices is element-wise,
+// so a float4 row costs 2 issue slots instead of 4.
+__device__ __forceinline__ float4 f4_scale(float4 a, float2 s) {
+  const float2 lo = __fmul2_rn(make_float2(a.x, a.y), s), hi = __fmul2_rn(make_float2(a.z, a.w), s);
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ float4 f4_fma(float4 a, float2 s, float4 c) {
+  const float2 lo = __ffma2_rn(make_float2(a.x, a.y), s, make_float2(c.x, c.y));
+  const float2 hi = __ffma2_rn(make_float2(a.z, a.w), s, make_float2(c.z, c.w));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
 // order-preserving float <-> int for atomic min/max
@@ -127,7 +159,6 @@ __device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); retur
 //      352-384 fromQuat) applied to the rotation part of two skin matrices.
 struct Q4 { float x, y, z, w; };
 __device__ __forceinline__ Q4 quat_from_rows(float4 r0, float4 r1, float4 r2) {
-  // r? are matrix rows: m[row][col]; reference names mRC
   const float m00 = r0.x, m01 = r0.y, m02 = r0.z;
   const float m10 = r1.x, m11 = r1.y, m12 = r1.z;
   const float m20 = r2.x, m21 = r2.y, m22 = r2.z;
@@ -162,50 +193,70 @@ __device__ __forceinline__ Q4 quat_slerp(Q4 a, Q4 b, float t) {
   return Q4{s0 * a.x + s1 * b.x, s0 * a.y + s1 * b.y, s0 * a.z + s1 * b.z, s0 * a.w + s1 * b.w};
 }
 
+template <int N> struct IntC { static constexpr int value = N; };
+
+// per-thread vertex record
+struct VRec {
+  float4 r0, r1, r2;
+  uint32_t meta;
+};
+
+// shared-memory control block at the start of dynamic smem; data starts at byte kCtrlBytes
+struct Ctrl {
+  unsigned long long palBar;
+  uint32_t item;
+  uint32_t pad;
+};
+constexpr uint32_t kCtrlBytes = 64;
+constexpr int kStageBufs = 2;
+
 // ------------------------------------------------------------------ the kernel
-// I      : instances evaluated per vertex pass (register-tiled)
-// NT     : threads per CTA (256 or 512); one vertex per thread per pass
-// STAGED : smem-staged TMA bulk stores instead of direct register stores
-// FEAT   : FEAT_* bit set
-template <int I, int NT, bool STAGED, int FEAT>
-__global__ void __launch_bounds__(NT, 1) deform_kernel(const DeformParams prm) {
+// I    : instances evaluated per vertex pass (palettes resident in shared memory)
+// NT   : threads per CTA (multiple of 256)
+// MINB : CTAs per SM the register budget is sized for
+// FEAT : FEAT_* bit set
+template <int I, int NT, int MINB, int FEAT>
+__global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm) {
   constexpr bool MORPH = (FEAT & FEAT_MORPH) != 0;
   constexpr bool SDEF = (FEAT & FEAT_SDEF) != 0;
   constexpr bool BOUNDS = (FEAT & FEAT_BOUNDS) != 0;
   constexpr bool GPAL = (FEAT & FEAT_GPAL) != 0;      // palette too large for smem: gather from global/L1
   constexpr bool NRM = (FEAT & FEAT_NONRM) == 0;
   constexpr int PLANES = NRM ? 2 : 1;
+  constexpr uint32_t kPlaneB = 32 * 12;                // bytes of one warp-private staging plane (32 vertices x float3)
+  constexpr uint32_t kInstB = PLANES * kPlaneB;        // one instance of one warp
+  constexpr uint32_t kBufB = I * kInstB;               // one staging buffer of one warp
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
-  volatile uint32_t* s_item = reinterpret_cast<volatile uint32_t*>(smem_raw + 8);
-  unsigned char* sp = smem_raw + 16;
-  float4* s_pal = reinterpret_cast<float4*>(sp);
-  if (!GPAL) sp += (size_t)I * prm.B * kRowF4 * sizeof(float4);
-  float* s_mw = reinterpret_cast<float*>(sp);
-  if (MORPH) sp += (size_t)I * prm.Mpad * sizeof(float);
-  float* s_stage = reinterpret_cast<float*>(sp);      // [2][I][PLANES][NT*3]
-  constexpr int kStagePlaneF = NT * 3;
-  constexpr int kStageBufF = I * PLANES * kStagePlaneF;
-
-  const int tid = threadIdx.x;
+  const uint32_t sbase = smem_u32(smem_raw);
+  Ctrl* ctrl = reinterpret_cast<Ctrl*>(smem_raw);
+  const uint32_t palBar = sbase + (uint32_t)offsetof(Ctrl, palBar);
   const uint32_t B = prm.B;
+  const uint32_t sPal = sbase + kCtrlBytes;
+  const uint32_t palBytes = GPAL ? 0u : B * 48u;
+  const uint32_t sMw = sPal + (uint32_t)I * palBytes;
+  const uint32_t mwBytes = MORPH ? prm.Mpad * 4u : 0u;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  // warp-private staging: [kStageBufs][I][PLANES][32*3 floats], laid out exactly like 32 vertices of the output planes
+  const uint32_t sStageW = sMw + (uint32_t)I * mwBytes + (uint32_t)warp * (kStageBufs * kBufB);
 
   if (tid == 0) {
-    mbar_init(bar, 1);
+    mbar_init(palBar, 1);
     fence_mbar_init();
   }
   __syncthreads();
 
-  uint32_t phase = 0;
-  uint32_t stageBuf = 0;
+  uint32_t palPhase = 0;
+  uint32_t sbuf = 0;                                   // which of the warp's two staging buffers the next pass fills
   const uint64_t polFirst = policy_evict_first();
   const uint64_t polLast = policy_evict_last();
 
   for (;;) {
-    if (tid == 0) *s_item = atomicAdd(prm.counter, 1u);
+    if (tid == 0) ctrl->item = atomicAdd(prm.counter, 1u);
     __syncthreads();
-    const uint32_t item = *s_item;
+    const uint32_t item = *reinterpret_cast<volatile uint32_t*>(&ctrl->item);
     if (item >= prm.nGroups * prm.nChunks) break;
     const uint32_t g = item / prm.nChunks;
     const uint32_t chunk = item - g * prm.nChunks;
@@ -218,21 +269,19 @@ __global__ void __launch_bounds__(NT, 1) deform_kernel(const DeformParams prm) {
     const float* gpal[I];
 #pragma unroll
     for (int i = 0; i < I; ++i) {
-      const uint32_t k = kBase + min((uint32_t)i, nInst - 1);    // clamp: unused lanes of a partial group recompute the last one
+      const uint32_t k = kBase + min((uint32_t)i, nInst - 1);    // a partial group re-evaluates its last instance (never stored)
       const uint32_t pidx = prm.inst2pal ? __ldg(prm.inst2pal + k) : k;
       gpal[i] = prm.skin + (size_t)pidx * B * 12;
     }
     if (!GPAL || MORPH) {
       if (tid == 0) {
-        const uint32_t palBytes = GPAL ? 0u : B * 48u;
-        const uint32_t mwBytes = MORPH ? prm.Mpad * 4u : 0u;
-        mbar_expect_tx(bar, (uint32_t)I * (palBytes + mwBytes));
+        mbar_expect_tx(palBar, (uint32_t)I * (palBytes + mwBytes));
 #pragma unroll
         for (int i = 0; i < I; ++i) {
-          if (!GPAL) bulk_g2s(s_pal + (size_t)i * B * kRowF4, gpal[i], palBytes, bar, polLast);
+          if (!GPAL) bulk_g2s(sPal + (uint32_t)i * palBytes, gpal[i], palBytes, palBar, polLast);
           if (MORPH) {
             const uint32_t k = kBase + min((uint32_t)i, nInst - 1);
-            bulk_g2s(s_mw + (size_t)i * prm.Mpad, prm.mweights + (size_t)k * prm.Mpad, mwBytes, bar, polLast);
+            bulk_g2s(sMw + (uint32_t)i * mwBytes, prm.mweights + (size_t)k * prm.Mpad, mwBytes, palBar, polLast);
           }
         }
       }
@@ -246,61 +295,60 @@ __global__ void __launch_bounds__(NT, 1) deform_kernel(const DeformParams prm) {
         for (int c = 0; c < 3; ++c) { bmin[i][c] = 3.4e38f; bmax[i][c] = -3.4e38f; }
     }
 
-    bool waited = false;
-    for (uint32_t t = tile0; t < tile1; t += NT / kTile) {
-      const uint32_t p = t * kTile + tid;                        // processing-order index
-      const uint32_t tileOfThread = t + tid / kTile;
-      const bool inRange = tileOfThread < tile1;                 // second half of a 512-thread pass may fall off the chunk
-      float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
-      uint2 jj = make_uint2(0u, 0u);
-      if (inRange) {
-        r0 = ldg_el(prm.rec0 + p, polLast);
-        r1 = ldg_el(prm.rec1 + p, polLast);
-        jj = ldg_el(prm.joints + p, polLast);
-      } else {
-        r0.w = __uint_as_float(255u);
+    // vertex record of a pass (the next pass is prefetched while the current one is evaluated)
+    auto load_rec = [&](uint32_t t) -> VRec {
+      VRec v;
+      const uint32_t p = t * kTile + tid;
+      if (t + tid / kTile < tile1) {
+        v.r0 = ldg_el(prm.rec0 + p, polLast);
+        v.r1 = ldg_el(prm.rec1 + p, polLast);
+        v.r2 = ldg_el(prm.rec2 + p, polLast);
+        v.meta = ldg_el(prm.meta + p, polLast);
+      } else {                                                  // the far tiles of a wide pass fall off the chunk
+        v.r0 = make_float4(0.f, 0.f, 0.f, 1.f);
+        v.r1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        v.r2 = make_float4(0.f, 0.f, 0.f, 0.f);
+        v.meta = (uint32_t)lane | (1u << kMetaNinfShift);
       }
-      const uint32_t meta = __float_as_uint(r1.w);
-      const uint32_t wb = __float_as_uint(r0.w);
-      const bool valid = inRange && (meta & kMetaValid);
-      const uint32_t slot = meta & kMetaSlotMask;
-      const int ninf = inRange ? (int)((meta >> kMetaNinfShift) & 7u) : 1;
+      return v;
+    };
+    VRec cur = load_rec(tile0);
 
-      // weights exactly as the vertex shader derives them (engine.ts:255-258): unorm8 -> f32, renormalise
-      float w0 = (float)(wb & 255u) / 255.0f, w1 = (float)((wb >> 8) & 255u) / 255.0f;
-      float w2 = (float)((wb >> 16) & 255u) / 255.0f, w3 = (float)(wb >> 24) / 255.0f;
-      {
-        const float wsum = w0 + w1 + w2 + w3;
-        if (wsum > 0.0001f) {
-          const float inv = 1.0f / wsum;
-          w0 *= inv; w1 *= inv; w2 *= inv; w3 *= inv;
-        } else {
-          w0 = 1.f; w1 = 0.f; w2 = 0.f; w3 = 0.f;
-        }
-      }
-      const uint32_t j0 = (jj.x & 0xFFFFu) * kRowF4, j1 = (jj.x >> 16) * kRowF4;
-      const uint32_t j2 = (jj.y & 0xFFFFu) * kRowF4, j3 = (jj.y >> 16) * kRowF4;
+    if (!GPAL || MORPH) mbar_wait(palBar, palPhase);
+    palPhase ^= 1u;
+
+    for (uint32_t t = tile0; t < tile1; t += NT / kTile) {
+      const VRec v = cur;
+      if (t + NT / kTile < tile1) cur = load_rec(t + NT / kTile);
+      if (t + tid / kTile >= tile1) continue;                     // warp-uniform: this warp has no tile in the pass
+
+      const uint32_t meta = v.meta;
+      const bool valid = (meta & kMetaValid) != 0;
+      const uint32_t slot = meta & 31u;                           // position among the warp's 32 output vertices
+      const int ninf = (int)((meta >> kMetaNinfShift) & 7u);
+      const int nmax = __reduce_max_sync(0xffffffffu, ninf);
+      const float w0 = v.r0.w, w1 = v.r1.w, w2 = v.r2.x, w3 = v.r2.y;
+      const uint32_t jb01 = __float_as_uint(v.r2.z), jb23 = __float_as_uint(v.r2.w);
+      const uint32_t j0 = (jb01 & 0xFFFFu) * 48u, j1 = (jb01 >> 16) * 48u;
+      const uint32_t j2 = (jb23 & 0xFFFFu) * 48u, j3 = (jb23 >> 16) * 48u;
+      const float vnx = v.r1.x, vny = v.r1.y, vnz = v.r1.z;
+      const uint32_t warpVtx0 = t * kTile + (uint32_t)(tid & ~31);      // first output vertex of this warp
+      const uint32_t nWarpVerts = min(32u, prm.V - min(prm.V, warpVtx0));
+      const uint32_t nAligned = nWarpVerts & ~3u;                 // bulk sizes must be multiples of 16 B
 
       // ---- morph accumulation: p~ = p + sum_m w[k][m] * delta_m[v]   (model space, before skinning)
-      float px[I], py[I], pz[I];
+      float px[MORPH ? I : 1], py[MORPH ? I : 1], pz[MORPH ? I : 1];
 #pragma unroll
-      for (int i = 0; i < I; ++i) { px[i] = r0.x; py[i] = r0.y; pz[i] = r0.z; }
-
-      if (!waited) {   // palettes / weights must have landed before the first gather of this item
-        if (!GPAL || MORPH) mbar_wait(bar, phase);
-        phase ^= 1u;
-        waited = true;
-      }
-
+      for (int i = 0; i < (MORPH ? I : 1); ++i) { px[i] = v.r0.x; py[i] = v.r0.y; pz[i] = v.r0.z; }
       if (MORPH) {
         if (meta & kMetaMorph) {
-          const uint2 mr = __ldg(prm.mrange + p);
+          const uint2 mr = __ldg(prm.mrange + (size_t)t * kTile + tid);
           for (uint32_t e = mr.x; e < mr.x + mr.y; ++e) {
             const float4 d = __ldg(prm.ments + e);
             const uint32_t m = __float_as_uint(d.w);
 #pragma unroll
             for (int i = 0; i < I; ++i) {
-              const float wgt = s_mw[(size_t)i * prm.Mpad + m];
+              const float wgt = lds32(sMw + ((uint32_t)i * prm.Mpad + m) * 4u);
               px[i] = fmaf(wgt, d.x, px[i]);
               py[i] = fmaf(wgt, d.y, py[i]);
               pz[i] = fmaf(wgt, d.z, pz[i]);
@@ -309,130 +357,171 @@ __global__ void __launch_bounds__(NT, 1) deform_kernel(const DeformParams prm) {
         }
       }
 
-      float ox[I], oy[I], oz[I], nx[I], ny[I], nz[I];
       const bool isSdef = SDEF && (meta & kMetaSdef);
-      if (!isSdef) {
+      float sC[3] = {0.f, 0.f, 0.f}, sc0[3] = {0.f, 0.f, 0.f}, sc1[3] = {0.f, 0.f, 0.f};
+      if (SDEF) {
+        if (isSdef) {
+          const uint32_t si = __ldg(prm.sdefIdx + (size_t)t * kTile + tid);
+          const float4 t0 = __ldg(prm.sdefTab + (size_t)si * 3), t1 = __ldg(prm.sdefTab + (size_t)si * 3 + 1),
+                       t2 = __ldg(prm.sdefTab + (size_t)si * 3 + 2);
+          sC[0] = t0.x; sC[1] = t0.y; sC[2] = t0.z;
+          sc0[0] = t0.w; sc0[1] = t1.x; sc0[2] = t1.y;
+          sc1[0] = t1.z; sc1[1] = t1.w; sc1[2] = t2.x;
+        }
+      }
+
+      // the bulk stores issued from this buffer two passes ago must have finished reading it
+      if (lane == 0) bulk_wait_read<kStageBufs - 1>();
+      __syncwarp();
+      const uint32_t stg = sStageW + sbuf * kBufB;
+      const bool staged = slot < nAligned;                        // ragged tail (< 4 vertices of the mesh): plain stores
+
+      // splats for the packed mat-vec (once per vertex unless morphing moves the position per instance)
+      const float2 nx2 = make_float2(vnx, vnx), ny2 = make_float2(vny, vny), nz2 = make_float2(vnz, vnz);
+      const float2 w0_2 = make_float2(w0, w0), w1_2 = make_float2(w1, w1), w2_2 = make_float2(w2, w2), w3_2 = make_float2(w3, w3);
+
+      auto body = [&](auto NM) {
+        constexpr int NV = decltype(NM)::value;                   // 0: rigid warp with unit weights, else warp-max influence count
+        constexpr int NMAX = NV == 0 ? 1 : NV;
+        // ---- phase 1: palette gathers of influences 0/1 for all I instances, issued back to back (latency overlaps).
+        // Lanes whose weight for an influence is zero skip that gather (their FFMA adds an exact 0); lanes are sorted by
+        // influence count inside the warp, so whole quarter-warps drop out of the shared-memory wavefronts.
+        float4 a0[I], a1[I], a2[I], b0[I], b1[I], b2[I];
+        const bool need1 = NMAX > 1 && (ninf > 1 || isSdef);
 #pragma unroll
         for (int i = 0; i < I; ++i) {
-          const float4* pal = GPAL ? reinterpret_cast<const float4*>(gpal[i]) : (s_pal + (size_t)i * B * kRowF4);
-          float4 m0 = f4_scale(pal[j0], w0), m1 = f4_scale(pal[j0 + 1], w0), m2 = f4_scale(pal[j0 + 2], w0);
-          if (ninf > 1) {
-            m0 = f4_fma(pal[j1], w1, m0); m1 = f4_fma(pal[j1 + 1], w1, m1); m2 = f4_fma(pal[j1 + 2], w1, m2);
-            if (ninf > 2) {
-              m0 = f4_fma(pal[j2], w2, m0); m1 = f4_fma(pal[j2 + 1], w2, m1); m2 = f4_fma(pal[j2 + 2], w2, m2);
-              if (ninf > 3) {
-                m0 = f4_fma(pal[j3], w3, m0); m1 = f4_fma(pal[j3 + 1], w3, m1); m2 = f4_fma(pal[j3 + 2], w3, m2);
+          b0[i] = b1[i] = b2[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (GPAL) {
+            const float4* pal = reinterpret_cast<const float4*>(gpal[i]);
+            a0[i] = pal[j0 / 16]; a1[i] = pal[j0 / 16 + 1]; a2[i] = pal[j0 / 16 + 2];
+            if (need1) { b0[i] = pal[j1 / 16]; b1[i] = pal[j1 / 16 + 1]; b2[i] = pal[j1 / 16 + 2]; }
+          } else {
+            const uint32_t pb = sPal + (uint32_t)i * palBytes;
+            a0[i] = lds128(pb + j0); a1[i] = lds128(pb + j0 + 16); a2[i] = lds128(pb + j0 + 32);
+            if (need1) { b0[i] = lds128(pb + j1); b1[i] = lds128(pb + j1 + 16); b2[i] = lds128(pb + j1 + 32); }
+          }
+        }
+        // ---- phase 2: blend + transform + staging
+#pragma unroll
+        for (int i = 0; i < I; ++i) {
+          const float qx = px[MORPH ? i : 0], qy = py[MORPH ? i : 0], qz = pz[MORPH ? i : 0];
+          float ox, oy, oz, nx = 0.f, ny = 0.f, nz = 0.f;
+          bool done = false;
+          if (SDEF && NMAX > 1) {
+            if (isSdef) {
+              // ---- SDEF: spherical blend of the two bone rotations around C; un-pair the rows first
+              const float4 r0 = make_float4(a0[i].x, a0[i].z, a1[i].x, a1[i].z), r1 = make_float4(a0[i].y, a0[i].w, a1[i].y, a1[i].w), r2 = a2[i];
+              const float4 s0 = make_float4(b0[i].x, b0[i].z, b1[i].x, b1[i].z), s1 = make_float4(b0[i].y, b0[i].w, b1[i].y, b1[i].w), s2 = b2[i];
+              const Q4 q = quat_slerp(quat_from_rows(r0, r1, r2), quat_from_rows(s0, s1, s2), w1);
+              const float x2 = q.x + q.x, y2 = q.y + q.y, z2 = q.z + q.z;
+              const float xx = q.x * x2, xy = q.x * y2, xz = q.x * z2, yy = q.y * y2, yz = q.y * z2, zz = q.z * z2;
+              const float wx = q.w * x2, wy = q.w * y2, wz = q.w * z2;
+              const float R00 = 1.f - (yy + zz), R01 = xy - wz, R02 = xz + wy;
+              const float R10 = xy + wz, R11 = 1.f - (xx + zz), R12 = yz - wx;
+              const float R20 = xz - wy, R21 = yz + wx, R22 = 1.f - (xx + yy);
+              const float dx = qx - sC[0], dy = qy - sC[1], dz = qz - sC[2];
+              const float e0x = fmaf(r0.x, sc0[0], fmaf(r0.y, sc0[1], fmaf(r0.z, sc0[2], r0.w)));
+              const float e0y = fmaf(r1.x, sc0[0], fmaf(r1.y, sc0[1], fmaf(r1.z, sc0[2], r1.w)));
+              const float e0z = fmaf(r2.x, sc0[0], fmaf(r2.y, sc0[1], fmaf(r2.z, sc0[2], r2.w)));
+              const float e1x = fmaf(s0.x, sc1[0], fmaf(s0.y, sc1[1], fmaf(s0.z, sc1[2], s0.w)));
+              const float e1y = fmaf(s1.x, sc1[0], fmaf(s1.y, sc1[1], fmaf(s1.z, sc1[2], s1.w)));
+              const float e1z = fmaf(s2.x, sc1[0], fmaf(s2.y, sc1[1], fmaf(s2.z, sc1[2], s2.w)));
+              ox = fmaf(R00, dx, fmaf(R01, dy, R02 * dz)) + w0 * e0x + w1 * e1x;
+              oy = fmaf(R10, dx, fmaf(R11, dy, R12 * dz)) + w0 * e0y + w1 * e1y;
+              oz = fmaf(R20, dx, fmaf(R21, dy, R22 * dz)) + w0 * e0z + w1 * e1z;
+              if (NRM) {
+                nx = fmaf(R00, vnx, fmaf(R01, vny, R02 * vnz));
+                ny = fmaf(R10, vnx, fmaf(R11, vny, R12 * vnz));
+                nz = fmaf(R20, vnx, fmaf(R21, vny, R22 * vnz));
               }
+              done = true;
             }
           }
-          ox[i] = fmaf(m0.x, px[i], fmaf(m0.y, py[i], fmaf(m0.z, pz[i], m0.w)));
-          oy[i] = fmaf(m1.x, px[i], fmaf(m1.y, py[i], fmaf(m1.z, pz[i], m1.w)));
-          oz[i] = fmaf(m2.x, px[i], fmaf(m2.y, py[i], fmaf(m2.z, pz[i], m2.w)));
+          if (!done) {
+            // ---- linear blend: M = sum_i w_i M_i (zero weights contribute exactly 0), then one packed mat-vec each
+            float4 mA, mB, mC;
+            if (NV == 0) { mA = a0[i]; mB = a1[i]; mC = a2[i]; }          // every lane has the single weight 1.0
+            else { mA = f4_scale(a0[i], w0_2); mB = f4_scale(a1[i], w0_2); mC = f4_scale(a2[i], w0_2); }
+            if (NMAX > 1) { mA = f4_fma(b0[i], w1_2, mA); mB = f4_fma(b1[i], w1_2, mB); mC = f4_fma(b2[i], w1_2, mC); }
+            if (NMAX > 2) {
+              float4 c0, c1, c2;
+              c0 = c1 = c2 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (ninf > 2) {
+                if (GPAL) { const float4* pal = reinterpret_cast<const float4*>(gpal[i]); c0 = pal[j2 / 16]; c1 = pal[j2 / 16 + 1]; c2 = pal[j2 / 16 + 2]; }
+                else { const uint32_t pb = sPal + (uint32_t)i * palBytes; c0 = lds128(pb + j2); c1 = lds128(pb + j2 + 16); c2 = lds128(pb + j2 + 32); }
+              }
+              mA = f4_fma(c0, w2_2, mA); mB = f4_fma(c1, w2_2, mB); mC = f4_fma(c2, w2_2, mC);
+            }
+            if (NMAX > 3) {
+              float4 c0, c1, c2;
+              c0 = c1 = c2 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (ninf > 3) {
+                if (GPAL) { const float4* pal = reinterpret_cast<const float4*>(gpal[i]); c0 = pal[j3 / 16]; c1 = pal[j3 / 16 + 1]; c2 = pal[j3 / 16 + 2]; }
+                else { const uint32_t pb = sPal + (uint32_t)i * palBytes; c0 = lds128(pb + j3); c1 = lds128(pb + j3 + 16); c2 = lds128(pb + j3 + 32); }
+              }
+              mA = f4_fma(c0, w3_2, mA); mB = f4_fma(c1, w3_2, mB); mC = f4_fma(c2, w3_2, mC);
+            }
+            // (ox,oy) = (m00,m10)*qx + (m01,m11)*qy + (m02,m12)*qz + (m03,m13);  oz = row 2 . (q,1)
+            const float2 qx2 = make_float2(qx, qx), qy2 = make_float2(qy, qy), qz2 = make_float2(qz, qz);
+            const float2 oxy = __ffma2_rn(make_float2(mA.x, mA.y), qx2,
+                               __ffma2_rn(make_float2(mA.z, mA.w), qy2, __ffma2_rn(make_float2(mB.x, mB.y), qz2, make_float2(mB.z, mB.w))));
+            ox = oxy.x; oy = oxy.y;
+            oz = fmaf(mC.x, qx, fmaf(mC.y, qy, fmaf(mC.z, qz, mC.w)));
+            if (NRM) {
+              const float2 nxy = __ffma2_rn(make_float2(mA.x, mA.y), nx2,
+                                 __ffma2_rn(make_float2(mA.z, mA.w), ny2, __fmul2_rn(make_float2(mB.x, mB.y), nz2)));
+              nx = nxy.x; ny = nxy.y;
+              nz = fmaf(mC.x, vnx, fmaf(mC.y, vny, mC.z * vnz));
+            }
+          }
           if (NRM) {
-            const float ax = fmaf(m0.x, r1.x, fmaf(m0.y, r1.y, m0.z * r1.z));
-            const float ay = fmaf(m1.x, r1.x, fmaf(m1.y, r1.y, m1.z * r1.z));
-            const float az = fmaf(m2.x, r1.x, fmaf(m2.y, r1.y, m2.z * r1.z));
-            const float l2 = fmaf(ax, ax, fmaf(ay, ay, az * az));
-            const float rl = l2 > 0.f ? rsqrtf(l2) : 0.f;        // normalize(0) := 0 (oracle convention)
-            nx[i] = ax * rl; ny[i] = ay * rl; nz[i] = az * rl;
+            const float l2 = fmaf(nx, nx, fmaf(ny, ny, nz * nz));
+            const float rl = l2 > 0.f ? rsqrtf(l2) : 0.f;        // normalize(0) := 0 (SURVEY 8c edge case)
+            nx *= rl; ny *= rl; nz *= rl;
+          }
+          if (BOUNDS) {
+            if (valid) {
+              bmin[i][0] = fminf(bmin[i][0], ox); bmax[i][0] = fmaxf(bmax[i][0], ox);
+              bmin[i][1] = fminf(bmin[i][1], oy); bmax[i][1] = fmaxf(bmax[i][1], oy);
+              bmin[i][2] = fminf(bmin[i][2], oz); bmax[i][2] = fmaxf(bmax[i][2], oz);
+            }
+          }
+          if (staged) {
+            const uint32_t sa = stg + (uint32_t)i * kInstB + slot * 12u;
+            sts3(sa, ox, oy, oz);
+            if (NRM) sts3(sa + kPlaneB, nx, ny, nz);
+          } else if (valid && (uint32_t)i < nInst) {
+            float* dst = prm.out + (size_t)(kBase + i) * prm.instStrideF + (size_t)(warpVtx0 + slot) * 3;
+            st_cs(dst, ox); st_cs(dst + 1, oy); st_cs(dst + 2, oz);
+            if (NRM) { st_cs(dst + prm.nrmOffF, nx); st_cs(dst + prm.nrmOffF + 1, ny); st_cs(dst + prm.nrmOffF + 2, nz); }
           }
         }
-      } else {
-        // ---- SDEF: spherical blend of the two bone rotations around C
-        const uint32_t si = __ldg(prm.sdefIdx + p);
-        const float4 t0 = __ldg(prm.sdefTab + (size_t)si * 3), t1 = __ldg(prm.sdefTab + (size_t)si * 3 + 1),
-                     t2 = __ldg(prm.sdefTab + (size_t)si * 3 + 2);
-        const float Cx = t0.x, Cy = t0.y, Cz = t0.z;
-        const float c0x = t0.w, c0y = t1.x, c0z = t1.y, c1x = t1.z, c1y = t1.w, c1z = t2.x;
-#pragma unroll
-        for (int i = 0; i < I; ++i) {
-          const float4* pal = GPAL ? reinterpret_cast<const float4*>(gpal[i]) : (s_pal + (size_t)i * B * kRowF4);
-          const float4 a0 = pal[j0], a1 = pal[j0 + 1], a2 = pal[j0 + 2];
-          const float4 b0 = pal[j1], b1 = pal[j1 + 1], b2 = pal[j1 + 2];
-          const Q4 q = quat_slerp(quat_from_rows(a0, a1, a2), quat_from_rows(b0, b1, b2), w1);
-          const float x2 = q.x + q.x, y2 = q.y + q.y, z2 = q.z + q.z;
-          const float xx = q.x * x2, xy = q.x * y2, xz = q.x * z2, yy = q.y * y2, yz = q.y * z2, zz = q.z * z2;
-          const float wx = q.w * x2, wy = q.w * y2, wz = q.w * z2;
-          const float R00 = 1.f - (yy + zz), R01 = xy - wz, R02 = xz + wy;
-          const float R10 = xy + wz, R11 = 1.f - (xx + zz), R12 = yz - wx;
-          const float R20 = xz - wy, R21 = yz + wx, R22 = 1.f - (xx + yy);
-          const float dx = px[i] - Cx, dy = py[i] - Cy, dz = pz[i] - Cz;
-          const float e0x = fmaf(a0.x, c0x, fmaf(a0.y, c0y, fmaf(a0.z, c0z, a0.w)));
-          const float e0y = fmaf(a1.x, c0x, fmaf(a1.y, c0y, fmaf(a1.z, c0z, a1.w)));
-          const float e0z = fmaf(a2.x, c0x, fmaf(a2.y, c0y, fmaf(a2.z, c0z, a2.w)));
-          const float e1x = fmaf(b0.x, c1x, fmaf(b0.y, c1y, fmaf(b0.z, c1z, b0.w)));
-          const float e1y = fmaf(b1.x, c1x, fmaf(b1.y, c1y, fmaf(b1.z, c1z, b1.w)));
-          const float e1z = fmaf(b2.x, c1x, fmaf(b2.y, c1y, fmaf(b2.z, c1z, b2.w)));
-          ox[i] = fmaf(R00, dx, fmaf(R01, dy, R02 * dz)) + w0 * e0x + w1 * e1x;
-          oy[i] = fmaf(R10, dx, fmaf(R11, dy, R12 * dz)) + w0 * e0y + w1 * e1y;
-          oz[i] = fmaf(R20, dx, fmaf(R21, dy, R22 * dz)) + w0 * e0z + w1 * e1z;
-          if (NRM) {
-            const float ax = fmaf(R00, r1.x, fmaf(R01, r1.y, R02 * r1.z));
-            const float ay = fmaf(R10, r1.x, fmaf(R11, r1.y, R12 * r1.z));
-            const float az = fmaf(R20, r1.x, fmaf(R21, r1.y, R22 * r1.z));
-            const float l2 = fmaf(ax, ax, fmaf(ay, ay, az * az));
-            const float rl = l2 > 0.f ? rsqrtf(l2) : 0.f;
-            nx[i] = ax * rl; ny[i] = ay * rl; nz[i] = az * rl;
-          }
-        }
+      };
+      const bool unitW = __all_sync(0xffffffffu, w0 == 1.0f);
+      switch (nmax) {
+        case 1: if (unitW) body(IntC<0>{}); else body(IntC<1>{}); break;
+        case 2: body(IntC<2>{}); break;
+        case 3: body(IntC<3>{}); break;
+        default: body(IntC<4>{}); break;
       }
 
-      if (BOUNDS && valid) {
-#pragma unroll
-        for (int i = 0; i < I; ++i) {
-          bmin[i][0] = fminf(bmin[i][0], ox[i]); bmax[i][0] = fmaxf(bmax[i][0], ox[i]);
-          bmin[i][1] = fminf(bmin[i][1], oy[i]); bmax[i][1] = fmaxf(bmax[i][1], oy[i]);
-          bmin[i][2] = fminf(bmin[i][2], oz[i]); bmax[i][2] = fmaxf(bmax[i][2], oz[i]);
-        }
-      }
-
-      // ---- write out
-      const uint32_t passBase = t * kTile;                        // first vertex id of this pass
-      const uint32_t vertsHere = min((uint32_t)NT, prm.V - passBase);
-      const uint32_t vertsInChunk = min(vertsHere, (tile1 - t) * (uint32_t)kTile);
-      const uint32_t vid = tileOfThread * kTile + slot;
-      const bool bulkOk = STAGED && ((vertsInChunk * 3u) & 3u) == 0u;
-      if (bulkOk) {
-        float* st = s_stage + (size_t)stageBuf * kStageBufF;
-        const int so = ((tid / kTile) * kTile + (int)slot) * 3;
-#pragma unroll
-        for (int i = 0; i < I; ++i) {
-          float* ps = st + (size_t)(i * PLANES) * kStagePlaneF + so;
-          ps[0] = ox[i]; ps[1] = oy[i]; ps[2] = oz[i];
-          if (NRM) {
-            float* ns = ps + kStagePlaneF;
-            ns[0] = nx[i]; ns[1] = ny[i]; ns[2] = nz[i];
-          }
-        }
-        fence_proxy_async();
-        if (tid == 0) bulk_wait_read0();        // the previous pass' bulk stores have released the other buffer
-        __syncthreads();
-        if (tid == 0) {
-          const uint32_t bytes = vertsInChunk * 12u;
+      // ---- drain: this warp's 32 vertices x I instances leave through the TMA (one elected lane)
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        if (nAligned) {
 #pragma unroll
           for (int i = 0; i < I; ++i) {
             if ((uint32_t)i < nInst) {
-              float* dst = prm.out + (size_t)(kBase + i) * prm.instStrideF + (size_t)passBase * 3;
-              bulk_s2g(dst, st + (size_t)(i * PLANES) * kStagePlaneF, bytes, polFirst);
-              if (NRM) bulk_s2g(dst + prm.nrmOffF, st + (size_t)(i * PLANES + 1) * kStagePlaneF, bytes, polFirst);
-            }
-          }
-          bulk_commit();
-        }
-        stageBuf ^= 1u;
-      } else if (valid) {
-#pragma unroll
-        for (int i = 0; i < I; ++i) {
-          if ((uint32_t)i < nInst) {
-            float* dst = prm.out + (size_t)(kBase + i) * prm.instStrideF + (size_t)vid * 3;
-            st_cs(dst, ox[i]); st_cs(dst + 1, oy[i]); st_cs(dst + 2, oz[i]);
-            if (NRM) {
-              float* dn = dst + prm.nrmOffF;
-              st_cs(dn, nx[i]); st_cs(dn + 1, ny[i]); st_cs(dn + 2, nz[i]);
+              float* dst = prm.out + (size_t)(kBase + i) * prm.instStrideF + (size_t)warpVtx0 * 3;
+              bulk_s2g(dst, stg + (uint32_t)i * kInstB, nAligned * 12u, polFirst);
+              if (NRM) bulk_s2g(dst + prm.nrmOffF, stg + (uint32_t)i * kInstB + kPlaneB, nAligned * 12u, polFirst);
             }
           }
         }
+        bulk_commit();
       }
+      sbuf ^= 1u;
     }
 
     if (BOUNDS) {
@@ -447,7 +536,7 @@ __global__ void __launch_bounds__(NT, 1) deform_kernel(const DeformParams prm) {
             lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
             hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
           }
-          if ((tid & 31) == 0 && (uint32_t)i < nInst) {
+          if (lane == 0 && (uint32_t)i < nInst) {
             int* bp = reinterpret_cast<int*>(prm.bounds) + (size_t)(kBase + i) * 6;
             atomicMin(bp + c, f2ord(lo));
             atomicMax(bp + 3 + c, f2ord(hi));
@@ -458,7 +547,7 @@ __global__ void __launch_bounds__(NT, 1) deform_kernel(const DeformParams prm) {
     __syncthreads();   // everyone is done with this item's palettes before they are overwritten
   }
 
-  if (STAGED && tid == 0) bulk_wait0();
+  if (lane == 0) bulk_wait0();                           // staging must outlive the TMA reads
 }
 
 }  // namespace rz

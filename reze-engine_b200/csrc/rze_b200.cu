@@ -15,7 +15,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 using namespace rz;
@@ -58,7 +60,10 @@ struct rz_ctx_impl {
   // device tables (processing order)
   uint32_t Vp = 0, nTiles = 0;
   std::vector<uint32_t> procToVertex;   // processing index -> caller vertex id (or ~0u for padding)
-  DevBuf d_rec0, d_rec1, d_joints, d_mrange, d_ments, d_sdefIdx, d_sdefTab, d_invBind;
+  std::vector<uint32_t> bonePos, boneAt; // palette row of bone b (bank-aware permutation) and its inverse
+  DevBuf d_bonePos;
+  int permMode = 1, colorMode = 1;       // vertex ordering inside a tile / bank-aware palette permutation
+  DevBuf d_rec0, d_rec1, d_rec2, d_meta, d_wbits, d_mrange, d_ments, d_sdefIdx, d_sdefTab, d_invBind;
   uint32_t morphNnz = 0, sdefActive = 0;
 
   // per-frame
@@ -82,6 +87,7 @@ struct rz_ctx_impl {
   uint64_t frames = 0, launches = 0;
   size_t devBytes = 0;
   uint32_t usedI = 0, usedStore = 0, usedCtas = 0, usedThreads = 0, usedSmem = 0;
+  int lastShape[3] = {0, 0, 0};
 };
 
 int fail(rz_ctx_impl* c, int code, const char* fmt, ...) {
@@ -144,14 +150,14 @@ int pinned_reserve(rz_ctx_impl* c, void*& p, size_t& have, size_t bytes) {
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-KernelEntry lookup_kernel(int feat, int I, int NT, bool staged) {
+KernelEntry lookup_kernel(int feat, int I, int NT, int MINB) {
   switch (feat) {
-#define RZ_CASE(f) case f: return lookup_feat_##f(I, NT, staged);
+#define RZ_CASE(f) case f: return lookup_feat_##f(I, NT, MINB);
     RZ_FEAT_LIST(RZ_CASE)
 #undef RZ_CASE
     default: break;
   }
-  KernelEntry none{nullptr, 0, 0, false, feat};
+  KernelEntry none{nullptr, 0, 0, 0, feat};
   return none;
 }
 
@@ -173,18 +179,18 @@ int resolve_feat(int need) {
   return best;
 }
 
-size_t smem_needed(int I, int NT, bool staged, int feat, uint32_t B, uint32_t Mpad) {
-  size_t s = 16;
+size_t smem_needed(int I, int NT, int feat, uint32_t B, uint32_t Mpad) {
+  size_t s = kCtrlBytes;
   if (!(feat & FEAT_GPAL)) s += (size_t)I * B * 48;
   if (feat & FEAT_MORPH) s += (size_t)I * Mpad * 4;
-  if (staged) s += (size_t)2 * I * ((feat & FEAT_NONRM) ? 1 : 2) * NT * 12;
+  s += (size_t)kStageBufs * I * ((feat & FEAT_NONRM) ? 1 : 2) * NT * 12;   // warp-private double-buffered staging (pos + normal planes)
   return s;
 }
 
 // ---- table preprocessing ------------------------------------------------------------------------
-// Tile = 256 consecutive vertices.  Inside a tile, which WARP evaluates a vertex is chosen by class
-// (SDEF, morphed, influence count) while its LANE stays slot % 32, so that (a) warps are homogeneous
-// and (b) staging writes of one warp hit 32 distinct banks (3*slot mod 32 is a bijection on lanes).
+// Tile = 256 consecutive vertices (work-item granularity).  A warp owns 32 consecutive vertices; which LANE evaluates
+// which of them is chosen at load time (see below).  Staging writes of a warp always hit 32 distinct banks
+// (3*slot mod 32 is a bijection on the 32 slots).
 int rebuild_tables(rz_ctx_impl* c) {
   const uint32_t V = c->V, B = c->B;
   const uint32_t nTiles = (V + kTile - 1) / kTile;
@@ -241,8 +247,9 @@ int rebuild_tables(rz_ctx_impl* c) {
     }
   }
 
-  std::vector<float4> rec0(Vp), rec1(Vp);
-  std::vector<uint2> jrec(Vp), mrange(Vp);
+  std::vector<float4> rec0(Vp), rec1(Vp), rec2(Vp);
+  std::vector<uint32_t> metaArr(Vp), wbits(Vp, 0);
+  std::vector<uint2> mrange(Vp);
   std::vector<uint32_t> sdefIdx(Vp, 0);
   c->procToVertex.assign(Vp, ~0u);
 
@@ -253,73 +260,168 @@ int rebuild_tables(rz_ctx_impl* c) {
     for (uint32_t k = 0; k < 4; ++k) if (w[k]) n = k + 1;
     return n;
   };
-  auto key_of = [&](uint32_t v) -> uint32_t {
-    return (sdefOf[v] >= 0 ? 1u << 16 : 0u) | (mcount[v] ? 1u << 15 : 0u) | (ninf_of(v) << 8) | std::min<uint32_t>(mcount[v], 255u);
+  const bool classSort = c->permMode != 0;
+  [[maybe_unused]] auto key_of = [&](uint32_t v) -> uint32_t {
+    if (!classSort) return (sdefOf[v] >= 0 ? 2u : 0u) | (mcount[v] ? 1u : 0u);   // natural order except for the rare classes
+    return (sdefOf[v] >= 0 ? 1u << 31 : 0u) | (mcount[v] ? 1u << 30 : 0u) | (ninf_of(v) << 27) | (std::min<uint32_t>(mcount[v], 63u) << 21) |
+           ((uint32_t)c->h_joints[(size_t)v * 4] & 0xFFFFu);
   };
 
-  for (uint32_t t = 0; t < nTiles; ++t) {
-    const uint32_t base = t * kTile;
-    for (uint32_t lane = 0; lane < 32; ++lane) {
-      uint32_t slots[kTile / 32];
-      uint32_t n = 0;
-      for (uint32_t w = 0; w < kTile / 32; ++w) {
-        const uint32_t s = w * 32 + lane;
-        if (base + s < V) slots[n++] = s;
-      }
-      std::stable_sort(slots, slots + n, [&](uint32_t a, uint32_t b) { return key_of(base + a) < key_of(base + b); });
-      for (uint32_t w = 0; w < kTile / 32; ++w) {
-        const uint32_t p = base + w * 32 + lane;
-        if (w < n) {
-          const uint32_t s = slots[w], v = base + s;
-          const float* x = &c->h_vtx8[(size_t)v * 8];
-          uint32_t wb;
-          memcpy(&wb, &c->h_weights[(size_t)v * 4], 4);
-          uint32_t meta = s | (ninf_of(v) << kMetaNinfShift) | kMetaValid;
-          if (mcount[v]) meta |= kMetaMorph;
-          if (sdefOf[v] >= 0) { meta |= kMetaSdef; sdefIdx[p] = (uint32_t)sdefOf[v]; }
-          float wbf, metaf;
-          memcpy(&wbf, &wb, 4);
-          memcpy(&metaf, &meta, 4);
-          rec0[p] = make_float4(x[0], x[1], x[2], wbf);
-          rec1[p] = make_float4(x[3], x[4], x[5], metaf);
-          const uint16_t* j = &c->h_joints[(size_t)v * 4];
-          jrec[p] = make_uint2((uint32_t)j[0] | ((uint32_t)j[1] << 16), (uint32_t)j[2] | ((uint32_t)j[3] << 16));
-          mrange[p] = make_uint2(mstart[v], mcount[v]);
-          c->procToVertex[p] = v;
-        } else {
-          // padding: a harmless rigid vertex on bone 0, parked on the first free slot of this lane column
-          const uint32_t s = w * 32 + lane;
-          const uint32_t wb = 255u, meta = s | (1u << kMetaNinfShift);
-          float wbf, metaf;
-          memcpy(&wbf, &wb, 4);
-          memcpy(&metaf, &meta, 4);
-          rec0[p] = make_float4(0.f, 0.f, 0.f, wbf);
-          rec1[p] = make_float4(0.f, 0.f, 0.f, metaf);
-          jrec[p] = make_uint2(0u, 0u);
-          mrange[p] = make_uint2(0u, 0u);
+  // lane order inside a warp: by influence count, then by bone ids, so that quarter-warps (the unit the shared-memory
+  // pipe serves per wavefront) are homogeneous: same influence count => whole quarters skip the zero-weight gathers,
+  // same bones => same address => no bank conflict.
+  auto key2_of = [&](uint32_t v) -> uint64_t {
+    const uint16_t* j = &c->h_joints[(size_t)v * 4];
+    const uint32_t n = ninf_of(v);
+    uint64_t k = (uint64_t)(sdefOf[v] >= 0 ? 1 : 0) << 63 | (uint64_t)n << 60;
+    k |= (uint64_t)(j[0] & 0x7FFF) << 45;
+    k |= (uint64_t)(n > 1 ? (j[1] & 0x7FFF) : 0) << 30;
+    k |= (uint64_t)(n > 2 ? (j[2] & 0x7FFF) : 0) << 15;
+    k |= (uint64_t)(n > 3 ? (j[3] & 0x7FFF) : 0);
+    return k;
+  };
+  auto emit_vertex = [&](uint32_t p, uint32_t v, uint32_t slot) {
+    const float* x = &c->h_vtx8[(size_t)v * 8];
+    const uint8_t* w8 = &c->h_weights[(size_t)v * 4];
+    uint32_t wb;
+    memcpy(&wb, w8, 4);
+    uint32_t meta = slot | (ninf_of(v) << kMetaNinfShift) | kMetaValid;
+    if (mcount[v]) meta |= kMetaMorph;
+    if (sdefOf[v] >= 0) { meta |= kMetaSdef; sdefIdx[p] = (uint32_t)sdefOf[v]; }
+    // weights exactly as the reference's vertex shader derives them (engine.ts:255-258): unorm8 -> f32,
+    // sum, renormalise when the sum exceeds 1e-4 else (1,0,0,0).  IEEE f32 on the host == on the device.
+    float w[4] = {(float)w8[0] / 255.0f, (float)w8[1] / 255.0f, (float)w8[2] / 255.0f, (float)w8[3] / 255.0f};
+    const float wsum = w[0] + w[1] + w[2] + w[3];
+    if (wsum > 0.0001f) {
+      const float inv = 1.0f / wsum;
+      for (int k = 0; k < 4; ++k) w[k] = w[k] * inv;
+    } else {
+      w[0] = 1.f; w[1] = w[2] = w[3] = 0.f;
+    }
+    const uint16_t* j = &c->h_joints[(size_t)v * 4];
+    const uint32_t q0 = c->bonePos[j[0]], q1 = c->bonePos[j[1]], q2 = c->bonePos[j[2]], q3 = c->bonePos[j[3]];   // palette rows
+    const uint32_t j01 = q0 | (q1 << 16), j23 = q2 | (q3 << 16);
+    float j01f, j23f;
+    memcpy(&j01f, &j01, 4);
+    memcpy(&j23f, &j23, 4);
+    rec0[p] = make_float4(x[0], x[1], x[2], w[0]);
+    rec1[p] = make_float4(x[3], x[4], x[5], w[1]);
+    rec2[p] = make_float4(w[2], w[3], j01f, j23f);
+    metaArr[p] = meta;
+    wbits[p] = wb;
+    mrange[p] = make_uint2(mstart[v], mcount[v]);
+    c->procToVertex[p] = v;
+  };
+  auto emit_padding = [&](uint32_t p, uint32_t slot) {
+    // a harmless rigid vertex on bone 0, parked on an unused slot of this warp's lane column
+    rec0[p] = make_float4(0.f, 0.f, 0.f, 1.f);
+    rec1[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+    rec2[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+    metaArr[p] = slot | (1u << kMetaNinfShift);
+    mrange[p] = make_uint2(0u, 0u);
+  };
+
+  // Processing order: every warp keeps its 32 CONSECUTIVE output vertices (its results leave as one contiguous
+  // 384-byte TMA bulk store per plane), only the lane order inside the warp is chosen: by influence count, then bones.
+  std::vector<uint32_t> procVertex(Vp, ~0u), procSlot(Vp, 0);
+  for (uint32_t w0 = 0; w0 < Vp; w0 += 32) {
+    uint32_t vs[32];
+    uint32_t n = 0;
+    for (uint32_t l = 0; l < 32; ++l) if (w0 + l < V) vs[n++] = w0 + l;
+    if (classSort) std::stable_sort(vs, vs + n, [&](uint32_t a, uint32_t b2) { return key2_of(a) < key2_of(b2); });
+    uint32_t lane = 0;
+    for (; lane < n; ++lane) { procVertex[w0 + lane] = vs[lane]; procSlot[w0 + lane] = vs[lane] - w0; }
+    for (uint32_t l = n; l < 32; ++l, ++lane) { procVertex[w0 + lane] = ~0u; procSlot[w0 + lane] = l; }
+  }
+
+  // ---- bank-aware palette permutation -------------------------------------------------------------------------
+  // A warp-wide LDS.128 costs max(2, distinct chunks / 4, 2 x chunks per 16-byte bank group) cycles on sm_100
+  // (profiles/r01_ubench_lds128.txt).  Rows are 48 B, so the bank group of row r of bone b is (3*pos(b)+r) mod 8:
+  // bones gathered by the same warp instruction should sit at positions that differ mod 8.  Greedy colouring of the
+  // bone co-occurrence graph into 8 classes, then class c occupies palette rows c, c+8, c+16, ...
+  c->bonePos.resize(B);
+  for (uint32_t b = 0; b < B; ++b) c->bonePos[b] = b;
+  if (c->colorMode && B >= 16) {
+    std::unordered_map<uint64_t, uint32_t> pairW;
+    std::vector<uint32_t> seen;
+    for (uint32_t w0 = 0; w0 < Vp; w0 += 32) {
+      for (uint32_t k = 0; k < 4; ++k) {
+        seen.clear();
+        for (uint32_t l = 0; l < 32; ++l) {
+          const uint32_t v = procVertex[w0 + l];
+          if (v == ~0u || ninf_of(v) <= k) continue;
+          const uint32_t b = c->h_joints[(size_t)v * 4 + k];
+          if (std::find(seen.begin(), seen.end(), b) == seen.end()) seen.push_back(b);
         }
+        for (size_t a = 0; a < seen.size(); ++a)
+          for (size_t b2 = a + 1; b2 < seen.size(); ++b2) {
+            const uint32_t lo = std::min(seen[a], seen[b2]), hi = std::max(seen[a], seen[b2]);
+            pairW[((uint64_t)lo << 32) | hi] += 1;
+          }
       }
     }
+    std::vector<std::vector<std::pair<uint32_t, uint32_t>>> adj(B);
+    std::vector<uint64_t> tot(B, 0);
+    for (const auto& kv : pairW) {
+      const uint32_t lo = (uint32_t)(kv.first >> 32), hi = (uint32_t)kv.first;
+      adj[lo].push_back({hi, kv.second});
+      adj[hi].push_back({lo, kv.second});
+      tot[lo] += kv.second;
+      tot[hi] += kv.second;
+    }
+    std::vector<uint32_t> order(B);
+    for (uint32_t b = 0; b < B; ++b) order[b] = b;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return tot[a] > tot[b]; });
+    uint32_t cap[8], cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (uint32_t cl = 0; cl < 8; ++cl) cap[cl] = (B - cl + 7) / 8;
+    std::vector<int> cls(B, -1);
+    for (uint32_t b : order) {
+      uint64_t cost[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (const auto& e : adj[b]) if (cls[e.first] >= 0) cost[cls[e.first]] += e.second;
+      int best = -1;
+      for (int cl = 0; cl < 8; ++cl) {
+        if (cnt[cl] >= cap[cl]) continue;
+        if (best < 0 || cost[cl] < cost[best] || (cost[cl] == cost[best] && cnt[cl] < cnt[best])) best = cl;
+      }
+      cls[b] = best;
+      cnt[best]++;
+    }
+    uint32_t next[8];
+    for (uint32_t cl = 0; cl < 8; ++cl) next[cl] = cl;
+    for (uint32_t b = 0; b < B; ++b) { c->bonePos[b] = next[cls[b]]; next[cls[b]] += 8; }
+  }
+  c->boneAt.assign(B, 0);
+  for (uint32_t b = 0; b < B; ++b) c->boneAt[c->bonePos[b]] = b;
+
+  for (uint32_t p = 0; p < Vp; ++p) {
+    if (procVertex[p] != ~0u) emit_vertex(p, procVertex[p], procSlot[p]);
+    else emit_padding(p, procSlot[p]);
   }
 
   int rc;
   if ((rc = dev_reserve(c, c->d_rec0, (size_t)Vp * 16))) return rc;
   if ((rc = dev_reserve(c, c->d_rec1, (size_t)Vp * 16))) return rc;
-  if ((rc = dev_reserve(c, c->d_joints, (size_t)Vp * 8))) return rc;
+  if ((rc = dev_reserve(c, c->d_rec2, (size_t)Vp * 16))) return rc;
+  if ((rc = dev_reserve(c, c->d_meta, (size_t)Vp * 4))) return rc;
+  if ((rc = dev_reserve(c, c->d_wbits, (size_t)Vp * 4))) return rc;
   if ((rc = dev_reserve(c, c->d_mrange, (size_t)Vp * 8))) return rc;
   if ((rc = dev_reserve(c, c->d_ments, ments.size() * 16))) return rc;
   if ((rc = dev_reserve(c, c->d_sdefIdx, (size_t)Vp * 4))) return rc;
   if ((rc = dev_reserve(c, c->d_sdefTab, std::max<size_t>(sdefTab.size(), 3) * 16))) return rc;
   if ((rc = dev_reserve(c, c->d_invBind, (size_t)B * 64))) return rc;
+  if ((rc = dev_reserve(c, c->d_bonePos, (size_t)B * 4))) return rc;
   CU_TRY(c, cudaMemcpyAsync(c->d_rec0.p, rec0.data(), (size_t)Vp * 16, cudaMemcpyHostToDevice, c->stream));
   CU_TRY(c, cudaMemcpyAsync(c->d_rec1.p, rec1.data(), (size_t)Vp * 16, cudaMemcpyHostToDevice, c->stream));
-  CU_TRY(c, cudaMemcpyAsync(c->d_joints.p, jrec.data(), (size_t)Vp * 8, cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(c->d_rec2.p, rec2.data(), (size_t)Vp * 16, cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(c->d_meta.p, metaArr.data(), (size_t)Vp * 4, cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(c->d_wbits.p, wbits.data(), (size_t)Vp * 4, cudaMemcpyHostToDevice, c->stream));
   CU_TRY(c, cudaMemcpyAsync(c->d_mrange.p, mrange.data(), (size_t)Vp * 8, cudaMemcpyHostToDevice, c->stream));
   CU_TRY(c, cudaMemcpyAsync(c->d_ments.p, ments.data(), ments.size() * 16, cudaMemcpyHostToDevice, c->stream));
   CU_TRY(c, cudaMemcpyAsync(c->d_sdefIdx.p, sdefIdx.data(), (size_t)Vp * 4, cudaMemcpyHostToDevice, c->stream));
   if (!sdefTab.empty())
     CU_TRY(c, cudaMemcpyAsync(c->d_sdefTab.p, sdefTab.data(), sdefTab.size() * 16, cudaMemcpyHostToDevice, c->stream));
   CU_TRY(c, cudaMemcpyAsync(c->d_invBind.p, c->h_invBind.data(), (size_t)B * 64, cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(c->d_bonePos.p, c->bonePos.data(), (size_t)B * 4, cudaMemcpyHostToDevice, c->stream));
   CU_TRY(c, cudaStreamSynchronize(c->stream));   // the std::vectors above go out of scope
 
   // output planes: pos plane then normal plane, both 16-byte aligned (TMA bulk stores)
@@ -402,6 +504,8 @@ int32_t rz_create(const rz_config* cfg, rz_ctx** out) {
     if (e != cudaSuccess) { delete c; return fail(nullptr, RZ_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
     c->ownStream = true;
   }
+  if (const char* e1 = getenv("RZ_PERM")) c->permMode = atoi(e1);        // experiment knobs (tuning)
+  if (const char* e2 = getenv("RZ_COLOR")) c->colorMode = atoi(e2);
   cudaEventCreate(&c->evStart);
   cudaEventCreate(&c->evStop);
   *out = c;
@@ -412,8 +516,8 @@ int32_t rz_destroy(rz_ctx* c) {
   if (!c) return RZ_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  DevBuf* bufs[] = {&c->d_rec0, &c->d_rec1, &c->d_joints, &c->d_mrange, &c->d_ments, &c->d_sdefIdx, &c->d_sdefTab,
-                    &c->d_invBind, &c->d_world, &c->d_skin, &c->d_inst2pal, &c->d_mwIn, &c->d_mwIds, &c->d_mwDense,
+  DevBuf* bufs[] = {&c->d_rec0, &c->d_rec1, &c->d_rec2, &c->d_meta, &c->d_wbits, &c->d_mrange, &c->d_ments, &c->d_sdefIdx, &c->d_sdefTab,
+                    &c->d_invBind, &c->d_bonePos, &c->d_world, &c->d_skin, &c->d_inst2pal, &c->d_mwIn, &c->d_mwIds, &c->d_mwDense,
                     &c->d_out, &c->d_bounds, &c->d_counter};
   for (DevBuf* b : bufs) dev_free(c, *b);
   if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -490,7 +594,7 @@ static int set_palettes_common(rz_ctx* c, const float* d_world, uint32_t P, uint
   const uint32_t n = P * c->B;
   skin_matrices_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(reinterpret_cast<const float4*>(d_world),
                                                               reinterpret_cast<const float4*>(c->d_invBind.p),
-                                                              reinterpret_cast<float4*>(c->d_skin.p), P, c->B);
+                                                              reinterpret_cast<float4*>(c->d_skin.p), reinterpret_cast<const uint32_t*>(c->d_bonePos.p), P, c->B);
   CU_TRY(c, cudaGetLastError());
   c->launches++;
   c->P = P;
@@ -613,41 +717,52 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
 
   // ---- pick the launch shape
   const size_t smemMax = (size_t)c->maxSmemOptin;
-  if (smem_needed(1, 256, false, need, c->B, Mpad) > smemMax) need |= FEAT_GPAL;   // palette does not fit: gather from global
+  if (smem_needed(1, 256, need, c->B, Mpad) > smemMax) need |= FEAT_GPAL;   // palette does not fit: gather from global
   const int feat = resolve_feat(need);
   if (feat < 0) return fail(c, RZ_ERR_INVALID_ARG, "rz_deform: feature combination 0x%x is not built", need);
-  const bool plain = feat == 0;
-  KernelEntry ke{nullptr, 0, 0, false, feat};
-  {
-    int wantI = c->tuneI ? (int)c->tuneI : 4;
-    while (wantI > 1 && (uint32_t)wantI > count) wantI >>= 1;
-    if (!plain && wantI > 4) wantI = 4;
-    const int wantStore = c->tuneStore ? (int)c->tuneStore : 2;
-    const int wantNT = c->tuneThreads ? (int)c->tuneThreads : 512;
-    // candidates in preference order; the first that is compiled and fits in shared memory wins
-    for (int I = wantI; I >= 1 && !ke.fn; I >>= 1) {
-      const int nts[2] = {wantNT, wantNT == 512 ? 256 : 512};
-      const bool sts[2] = {wantStore == 2, wantStore != 2};
-      for (int a = 0; a < 2 && !ke.fn; ++a)
-        for (int b = 0; b < 2 && !ke.fn; ++b) {
-          KernelEntry e = lookup_kernel(feat, I, nts[b], sts[a]);
-          if (e.fn && smem_needed(I, nts[b], sts[a], feat, c->B, Mpad) <= smemMax) ke = e;
-        }
-    }
-    if (!ke.fn) return fail(c, RZ_ERR_INVALID_ARG, "rz_deform: no kernel shape fits B=%u (smem limit %zu)", c->B, smemMax);
-  }
-  const size_t smem = smem_needed(ke.I, ke.NT, ke.staged, feat, c->B, Mpad);
-  CU_TRY(c, cudaFuncSetAttribute(ke.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  KernelEntry ke{nullptr, 0, 0, 0, feat};
+  size_t smem = 0;
   int occ = 0;
-  CU_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ke.fn, ke.NT, smem));
-  if (occ < 1) return fail(c, RZ_ERR_CUDA, "rz_deform: kernel does not fit on an SM (smem %zu)", smem);
+  auto try_shape = [&](int I, int NT, int MINB) -> bool {
+    if ((uint32_t)I > count && I > 1) return false;                 // never wider than the instance range
+    KernelEntry e = lookup_kernel(feat, I, NT, MINB);
+    if (!e.fn) return false;
+    const size_t sm = smem_needed(e.I, e.NT, feat, c->B, Mpad);
+    if (sm > smemMax) return false;
+    if (cudaFuncSetAttribute(e.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) { cudaGetLastError(); return false; }
+    int o = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, e.fn, e.NT, sm) != cudaSuccess || o < 1) { cudaGetLastError(); return false; }
+    ke = e; smem = sm; occ = o;
+    return true;
+  };
+  if (c->tuneI || c->tuneThreads) {
+    const int I = c->tuneI ? (int)c->tuneI : 2, NT = c->tuneThreads ? (int)c->tuneThreads : 256;
+    if (!try_shape(I, NT, (int)c->tuneCtas) && !try_shape(I, NT, 0))
+      return fail(c, RZ_ERR_INVALID_ARG, "rz_deform: requested launch shape I=%d threads=%d ctas/SM=%u is not built or does not fit (B=%u)",
+                  I, NT, c->tuneCtas, c->B);
+  } else {
+    // preference order (measured on B200, profiles/): most resident warps first, then wider instance groups
+    static const int pref[][3] = {{2, 512, 2}, {2, 256, 3}, {3, 256, 2}, {4, 512, 1}, {2, 256, 2}, {4, 256, 1}, {2, 512, 1},
+                                  {1, 256, 4}, {1, 256, 2}, {1, 512, 2}};
+    bool ok = false;
+    for (const auto& p : pref) {
+      if (try_shape(p[0], p[1], p[2])) {
+        if (occ >= p[2]) { ok = true; break; }                     // the shape only pays off at its intended occupancy
+      }
+    }
+    if (!ok) {
+      for (const auto& p : pref) if (try_shape(p[0], p[1], p[2])) { ok = true; break; }
+      if (!ok) for (const auto& p : pref) if (try_shape(p[0], p[1], 0)) { ok = true; break; }
+    }
+    if (!ok) return fail(c, RZ_ERR_INVALID_ARG, "rz_deform: no kernel shape fits B=%u (smem limit %zu)", c->B, smemMax);
+  }
   if (c->tuneCtas && (int)c->tuneCtas < occ) occ = (int)c->tuneCtas;
-
   DeformParams prm;
   memset(&prm, 0, sizeof prm);
   prm.rec0 = reinterpret_cast<const float4*>(c->d_rec0.p);
   prm.rec1 = reinterpret_cast<const float4*>(c->d_rec1.p);
-  prm.joints = reinterpret_cast<const uint2*>(c->d_joints.p);
+  prm.rec2 = reinterpret_cast<const float4*>(c->d_rec2.p);
+  prm.meta = reinterpret_cast<const uint32_t*>(c->d_meta.p);
   prm.mrange = reinterpret_cast<const uint2*>(c->d_mrange.p);
   prm.ments = reinterpret_cast<const float4*>(c->d_ments.p);
   prm.sdefIdx = reinterpret_cast<const uint32_t*>(c->d_sdefIdx.p);
@@ -685,7 +800,7 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
   c->launches++;
   c->evPending = true;
   c->frames++;
-  c->usedI = ke.I; c->usedStore = ke.staged ? 2 : 1; c->usedCtas = grid; c->usedThreads = ke.NT; c->usedSmem = (uint32_t)smem;
+  c->usedI = ke.I; c->usedStore = 2; c->usedCtas = grid; c->usedThreads = ke.NT; c->usedSmem = (uint32_t)smem;
   c->lastVerts = (uint64_t)count * c->V;
   // compulsory DRAM bytes: outputs + mesh + palettes + invBind + morph entries/weights + sdef records
   const double planes = (feat & FEAT_NONRM) ? 1.0 : 2.0;
@@ -748,19 +863,23 @@ int32_t rz_read_skinning(rz_ctx* c, uint16_t* joints, uint8_t* weights) {
   if (!c) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_read_skinning: null ctx");
   if (c->V == 0) return fail(c, RZ_ERR_STATE, "rz_read_skinning before rz_load_mesh");
   CU_TRY(c, cudaSetDevice(c->device));
-  std::vector<float4> rec0(c->Vp);
-  std::vector<uint2> jrec(c->Vp);
-  CU_TRY(c, cudaMemcpyAsync(rec0.data(), c->d_rec0.p, (size_t)c->Vp * 16, cudaMemcpyDeviceToHost, c->stream));
-  CU_TRY(c, cudaMemcpyAsync(jrec.data(), c->d_joints.p, (size_t)c->Vp * 8, cudaMemcpyDeviceToHost, c->stream));
+  std::vector<float4> rec2(c->Vp);
+  std::vector<uint32_t> wb(c->Vp);
+  CU_TRY(c, cudaMemcpyAsync(rec2.data(), c->d_rec2.p, (size_t)c->Vp * 16, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(wb.data(), c->d_wbits.p, (size_t)c->Vp * 4, cudaMemcpyDeviceToHost, c->stream));
   CU_TRY(c, cudaStreamSynchronize(c->stream));
   for (uint32_t p = 0; p < c->Vp; ++p) {
     const uint32_t v = c->procToVertex[p];
     if (v == ~0u) continue;
     if (joints) {
-      joints[(size_t)v * 4] = (uint16_t)(jrec[p].x & 0xFFFF); joints[(size_t)v * 4 + 1] = (uint16_t)(jrec[p].x >> 16);
-      joints[(size_t)v * 4 + 2] = (uint16_t)(jrec[p].y & 0xFFFF); joints[(size_t)v * 4 + 3] = (uint16_t)(jrec[p].y >> 16);
+      uint32_t j01, j23;
+      memcpy(&j01, &rec2[p].z, 4);
+      memcpy(&j23, &rec2[p].w, 4);
+      // the device stores palette rows; map them back to the caller's bone ids
+      joints[(size_t)v * 4] = (uint16_t)c->boneAt[j01 & 0xFFFF]; joints[(size_t)v * 4 + 1] = (uint16_t)c->boneAt[j01 >> 16];
+      joints[(size_t)v * 4 + 2] = (uint16_t)c->boneAt[j23 & 0xFFFF]; joints[(size_t)v * 4 + 3] = (uint16_t)c->boneAt[j23 >> 16];
     }
-    if (weights) memcpy(&weights[(size_t)v * 4], &rec0[p].w, 4);
+    if (weights) memcpy(&weights[(size_t)v * 4], &wb[p], 4);
   }
   return RZ_OK;
 }
@@ -770,9 +889,17 @@ int32_t rz_read_skin_matrices(rz_ctx* c, uint32_t palette, float* skin3x4) {
   if (!c->palettesSet) return fail(c, RZ_ERR_STATE, "rz_read_skin_matrices before rz_set_palettes");
   if (palette >= c->P) return fail(c, RZ_ERR_INVALID_ARG, "rz_read_skin_matrices: palette %u >= P=%u", palette, c->P);
   CU_TRY(c, cudaSetDevice(c->device));
-  CU_TRY(c, cudaMemcpyAsync(skin3x4, reinterpret_cast<const float*>(c->d_skin.p) + (size_t)palette * c->B * 12, (size_t)c->B * 48,
+  std::vector<float> tmp((size_t)c->B * 12);
+  CU_TRY(c, cudaMemcpyAsync(tmp.data(), reinterpret_cast<const float*>(c->d_skin.p) + (size_t)palette * c->B * 12, (size_t)c->B * 48,
                             cudaMemcpyDeviceToHost, c->stream));
   CU_TRY(c, cudaStreamSynchronize(c->stream));
+  for (uint32_t b = 0; b < c->B; ++b) {   // un-permute and un-pair (deform_kernel.cuh kRowF4) back to 3x4 row-major
+    const float* t = tmp.data() + (size_t)c->bonePos[b] * 12;
+    float* o = skin3x4 + (size_t)b * 12;
+    o[0] = t[0]; o[4] = t[1]; o[1] = t[2]; o[5] = t[3];
+    o[2] = t[4]; o[6] = t[5]; o[3] = t[6]; o[7] = t[7];
+    o[8] = t[8]; o[9] = t[9]; o[10] = t[10]; o[11] = t[11];
+  }
   return RZ_OK;
 }
 

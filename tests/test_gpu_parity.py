@@ -39,21 +39,22 @@ def wl_small():
     return synth.make_workload(5000, 64, M=8, sdef=True)
 
 
-SHAPES = [(I, nt, st) for I in (1, 2, 4, 8) for nt in (256, 512) for st in (1, 2)]
+SHAPES = [(1, 256, 4), (2, 256, 3), (2, 256, 2), (3, 256, 2), (4, 256, 1), (1, 512, 2), (2, 512, 2), (2, 512, 1), (3, 512, 1),
+          (4, 512, 1), (2, 768, 1), (3, 768, 1), (2, 1024, 1), (3, 1024, 1)]     # csrc/kernel_table.h RZ_SHAPES_FULL
 
 
-@pytest.mark.parametrize("I,nt,st", SHAPES)
-def test_every_launch_shape_matches_oracle(rzlib, orc, wl_small, I, nt, st):
+@pytest.mark.parametrize("I,nt,mb", SHAPES)
+def test_every_launch_shape_matches_oracle(rzlib, orc, wl_small, I, nt, mb):
     wl = wl_small
     K, P = 11, 4                                    # partial last group for every I; shared palettes
     world = synth.make_palettes(wl.bones, P, np.random.default_rng(1))
     i2p = (np.arange(K) * 3) % P
-    with capi.DeformContext(max_instances=K, instances_per_group=I, threads=nt, store_mode=st) as ctx:
+    with capi.DeformContext(max_instances=K, instances_per_group=I, threads=nt, ctas_per_sm=mb) as ctx:
         ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
         ctx.set_palettes(world, i2p)
         ctx.deform()
         s = ctx.stats()
-        assert (s["instancesPerGroup"], s["threads"], s["storeMode"]) == (I, nt, st)
+        assert (s["instancesPerGroup"], s["threads"]) == (I, nt)
         check_all(orc, ctx, wl, world, i2p, K)
         # instances that share a palette are bit-identical
         a, b = ctx.read_instance(0), ctx.read_instance(4)
@@ -64,8 +65,8 @@ def test_every_launch_shape_matches_oracle(rzlib, orc, wl_small, I, nt, st):
 def test_ragged_vertex_counts(rzlib, orc, V):
     wl = synth.make_workload(V, 16, seed=100 + V)
     world = synth.make_palettes(wl.bones, 3, np.random.default_rng(2))
-    for st in (1, 2):
-        with capi.DeformContext(max_instances=3, store_mode=st) as ctx:
+    for I, nt in ((0, 0), (1, 256), (2, 512), (2, 768)):
+        with capi.DeformContext(max_instances=3, instances_per_group=I, threads=nt) as ctx:
             ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
             ctx.set_palettes(world)
             ctx.deform()
@@ -106,8 +107,8 @@ def test_morphs(rzlib, orc, wl_small):
     w = rng.uniform(0, 1, (K, 3)).astype(np.float32)
     dense = np.zeros((K, wl.morphs.count), np.float32)
     dense[:, active] = w
-    for I, st in ((1, 1), (4, 2), (2, 1)):
-        with capi.DeformContext(max_instances=K, instances_per_group=I, store_mode=st) as ctx:
+    for I, nt in ((1, 256), (4, 512), (2, 256), (2, 512)):
+        with capi.DeformContext(max_instances=K, instances_per_group=I, threads=nt) as ctx:
             ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
             ctx.load_morphs(wl.morphs.offsets, wl.morphs.vertexIndex, wl.morphs.delta)
             ctx.set_palettes(world)

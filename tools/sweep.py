@@ -20,10 +20,7 @@ def main():
     ap.add_argument("--bones", type=int, default=512)
     ap.add_argument("--instances", type=int, default=2048)
     ap.add_argument("--iters", type=int, default=5)
-    ap.add_argument("--ipg", default="1,2,4,8")
-    ap.add_argument("--threads", default="256,512")
-    ap.add_argument("--store", default="1,2")
-    ap.add_argument("--ctas", default="0")
+    ap.add_argument("--shapes", default="1:256:4,2:256:3,2:256:2,3:256:2,4:256:1,1:512:2,2:512:2,2:512:1,3:512:1,4:512:1,2:768:1,3:768:1,2:1024:1,3:1024:1")
     ap.add_argument("--chunks", default="0")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.jsonl"))
     a = ap.parse_args()
@@ -38,9 +35,11 @@ def main():
     torch.cuda.set_stream(stream)
     rows = []
     L = lambda s: [int(x) for x in s.split(",")]
-    for I, nt, st, ctas, chunks in itertools.product(L(a.ipg), L(a.threads), L(a.store), L(a.ctas), L(a.chunks)):
+    shapes = [tuple(int(x) for x in sh.split(":")) for sh in a.shapes.split(",")]
+    for (I, nt, ctas), chunks in itertools.product(shapes, L(a.chunks)):
+        st = 2
         try:
-            ctx = capi.DeformContext(max_instances=K, stream=stream.cuda_stream, instances_per_group=I, threads=nt, store_mode=st,
+            ctx = capi.DeformContext(max_instances=K, stream=stream.cuda_stream, instances_per_group=I, threads=nt,
                                      ctas_per_sm=ctas, chunks=chunks)
             ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
             ctx.set_palettes_device(dw.data_ptr(), P, i2p.data_ptr(), K)
