@@ -9,7 +9,7 @@ namespace rz {
 // Replaces the reference's only compute shader (engine.ts:920-929).  One thread per (palette, bone);
 // keeps rows 0..2 of the column-major product (row 3 never reaches the blend's outputs, engine.ts:260-272).
 __global__ void skin_matrices_kernel(const float4* __restrict__ world, const float4* __restrict__ invBind,
-                                     float4* __restrict__ skin, const uint32_t* __restrict__ bonePos, uint32_t P, uint32_t B) {
+                                     float4* __restrict__ skin, const uint32_t* __restrict__ bonePos, uint32_t P, uint32_t B, uint32_t soa) {
   const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= P * B) return;
   const uint32_t b = idx % B;
@@ -25,9 +25,15 @@ __global__ void skin_matrices_kernel(const float4* __restrict__ world, const flo
   }
   const size_t row = (size_t)(idx - b) + __ldg(bonePos + b);         // bank-aware palette permutation (rze_b200.cu rebuild_tables)
   // pair layout (deform_kernel.cuh kRowF4): rows 0/1 interleaved, row 2 as is
-  skin[row * 3 + 0] = make_float4(r[0][0], r[1][0], r[0][1], r[1][1]);
-  skin[row * 3 + 1] = make_float4(r[0][2], r[1][2], r[0][3], r[1][3]);
-  skin[row * 3 + 2] = make_float4(r[2][0], r[2][1], r[2][2], r[2][3]);
+  const float4 cA = make_float4(r[0][0], r[1][0], r[0][1], r[1][1]);
+  const float4 cB = make_float4(r[0][2], r[1][2], r[0][3], r[1][3]);
+  const float4 cC = make_float4(r[2][0], r[2][1], r[2][2], r[2][3]);
+  if (soa) {          // [P][3][B] float4: chunk r of all bones contiguous (8 consecutive palette rows = one 128-byte line)
+    const size_t pbase = (size_t)(idx - b) * 3, pos = __ldg(bonePos + b);
+    skin[pbase + pos] = cA; skin[pbase + B + pos] = cB; skin[pbase + 2 * (size_t)B + pos] = cC;
+  } else {            // [P][B][3] float4
+    skin[row * 3 + 0] = cA; skin[row * 3 + 1] = cB; skin[row * 3 + 2] = cC;
+  }
 }
 
 // dense per-instance morph weights: dense[k][m] = 0, dense[k][activeIds[a]] += w[k][a]

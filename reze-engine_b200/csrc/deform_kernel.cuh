@@ -58,6 +58,7 @@ struct DeformParams {
   unsigned long long nrmOffF;          // floats from pos plane to normal plane
   uint32_t V, B, nTiles, K0, Kcount, Mpad;
   uint32_t nGroups, nChunks, tilesPerChunk;
+  uint32_t posStride, rowStride;       // palette addressing: chunk r of palette row `pos` sits at pos*posStride + r*rowStride bytes
   uint32_t* counter;
 };
 
@@ -112,6 +113,12 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// exactly one lane of a converged warp (lets the compiler keep TMA operands in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ float4 ldg_el(const float4* p, uint64_t pol) {   // read-only, keep in L2 (mesh is re-read by every group)
@@ -238,7 +245,7 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
   const uint32_t mwBytes = MORPH ? prm.Mpad * 4u : 0u;
   const int tid = threadIdx.x;
   const int lane = tid & 31;
-  const int warp = tid >> 5;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform by construction: TMA operands stay in uniform registers
   // warp-private staging: [kStageBufs][I][PLANES][32*3 floats], laid out exactly like 32 vertices of the output planes
   const uint32_t sStageW = sMw + (uint32_t)I * mwBytes + (uint32_t)warp * (kStageBufs * kBufB);
 
@@ -264,6 +271,7 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
     const uint32_t nInst = min((uint32_t)I, prm.K0 + prm.Kcount - kBase);
     const uint32_t tile0 = chunk * prm.tilesPerChunk;
     const uint32_t tile1 = min(prm.nTiles, tile0 + prm.tilesPerChunk);
+    float* const outItem = prm.out + (size_t)kBase * prm.instStrideF;   // pos plane of the group's first instance
 
     // ---- stage the palettes (+ morph weights) of the I instances: TMA bulk copies on one mbarrier
     const float* gpal[I];
@@ -320,7 +328,7 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
     for (uint32_t t = tile0; t < tile1; t += NT / kTile) {
       const VRec v = cur;
       if (t + NT / kTile < tile1) cur = load_rec(t + NT / kTile);
-      if (t + tid / kTile >= tile1) continue;                     // warp-uniform: this warp has no tile in the pass
+      if (t + (uint32_t)warp / (kTile / 32) >= tile1) continue;       // warp-uniform: this warp has no tile in the pass
 
       const uint32_t meta = v.meta;
       const bool valid = (meta & kMetaValid) != 0;
@@ -329,10 +337,11 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
       const int nmax = __reduce_max_sync(0xffffffffu, ninf);
       const float w0 = v.r0.w, w1 = v.r1.w, w2 = v.r2.x, w3 = v.r2.y;
       const uint32_t jb01 = __float_as_uint(v.r2.z), jb23 = __float_as_uint(v.r2.w);
-      const uint32_t j0 = (jb01 & 0xFFFFu) * 48u, j1 = (jb01 >> 16) * 48u;
-      const uint32_t j2 = (jb23 & 0xFFFFu) * 48u, j3 = (jb23 >> 16) * 48u;
+      const uint32_t pS = prm.posStride, rS = prm.rowStride, rS2 = 2u * rS;
+      const uint32_t j0 = (jb01 & 0xFFFFu) * pS, j1 = (jb01 >> 16) * pS;
+      const uint32_t j2 = (jb23 & 0xFFFFu) * pS, j3 = (jb23 >> 16) * pS;
       const float vnx = v.r1.x, vny = v.r1.y, vnz = v.r1.z;
-      const uint32_t warpVtx0 = t * kTile + (uint32_t)(tid & ~31);      // first output vertex of this warp
+      const uint32_t warpVtx0 = t * kTile + (uint32_t)warp * 32u;        // first output vertex of this warp (uniform)
       const uint32_t nWarpVerts = min(32u, prm.V - min(prm.V, warpVtx0));
       const uint32_t nAligned = nWarpVerts & ~3u;                 // bulk sizes must be multiples of 16 B
 
@@ -371,10 +380,10 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
       }
 
       // the bulk stores issued from this buffer two passes ago must have finished reading it
-      if (lane == 0) bulk_wait_read<kStageBufs - 1>();
+      if (elect_one()) bulk_wait_read<kStageBufs - 1>();
       __syncwarp();
       const uint32_t stg = sStageW + sbuf * kBufB;
-      const bool staged = slot < nAligned;                        // ragged tail (< 4 vertices of the mesh): plain stores
+      const uint32_t stgLane = stg + slot * 12u;
 
       // splats for the packed mat-vec (once per vertex unless morphing moves the position per instance)
       const float2 nx2 = make_float2(vnx, vnx), ny2 = make_float2(vny, vny), nz2 = make_float2(vnz, vnz);
@@ -384,21 +393,20 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
         constexpr int NV = decltype(NM)::value;                   // 0: rigid warp with unit weights, else warp-max influence count
         constexpr int NMAX = NV == 0 ? 1 : NV;
         // ---- phase 1: palette gathers of influences 0/1 for all I instances, issued back to back (latency overlaps).
-        // Lanes whose weight for an influence is zero skip that gather (their FFMA adds an exact 0); lanes are sorted by
-        // influence count inside the warp, so whole quarter-warps drop out of the shared-memory wavefronts.
+        // No predication: a lane whose weight for influence k is zero carries (set at load time, rze_b200.cu) the joint of
+        // an ACTIVE lane of its own warp, so its gather costs no extra shared-memory wavefront (same 16-byte chunk is
+        // broadcast) and its FFMA adds an exact 0.
         float4 a0[I], a1[I], a2[I], b0[I], b1[I], b2[I];
-        const bool need1 = NMAX > 1 && (ninf > 1 || isSdef);
 #pragma unroll
         for (int i = 0; i < I; ++i) {
-          b0[i] = b1[i] = b2[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (GPAL) {
             const float4* pal = reinterpret_cast<const float4*>(gpal[i]);
-            a0[i] = pal[j0 / 16]; a1[i] = pal[j0 / 16 + 1]; a2[i] = pal[j0 / 16 + 2];
-            if (need1) { b0[i] = pal[j1 / 16]; b1[i] = pal[j1 / 16 + 1]; b2[i] = pal[j1 / 16 + 2]; }
+            a0[i] = pal[j0 / 16]; a1[i] = pal[(j0 + rS) / 16]; a2[i] = pal[(j0 + rS2) / 16];
+            if (NMAX > 1) { b0[i] = pal[j1 / 16]; b1[i] = pal[(j1 + rS) / 16]; b2[i] = pal[(j1 + rS2) / 16]; }
           } else {
             const uint32_t pb = sPal + (uint32_t)i * palBytes;
-            a0[i] = lds128(pb + j0); a1[i] = lds128(pb + j0 + 16); a2[i] = lds128(pb + j0 + 32);
-            if (need1) { b0[i] = lds128(pb + j1); b1[i] = lds128(pb + j1 + 16); b2[i] = lds128(pb + j1 + 32); }
+            a0[i] = lds128(pb + j0); a1[i] = lds128(pb + j0 + rS); a2[i] = lds128(pb + j0 + rS2);
+            if (NMAX > 1) { b0[i] = lds128(pb + j1); b1[i] = lds128(pb + j1 + rS); b2[i] = lds128(pb + j1 + rS2); }
           }
         }
         // ---- phase 2: blend + transform + staging
@@ -445,20 +453,14 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
             if (NMAX > 1) { mA = f4_fma(b0[i], w1_2, mA); mB = f4_fma(b1[i], w1_2, mB); mC = f4_fma(b2[i], w1_2, mC); }
             if (NMAX > 2) {
               float4 c0, c1, c2;
-              c0 = c1 = c2 = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (ninf > 2) {
-                if (GPAL) { const float4* pal = reinterpret_cast<const float4*>(gpal[i]); c0 = pal[j2 / 16]; c1 = pal[j2 / 16 + 1]; c2 = pal[j2 / 16 + 2]; }
-                else { const uint32_t pb = sPal + (uint32_t)i * palBytes; c0 = lds128(pb + j2); c1 = lds128(pb + j2 + 16); c2 = lds128(pb + j2 + 32); }
-              }
+              if (GPAL) { const float4* pal = reinterpret_cast<const float4*>(gpal[i]); c0 = pal[j2 / 16]; c1 = pal[(j2 + rS) / 16]; c2 = pal[(j2 + rS2) / 16]; }
+              else { const uint32_t pb = sPal + (uint32_t)i * palBytes; c0 = lds128(pb + j2); c1 = lds128(pb + j2 + rS); c2 = lds128(pb + j2 + rS2); }
               mA = f4_fma(c0, w2_2, mA); mB = f4_fma(c1, w2_2, mB); mC = f4_fma(c2, w2_2, mC);
             }
             if (NMAX > 3) {
               float4 c0, c1, c2;
-              c0 = c1 = c2 = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (ninf > 3) {
-                if (GPAL) { const float4* pal = reinterpret_cast<const float4*>(gpal[i]); c0 = pal[j3 / 16]; c1 = pal[j3 / 16 + 1]; c2 = pal[j3 / 16 + 2]; }
-                else { const uint32_t pb = sPal + (uint32_t)i * palBytes; c0 = lds128(pb + j3); c1 = lds128(pb + j3 + 16); c2 = lds128(pb + j3 + 32); }
-              }
+              if (GPAL) { const float4* pal = reinterpret_cast<const float4*>(gpal[i]); c0 = pal[j3 / 16]; c1 = pal[(j3 + rS) / 16]; c2 = pal[(j3 + rS2) / 16]; }
+              else { const uint32_t pb = sPal + (uint32_t)i * palBytes; c0 = lds128(pb + j3); c1 = lds128(pb + j3 + rS); c2 = lds128(pb + j3 + rS2); }
               mA = f4_fma(c0, w3_2, mA); mB = f4_fma(c1, w3_2, mB); mC = f4_fma(c2, w3_2, mC);
             }
             // (ox,oy) = (m00,m10)*qx + (m01,m11)*qy + (m02,m12)*qz + (m03,m13);  oz = row 2 . (q,1)
@@ -486,14 +488,10 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
               bmin[i][2] = fminf(bmin[i][2], oz); bmax[i][2] = fmaxf(bmax[i][2], oz);
             }
           }
-          if (staged) {
-            const uint32_t sa = stg + (uint32_t)i * kInstB + slot * 12u;
+          {
+            const uint32_t sa = stgLane + (uint32_t)i * kInstB;
             sts3(sa, ox, oy, oz);
             if (NRM) sts3(sa + kPlaneB, nx, ny, nz);
-          } else if (valid && (uint32_t)i < nInst) {
-            float* dst = prm.out + (size_t)(kBase + i) * prm.instStrideF + (size_t)(warpVtx0 + slot) * 3;
-            st_cs(dst, ox); st_cs(dst + 1, oy); st_cs(dst + 2, oz);
-            if (NRM) { st_cs(dst + prm.nrmOffF, nx); st_cs(dst + prm.nrmOffF + 1, ny); st_cs(dst + prm.nrmOffF + 2, nz); }
           }
         }
       };
@@ -508,18 +506,32 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
       // ---- drain: this warp's 32 vertices x I instances leave through the TMA (one elected lane)
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) {
+      if (elect_one()) {
         if (nAligned) {
+          float* dst = outItem + (size_t)warpVtx0 * 3;
 #pragma unroll
           for (int i = 0; i < I; ++i) {
             if ((uint32_t)i < nInst) {
-              float* dst = prm.out + (size_t)(kBase + i) * prm.instStrideF + (size_t)warpVtx0 * 3;
               bulk_s2g(dst, stg + (uint32_t)i * kInstB, nAligned * 12u, polFirst);
               if (NRM) bulk_s2g(dst + prm.nrmOffF, stg + (uint32_t)i * kInstB + kPlaneB, nAligned * 12u, polFirst);
             }
+            dst += prm.instStrideF;
           }
         }
         bulk_commit();
+      }
+      if (nAligned != nWarpVerts) {
+        // cold path (at most one warp of the whole mesh): the ragged tail (< 4 vertices) leaves with plain stores
+        const uint32_t nf = (nWarpVerts - nAligned) * 3u;
+        if ((uint32_t)lane < nf) {
+          const uint32_t o = nAligned * 3u + (uint32_t)lane;
+          for (uint32_t i = 0; i < nInst; ++i) {
+            float* dst = outItem + (size_t)i * prm.instStrideF + (size_t)warpVtx0 * 3 + o;
+            st_cs(dst, lds32(stg + i * kInstB + o * 4u));
+            if (NRM) st_cs(dst + prm.nrmOffF, lds32(stg + i * kInstB + kPlaneB + o * 4u));
+          }
+        }
+        __syncwarp();
       }
       sbuf ^= 1u;
     }

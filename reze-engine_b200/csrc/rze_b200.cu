@@ -62,7 +62,7 @@ struct rz_ctx_impl {
   std::vector<uint32_t> procToVertex;   // processing index -> caller vertex id (or ~0u for padding)
   std::vector<uint32_t> bonePos, boneAt; // palette row of bone b (bank-aware permutation) and its inverse
   DevBuf d_bonePos;
-  int permMode = 1, colorMode = 1;       // vertex ordering inside a tile / bank-aware palette permutation
+  int permMode = 1, colorMode = 1, layoutMode = 0;   // layoutMode 1: palette as [3][B] float4 + co-occurrence clustering       // vertex ordering inside a tile / bank-aware palette permutation
   DevBuf d_rec0, d_rec1, d_rec2, d_meta, d_wbits, d_mrange, d_ments, d_sdefIdx, d_sdefTab, d_invBind;
   uint32_t morphNnz = 0, sdefActive = 0;
 
@@ -280,6 +280,7 @@ int rebuild_tables(rz_ctx_impl* c) {
     k |= (uint64_t)(n > 3 ? (j[3] & 0x7FFF) : 0);
     return k;
   };
+  std::vector<uint16_t> gatherJ;   // filled below, before the first emit_* call
   auto emit_vertex = [&](uint32_t p, uint32_t v, uint32_t slot) {
     const float* x = &c->h_vtx8[(size_t)v * 8];
     const uint8_t* w8 = &c->h_weights[(size_t)v * 4];
@@ -298,7 +299,7 @@ int rebuild_tables(rz_ctx_impl* c) {
     } else {
       w[0] = 1.f; w[1] = w[2] = w[3] = 0.f;
     }
-    const uint16_t* j = &c->h_joints[(size_t)v * 4];
+    const uint16_t* j = &gatherJ[(size_t)p * 4];
     const uint32_t q0 = c->bonePos[j[0]], q1 = c->bonePos[j[1]], q2 = c->bonePos[j[2]], q3 = c->bonePos[j[3]];   // palette rows
     const uint32_t j01 = q0 | (q1 << 16), j23 = q2 | (q3 << 16);
     float j01f, j23f;
@@ -316,7 +317,12 @@ int rebuild_tables(rz_ctx_impl* c) {
     // a harmless rigid vertex on bone 0, parked on an unused slot of this warp's lane column
     rec0[p] = make_float4(0.f, 0.f, 0.f, 1.f);
     rec1[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-    rec2[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint16_t* j = &gatherJ[(size_t)p * 4];
+    const uint32_t j01 = c->bonePos[j[0]] | (c->bonePos[j[1]] << 16), j23 = c->bonePos[j[2]] | (c->bonePos[j[3]] << 16);
+    float j01f, j23f;
+    memcpy(&j01f, &j01, 4);
+    memcpy(&j23f, &j23, 4);
+    rec2[p] = make_float4(0.f, 0.f, j01f, j23f);
     metaArr[p] = slot | (1u << kMetaNinfShift);
     mrange[p] = make_uint2(0u, 0u);
   };
@@ -389,10 +395,63 @@ int rebuild_tables(rz_ctx_impl* c) {
     uint32_t next[8];
     for (uint32_t cl = 0; cl < 8; ++cl) next[cl] = cl;
     for (uint32_t b = 0; b < B; ++b) { c->bonePos[b] = next[cls[b]]; next[cls[b]] += 8; }
+    if (c->layoutMode == 1) {
+      // [3][B] layout: 8 consecutive palette rows share one 128-byte line per chunk, so bones gathered together should be
+      // NEIGHBOURS: greedy chaining -- start a group of 8 with the heaviest unplaced bone, then keep appending the unplaced
+      // bone with the largest co-occurrence weight to the bones already in the group.
+      std::vector<char> placed(B, 0);
+      std::vector<uint64_t> gain(B, 0);
+      uint32_t pos = 0;
+      size_t oi = 0;
+      while (pos < B) {
+        while (oi < B && placed[order[oi]]) ++oi;
+        uint32_t seed = order[oi];
+        std::vector<uint32_t> touched;
+        uint32_t cur = seed;
+        for (uint32_t g = 0; g < 8 && pos < B; ++g) {
+          placed[cur] = 1;
+          c->bonePos[cur] = pos++;
+          for (const auto& e : adj[cur]) if (!placed[e.first]) { if (!gain[e.first]) touched.push_back(e.first); gain[e.first] += e.second; }
+          uint32_t best = ~0u;
+          for (uint32_t t : touched) if (!placed[t] && (best == ~0u || gain[t] > gain[best])) best = t;
+          if (best == ~0u) {               // nothing related left: take the next heaviest bone
+            size_t oj = oi;
+            while (oj < B && placed[order[oj]]) ++oj;
+            if (oj >= B) break;
+            best = order[oj];
+          }
+          cur = best;
+        }
+        for (uint32_t t : touched) gain[t] = 0;
+      }
+    }
   }
   c->boneAt.assign(B, 0);
   for (uint32_t b = 0; b < B; ++b) c->boneAt[c->bonePos[b]] = b;
 
+  // joints the kernel gathers: a lane whose weight for influence k is zero borrows the joint of an ACTIVE lane of its
+  // own warp (same quarter-warp if possible), so the unconditional gather adds no shared-memory wavefront.
+  gatherJ.assign((size_t)Vp * 4, 0);
+  for (uint32_t w0 = 0; w0 < Vp; w0 += 32) {
+    for (uint32_t k = 0; k < 4; ++k) {
+      int firstWarp = -1, firstQ[4] = {-1, -1, -1, -1};
+      for (uint32_t l = 0; l < 32; ++l) {
+        const uint32_t v = procVertex[w0 + l];
+        if (v == ~0u || ninf_of(v) <= k) continue;
+        if (firstWarp < 0) firstWarp = (int)l;
+        if (firstQ[l / 8] < 0) firstQ[l / 8] = (int)l;
+      }
+      for (uint32_t l = 0; l < 32; ++l) {
+        const uint32_t v = procVertex[w0 + l];
+        const bool active = v != ~0u && ninf_of(v) > k;
+        int src = active ? (int)l : (firstQ[l / 8] >= 0 ? firstQ[l / 8] : firstWarp);
+        uint16_t j = 0;
+        if (src >= 0) j = c->h_joints[(size_t)procVertex[w0 + src] * 4 + k];
+        else if (v != ~0u) j = c->h_joints[(size_t)v * 4 + k];
+        gatherJ[(size_t)(w0 + l) * 4 + k] = j;
+      }
+    }
+  }
   for (uint32_t p = 0; p < Vp; ++p) {
     if (procVertex[p] != ~0u) emit_vertex(p, procVertex[p], procSlot[p]);
     else emit_padding(p, procSlot[p]);
@@ -506,6 +565,7 @@ int32_t rz_create(const rz_config* cfg, rz_ctx** out) {
   }
   if (const char* e1 = getenv("RZ_PERM")) c->permMode = atoi(e1);        // experiment knobs (tuning)
   if (const char* e2 = getenv("RZ_COLOR")) c->colorMode = atoi(e2);
+  if (const char* e3 = getenv("RZ_LAYOUT")) c->layoutMode = atoi(e3);
   cudaEventCreate(&c->evStart);
   cudaEventCreate(&c->evStop);
   *out = c;
@@ -594,7 +654,7 @@ static int set_palettes_common(rz_ctx* c, const float* d_world, uint32_t P, uint
   const uint32_t n = P * c->B;
   skin_matrices_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(reinterpret_cast<const float4*>(d_world),
                                                               reinterpret_cast<const float4*>(c->d_invBind.p),
-                                                              reinterpret_cast<float4*>(c->d_skin.p), reinterpret_cast<const uint32_t*>(c->d_bonePos.p), P, c->B);
+                                                              reinterpret_cast<float4*>(c->d_skin.p), reinterpret_cast<const uint32_t*>(c->d_bonePos.p), P, c->B, (uint32_t)c->layoutMode);
   CU_TRY(c, cudaGetLastError());
   c->launches++;
   c->P = P;
@@ -785,6 +845,8 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
   prm.tilesPerChunk = passesPerChunk * tilesPerPass;
   prm.nChunks = (c->nTiles + prm.tilesPerChunk - 1) / prm.tilesPerChunk;
   prm.counter = reinterpret_cast<uint32_t*>(c->d_counter.p);
+  prm.posStride = c->layoutMode ? 16u : 48u;
+  prm.rowStride = c->layoutMode ? c->B * 16u : 16u;
   const uint32_t nItems = prm.nGroups * prm.nChunks;
   grid = std::min(grid, nItems);
 
@@ -876,8 +938,14 @@ int32_t rz_read_skinning(rz_ctx* c, uint16_t* joints, uint8_t* weights) {
       memcpy(&j01, &rec2[p].z, 4);
       memcpy(&j23, &rec2[p].w, 4);
       // the device stores palette rows; map them back to the caller's bone ids
-      joints[(size_t)v * 4] = (uint16_t)c->boneAt[j01 & 0xFFFF]; joints[(size_t)v * 4 + 1] = (uint16_t)c->boneAt[j01 >> 16];
-      joints[(size_t)v * 4 + 2] = (uint16_t)c->boneAt[j23 & 0xFFFF]; joints[(size_t)v * 4 + 3] = (uint16_t)c->boneAt[j23 >> 16];
+      uint16_t dj[4] = {(uint16_t)c->boneAt[j01 & 0xFFFF], (uint16_t)c->boneAt[j01 >> 16], (uint16_t)c->boneAt[j23 & 0xFFFF],
+                        (uint16_t)c->boneAt[j23 >> 16]};
+      // slots beyond the vertex' last non-zero weight hold a borrowed joint on the device (gather coalescing, see
+      // rebuild_tables); they never influence the result, report the caller's value there
+      const uint8_t* w8 = reinterpret_cast<const uint8_t*>(&wb[p]);
+      uint32_t n = 1;
+      if ((uint32_t)w8[0] + w8[1] + w8[2] + w8[3] != 0) for (uint32_t k = 0; k < 4; ++k) if (w8[k]) n = k + 1;
+      for (uint32_t k = 0; k < 4; ++k) joints[(size_t)v * 4 + k] = k < n ? dj[k] : c->h_joints[(size_t)v * 4 + k];
     }
     if (weights) memcpy(&weights[(size_t)v * 4], &wb[p], 4);
   }
@@ -894,7 +962,9 @@ int32_t rz_read_skin_matrices(rz_ctx* c, uint32_t palette, float* skin3x4) {
                             cudaMemcpyDeviceToHost, c->stream));
   CU_TRY(c, cudaStreamSynchronize(c->stream));
   for (uint32_t b = 0; b < c->B; ++b) {   // un-permute and un-pair (deform_kernel.cuh kRowF4) back to 3x4 row-major
-    const float* t = tmp.data() + (size_t)c->bonePos[b] * 12;
+    float t[12];
+    if (c->layoutMode) { for (int r = 0; r < 3; ++r) memcpy(t + r * 4, tmp.data() + ((size_t)r * c->B + c->bonePos[b]) * 4, 16); }
+    else memcpy(t, tmp.data() + (size_t)c->bonePos[b] * 12, 48);
     float* o = skin3x4 + (size_t)b * 12;
     o[0] = t[0]; o[4] = t[1]; o[1] = t[2]; o[5] = t[3];
     o[2] = t[4]; o[6] = t[5]; o[3] = t[6]; o[7] = t[7];
