@@ -100,11 +100,11 @@ class ClockSampler:
                 "power_w_max": float(np.nanmax([s[2] for s in self.samples])), "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def make_inputs(V, B, K, P, seed=None):
+def make_inputs(V, B, K, P, seed=None, first=0):
     from reze_engine_b200 import synth
     t = time.time()
     wl = synth.make_workload(V, B) if seed is None else synth.make_workload(V, B, seed=seed)
-    world = synth.make_palettes(wl.bones, P, np.random.default_rng(synth.SEED + 1))
+    world = synth.make_palettes(wl.bones, P, np.random.default_rng(synth.SEED + 1), first=first)
     log(f"[bench] synthetic workload V={V} B={B} P={P}: {time.time() - t:.1f}s")
     return wl, world
 
@@ -185,7 +185,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from reze_engine_b200 import capi
+    from reze_engine_b200 import capi, sharding
 
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -199,7 +199,7 @@ def main():
 
     V, B, K = args.verts, args.bones, args.instances
     P = args.palettes or K
-    wl, world = make_inputs(V, B, K, P)
+    wl, world = make_inputs(V, B, K, P, first=rank * K)          # rank r owns global instances [r*K, (r+1)*K)
     i2p = None if P >= K else (np.arange(K) % P).astype(np.uint32)
 
     # a real (non-default) stream: the library launches on it and torch.cuda.Event times it
@@ -245,10 +245,7 @@ def main():
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
     st = ctx.stats()
     launches = int(st["kernelLaunches"] - launches0)
-    if world_size > 1:
-        tt = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        total_ms = float(tt.item())
+    total_ms = sharding.max_over_ranks(total_ms)               # device time, max over ranks
     ms_per_step = total_ms / args.steps
     value = world_size * K * V / (ms_per_step * 1e-3)
 
@@ -269,20 +266,14 @@ def main():
     e1.record()
     barrier()
     e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - wall0) * 1e3) / esteps
-    if world_size > 1:
-        tt = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_ms = float(tt.item())
+    e2e_ms = sharding.max_over_ranks(e2e_ms)
     e2e_value = world_size * K * V / (e2e_ms * 1e-3)
     h2d = P * B * 64 + (K * 4 if i2p is not None else 0)
     d2h = V * 24
 
     # trivial result gather (the only collective): one small record per GPU
     if world_size > 1:
-        rec = torch.tensor([float(K * V), kernel_ms, float(launches)], device="cuda", dtype=torch.float64)
-        allrec = [torch.zeros_like(rec) for _ in range(world_size)]
-        dist.all_gather(allrec, rec)
-        per_gpu = [[float(x) for x in r.tolist()] for r in allrec]
+        per_gpu = sharding.gather_records([float(K * V), kernel_ms, float(launches), K * V / (kernel_ms * 1e-3)])
         launches = int(sum(r[2] for r in per_gpu))
     else:
         per_gpu = None
@@ -291,11 +282,13 @@ def main():
         peak, peak_src = measured_peak()
         alg = st["algorithmicBytes"]
         achieved = alg / (kernel_ms * 1e-3) / 1e9
-        traffic = None
+        traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of one launch of THIS workload (ncu --set full), if captured
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                tj = json.load(open(tp))
+                if tj.get("workload") == [V, B, K, P]:
+                    traffic = tj.get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
         out = {
@@ -316,7 +309,7 @@ def main():
                          "peak_source": peak_src, "kernel": "rz::deform_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg},
         }
         if per_gpu:
-            out["per_gpu"] = per_gpu
+            out["per_gpu"] = [{"verts_per_step": r[0], "deform_kernel_ms": r[1], "launches": r[2], "verts_per_s_kernel": r[3]} for r in per_gpu]
         if not args.no_cpu and world_size == 1:
             threads = os.cpu_count() or 1
             rate, Ks, dt = cpu_reference_rate(wl, world, K, args.cpu_seconds, threads)

@@ -802,7 +802,7 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
                   I, NT, c->tuneCtas, c->B);
   } else {
     // preference order (measured on B200, profiles/): most resident warps first, then wider instance groups
-    static const int pref[][3] = {{2, 512, 2}, {2, 256, 3}, {3, 256, 2}, {4, 512, 1}, {2, 256, 2}, {4, 256, 1}, {2, 512, 1},
+    static const int pref[][3] = {{3, 256, 2}, {4, 512, 1}, {2, 512, 2}, {2, 256, 3}, {3, 512, 1}, {2, 256, 2}, {2, 512, 1}, {4, 256, 1},
                                   {1, 256, 4}, {1, 256, 2}, {1, 512, 2}};
     bool ok = false;
     for (const auto& p : pref) {

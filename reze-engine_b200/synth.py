@@ -129,11 +129,11 @@ def make_pose_keys(B: int, rng, max_angle: float = 0.6):
     return rnd(), rnd()
 
 
-def make_palettes(bones: List[Bone], P: int, rng, stagger: bool = True) -> np.ndarray:
-    """World matrices [P,B,16] f32: instance p sits at phase (p*0.618...) mod 1 of a two-key tween
-    evaluated with the reference rule (quadratic ease + slerp) -- "staggered VMD phase"."""
+def make_palettes(bones: List[Bone], P: int, rng, stagger: bool = True, first: int = 0) -> np.ndarray:
+    """World matrices [P,B,16] f32: instance p (global id first+p) sits at phase ((first+p)*0.618...) mod 1 of a
+    two-key tween evaluated with the reference rule (quadratic ease + slerp) -- "staggered VMD phase"."""
     qa, qb = make_pose_keys(len(bones), rng)
-    phase = (np.arange(P) * GOLDEN) % 1.0 if stagger else np.zeros(P)
+    phase = ((first + np.arange(P)) * GOLDEN) % 1.0 if stagger else np.zeros(P)
     lr = tween_pose_batch(qa, qb, phase)
     return world_matrices_batch(bones, lr)
 
