@@ -103,8 +103,11 @@ class ClockSampler:
 def make_inputs(V, B, K, P, seed=None, first=0):
     from reze_engine_b200 import synth
     t = time.time()
+    from reze_engine_b200 import crowd
     wl = synth.make_workload(V, B) if seed is None else synth.make_workload(V, B, seed=seed)
-    world = synth.make_palettes(wl.bones, P, np.random.default_rng(synth.SEED + 1), first=first)
+    qa, qb, phase = synth.make_crowd_tween(B, P, np.random.default_rng(synth.SEED + 1), first=first)
+    world = crowd.world_matrices_batch(wl.bones, crowd.tween_pose_batch(qa, qb, phase))
+    wl.tween = (qa.astype(np.float32), qb.astype(np.float32), phase)
     log(f"[bench] synthetic workload V={V} B={B} P={P}: {time.time() - t:.1f}s")
     return wl, world
 
@@ -271,6 +274,30 @@ def main():
     h2d = P * B * 64 + (K * 4 if i2p is not None else 0)
     d2h = V * 24
 
+    # ---- e2e, pose evaluated on the device: the same staggered-phase crowd, host provides one clock value per palette ----
+    qa, qb, phase = wl.tween
+    ctx.load_skeleton(wl.bones)
+    ident = np.tile(np.array([0, 0, 0, 1], np.float32), (B, 1))
+    ctx.set_tweens(qa, qb, np.zeros(B, np.float32), np.full(B, 1000.0, np.float32), np.ones(B, np.uint8), ident)
+    clocks = (phase * 1000.0).astype(np.float32)
+    for _ in range(2):
+        ctx.set_instance_clocks(clocks, i2p, K=K)
+        ctx.deform()
+        ctx.read_instance(0)
+    barrier()
+    wall0 = time.perf_counter()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for s in range(esteps):
+        ctx.set_instance_clocks(clocks, i2p, K=K)
+        ctx.deform()
+        ctx.read_instance(s % K)
+    g1.record()
+    barrier()
+    pose_ms = sharding.max_over_ranks(max(g0.elapsed_time(g1), (time.perf_counter() - wall0) * 1e3) / esteps)
+    pose_value = world_size * K * V / (pose_ms * 1e-3)
+    pose_h2d = P * 4 + (K * 4 if i2p is not None else 0)
+
     # trivial result gather (the only collective): one small record per GPU
     if world_size > 1:
         per_gpu = sharding.gather_records([float(K * V), kernel_ms, float(launches), K * V / (kernel_ms * 1e-3)])
@@ -302,8 +329,10 @@ def main():
                                   "store_mode": {1: "direct st.global.cs", 2: "smem-staged TMA bulk store"}.get(st["storeMode"]),
                                   "ctas": st["ctas"], "smem_bytes": st["smemBytes"]}},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "verts/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "path": "rz_set_palettes(pinned host) + rz_deform + rz_read_instance"},
+            "e2e": {"value": pose_value, "unit": "verts/s", "ms_per_step": pose_ms, "h2d_bytes_per_step": pose_h2d, "d2h_bytes_per_step": d2h,
+                    "path": "rz_set_instance_clocks(host clocks; tween + bone hierarchy + skin matrices on the device) + rz_deform + rz_read_instance"},
+            "e2e_world_upload": {"value": e2e_value, "unit": "verts/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                                 "path": "rz_set_palettes(pinned host world matrices, as the reference uploads them) + rz_deform + rz_read_instance"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "kernel": "rz::deform_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg},

@@ -111,6 +111,24 @@ int32_t rz_set_palettes_device(rz_ctx* ctx, const float* d_world, uint32_t P, co
  * valid until the next call that asks for a larger size or rz_destroy */
 int32_t rz_palette_staging(rz_ctx* ctx, size_t bytes, void** host_ptr);
 
+/* ---- GPU pose evaluation (replaces Model.evaluatePose, model.ts:325-328, + the palette upload for crowds) ----
+ * rz_load_skeleton: the static part of Skeleton (model.ts:31-45) the hierarchy walk needs.
+ *   parent[B] (-1 / out of range = root), bindTranslation[3B] (Bone.bindTranslation as f32, pmx-loader.ts:423),
+ *   appendParent[B] / appendRatio[B] / appendRotate[B] may be NULL (no append bones); the ratio is clamped to [-1,1]
+ *   and ignored unless appendRotate != 0 and the parent index is valid (model.ts:356-361). */
+int32_t rz_load_skeleton(rz_ctx* ctx, const int32_t* parent, const float* bindTranslation, const int32_t* appendParent,
+                         const float* appendRatio, const uint8_t* appendRotate, uint32_t B);
+/* Local bone rotations (SkeletonRuntime.localRotations, model.ts:55: xyzw per bone) of P poses; the device walks the
+ * hierarchy (model.ts:330-420), multiplies by invBind and fills the palettes.  Same (P, instToPalette, K) meaning as
+ * rz_set_palettes; 4x less host->device traffic than world matrices. */
+int32_t rz_set_local_rotations(rz_ctx* ctx, const float* quats /* P*B*4 */, uint32_t P, const uint32_t* instToPalette, uint32_t K);
+/* Rotation tween state shared by the crowd (RotationTweenState, model.ts:62-68) + rest rotations of inactive bones. */
+int32_t rz_set_tweens(rz_ctx* ctx, const float* startQuat /* 4B */, const float* targetQuat /* 4B */, const float* startTimeMs /* B */,
+                      const float* durationMs /* B */, const uint8_t* active /* B */, const float* restQuat /* 4B */);
+/* Evaluate the tweens (model.ts:158-194: slerp + quadratic ease) at P clock values and fill the palettes: instance k
+ * plays the shared animation at time nowMs[instToPalette[k]] ("staggered phase" crowds).  Host->device traffic: 4*P bytes. */
+int32_t rz_set_instance_clocks(rz_ctx* ctx, const float* nowMs /* P */, uint32_t P, const uint32_t* instToPalette, uint32_t K);
+
 /* Per-instance weights of the active morphs: w[k*M_active + a] scales morph activeIds[a] for instance k.
  * K must match the instance count in use; M_active = 0 disables morphing. */
 int32_t rz_set_morph_weights(rz_ctx* ctx, const float* w, const uint32_t* activeIds, uint32_t M_active, uint32_t K);

@@ -23,7 +23,8 @@ RZ_FLAG_BOUNDS = 0x4
 
 EXPORTS = [
     "rz_create", "rz_destroy", "rz_abi_version", "rz_load_mesh", "rz_load_morphs", "rz_load_sdef",
-    "rz_set_palettes", "rz_set_palettes_device", "rz_palette_staging", "rz_set_morph_weights", "rz_deform",
+    "rz_set_palettes", "rz_set_palettes_device", "rz_palette_staging", "rz_load_skeleton", "rz_set_local_rotations",
+    "rz_set_tweens", "rz_set_instance_clocks", "rz_set_morph_weights", "rz_deform",
     "rz_sync", "rz_output_device_ptr", "rz_read_instance", "rz_read_bounds", "rz_read_skinning",
     "rz_read_skin_matrices", "rz_get_stats", "rz_last_error",
 ]
@@ -82,6 +83,10 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.rz_set_palettes.argtypes = [vp, vp, u32, vp, u32]
     lib.rz_set_palettes_device.argtypes = [vp, vp, u32, vp, u32]
     lib.rz_palette_staging.argtypes = [vp, sz, P(vp)]
+    lib.rz_load_skeleton.argtypes = [vp, vp, vp, vp, vp, vp, u32]
+    lib.rz_set_local_rotations.argtypes = [vp, vp, u32, vp, u32]
+    lib.rz_set_tweens.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    lib.rz_set_instance_clocks.argtypes = [vp, vp, u32, vp, u32]
     lib.rz_set_morph_weights.argtypes = [vp, vp, vp, u32, u32]
     lib.rz_deform.argtypes = [vp, u32, u32]
     lib.rz_sync.argtypes = [vp]
@@ -209,6 +214,41 @@ class DeformContext:
         K = P if K is None else K
         self._check(self.lib.rz_set_palettes_device(self.h, C.c_void_p(d_world_ptr), P,
                                                     C.c_void_p(d_inst_to_palette_ptr) if d_inst_to_palette_ptr else None, K))
+        self.K = K
+
+    # -- GPU pose evaluation
+    def load_skeleton(self, bones):
+        """bones: sequence of model.Bone (parentIndex, bindTranslation, append*)."""
+        B = len(bones)
+        parent = np.asarray([b.parentIndex for b in bones], np.int32)
+        bt = np.asarray([b.bindTranslation for b in bones], np.float64).astype(np.float32).reshape(-1)
+        ap = np.asarray([-1 if b.appendParentIndex is None else b.appendParentIndex for b in bones], np.int32)
+        ar = np.asarray([np.nan if b.appendRatio is None else b.appendRatio for b in bones], np.float32)
+        rot = np.asarray([1 if b.appendRotate else 0 for b in bones], np.uint8)
+        self._check(self.lib.rz_load_skeleton(self.h, _ptr(parent), _ptr(bt), _ptr(ap), _ptr(ar), _ptr(rot), B))
+
+    def set_local_rotations(self, quats, inst_to_palette=None, K: Optional[int] = None):
+        q = np.asarray(quats)
+        if q.dtype != np.float32 or not q.flags.c_contiguous:
+            q = _arr(q, np.float32)
+        P = q.size // (self.B * 4)
+        i2p = None if inst_to_palette is None else _arr(inst_to_palette, np.uint32).reshape(-1)
+        if K is None:
+            K = P if i2p is None else i2p.size
+        self._check(self.lib.rz_set_local_rotations(self.h, _ptr(q), P, _ptr(i2p), K))
+        self.K = K
+
+    def set_tweens(self, start, target, start_ms, dur_ms, active, rest):
+        a = [_arr(start, np.float32), _arr(target, np.float32), _arr(start_ms, np.float32), _arr(dur_ms, np.float32),
+             _arr(active, np.uint8), _arr(rest, np.float32)]
+        self._check(self.lib.rz_set_tweens(self.h, *[_ptr(x) for x in a]))
+
+    def set_instance_clocks(self, now_ms, inst_to_palette=None, K: Optional[int] = None):
+        t = _arr(now_ms, np.float32).reshape(-1)
+        i2p = None if inst_to_palette is None else _arr(inst_to_palette, np.uint32).reshape(-1)
+        if K is None:
+            K = t.size if i2p is None else i2p.size
+        self._check(self.lib.rz_set_instance_clocks(self.h, _ptr(t), t.size, _ptr(i2p), K))
         self.K = K
 
     def set_morph_weights(self, w, active_ids, K: Optional[int] = None):

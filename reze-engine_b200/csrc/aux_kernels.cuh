@@ -46,6 +46,149 @@ __global__ void morph_weights_kernel(const float* __restrict__ w, const uint32_t
   for (uint32_t a = threadIdx.x; a < Mact; a += blockDim.x) atomicAdd(&dense[(size_t)k * Mpad + ids[a]], w[(size_t)k * Mact + a]);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// GPU pose evaluation: replaces Model.evaluatePose (model.ts:325-328) + the palette upload for crowds.
+//   tween  : q = slerp(start, target, easeInOut(clamp((now-start)/max(1,dur))))            model.ts:158-194, math.ts:2-4,156-189
+//   local  : R = fromQuat(append) * fromQuat(q), append = slerp(identity, +/-q[appendParent], |ratio|)   model.ts:356-386
+//   world  : world[b] = world[parent] * (T(bind) * R)      parents first (level order)     model.ts:397-414
+//   skin   : world * invBind, rows 0..2, written straight into the deform kernel's palette layout
+// One CTA per palette; bones of one hierarchy level are evaluated in parallel, world matrices live in shared memory
+// as 3x4 affine (the reference's products never leave the affine group: bottom row stays 0,0,0,1).
+struct PoseSkeleton {
+  const int32_t* __restrict__ parent;        // [B]
+  const float* __restrict__ bindT;           // [B][3]
+  const int32_t* __restrict__ appendParent;  // [B] (-1: none)
+  const float* __restrict__ appendRatio;     // [B] clamped to [-1,1]; 0 when no append rotation
+  const uint32_t* __restrict__ levelBones;   // bones sorted by depth
+  const uint32_t* __restrict__ levelStart;   // [nLevels+1]
+  uint32_t nLevels, B;
+};
+struct PoseTweens {
+  const float4* __restrict__ start;   // [B] xyzw
+  const float4* __restrict__ target;  // [B]
+  const float4* __restrict__ rest;    // [B] local rotation of bones without an active tween
+  const float* __restrict__ startMs;  // [B]
+  const float* __restrict__ durMs;    // [B]
+  const uint8_t* __restrict__ active; // [B]
+};
+
+__device__ __forceinline__ float4 q_slerp(float4 a, float4 b, float t) {   // math.ts:156-189
+  float c = a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+  if (c < 0.f) { c = -c; b.x = -b.x; b.y = -b.y; b.z = -b.z; b.w = -b.w; }
+  if (c > 0.9995f) {
+    const float x = a.x + t * (b.x - a.x), y = a.y + t * (b.y - a.y), z = a.z + t * (b.z - a.z), w = a.w + t * (b.w - a.w);
+    const float inv = 1.0f / sqrtf(x * x + y * y + z * z + w * w);
+    return make_float4(x * inv, y * inv, z * inv, w * inv);
+  }
+  const float th0 = acosf(c), s = sinf(th0), th = th0 * t;
+  const float s0 = sinf(th0 - th) / s, s1 = sinf(th) / s;
+  return make_float4(s0 * a.x + s1 * b.x, s0 * a.y + s1 * b.y, s0 * a.z + s1 * b.z, s0 * a.w + s1 * b.w);
+}
+__device__ __forceinline__ void q_to_rows(float4 q, float r[3][3]) {     // math.ts:352-384 (row r, column c)
+  const float x2 = q.x + q.x, y2 = q.y + q.y, z2 = q.z + q.z;
+  const float xx = q.x * x2, xy = q.x * y2, xz = q.x * z2, yy = q.y * y2, yz = q.y * z2, zz = q.z * z2;
+  const float wx = q.w * x2, wy = q.w * y2, wz = q.w * z2;
+  r[0][0] = 1.f - (yy + zz); r[0][1] = xy - wz; r[0][2] = xz + wy;
+  r[1][0] = xy + wz; r[1][1] = 1.f - (xx + zz); r[1][2] = yz - wx;
+  r[2][0] = xz - wy; r[2][1] = yz + wx; r[2][2] = 1.f - (xx + yy);
+}
+
+// MODE 0: local rotations uploaded ([P][B] float4);  MODE 1: rotations from the shared tween table at time nowMs[p]
+template <int MODE>
+__global__ void pose_kernel(PoseSkeleton sk, PoseTweens tw, const float4* __restrict__ localRot, const float* __restrict__ nowMs,
+                            const float4* __restrict__ invBind, const uint32_t* __restrict__ bonePos, float4* __restrict__ skin,
+                            float4* __restrict__ worldOut /* optional [P][B][3] rows, may be null */, uint32_t soa) {
+  extern __shared__ float4 s_world[];            // [B][3] rows of the 3x4 world matrices
+  float4* s_q = s_world + (size_t)sk.B * 3;      // [B] local rotations (needed by append children)
+  const uint32_t p = blockIdx.x, B = sk.B;
+  for (uint32_t b = threadIdx.x; b < B; b += blockDim.x) {
+    float4 q;
+    if (MODE == 0) {
+      q = localRot[(size_t)p * B + b];
+    } else {
+      if (tw.active[b]) {
+        const float dur = fmaxf(1.0f, tw.durMs[b]);
+        float t = (nowMs[p] - tw.startMs[b]) / dur;
+        t = fminf(1.0f, fmaxf(0.0f, t));
+        const float u = -2.0f * t + 2.0f;
+        const float e = t < 0.5f ? 2.0f * t * t : 1.0f - (u * u) * 0.5f;
+        q = q_slerp(tw.start[b], tw.target[b], e);
+      } else {
+        q = tw.rest[b];
+      }
+    }
+    s_q[b] = q;
+  }
+  __syncthreads();
+  for (uint32_t L = 0; L < sk.nLevels; ++L) {
+    const uint32_t l0 = sk.levelStart[L], l1 = sk.levelStart[L + 1];
+    for (uint32_t i = l0 + threadIdx.x; i < l1; i += blockDim.x) {
+      const uint32_t b = sk.levelBones[i];
+      float R[3][3];
+      q_to_rows(s_q[b], R);
+      const int32_t ap = sk.appendParent[b];
+      const float ratio = sk.appendRatio[b];
+      if (ap >= 0 && fabsf(ratio) > 1e-6f) {
+        float4 a = s_q[ap];
+        if (ratio < 0.f) { a.x = -a.x; a.y = -a.y; a.z = -a.z; }
+        const float4 aq = q_slerp(make_float4(0.f, 0.f, 0.f, 1.f), a, fabsf(ratio));
+        float A[3][3], T[3][3];
+        q_to_rows(aq, A);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) T[r][c] = A[r][0] * R[0][c] + A[r][1] * R[1][c] + A[r][2] * R[2][c];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) R[r][c] = T[r][c];
+      }
+      const float tx = sk.bindT[(size_t)b * 3], ty = sk.bindT[(size_t)b * 3 + 1], tz = sk.bindT[(size_t)b * 3 + 2];
+      float W[3][4];
+      const int32_t par = sk.parent[b];
+      if (par >= 0) {
+        const float4 p0 = s_world[(size_t)par * 3], p1 = s_world[(size_t)par * 3 + 1], p2 = s_world[(size_t)par * 3 + 2];
+        const float P[3][4] = {{p0.x, p0.y, p0.z, p0.w}, {p1.x, p1.y, p1.z, p1.w}, {p2.x, p2.y, p2.z, p2.w}};
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) W[r][c] = P[r][0] * R[0][c] + P[r][1] * R[1][c] + P[r][2] * R[2][c];
+          W[r][3] = P[r][0] * tx + P[r][1] * ty + P[r][2] * tz + P[r][3];
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { W[r][0] = R[r][0]; W[r][1] = R[r][1]; W[r][2] = R[r][2]; }
+        W[0][3] = tx; W[1][3] = ty; W[2][3] = tz;
+      }
+#pragma unroll
+      for (int r = 0; r < 3; ++r) s_world[(size_t)b * 3 + r] = make_float4(W[r][0], W[r][1], W[r][2], W[r][3]);
+      if (worldOut)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) worldOut[((size_t)p * B + b) * 3 + r] = make_float4(W[r][0], W[r][1], W[r][2], W[r][3]);
+      // skin = world * invBind (rows 0..2); invBind column-major mat4
+      float S[3][4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 ib = __ldg(invBind + (size_t)b * 4 + c);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) S[r][c] = W[r][0] * ib.x + W[r][1] * ib.y + W[r][2] * ib.z + W[r][3] * ib.w;
+      }
+      const float4 cA = make_float4(S[0][0], S[1][0], S[0][1], S[1][1]);
+      const float4 cB = make_float4(S[0][2], S[1][2], S[0][3], S[1][3]);
+      const float4 cC = make_float4(S[2][0], S[2][1], S[2][2], S[2][3]);
+      const size_t pos = __ldg(bonePos + b);
+      if (soa) {
+        const size_t pb = (size_t)p * B * 3;
+        skin[pb + pos] = cA; skin[pb + B + pos] = cB; skin[pb + 2 * (size_t)B + pos] = cC;
+      } else {
+        const size_t row = (size_t)p * B + pos;
+        skin[row * 3] = cA; skin[row * 3 + 1] = cB; skin[row * 3 + 2] = cC;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void bounds_reset_kernel(int* b, uint32_t n6) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n6) b[i] = (i % 6) < 3 ? 0x7F7FFFFF : (int)(0x7F7FFFFF ^ 0x7FFFFFFF) | (int)0x80000000;

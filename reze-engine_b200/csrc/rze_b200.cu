@@ -66,6 +66,12 @@ struct rz_ctx_impl {
   DevBuf d_rec0, d_rec1, d_rec2, d_meta, d_wbits, d_mrange, d_ments, d_sdefIdx, d_sdefTab, d_invBind;
   uint32_t morphNnz = 0, sdefActive = 0;
 
+  // skeleton for GPU pose evaluation
+  bool haveSkeleton = false, haveTweens = false;
+  uint32_t nLevels = 0;
+  DevBuf d_skParent, d_skBindT, d_skAppendParent, d_skAppendRatio, d_skLevelBones, d_skLevelStart;
+  DevBuf d_twStart, d_twTarget, d_twRest, d_twStartMs, d_twDurMs, d_twActive, d_localRot, d_nowMs;
+
   // per-frame
   uint32_t P = 0, K = 0;
   DevBuf d_world, d_skin, d_inst2pal, d_mwIn, d_mwIds, d_mwDense, d_out, d_bounds, d_counter;
@@ -578,7 +584,9 @@ int32_t rz_destroy(rz_ctx* c) {
   cudaStreamSynchronize(c->stream);
   DevBuf* bufs[] = {&c->d_rec0, &c->d_rec1, &c->d_rec2, &c->d_meta, &c->d_wbits, &c->d_mrange, &c->d_ments, &c->d_sdefIdx, &c->d_sdefTab,
                     &c->d_invBind, &c->d_bonePos, &c->d_world, &c->d_skin, &c->d_inst2pal, &c->d_mwIn, &c->d_mwIds, &c->d_mwDense,
-                    &c->d_out, &c->d_bounds, &c->d_counter};
+                    &c->d_out, &c->d_bounds, &c->d_counter, &c->d_skParent, &c->d_skBindT, &c->d_skAppendParent, &c->d_skAppendRatio,
+                    &c->d_skLevelBones, &c->d_skLevelStart, &c->d_twStart, &c->d_twTarget, &c->d_twRest, &c->d_twStartMs, &c->d_twDurMs,
+                    &c->d_twActive, &c->d_localRot, &c->d_nowMs};
   for (DevBuf* b : bufs) dev_free(c, *b);
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->h_small) cudaFreeHost(c->h_small);
@@ -608,6 +616,8 @@ int32_t rz_load_mesh(rz_ctx* c, const float* vtx8, const uint16_t* joints, const
   c->h_moff.clear(); c->h_mvert.clear(); c->h_mdelta.clear();
   c->h_sdefVert.clear(); c->h_sdefVec.clear();
   c->palettesSet = false;
+  c->haveSkeleton = false;
+  c->haveTweens = false;
   c->Mact = 0;
   c->Mpad = 0;
   c->tablesDirty = true;
@@ -722,6 +732,187 @@ int32_t rz_set_palettes_device(rz_ctx* c, const float* d_world, uint32_t P, cons
   }
   c->haveInst2pal = d_inst2pal != nullptr;
   return set_palettes_common(c, d_world, P, K);
+}
+
+
+// ---- GPU pose evaluation ------------------------------------------------------------------------------------------
+static int upload(rz_ctx* c, DevBuf& b, const void* src, size_t bytes) {
+  int rc;
+  if ((rc = dev_reserve(c, b, bytes))) return rc;
+  CU_TRY(c, cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  return RZ_OK;
+}
+
+int32_t rz_load_skeleton(rz_ctx* c, const int32_t* parent, const float* bindT, const int32_t* appendParent, const float* appendRatio,
+                         const uint8_t* appendRotate, uint32_t B) {
+  if (!c) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_load_skeleton: null ctx");
+  if (c->V == 0) return fail(c, RZ_ERR_STATE, "rz_load_skeleton before rz_load_mesh");
+  if (!parent || !bindT) return fail(c, RZ_ERR_INVALID_ARG, "rz_load_skeleton: null table");
+  if (B != c->B) return fail(c, RZ_ERR_INVALID_ARG, "rz_load_skeleton: B=%u differs from the mesh's bone count %u", B, c->B);
+  CU_TRY(c, cudaSetDevice(c->device));
+  // depth of every bone (parents first, like the reference's memoised recursion model.ts:340-419); cycles are rejected
+  std::vector<int32_t> par(B), depth(B, -1);
+  for (uint32_t b = 0; b < B; ++b) par[b] = (parent[b] >= 0 && (uint32_t)parent[b] < B) ? parent[b] : -1;
+  for (uint32_t b = 0; b < B; ++b) {
+    if (depth[b] >= 0) continue;
+    std::vector<uint32_t> chain;
+    int32_t cur = (int32_t)b;
+    while (cur >= 0 && depth[cur] < 0) {
+      chain.push_back((uint32_t)cur);
+      if (chain.size() > B) return fail(c, RZ_ERR_INVALID_ARG, "rz_load_skeleton: parent cycle through bone %u", b);
+      cur = par[cur];
+    }
+    int32_t d = cur >= 0 ? depth[cur] + 1 : 0;
+    for (size_t i = chain.size(); i-- > 0;) depth[chain[i]] = d++;
+  }
+  uint32_t nLevels = 0;
+  for (uint32_t b = 0; b < B; ++b) nLevels = std::max<uint32_t>(nLevels, (uint32_t)depth[b] + 1);
+  std::vector<uint32_t> levelStart(nLevels + 1, 0), levelBones(B);
+  for (uint32_t b = 0; b < B; ++b) levelStart[(uint32_t)depth[b] + 1]++;
+  for (uint32_t L = 0; L < nLevels; ++L) levelStart[L + 1] += levelStart[L];
+  {
+    std::vector<uint32_t> fill(levelStart.begin(), levelStart.end() - 1);
+    for (uint32_t b = 0; b < B; ++b) levelBones[fill[(uint32_t)depth[b]]++] = b;
+  }
+  std::vector<int32_t> ap(B, -1);
+  std::vector<float> ar(B, 0.f);
+  for (uint32_t b = 0; b < B; ++b) {
+    const bool rot = appendRotate && appendRotate[b] && appendParent && appendParent[b] >= 0 && (uint32_t)appendParent[b] < B;
+    if (!rot) continue;
+    float r = appendRatio ? appendRatio[b] : 1.0f;
+    if (r != r) r = 1.0f;                                   // "undefined" ratio means 1 (model.ts:360)
+    ap[b] = appendParent[b];
+    ar[b] = std::max(-1.0f, std::min(1.0f, r));
+  }
+  int rc;
+  if ((rc = upload(c, c->d_skParent, par.data(), (size_t)B * 4))) return rc;
+  if ((rc = upload(c, c->d_skBindT, bindT, (size_t)B * 12))) return rc;
+  if ((rc = upload(c, c->d_skAppendParent, ap.data(), (size_t)B * 4))) return rc;
+  if ((rc = upload(c, c->d_skAppendRatio, ar.data(), (size_t)B * 4))) return rc;
+  if ((rc = upload(c, c->d_skLevelBones, levelBones.data(), (size_t)B * 4))) return rc;
+  if ((rc = upload(c, c->d_skLevelStart, levelStart.data(), (size_t)(nLevels + 1) * 4))) return rc;
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  c->nLevels = nLevels;
+  c->haveSkeleton = true;
+  return RZ_OK;
+}
+
+extern "C++" {
+template <int MODE>
+static int launch_pose(rz_ctx* c, uint32_t P) {
+  const size_t smem = (size_t)c->B * 64;
+  if (smem > (size_t)c->maxSmemOptin)
+    return fail(c, RZ_ERR_INVALID_ARG, "GPU pose evaluation supports up to %d bones (B=%u): use rz_set_palettes", c->maxSmemOptin / 64, c->B);
+  CU_TRY(c, cudaFuncSetAttribute(pose_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int rc;
+  if ((rc = dev_reserve(c, c->d_skin, (size_t)P * c->B * 48))) return rc;
+  PoseSkeleton sk;
+  sk.parent = reinterpret_cast<const int32_t*>(c->d_skParent.p);
+  sk.bindT = reinterpret_cast<const float*>(c->d_skBindT.p);
+  sk.appendParent = reinterpret_cast<const int32_t*>(c->d_skAppendParent.p);
+  sk.appendRatio = reinterpret_cast<const float*>(c->d_skAppendRatio.p);
+  sk.levelBones = reinterpret_cast<const uint32_t*>(c->d_skLevelBones.p);
+  sk.levelStart = reinterpret_cast<const uint32_t*>(c->d_skLevelStart.p);
+  sk.nLevels = c->nLevels;
+  sk.B = c->B;
+  PoseTweens tw;
+  tw.start = reinterpret_cast<const float4*>(c->d_twStart.p);
+  tw.target = reinterpret_cast<const float4*>(c->d_twTarget.p);
+  tw.rest = reinterpret_cast<const float4*>(c->d_twRest.p);
+  tw.startMs = reinterpret_cast<const float*>(c->d_twStartMs.p);
+  tw.durMs = reinterpret_cast<const float*>(c->d_twDurMs.p);
+  tw.active = reinterpret_cast<const uint8_t*>(c->d_twActive.p);
+  pose_kernel<MODE><<<P, 128, smem, c->stream>>>(sk, tw, reinterpret_cast<const float4*>(c->d_localRot.p),
+                                                 reinterpret_cast<const float*>(c->d_nowMs.p),
+                                                 reinterpret_cast<const float4*>(c->d_invBind.p),
+                                                 reinterpret_cast<const uint32_t*>(c->d_bonePos.p),
+                                                 reinterpret_cast<float4*>(c->d_skin.p), nullptr, (uint32_t)c->layoutMode);
+  CU_TRY(c, cudaGetLastError());
+  c->launches++;
+  return RZ_OK;
+}
+}  // extern "C++"
+
+static int set_mapping(rz_ctx* c, const uint32_t* inst2pal, uint32_t P, uint32_t K, const char* who) {
+  if (P == 0 || K == 0) return fail(c, RZ_ERR_INVALID_ARG, "%s: P and K must be non-zero", who);
+  if (K > c->maxK) return fail(c, RZ_ERR_INVALID_ARG, "%s: K=%u exceeds max_instances=%u", who, K, c->maxK);
+  if (!inst2pal && P < K) return fail(c, RZ_ERR_INVALID_ARG, "%s: identity mapping needs P >= K (P=%u K=%u)", who, P, K);
+  if (inst2pal) {
+    for (uint32_t k = 0; k < K; ++k)
+      if (inst2pal[k] >= P) return fail(c, RZ_ERR_INVALID_ARG, "%s: instToPalette[%u]=%u >= P=%u", who, k, inst2pal[k], P);
+    int rc;
+    if ((rc = dev_reserve(c, c->d_inst2pal, (size_t)c->maxK * 4))) return rc;
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    if ((rc = pinned_reserve(c, c->h_small, c->h_smallBytes, (size_t)c->maxK * 4))) return rc;
+    memcpy(c->h_small, inst2pal, (size_t)K * 4);
+    CU_TRY(c, cudaMemcpyAsync(c->d_inst2pal.p, c->h_small, (size_t)K * 4, cudaMemcpyHostToDevice, c->stream));
+  }
+  c->haveInst2pal = inst2pal != nullptr;
+  return RZ_OK;
+}
+
+int32_t rz_set_local_rotations(rz_ctx* c, const float* quats, uint32_t P, const uint32_t* inst2pal, uint32_t K) {
+  if (!c) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_set_local_rotations: null ctx");
+  if (!c->haveSkeleton) return fail(c, RZ_ERR_STATE, "rz_set_local_rotations before rz_load_skeleton");
+  if (!quats) return fail(c, RZ_ERR_INVALID_ARG, "rz_set_local_rotations: null quats");
+  CU_TRY(c, cudaSetDevice(c->device));
+  int rc;
+  if ((rc = set_mapping(c, inst2pal, P, K, "rz_set_local_rotations"))) return rc;
+  const size_t bytes = (size_t)P * c->B * 16;
+  if ((rc = dev_reserve(c, c->d_localRot, bytes))) return rc;
+  const char* src = reinterpret_cast<const char*>(quats);
+  const bool inStage = c->h_stage && src >= (char*)c->h_stage && src + bytes <= (char*)c->h_stage + c->h_stageBytes;
+  if (!inStage) {
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    if ((rc = pinned_reserve(c, c->h_stage, c->h_stageBytes, bytes))) return rc;
+    memcpy(c->h_stage, quats, bytes);
+    src = reinterpret_cast<const char*>(c->h_stage);
+  }
+  CU_TRY(c, cudaMemcpyAsync(c->d_localRot.p, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = launch_pose<0>(c, P))) return rc;
+  c->P = P; c->K = K; c->palettesSet = true;
+  return RZ_OK;
+}
+
+int32_t rz_set_tweens(rz_ctx* c, const float* startQ, const float* targetQ, const float* startMs, const float* durMs,
+                      const uint8_t* active, const float* restQ) {
+  if (!c) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_set_tweens: null ctx");
+  if (!c->haveSkeleton) return fail(c, RZ_ERR_STATE, "rz_set_tweens before rz_load_skeleton");
+  if (!startQ || !targetQ || !startMs || !durMs || !active || !restQ) return fail(c, RZ_ERR_INVALID_ARG, "rz_set_tweens: null table");
+  CU_TRY(c, cudaSetDevice(c->device));
+  const size_t B = c->B;
+  int rc;
+  if ((rc = upload(c, c->d_twStart, startQ, B * 16))) return rc;
+  if ((rc = upload(c, c->d_twTarget, targetQ, B * 16))) return rc;
+  if ((rc = upload(c, c->d_twRest, restQ, B * 16))) return rc;
+  if ((rc = upload(c, c->d_twStartMs, startMs, B * 4))) return rc;
+  if ((rc = upload(c, c->d_twDurMs, durMs, B * 4))) return rc;
+  if ((rc = upload(c, c->d_twActive, active, B))) return rc;
+  CU_TRY(c, cudaStreamSynchronize(c->stream));    // pageable sources
+  c->haveTweens = true;
+  return RZ_OK;
+}
+
+int32_t rz_set_instance_clocks(rz_ctx* c, const float* nowMs, uint32_t P, const uint32_t* inst2pal, uint32_t K) {
+  if (!c) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_set_instance_clocks: null ctx");
+  if (!c->haveTweens) return fail(c, RZ_ERR_STATE, "rz_set_instance_clocks before rz_set_tweens");
+  if (!nowMs) return fail(c, RZ_ERR_INVALID_ARG, "rz_set_instance_clocks: null clocks");
+  CU_TRY(c, cudaSetDevice(c->device));
+  int rc;
+  if ((rc = set_mapping(c, inst2pal, P, K, "rz_set_instance_clocks"))) return rc;
+  if ((rc = dev_reserve(c, c->d_nowMs, (size_t)P * 4))) return rc;
+  const char* src = reinterpret_cast<const char*>(nowMs);
+  const bool inStage = c->h_stage && src >= (char*)c->h_stage && src + (size_t)P * 4 <= (char*)c->h_stage + c->h_stageBytes;
+  if (!inStage) {
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    if ((rc = pinned_reserve(c, c->h_stage, c->h_stageBytes, (size_t)P * 4))) return rc;
+    memcpy(c->h_stage, nowMs, (size_t)P * 4);
+    src = reinterpret_cast<const char*>(c->h_stage);
+  }
+  CU_TRY(c, cudaMemcpyAsync(c->d_nowMs.p, src, (size_t)P * 4, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = launch_pose<1>(c, P))) return rc;
+  c->P = P; c->K = K; c->palettesSet = true;
+  return RZ_OK;
 }
 
 int32_t rz_set_morph_weights(rz_ctx* c, const float* w, const uint32_t* ids, uint32_t Mact, uint32_t K) {

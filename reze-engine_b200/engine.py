@@ -63,7 +63,8 @@ class ManualClock:
 
 class Engine:
     def __init__(self, canvas=None, options: Optional[dict] = None, *, instances: int = 1, device: int = 0,
-                 clock: Optional[Callable[[], float]] = None, sdef: bool = False, bounds: bool = False, stream: int = 0):
+                 clock: Optional[Callable[[], float]] = None, sdef: bool = False, bounds: bool = False, stream: int = 0,
+                 gpu_pose: bool = False):
         o = options or {}
         # EngineOptions (engine.ts:8-14): kept so existing call sites construct unchanged; they only
         # parameterise passes this repo does not replace.
@@ -77,6 +78,7 @@ class Engine:
         self.clock = clock or (lambda: time.perf_counter() * 1000.0)
         self._flags = (capi.RZ_FLAG_SDEF if sdef else 0) | (capi.RZ_FLAG_BOUNDS if bounds else 0)
         self._stream = stream
+        self.gpu_pose = gpu_pose      # walk the bone hierarchy on the GPU (rz_set_local_rotations) instead of in Model
         self.ctx: Optional[capi.DeformContext] = None
         self.currentModel: Optional[Model] = None
         self.models: List[Model] = []
@@ -148,6 +150,9 @@ class Engine:
         if model.sdef.vertexIndex.size:
             self.ctx.load_sdef(model.sdef.vertexIndex, model.sdef.c_r0_r1)
         self._world_stage = self.ctx.palette_staging(self.instances)
+        if self.gpu_pose:
+            self.ctx.load_skeleton(model.getSkeleton().bones)
+            self._rot_stage = np.zeros((self.instances, len(model.getSkeleton().bones), 4), np.float32)
         return model
 
     def loadAnimation(self, url: str):
@@ -272,10 +277,17 @@ class Engine:
             return
         self._pumpTimers()
         B = len(self.currentModel.skeleton.bones)
-        for k, m in enumerate(self.models):
-            m.evaluatePose()
-            self._world_stage[k] = m.getBoneWorldMatrices().reshape(B, 16)
-        self.ctx.set_palettes(self._world_stage, K=self.instances)
+        if self.gpu_pose:
+            # host: tweens only (model.ts:158-194); device: hierarchy + append + skin matrices (model.ts:330-420)
+            for k, m in enumerate(self.models):
+                m.updateRotationTweens()
+                self._rot_stage[k] = m.localRotations.reshape(B, 4)
+            self.ctx.set_local_rotations(self._rot_stage, K=self.instances)
+        else:
+            for k, m in enumerate(self.models):
+                m.evaluatePose()
+                self._world_stage[k] = m.getBoneWorldMatrices().reshape(B, 16)
+            self.ctx.set_palettes(self._world_stage, K=self.instances)
         self.ctx.deform()
 
     def runRenderLoop(self, callback: Optional[Callable[[], None]] = None, frames: Optional[int] = None,

@@ -132,10 +132,16 @@ def make_pose_keys(B: int, rng, max_angle: float = 0.6):
 def make_palettes(bones: List[Bone], P: int, rng, stagger: bool = True, first: int = 0) -> np.ndarray:
     """World matrices [P,B,16] f32: instance p (global id first+p) sits at phase ((first+p)*0.618...) mod 1 of a
     two-key tween evaluated with the reference rule (quadratic ease + slerp) -- "staggered VMD phase"."""
-    qa, qb = make_pose_keys(len(bones), rng)
-    phase = ((first + np.arange(P)) * GOLDEN) % 1.0 if stagger else np.zeros(P)
+    qa, qb, phase = make_crowd_tween(len(bones), P, rng, stagger=stagger, first=first)
     lr = tween_pose_batch(qa, qb, phase)
     return world_matrices_batch(bones, lr)
+
+
+def make_crowd_tween(B: int, P: int, rng, stagger: bool = True, first: int = 0):
+    """The two-key tween behind make_palettes: (start quats [B,4], target quats [B,4], phase [P] in [0,1))."""
+    qa, qb = make_pose_keys(B, rng)
+    phase = ((first + np.arange(P)) * GOLDEN) % 1.0 if stagger else np.zeros(P)
+    return qa, qb, phase
 
 
 def make_morphs(V: int, M: int, rng, face_frac: float = 0.12, touch_frac: float = 0.03) -> VertexMorphs:

@@ -236,7 +236,8 @@ def test_error_paths(rzlib, wl_small):
             ctx.load_morphs([0, 1], [wl.V], [0, 0, 0])
 
 
-def test_engine_facade_drives_the_path(rzlib, orc, tmp_path):
+@pytest.mark.parametrize("gpu_pose", [False, True])
+def test_engine_facade_drives_the_path(rzlib, orc, tmp_path, gpu_pose):
     rng = np.random.default_rng(12)
     data, *_ = random_pmx(rng, V=700, B=12)
     pmx_path = tmp_path / "m.pmx"
@@ -245,7 +246,7 @@ def test_engine_facade_drives_the_path(rzlib, orc, tmp_path):
     vmd_path = tmp_path / "a.vmd"
     vmd_path.write_bytes(write_vmd([("骨1", 0, (0, 0, 0, 1)), ("骨1", 30, q1.toArray()), ("骨6", 15, (0.2, 0, 0, 0.98))]))
     clock = ManualClock()
-    eng = Engine(None, {"ambient": 1.0, "bloomIntensity": 0.1}, instances=2, clock=clock, sdef=True).init()
+    eng = Engine(None, {"ambient": 1.0, "bloomIntensity": 0.1}, instances=2, clock=clock, sdef=True, gpu_pose=gpu_pose).init()
     model = eng.loadModel(str(pmx_path))
     eng.loadAnimation(str(vmd_path))
     eng.runRenderLoop(frames=1)                        # T pose frame
@@ -261,6 +262,8 @@ def test_engine_facade_drives_the_path(rzlib, orc, tmp_path):
     assert st.frameTime > 0 and st.gpuMemory > 0
     for k in range(2):
         m = eng.models[k]
+        if gpu_pose:
+            m.computeWorldMatrices()          # the host never walked the hierarchy in this mode: do it for the reference
         skin = orc.skin_matrices(m.getBoneWorldMatrices(), m.getBoneInverseBindMatrices())
         dense = np.zeros(m.morphs.count, np.float32)
         dense[0] = [0.7, 0.2][k]
@@ -272,6 +275,61 @@ def test_engine_facade_drives_the_path(rzlib, orc, tmp_path):
     a, b = eng.readSkinned(0)[0], eng.readSkinned(1)[0]
     assert not np.array_equal(a, b)
     eng.dispose()
+
+
+def test_gpu_pose_evaluation_local_rotations(rzlib, orc):
+    """hierarchy walk + append rotation + skin matrices on the device vs the host Model restatement."""
+    rng = np.random.default_rng(31)
+    data, *_ = random_pmx(rng, V=600, B=12)                       # has append bones with ratios -1 / 0.25 / 0.5 / 1.5(clamped)
+    m = PmxLoader.loadFromBuffer(data, clock=ManualClock())
+    cases = [(m.skeleton.bones, m.getVertices(), m.skinning.joints, m.skinning.weights, m.getBoneInverseBindMatrices())]
+    wl = synth.make_workload(3000, 200, seed=9)
+    cases.append((wl.bones, wl.vtx8, wl.joints, wl.weights, wl.invBind))
+    for bones, vtx, J, W, inv in cases:
+        B, P = len(bones), 5
+        qa, qb, _ = synth.make_crowd_tween(B, P, rng)
+        lr = crowd.tween_pose_batch(qa, qb, rng.uniform(0, 1, P))          # [P,B,4] f32
+        world = crowd.world_matrices_batch(bones, lr)                       # bit-exact host evaluation (test_host.py)
+        i2p = np.array([4, 0, 2, 2, 1, 3, 0], np.uint32)
+        with capi.DeformContext(max_instances=7) as ctx:
+            ctx.load_mesh(vtx, J, W, inv)
+            ctx.load_skeleton(bones)
+            ctx.set_local_rotations(lr, i2p)
+            ref = orc.skin_matrices(world[3], inv).reshape(-1, 4, 4).transpose(0, 2, 1)[:, :3, :].reshape(-1, 12)
+            assert rel_err(ctx.read_skin_matrices(3), ref) <= TOL
+            ctx.deform()
+            for k in range(7):
+                rp, rn = orc.deform(vtx, J, W, orc.skin_matrices(world[i2p[k]], inv))
+                gp, gn = ctx.read_instance(k)
+                assert rel_err(gp, rp) <= TOL and rel_err(gn, rn) <= TOL
+
+
+def test_gpu_pose_evaluation_tweens_with_instance_clocks(rzlib, orc):
+    """Crowd playback: one shared tween state, instance k evaluated at its own clock (staggered phase)."""
+    rng = np.random.default_rng(32)
+    wl = synth.make_workload(2000, 96, seed=12)
+    B = wl.B
+    clock = ManualClock(1000.0)
+    model = wl.model(clock=clock)
+    names = [b.name for b in wl.bones]
+    quats = [Quat(*rng.normal(size=4)) for _ in range(B)]
+    model.rotateBones(names[:60], quats[:60], 800)                       # 60 bones tweening, 20 set instantly, 16 at rest
+    model.rotateBones(names[60:80], quats[60:80], 0)
+    offsets = np.array([0.0, 100.0, 399.5, 800.0, 2000.0, -50.0], np.float32)
+    with capi.DeformContext(max_instances=6) as ctx:
+        ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
+        ctx.load_skeleton(wl.bones)
+        ctx.set_tweens(model._startQuat, model._targetQuat, model._startTimeMs, model._durationMs, model._active, model.localRotations)
+        ctx.set_instance_clocks(1000.0 + offsets)
+        ctx.deform()
+        for k, off in enumerate(offsets):
+            ref = wl.model(clock=ManualClock(1000.0 + float(off)))
+            for arr in ("_startQuat", "_targetQuat", "_startTimeMs", "_durationMs", "_active", "localRotations"):
+                getattr(ref, arr)[:] = getattr(model, arr)
+            ref.evaluatePose()
+            rp, rn = orc.deform(wl.vtx8, wl.joints, wl.weights, orc.skin_matrices(ref.getBoneWorldMatrices(), wl.invBind))
+            gp, gn = ctx.read_instance(k)
+            assert rel_err(gp, rp) <= TOL and rel_err(gn, rn) <= TOL, k
 
 
 def _load_local(name):
