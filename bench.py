@@ -279,9 +279,9 @@ def main():
     ctx.load_skeleton(wl.bones)
     ident = np.tile(np.array([0, 0, 0, 1], np.float32), (B, 1))
     ctx.set_tweens(qa, qb, np.zeros(B, np.float32), np.full(B, 1000.0, np.float32), np.ones(B, np.uint8), ident)
-    clocks = (phase * 1000.0).astype(np.float32)
+    clock_ms = (phase * 1000.0).astype(np.float32)
     for _ in range(2):
-        ctx.set_instance_clocks(clocks, i2p, K=K)
+        ctx.set_instance_clocks(clock_ms, i2p, K=K)
         ctx.deform()
         ctx.read_instance(0)
     barrier()
@@ -289,7 +289,7 @@ def main():
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g0.record()
     for s in range(esteps):
-        ctx.set_instance_clocks(clocks, i2p, K=K)
+        ctx.set_instance_clocks(clock_ms, i2p, K=K)
         ctx.deform()
         ctx.read_instance(s % K)
     g1.record()
