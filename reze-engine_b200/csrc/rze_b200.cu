@@ -995,10 +995,17 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
     // preference order (measured on B200, profiles/): most resident warps first, then wider instance groups
     static const int pref[][3] = {{3, 256, 2}, {4, 512, 1}, {2, 512, 2}, {2, 256, 3}, {3, 512, 1}, {2, 256, 2}, {2, 512, 1}, {4, 256, 1},
                                   {1, 256, 4}, {1, 256, 2}, {1, 512, 2}};
+    // feature kernels (morph / SDEF / bounds / ...) are compiled for fewer shapes; prefer the ones without register spills
+    static const int prefLite[][3] = {{2, 256, 2}, {2, 512, 1}, {4, 512, 1}, {1, 256, 2}};
     bool ok = false;
-    for (const auto& p : pref) {
-      if (try_shape(p[0], p[1], p[2])) {
-        if (occ >= p[2]) { ok = true; break; }                     // the shape only pays off at its intended occupancy
+    if (feat != 0) {
+      for (const auto& p : prefLite) if (try_shape(p[0], p[1], p[2])) { ok = true; break; }
+    }
+    if (!ok) {
+      for (const auto& p : pref) {
+        if (try_shape(p[0], p[1], p[2])) {
+          if (occ >= p[2]) { ok = true; break; }                   // the shape only pays off at its intended occupancy
+        }
       }
     }
     if (!ok) {
