@@ -271,9 +271,13 @@ class DeformContext:
         self._check(self.lib.rz_output_device_ptr(self.h, C.byref(base), C.byref(stride), C.byref(noff)))
         return base.value, stride.value, noff.value
 
-    def read_instance(self, inst: int, normals: bool = True):
-        pos = np.empty((self.V, 3), dtype=np.float32)
-        nrm = np.empty((self.V, 3), dtype=np.float32) if normals and not (self.flags & RZ_FLAG_NO_NORMALS) else None
+    def read_instance(self, inst: int, normals: bool = True, out_pos: Optional[np.ndarray] = None, out_nrm: Optional[np.ndarray] = None):
+        """Skinned positions / normals of one instance as [V,3] float32.  `out_pos` / `out_nrm` let the caller supply
+        (e.g. pinned) destination arrays."""
+        pos = out_pos if out_pos is not None else np.empty((self.V, 3), dtype=np.float32)
+        nrm = None
+        if normals and not (self.flags & RZ_FLAG_NO_NORMALS):
+            nrm = out_nrm if out_nrm is not None else np.empty((self.V, 3), dtype=np.float32)
         self._check(self.lib.rz_read_instance(self.h, inst, _ptr(pos), _ptr(nrm)))
         return pos, nrm
 

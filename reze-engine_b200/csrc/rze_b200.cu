@@ -69,7 +69,8 @@ struct rz_ctx_impl {
   // skeleton for GPU pose evaluation
   bool haveSkeleton = false, haveTweens = false;
   uint32_t nLevels = 0;
-  DevBuf d_skParent, d_skBindT, d_skAppendParent, d_skAppendRatio, d_skLevelBones, d_skLevelStart;
+  DevBuf d_skParent, d_skBindT, d_skAppendParent, d_skAppendRatio, d_skLevelBones, d_skLevelStart, d_skChainStart, d_skChainBones;
+  bool useChains = false;
   DevBuf d_twStart, d_twTarget, d_twRest, d_twStartMs, d_twDurMs, d_twActive, d_localRot, d_nowMs;
 
   // per-frame
@@ -585,7 +586,7 @@ int32_t rz_destroy(rz_ctx* c) {
   DevBuf* bufs[] = {&c->d_rec0, &c->d_rec1, &c->d_rec2, &c->d_meta, &c->d_wbits, &c->d_mrange, &c->d_ments, &c->d_sdefIdx, &c->d_sdefTab,
                     &c->d_invBind, &c->d_bonePos, &c->d_world, &c->d_skin, &c->d_inst2pal, &c->d_mwIn, &c->d_mwIds, &c->d_mwDense,
                     &c->d_out, &c->d_bounds, &c->d_counter, &c->d_skParent, &c->d_skBindT, &c->d_skAppendParent, &c->d_skAppendRatio,
-                    &c->d_skLevelBones, &c->d_skLevelStart, &c->d_twStart, &c->d_twTarget, &c->d_twRest, &c->d_twStartMs, &c->d_twDurMs,
+                    &c->d_skLevelBones, &c->d_skLevelStart, &c->d_skChainStart, &c->d_skChainBones, &c->d_twStart, &c->d_twTarget, &c->d_twRest, &c->d_twStartMs, &c->d_twDurMs,
                     &c->d_twActive, &c->d_localRot, &c->d_nowMs};
   for (DevBuf* b : bufs) dev_free(c, *b);
   if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -791,6 +792,23 @@ int32_t rz_load_skeleton(rz_ctx* c, const int32_t* parent, const float* bindT, c
   if ((rc = upload(c, c->d_skAppendRatio, ar.data(), (size_t)B * 4))) return rc;
   if ((rc = upload(c, c->d_skLevelBones, levelBones.data(), (size_t)B * 4))) return rc;
   if ((rc = upload(c, c->d_skLevelStart, levelStart.data(), (size_t)(nLevels + 1) * 4))) return rc;
+  // ancestor chains (root .. bone) for the barrier-free evaluation; skipped for pathologically deep skeletons
+  {
+    size_t total = 0;
+    for (uint32_t b = 0; b < B; ++b) total += (size_t)depth[b] + 1;
+    c->useChains = total <= (size_t)B * 96;
+    if (c->useChains) {
+      std::vector<uint32_t> chainStart(B + 1, 0), chainBones(total);
+      for (uint32_t b = 0; b < B; ++b) chainStart[b + 1] = chainStart[b] + (uint32_t)depth[b] + 1;
+      for (uint32_t b = 0; b < B; ++b) {
+        uint32_t i = chainStart[b + 1];
+        for (int32_t cur = (int32_t)b; cur >= 0; cur = par[cur]) chainBones[--i] = (uint32_t)cur;
+      }
+      if ((rc = upload(c, c->d_skChainStart, chainStart.data(), (size_t)(B + 1) * 4))) return rc;
+      if ((rc = upload(c, c->d_skChainBones, chainBones.data(), total * 4))) return rc;
+      CU_TRY(c, cudaStreamSynchronize(c->stream));
+    }
+  }
   CU_TRY(c, cudaStreamSynchronize(c->stream));
   c->nLevels = nLevels;
   c->haveSkeleton = true;
@@ -822,6 +840,19 @@ static int launch_pose(rz_ctx* c, uint32_t P) {
   tw.startMs = reinterpret_cast<const float*>(c->d_twStartMs.p);
   tw.durMs = reinterpret_cast<const float*>(c->d_twDurMs.p);
   tw.active = reinterpret_cast<const uint8_t*>(c->d_twActive.p);
+  if (c->useChains) {
+    CU_TRY(c, cudaFuncSetAttribute(pose_chain_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pose_chain_kernel<MODE><<<P, 256, smem, c->stream>>>(sk, tw, reinterpret_cast<const uint32_t*>(c->d_skChainStart.p),
+                                                         reinterpret_cast<const uint32_t*>(c->d_skChainBones.p),
+                                                         reinterpret_cast<const float4*>(c->d_localRot.p),
+                                                         reinterpret_cast<const float*>(c->d_nowMs.p),
+                                                         reinterpret_cast<const float4*>(c->d_invBind.p),
+                                                         reinterpret_cast<const uint32_t*>(c->d_bonePos.p),
+                                                         reinterpret_cast<float4*>(c->d_skin.p), (uint32_t)c->layoutMode);
+    CU_TRY(c, cudaGetLastError());
+    c->launches++;
+    return RZ_OK;
+  }
   pose_kernel<MODE><<<P, 128, smem, c->stream>>>(sk, tw, reinterpret_cast<const float4*>(c->d_localRot.p),
                                                  reinterpret_cast<const float*>(c->d_nowMs.p),
                                                  reinterpret_cast<const float4*>(c->d_invBind.p),

@@ -285,6 +285,13 @@ def test_gpu_pose_evaluation_local_rotations(rzlib, orc):
     cases = [(m.skeleton.bones, m.getVertices(), m.skinning.joints, m.skinning.weights, m.getBoneInverseBindMatrices())]
     wl = synth.make_workload(3000, 200, seed=9)
     cases.append((wl.bones, wl.vtx8, wl.joints, wl.weights, wl.invBind))
+    # a 300-bone spine (depth 300): too deep for ancestor chains -> exercises the level-ordered kernel
+    wl2 = synth.make_workload(1500, 300, seed=10)
+    from reze_engine_b200.pmx import compute_inverse_bind
+    for i, b in enumerate(wl2.bones):
+        b.parentIndex = i - 1
+    inv2 = compute_inverse_bind(wl2.bones)
+    cases.append((wl2.bones, wl2.vtx8, wl2.joints, wl2.weights, inv2))
     for bones, vtx, J, W, inv in cases:
         B, P = len(bones), 5
         qa, qb, _ = synth.make_crowd_tween(B, P, rng)
