@@ -128,6 +128,13 @@ int32_t rz_set_tweens(rz_ctx* ctx, const float* startQuat /* 4B */, const float*
 /* Evaluate the tweens (model.ts:158-194: slerp + quadratic ease) at P clock values and fill the palettes: instance k
  * plays the shared animation at time nowMs[instToPalette[k]] ("staggered phase" crowds).  Host->device traffic: 4*P bytes. */
 int32_t rz_set_instance_clocks(rz_ctx* ctx, const float* nowMs /* P */, uint32_t P, const uint32_t* instToPalette, uint32_t K);
+/* Keyframe tracks of one clip (what loadAnimation + playAnimation schedule, engine.ts:1419-1423, 1451-1553): bone b owns keys
+ * keyOffsets[b] .. keyOffsets[b+1]-1 (times in ms, ascending; quaternions xyzw, normalised on load like rotateBones does).
+ * While a clip is loaded rz_set_instance_clocks evaluates it instead of the tween table: a key at t = 0 applies instantly,
+ * bones without one start from identity, key i is reached from key i-1 by slerp + quadratic ease over [t(i-1), t(i)], the
+ * last key is held; bones without keys take restQuat (NULL = identity).  keyOffsets == NULL unloads the clip. */
+int32_t rz_load_animation(rz_ctx* ctx, const uint32_t* keyOffsets /* B+1 */, const float* keyTimesMs, const float* keyQuats /* 4*nKeys */,
+                          const float* restQuat /* 4B or NULL */);
 
 /* Per-instance weights of the active morphs: w[k*M_active + a] scales morph activeIds[a] for instance k.
  * K must match the instance count in use; M_active = 0 disables morphing. */

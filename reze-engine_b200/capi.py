@@ -24,7 +24,7 @@ RZ_FLAG_BOUNDS = 0x4
 EXPORTS = [
     "rz_create", "rz_destroy", "rz_abi_version", "rz_load_mesh", "rz_load_morphs", "rz_load_sdef",
     "rz_set_palettes", "rz_set_palettes_device", "rz_palette_staging", "rz_load_skeleton", "rz_set_local_rotations",
-    "rz_set_tweens", "rz_set_instance_clocks", "rz_set_morph_weights", "rz_deform",
+    "rz_set_tweens", "rz_set_instance_clocks", "rz_load_animation", "rz_set_morph_weights", "rz_deform",
     "rz_sync", "rz_output_device_ptr", "rz_read_instance", "rz_read_bounds", "rz_read_skinning",
     "rz_read_skin_matrices", "rz_get_stats", "rz_last_error",
 ]
@@ -87,6 +87,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.rz_set_local_rotations.argtypes = [vp, vp, u32, vp, u32]
     lib.rz_set_tweens.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.rz_set_instance_clocks.argtypes = [vp, vp, u32, vp, u32]
+    lib.rz_load_animation.argtypes = [vp, vp, vp, vp, vp]
     lib.rz_set_morph_weights.argtypes = [vp, vp, vp, u32, u32]
     lib.rz_deform.argtypes = [vp, u32, u32]
     lib.rz_sync.argtypes = [vp]
@@ -242,6 +243,17 @@ class DeformContext:
         a = [_arr(start, np.float32), _arr(target, np.float32), _arr(start_ms, np.float32), _arr(dur_ms, np.float32),
              _arr(active, np.uint8), _arr(rest, np.float32)]
         self._check(self.lib.rz_set_tweens(self.h, *[_ptr(x) for x in a]))
+
+    def load_animation(self, key_offsets, key_times_ms, key_quats, rest_quat=None):
+        """Keyframe tracks per bone (CSR): see rz_load_animation.  key_offsets=None unloads."""
+        if key_offsets is None:
+            self._check(self.lib.rz_load_animation(self.h, None, None, None, None))
+            return
+        off = _arr(key_offsets, np.uint32).reshape(-1)
+        t = _arr(key_times_ms, np.float32).reshape(-1)
+        q = _arr(key_quats, np.float32).reshape(-1)
+        r = None if rest_quat is None else _arr(rest_quat, np.float32).reshape(-1)
+        self._check(self.lib.rz_load_animation(self.h, _ptr(off), _ptr(t) if t.size else None, _ptr(q) if q.size else None, _ptr(r)))
 
     def set_instance_clocks(self, now_ms, inst_to_palette=None, K: Optional[int] = None):
         t = _arr(now_ms, np.float32).reshape(-1)

@@ -72,6 +72,16 @@ struct PoseTweens {
   const uint8_t* __restrict__ active; // [B]
 };
 
+// Keyframe tracks of one animation clip: bone b owns keys keyStart[b] .. keyStart[b+1]-1 (times ascending, ms).
+// Evaluation = what the reference's playback produces when its timers fire on time (engine.ts:1451-1553 + the tween
+// rule model.ts:158-194): a key at t = 0 is applied instantly, bones without one start from identity; key i is reached
+// by a tween from key i-1 over [t(i-1), t(i)] with quadratic ease + slerp; the last key is held.
+struct PoseTracks {
+  const uint32_t* __restrict__ keyStart;   // [B+1]
+  const float* __restrict__ keyMs;         // [nKeys]
+  const float4* __restrict__ keyQ;         // [nKeys] normalised xyzw
+};
+
 __device__ __forceinline__ float4 q_slerp(float4 a, float4 b, float t) {   // math.ts:156-189
   float c = a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
   if (c < 0.f) { c = -c; b.x = -b.x; b.y = -b.y; b.z = -b.z; b.w = -b.w; }
@@ -93,32 +103,50 @@ __device__ __forceinline__ void q_to_rows(float4 q, float r[3][3]) {     // math
   r[2][0] = xz - wy; r[2][1] = yz + wx; r[2][2] = 1.f - (xx + yy);
 }
 
-// MODE 0: local rotations uploaded ([P][B] float4);  MODE 1: rotations from the shared tween table at time nowMs[p]
+__device__ __forceinline__ float ease_in_out(float t) {          // math.ts:2-4
+  const float u = -2.0f * t + 2.0f;
+  return t < 0.5f ? 2.0f * t * t : 1.0f - (u * u) * 0.5f;
+}
+
+// local rotation of bone b of pose p.  MODE 0: uploaded; MODE 1: shared tween table at nowMs[p]; MODE 2: keyframe tracks at nowMs[p]
 template <int MODE>
-__global__ void pose_kernel(PoseSkeleton sk, PoseTweens tw, const float4* __restrict__ localRot, const float* __restrict__ nowMs,
+__device__ __forceinline__ float4 eval_rotation(uint32_t b, uint32_t p, uint32_t B, const PoseTweens& tw, const PoseTracks& tr,
+                                                const float4* __restrict__ localRot, const float* __restrict__ nowMs) {
+  if (MODE == 0) return localRot[(size_t)p * B + b];
+  if (MODE == 1) {
+    if (!tw.active[b]) return tw.rest[b];
+    const float dur = fmaxf(1.0f, tw.durMs[b]);
+    const float t = fminf(1.0f, fmaxf(0.0f, (nowMs[p] - tw.startMs[b]) / dur));
+    return q_slerp(tw.start[b], tw.target[b], ease_in_out(t));
+  }
+  const uint32_t k0 = tr.keyStart[b], k1 = tr.keyStart[b + 1];
+  if (k0 == k1) return tw.rest[b];                               // bone not animated by the clip
+  const float now = nowMs[p];
+  float tPrev = 0.0f;
+  float4 qPrev = make_float4(0.f, 0.f, 0.f, 1.f);                // reset to identity unless a key sits at t = 0
+  for (uint32_t k = k0; k < k1; ++k) {
+    const float tk = tr.keyMs[k];
+    const float4 qk = tr.keyQ[k];
+    if (tk <= 0.0f) { qPrev = qk; tPrev = 0.0f; continue; }
+    if (now <= tPrev) return qPrev;
+    if (now < tk) {
+      const float t = fminf(1.0f, fmaxf(0.0f, (now - tPrev) / fmaxf(1.0f, tk - tPrev)));
+      return q_slerp(qPrev, qk, ease_in_out(t));
+    }
+    qPrev = qk; tPrev = tk;
+  }
+  return qPrev;
+}
+
+// MODE 0: local rotations uploaded ([P][B] float4);  MODE 1: rotations from the shared tween table at time nowMs[p];  MODE 2: tracks
+template <int MODE>
+__global__ void pose_kernel(PoseSkeleton sk, PoseTweens tw, PoseTracks tr, const float4* __restrict__ localRot, const float* __restrict__ nowMs,
                             const float4* __restrict__ invBind, const uint32_t* __restrict__ bonePos, float4* __restrict__ skin,
                             float4* __restrict__ worldOut /* optional [P][B][3] rows, may be null */, uint32_t soa) {
   extern __shared__ float4 s_world[];            // [B][3] rows of the 3x4 world matrices
   float4* s_q = s_world + (size_t)sk.B * 3;      // [B] local rotations (needed by append children)
   const uint32_t p = blockIdx.x, B = sk.B;
-  for (uint32_t b = threadIdx.x; b < B; b += blockDim.x) {
-    float4 q;
-    if (MODE == 0) {
-      q = localRot[(size_t)p * B + b];
-    } else {
-      if (tw.active[b]) {
-        const float dur = fmaxf(1.0f, tw.durMs[b]);
-        float t = (nowMs[p] - tw.startMs[b]) / dur;
-        t = fminf(1.0f, fmaxf(0.0f, t));
-        const float u = -2.0f * t + 2.0f;
-        const float e = t < 0.5f ? 2.0f * t * t : 1.0f - (u * u) * 0.5f;
-        q = q_slerp(tw.start[b], tw.target[b], e);
-      } else {
-        q = tw.rest[b];
-      }
-    }
-    s_q[b] = q;
-  }
+  for (uint32_t b = threadIdx.x; b < B; b += blockDim.x) s_q[b] = eval_rotation<MODE>(b, p, B, tw, tr, localRot, nowMs);
   __syncthreads();
   for (uint32_t L = 0; L < sk.nLevels; ++L) {
     const uint32_t l0 = sk.levelStart[L], l1 = sk.levelStart[L + 1];
@@ -193,30 +221,13 @@ __global__ void pose_kernel(PoseSkeleton sk, PoseTweens tw, const float4* __rest
 // chain root -> bone (the association order of the reference's recursion, model.ts:405-411), so one CTA needs only
 // two barriers per palette.  ~depth x 36 FMA per bone instead of 36, but no 40-level latency chain: 4x faster for crowds.
 template <int MODE>
-__global__ void pose_chain_kernel(PoseSkeleton sk, PoseTweens tw, const uint32_t* __restrict__ chainStart, const uint32_t* __restrict__ chainBones,
+__global__ void pose_chain_kernel(PoseSkeleton sk, PoseTweens tw, PoseTracks tr, const uint32_t* __restrict__ chainStart, const uint32_t* __restrict__ chainBones,
                                   const float4* __restrict__ localRot, const float* __restrict__ nowMs, const float4* __restrict__ invBind,
                                   const uint32_t* __restrict__ bonePos, float4* __restrict__ skin, uint32_t soa) {
   extern __shared__ float4 s_loc[];              // [B][3] rows of the local 3x4 transforms T(bind) * R
   float4* s_q = s_loc + (size_t)sk.B * 3;        // [B] local rotations
   const uint32_t p = blockIdx.x, B = sk.B;
-  for (uint32_t b = threadIdx.x; b < B; b += blockDim.x) {
-    float4 q;
-    if (MODE == 0) {
-      q = localRot[(size_t)p * B + b];
-    } else {
-      if (tw.active[b]) {
-        const float dur = fmaxf(1.0f, tw.durMs[b]);
-        float t = (nowMs[p] - tw.startMs[b]) / dur;
-        t = fminf(1.0f, fmaxf(0.0f, t));
-        const float u = -2.0f * t + 2.0f;
-        const float e = t < 0.5f ? 2.0f * t * t : 1.0f - (u * u) * 0.5f;
-        q = q_slerp(tw.start[b], tw.target[b], e);
-      } else {
-        q = tw.rest[b];
-      }
-    }
-    s_q[b] = q;
-  }
+  for (uint32_t b = threadIdx.x; b < B; b += blockDim.x) s_q[b] = eval_rotation<MODE>(b, p, B, tw, tr, localRot, nowMs);
   __syncthreads();
   for (uint32_t b = threadIdx.x; b < B; b += blockDim.x) {
     float R[3][3];

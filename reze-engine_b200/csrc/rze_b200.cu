@@ -15,6 +15,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cmath>
 #include <cstdlib>
 #include <string>
 #include <unordered_map>
@@ -67,7 +68,8 @@ struct rz_ctx_impl {
   uint32_t morphNnz = 0, sdefActive = 0;
 
   // skeleton for GPU pose evaluation
-  bool haveSkeleton = false, haveTweens = false;
+  bool haveSkeleton = false, haveTweens = false, haveAnimation = false;
+  DevBuf d_trStart, d_trMs, d_trQ;
   uint32_t nLevels = 0;
   DevBuf d_skParent, d_skBindT, d_skAppendParent, d_skAppendRatio, d_skLevelBones, d_skLevelStart, d_skChainStart, d_skChainBones;
   bool useChains = false;
@@ -587,7 +589,7 @@ int32_t rz_destroy(rz_ctx* c) {
                     &c->d_invBind, &c->d_bonePos, &c->d_world, &c->d_skin, &c->d_inst2pal, &c->d_mwIn, &c->d_mwIds, &c->d_mwDense,
                     &c->d_out, &c->d_bounds, &c->d_counter, &c->d_skParent, &c->d_skBindT, &c->d_skAppendParent, &c->d_skAppendRatio,
                     &c->d_skLevelBones, &c->d_skLevelStart, &c->d_skChainStart, &c->d_skChainBones, &c->d_twStart, &c->d_twTarget, &c->d_twRest, &c->d_twStartMs, &c->d_twDurMs,
-                    &c->d_twActive, &c->d_localRot, &c->d_nowMs};
+                    &c->d_twActive, &c->d_localRot, &c->d_nowMs, &c->d_trStart, &c->d_trMs, &c->d_trQ};
   for (DevBuf* b : bufs) dev_free(c, *b);
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->h_small) cudaFreeHost(c->h_small);
@@ -619,6 +621,7 @@ int32_t rz_load_mesh(rz_ctx* c, const float* vtx8, const uint16_t* joints, const
   c->palettesSet = false;
   c->haveSkeleton = false;
   c->haveTweens = false;
+  c->haveAnimation = false;
   c->Mact = 0;
   c->Mpad = 0;
   c->tablesDirty = true;
@@ -840,9 +843,13 @@ static int launch_pose(rz_ctx* c, uint32_t P) {
   tw.startMs = reinterpret_cast<const float*>(c->d_twStartMs.p);
   tw.durMs = reinterpret_cast<const float*>(c->d_twDurMs.p);
   tw.active = reinterpret_cast<const uint8_t*>(c->d_twActive.p);
+  PoseTracks tr;
+  tr.keyStart = reinterpret_cast<const uint32_t*>(c->d_trStart.p);
+  tr.keyMs = reinterpret_cast<const float*>(c->d_trMs.p);
+  tr.keyQ = reinterpret_cast<const float4*>(c->d_trQ.p);
   if (c->useChains) {
     CU_TRY(c, cudaFuncSetAttribute(pose_chain_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pose_chain_kernel<MODE><<<P, 256, smem, c->stream>>>(sk, tw, reinterpret_cast<const uint32_t*>(c->d_skChainStart.p),
+    pose_chain_kernel<MODE><<<P, 256, smem, c->stream>>>(sk, tw, tr, reinterpret_cast<const uint32_t*>(c->d_skChainStart.p),
                                                          reinterpret_cast<const uint32_t*>(c->d_skChainBones.p),
                                                          reinterpret_cast<const float4*>(c->d_localRot.p),
                                                          reinterpret_cast<const float*>(c->d_nowMs.p),
@@ -853,7 +860,7 @@ static int launch_pose(rz_ctx* c, uint32_t P) {
     c->launches++;
     return RZ_OK;
   }
-  pose_kernel<MODE><<<P, 128, smem, c->stream>>>(sk, tw, reinterpret_cast<const float4*>(c->d_localRot.p),
+  pose_kernel<MODE><<<P, 128, smem, c->stream>>>(sk, tw, tr, reinterpret_cast<const float4*>(c->d_localRot.p),
                                                  reinterpret_cast<const float*>(c->d_nowMs.p),
                                                  reinterpret_cast<const float4*>(c->d_invBind.p),
                                                  reinterpret_cast<const uint32_t*>(c->d_bonePos.p),
@@ -926,7 +933,7 @@ int32_t rz_set_tweens(rz_ctx* c, const float* startQ, const float* targetQ, cons
 
 int32_t rz_set_instance_clocks(rz_ctx* c, const float* nowMs, uint32_t P, const uint32_t* inst2pal, uint32_t K) {
   if (!c) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_set_instance_clocks: null ctx");
-  if (!c->haveTweens) return fail(c, RZ_ERR_STATE, "rz_set_instance_clocks before rz_set_tweens");
+  if (!c->haveTweens && !c->haveAnimation) return fail(c, RZ_ERR_STATE, "rz_set_instance_clocks before rz_set_tweens / rz_load_animation");
   if (!nowMs) return fail(c, RZ_ERR_INVALID_ARG, "rz_set_instance_clocks: null clocks");
   CU_TRY(c, cudaSetDevice(c->device));
   int rc;
@@ -941,8 +948,47 @@ int32_t rz_set_instance_clocks(rz_ctx* c, const float* nowMs, uint32_t P, const 
     src = reinterpret_cast<const char*>(c->h_stage);
   }
   CU_TRY(c, cudaMemcpyAsync(c->d_nowMs.p, src, (size_t)P * 4, cudaMemcpyHostToDevice, c->stream));
-  if ((rc = launch_pose<1>(c, P))) return rc;
+  if ((rc = c->haveAnimation ? launch_pose<2>(c, P) : launch_pose<1>(c, P))) return rc;
   c->P = P; c->K = K; c->palettesSet = true;
+  return RZ_OK;
+}
+
+int32_t rz_load_animation(rz_ctx* c, const uint32_t* keyOffsets, const float* keyTimesMs, const float* keyQuats, const float* restQuat) {
+  if (!c) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_load_animation: null ctx");
+  if (!c->haveSkeleton) return fail(c, RZ_ERR_STATE, "rz_load_animation before rz_load_skeleton");
+  CU_TRY(c, cudaSetDevice(c->device));
+  if (!keyOffsets) {                       // unload: rz_set_instance_clocks evaluates the tween table again
+    c->haveAnimation = false;
+    return RZ_OK;
+  }
+  const uint32_t B = c->B, n = keyOffsets[B];
+  if (keyOffsets[0] != 0) return fail(c, RZ_ERR_INVALID_ARG, "rz_load_animation: keyOffsets[0] must be 0");
+  for (uint32_t b = 0; b < B; ++b) {
+    if (keyOffsets[b + 1] < keyOffsets[b]) return fail(c, RZ_ERR_INVALID_ARG, "rz_load_animation: offsets not monotone at bone %u", b);
+    for (uint32_t k = keyOffsets[b] + 1; k < keyOffsets[b + 1]; ++k)
+      if (keyTimesMs[k] < keyTimesMs[k - 1]) return fail(c, RZ_ERR_INVALID_ARG, "rz_load_animation: key times of bone %u not ascending", b);
+  }
+  if (n && (!keyTimesMs || !keyQuats)) return fail(c, RZ_ERR_INVALID_ARG, "rz_load_animation: null keys");
+  // normalise like Model.rotateBones does (model.ts:248; zero-length -> identity, math.ts:96-100)
+  std::vector<float> q((size_t)std::max<uint32_t>(n, 1) * 4, 0.f);
+  for (uint32_t k = 0; k < n; ++k) {
+    const double x = keyQuats[k * 4], y = keyQuats[k * 4 + 1], z = keyQuats[k * 4 + 2], w = keyQuats[k * 4 + 3];
+    const double len = std::sqrt(x * x + y * y + z * z + w * w);
+    if (len == 0) { q[k * 4 + 3] = 1.f; continue; }
+    q[k * 4] = (float)(x / len); q[k * 4 + 1] = (float)(y / len); q[k * 4 + 2] = (float)(z / len); q[k * 4 + 3] = (float)(w / len);
+  }
+  std::vector<float> rest((size_t)B * 4, 0.f);
+  for (uint32_t b = 0; b < B; ++b) {
+    if (restQuat) memcpy(&rest[(size_t)b * 4], restQuat + (size_t)b * 4, 16);
+    else rest[(size_t)b * 4 + 3] = 1.f;   // playAnimation resets bones without keys to identity (engine.ts:1489-1505)
+  }
+  int rc;
+  if ((rc = upload(c, c->d_trStart, keyOffsets, (size_t)(B + 1) * 4))) return rc;
+  if ((rc = upload(c, c->d_trMs, n ? keyTimesMs : rest.data(), (size_t)std::max<uint32_t>(n, 1) * 4))) return rc;
+  if ((rc = upload(c, c->d_trQ, q.data(), q.size() * 4))) return rc;
+  if ((rc = upload(c, c->d_twRest, rest.data(), (size_t)B * 16))) return rc;
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  c->haveAnimation = true;
   return RZ_OK;
 }
 

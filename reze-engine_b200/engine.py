@@ -64,7 +64,7 @@ class ManualClock:
 class Engine:
     def __init__(self, canvas=None, options: Optional[dict] = None, *, instances: int = 1, device: int = 0,
                  clock: Optional[Callable[[], float]] = None, sdef: bool = False, bounds: bool = False, stream: int = 0,
-                 gpu_pose: bool = False):
+                 gpu_pose: bool = False, crowd: bool = False):
         o = options or {}
         # EngineOptions (engine.ts:8-14): kept so existing call sites construct unchanged; they only
         # parameterise passes this repo does not replace.
@@ -78,7 +78,13 @@ class Engine:
         self.clock = clock or (lambda: time.perf_counter() * 1000.0)
         self._flags = (capi.RZ_FLAG_SDEF if sdef else 0) | (capi.RZ_FLAG_BOUNDS if bounds else 0)
         self._stream = stream
-        self.gpu_pose = gpu_pose      # walk the bone hierarchy on the GPU (rz_set_local_rotations) instead of in Model
+        self.gpu_pose = gpu_pose or crowd   # walk the bone hierarchy on the GPU (rz_set_local_rotations) instead of in Model
+        # crowd mode: ONE shared skeleton runtime + animation clip, every instance plays it at its own clock offset; tweens /
+        # keyframe tracks are evaluated on the device (rz_set_tweens / rz_load_animation + rz_set_instance_clocks)
+        self.crowd = crowd
+        self._crowd_playing = False
+        self._anim_start_ms = 0.0
+        self._offsets_ms = np.zeros(int(instances), np.float64)
         self.ctx: Optional[capi.DeformContext] = None
         self.currentModel: Optional[Model] = None
         self.models: List[Model] = []
@@ -140,7 +146,7 @@ class Engine:
         model.clock = self.clock
         self.currentModel = model
         self.models = [model]
-        for _ in range(1, self.instances):
+        for _ in range(1, 1 if self.crowd else self.instances):
             self.models.append(Model(model.vertexData, model.indexData, model.textures, model.materials, model.skeleton,
                                      model.skinning, morphs=model.morphs, sdef=model.sdef, clock=self.clock))
         sk = model.getSkinning()
@@ -176,12 +182,41 @@ class Engine:
         self.ctx.set_morph_weights(w, np.asarray(ids, np.uint32), K=self.instances)
 
     # ---- animation playback (engine.ts:1425-1662) ----------------------------------------------
+    def setInstanceOffsets(self, offsets_ms):
+        """Crowd mode: instance k plays the shared animation `offsets_ms[k]` milliseconds behind instance 0."""
+        self._offsets_ms = np.ascontiguousarray(offsets_ms, dtype=np.float64).reshape(self.instances)
+
+    def _playCrowd(self):
+        """Crowd playback: the clip becomes per-bone keyframe tracks on the device (same rule as the timers below
+        produce when they fire on time: key at t=0 instant, others tween from the previous key with ease + slerp)."""
+        bones = self.currentModel.getSkeleton().bones
+        idx = self.currentModel.nameIndex
+        per: List[list] = [[] for _ in bones]
+        for kf in self.animationFrames:
+            for bf in kf.boneFrames:
+                i = idx.get(bf.boneName, -1)
+                if i >= 0:
+                    per[i].append((kf.time * 1000.0, bf.rotation))
+        off = np.zeros(len(bones) + 1, np.uint32)
+        times, quats = [], []
+        for i, keys in enumerate(per):
+            keys.sort(key=lambda tq: tq[0])
+            off[i + 1] = off[i] + len(keys)
+            for t, q in keys:
+                times.append(t)
+                quats.append(q.toArray())
+        self.ctx.load_animation(off, np.asarray(times, np.float32), np.asarray(quats, np.float32).reshape(-1, 4))
+        self._anim_start_ms = self.clock()
+        self._crowd_playing = True
+
     def playAnimation(self, options: Optional[dict] = None, instance: Optional[int] = 0):
         if not self.animationFrames:
             return
         self.stopAnimation()
         self._stopBreathing()
         self.playingAnimation = True
+        if self.crowd:
+            return self._playCrowd()
         opts = options or {}
         bb = opts.get("breathBones")
         enableBreath = bb is not None
@@ -240,6 +275,9 @@ class Engine:
             self._clearTimeout(t)
         self._animationTimeouts = []
         self.playingAnimation = False
+        if self.crowd and self._crowd_playing and self.ctx:
+            self.ctx.load_animation(None, None, None)
+            self._crowd_playing = False
 
     def _stopBreathing(self):
         self._clearTimeout(self._breathingTimeout)
@@ -277,7 +315,20 @@ class Engine:
             return
         self._pumpTimers()
         B = len(self.currentModel.skeleton.bones)
-        if self.gpu_pose:
+        if self.crowd:
+            m = self.currentModel
+            now = self.clock()
+            if self._crowd_playing:
+                self.ctx.set_instance_clocks((now - self._anim_start_ms - self._offsets_ms).astype(np.float32), K=self.instances)
+            else:
+                # shared rotateBones tweens, evaluated per instance on the device; times are sent relative to `now`
+                # (f32 has ~0.1 ms resolution only near zero)
+                self.ctx.set_tweens(m._startQuat, m._targetQuat, (m._startTimeMs.astype(np.float64) - now).astype(np.float32),
+                                    m._durationMs, m._active, m.localRotations)
+                self.ctx.set_instance_clocks((-self._offsets_ms).astype(np.float32), K=self.instances)
+                # (the host copy of the tween state is NOT advanced: a finished tween keeps evaluating to its target, and
+                #  instances that lag behind still have to play it)
+        elif self.gpu_pose:
             # host: tweens only (model.ts:158-194); device: hierarchy + append + skin matrices (model.ts:330-420)
             for k, m in enumerate(self.models):
                 m.updateRotationTweens()

@@ -339,6 +339,58 @@ def test_gpu_pose_evaluation_tweens_with_instance_clocks(rzlib, orc):
             assert rel_err(gp, rp) <= TOL and rel_err(gn, rn) <= TOL, k
 
 
+def test_engine_crowd_playback_matches_timer_driven_reference_playback(rzlib, orc, tmp_path):
+    """BASELINE config 2 through the facade: K instances play one VMD at staggered offsets, keyframe tracks evaluated
+    on the device, vs the reference-style playback (timers + rotateBones tweens on the host) sampled at the same times."""
+    rng = np.random.default_rng(41)
+    data, *_ = random_pmx(rng, V=500, B=12, n_morph=0, with_sdef=False)
+    pmx_path = tmp_path / "m.pmx"
+    pmx_path.write_bytes(data)
+    qs = [Quat(*rng.normal(size=4)).normalize() for _ in range(5)]
+    vmd_path = tmp_path / "a.vmd"
+    vmd_path.write_bytes(write_vmd([("骨1", 0, qs[0].toArray()), ("骨1", 15, qs[1].toArray()), ("骨1", 30, qs[2].toArray()),
+                                    ("骨6", 15, qs[3].toArray()), ("骨9", 45, qs[4].toArray()), ("ghost", 10, (0, 0, 0, 1))]))
+    step = 50.0
+    # reference-style playback, one instance, sampled every 50 ms (all key times are multiples of 50 ms)
+    rclock = ManualClock()
+    ref = Engine(None, None, instances=1, clock=rclock).init()
+    rmodel = ref.loadModel(str(pmx_path))
+    ref.loadAnimation(str(vmd_path))
+    ref.playAnimation()
+    samples = {}
+    for f in range(0, 45):
+        ref.render()
+        samples[f * step] = rmodel.getBoneWorldMatrices().copy()
+        rclock.advance(step)
+    ref.dispose()
+    # crowd playback
+    offsets = np.array([0.0, 100.0, 250.0, 500.0, 1000.0, 1700.0])
+    clock = ManualClock()
+    eng = Engine(None, None, instances=6, clock=clock, crowd=True).init()
+    model = eng.loadModel(str(pmx_path))
+    eng.loadAnimation(str(vmd_path))
+    eng.setInstanceOffsets(offsets)
+    eng.playAnimation()
+    vt, J, W, inv = model.getVertices(), model.skinning.joints, model.skinning.weights, model.getBoneInverseBindMatrices()
+    for f in range(0, 40, 3):
+        clock.now_ms = f * step
+        eng.render()
+        for k, off in enumerate(offsets):
+            tau = max(0.0, f * step - off)               # before its start an instance shows the t=0 pose
+            rp, rn = orc.deform(vt, J, W, orc.skin_matrices(samples[tau], inv))
+            gp, gn = eng.readSkinned(k)
+            assert rel_err(gp, rp) <= TOL and rel_err(gn, rn) <= TOL, (f, k)
+    # stop: back to the shared rotateBones pose, still per-instance clocks
+    eng.stopAnimation()
+    eng.rotateBones(["骨2"], [qs[0]], 400)
+    clock.advance(200.0)
+    eng.render()
+    a, b = eng.readSkinned(0)[0], eng.readSkinned(2)[0]      # instance 2 is 250 ms behind: its tween has not started
+    assert not np.array_equal(a, b)
+    assert rel_err(b, eng.readSkinned(5)[0]) <= 1e-6
+    eng.dispose()
+
+
 def _load_local(name):
     path = os.path.join(LOCAL, name)
     if not os.path.exists(path):
