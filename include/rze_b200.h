@@ -52,8 +52,8 @@ typedef struct rz_config {
   void*    stream;         /* optional cudaStream_t to launch on (e.g. the caller's current stream);
                               NULL = the context creates its own non-blocking stream */
   uint32_t tune_instances_per_group; /* 0 = auto; kernel tuning knob (instances sharing one vertex pass) */
-  uint32_t tune_store_mode;          /* 0 = auto; 1 = direct register stores; 2 = smem-staged bulk (TMA) stores */
-  uint32_t tune_threads;             /* 0 = auto; 256 or 512 threads per CTA */
+  uint32_t tune_store_mode;          /* reserved (ignored): results always leave through smem-staged TMA bulk stores */
+  uint32_t tune_threads;             /* 0 = auto; threads per CTA: 256, 512, 768 or 1024 (must be a compiled launch shape) */
   uint32_t tune_chunks;              /* 0 = auto; vertex chunks per instance group (work-item granularity) */
   uint32_t tune_ctas_per_sm;         /* 0 = auto; persistent CTAs per SM */
   uint32_t tune_reserved[3];

@@ -63,7 +63,11 @@ struct rz_ctx_impl {
   std::vector<uint32_t> procToVertex;   // processing index -> caller vertex id (or ~0u for padding)
   std::vector<uint32_t> bonePos, boneAt; // palette row of bone b (bank-aware permutation) and its inverse
   DevBuf d_bonePos;
-  int permMode = 1, colorMode = 1, layoutMode = 0;   // layoutMode 1: palette as [3][B] float4 + co-occurrence clustering       // vertex ordering inside a tile / bank-aware palette permutation
+  // experiment knobs (environment RZ_PERM / RZ_COLOR / RZ_LAYOUT, see DESIGN.md "tuning knobs"):
+  //   permMode   1: lanes of a warp sorted by (influence count, bones); 0: natural lane order
+  //   colorMode  1: bank-aware palette permutation (8-colouring of the bone co-occurrence graph); 0: identity
+  //   layoutMode 0: palette rows of 48 B ([B][3] float4); 1: [3][B] float4 + co-occurrence clustering (measured slower)
+  int permMode = 1, colorMode = 1, layoutMode = 0;       // vertex ordering inside a tile / bank-aware palette permutation
   DevBuf d_rec0, d_rec1, d_rec2, d_meta, d_wbits, d_mrange, d_ments, d_sdefIdx, d_sdefTab, d_invBind;
   uint32_t morphNnz = 0, sdefActive = 0;
 
@@ -270,11 +274,6 @@ int rebuild_tables(rz_ctx_impl* c) {
     return n;
   };
   const bool classSort = c->permMode != 0;
-  [[maybe_unused]] auto key_of = [&](uint32_t v) -> uint32_t {
-    if (!classSort) return (sdefOf[v] >= 0 ? 2u : 0u) | (mcount[v] ? 1u : 0u);   // natural order except for the rare classes
-    return (sdefOf[v] >= 0 ? 1u << 31 : 0u) | (mcount[v] ? 1u << 30 : 0u) | (ninf_of(v) << 27) | (std::min<uint32_t>(mcount[v], 63u) << 21) |
-           ((uint32_t)c->h_joints[(size_t)v * 4] & 0xFFFFu);
-  };
 
   // lane order inside a warp: by influence count, then by bone ids, so that quarter-warps (the unit the shared-memory
   // pipe serves per wavefront) are homogeneous: same influence count => whole quarters skip the zero-weight gathers,

@@ -101,6 +101,8 @@ class Engine:
         self._renderLoopCallback = None
         self._stats = EngineStats()
         self._morph_ids = np.zeros(0, np.uint32)
+        self._morphTracks: Dict[str, list] = {}
+        self._morphPlaying = False
 
     # ---- lifecycle ---------------------------------------------------------------------------
     def init(self):
@@ -162,9 +164,30 @@ class Engine:
         return model
 
     def loadAnimation(self, url: str):
-        """engine.ts:1419-1423."""
-        self.animationFrames = VMDLoader.load(url)
+        """engine.ts:1419-1423.  Extension: the clip's vertex-morph track (which the reference never reads,
+        vmd-loader.ts stops after the bone table) is kept and played back by playAnimation."""
+        self.animationFrames, morphFrames = VMDLoader.loadWithMorphs(url)
         self.hasAnimation = True
+        self._morphTracks = {}
+        for mf in morphFrames:
+            self._morphTracks.setdefault(mf.morphName, []).append((mf.frame / 30.0 * 1000.0, float(mf.weight)))
+        for v in self._morphTracks.values():
+            v.sort(key=lambda tw: tw[0])
+
+    def _evalMorphTracks(self, tau_ms: np.ndarray):
+        """Morph weights [K, n] at per-instance clip times (MMD rule: linear interpolation between keys, held outside)."""
+        names = self.currentModel.morphs.names
+        ids, cols = [], []
+        for name, keys in self._morphTracks.items():
+            if name not in names:
+                continue
+            t = np.asarray([k[0] for k in keys], np.float64)
+            w = np.asarray([k[1] for k in keys], np.float64)
+            ids.append(names.index(name))
+            cols.append(np.interp(tau_ms, t, w))
+        if not ids:
+            return None, None
+        return np.asarray(ids, np.uint32), np.stack(cols, axis=1).astype(np.float32)
 
     # ---- bone API ----------------------------------------------------------------------------
     def rotateBones(self, bones: Sequence[str], rotations: Sequence[Quat], durationMs: Optional[float] = None,
@@ -215,6 +238,8 @@ class Engine:
         self.stopAnimation()
         self._stopBreathing()
         self.playingAnimation = True
+        self._anim_start_ms = self.clock()
+        self._morphPlaying = bool(self._morphTracks) and self.currentModel is not None and self.currentModel.morphs.count > 0
         if self.crowd:
             return self._playCrowd()
         opts = options or {}
@@ -275,6 +300,7 @@ class Engine:
             self._clearTimeout(t)
         self._animationTimeouts = []
         self.playingAnimation = False
+        self._morphPlaying = False
         if self.crowd and self._crowd_playing and self.ctx:
             self.ctx.load_animation(None, None, None)
             self._crowd_playing = False
@@ -315,6 +341,11 @@ class Engine:
             return
         self._pumpTimers()
         B = len(self.currentModel.skeleton.bones)
+        if self._morphPlaying:
+            tau = self.clock() - self._anim_start_ms - (self._offsets_ms if self.crowd else np.zeros(self.instances))
+            ids, w = self._evalMorphTracks(np.maximum(tau, 0.0))
+            if ids is not None:
+                self.ctx.set_morph_weights(w, ids, K=self.instances)
         if self.crowd:
             m = self.currentModel
             now = self.clock()

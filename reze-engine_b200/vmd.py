@@ -61,6 +61,13 @@ class VMDLoader:
             return VMDLoader(f.read()).parse()
 
     @staticmethod
+    def loadWithMorphs(path: str):
+        """(bone key frames, morph frames): the second table is an extension, the reference never reads it."""
+        with open(path, "rb") as f:
+            ld = VMDLoader(f.read())
+        return ld.parse(), ld.morphFrames
+
+    @staticmethod
     def loadFromBuffer(data: bytes) -> List[VMDKeyFrame]:
         return VMDLoader(data).parse()
 

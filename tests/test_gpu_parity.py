@@ -391,6 +391,42 @@ def test_engine_crowd_playback_matches_timer_driven_reference_playback(rzlib, or
     eng.dispose()
 
 
+def test_vmd_morph_track_playback(rzlib, orc, tmp_path):
+    """the VMD morph table drives per-instance morph weights (linear between keys), crowd offsets included."""
+    rng = np.random.default_rng(43)
+    data, *_ = random_pmx(rng, V=400, B=8, n_morph=3, with_sdef=False)
+    (tmp_path / "m.pmx").write_bytes(data)
+    (tmp_path / "a.vmd").write_bytes(write_vmd([("骨1", 0, (0, 0, 0, 1)), ("骨1", 30, (0, 0.3, 0, 0.95))],
+                                               [("m0", 0, 0.0), ("m0", 30, 1.0), ("m2", 15, 0.5), ("nope", 3, 1.0)]))
+    clock = ManualClock()
+    eng = Engine(None, None, instances=3, clock=clock, crowd=True).init()
+    model = eng.loadModel(str(tmp_path / "m.pmx"))
+    eng.loadAnimation(str(tmp_path / "a.vmd"))
+    eng.setInstanceOffsets([0.0, 250.0, 2000.0])
+    eng.playAnimation()
+    clock.now_ms = 500.0
+    eng.render()
+    names = model.morphs.names
+    for k, tau in enumerate((500.0, 250.0, 0.0)):
+        dense = np.zeros(model.morphs.count, np.float32)
+        dense[names.index("m0")] = min(1.0, tau / 1000.0)
+        dense[names.index("m2")] = 0.5                      # single key: held
+        e = min(1.0, tau / 1000.0)
+        from reze_engine_b200.math3d import easeInOut
+        q = Quat.slerp(Quat(0, 0, 0, 1), Quat(0, 0.3, 0, 0.95).normalize(), easeInOut(e))
+        ref = Engine(None, None, instances=1, clock=ManualClock()).init()
+        rm = ref.loadModel(str(tmp_path / "m.pmx"))
+        rm.rotateBones(["骨1"], [q], 0)
+        rm.evaluatePose()
+        rp, rn = orc.deform(rm.getVertices(), rm.skinning.joints, rm.skinning.weights,
+                            orc.skin_matrices(rm.getBoneWorldMatrices(), rm.getBoneInverseBindMatrices()),
+                            morph=(rm.morphs.offsets, rm.morphs.vertexIndex, rm.morphs.delta), morphW=dense)
+        ref.dispose()
+        gp, gn = eng.readSkinned(k)
+        assert rel_err(gp, rp) <= TOL and rel_err(gn, rn) <= TOL, k
+    eng.dispose()
+
+
 def _load_local(name):
     path = os.path.join(LOCAL, name)
     if not os.path.exists(path):

@@ -115,6 +115,20 @@ def test_play_animation_schedules_like_the_reference():
     assert not eng.playingAnimation
 
 
+def test_vmd_morph_tracks_are_kept_and_interpolated(tmp_path):
+    clock = ManualClock()
+    data, *_ = random_pmx(np.random.default_rng(8), V=40, B=5, n_morph=3, with_sdef=False)
+    eng = Engine(None, None, instances=2, clock=clock)
+    eng.currentModel = PmxLoader.loadFromBuffer(data, clock=clock)
+    p = tmp_path / "a.vmd"
+    p.write_bytes(write_vmd([("骨1", 0, (0, 0, 0, 1))], [("m1", 0, 0.2), ("m1", 30, 1.0), ("m1", 60, 0.0), ("unknown", 5, 1.0)]))
+    eng.loadAnimation(str(p))
+    assert np.allclose(eng._morphTracks["m1"], [(0.0, 0.2), (1000.0, 1.0), (2000.0, 0.0)])       # weights are f32 in the file
+    ids, w = eng._evalMorphTracks(np.array([500.0, 2500.0]))
+    assert ids.tolist() == [eng.currentModel.morphs.names.index("m1")]
+    assert np.allclose(w[:, 0], [0.6, 0.0])
+
+
 def test_oracle_against_independent_numpy_restatement(orc):
     wl = synth.make_workload(3000, 48)
     world = synth.make_palettes(wl.bones, 2, np.random.default_rng(4))[1]
