@@ -100,7 +100,11 @@ struct rz_ctx_impl {
   uint64_t frames = 0, launches = 0;
   size_t devBytes = 0;
   uint32_t usedI = 0, usedStore = 0, usedCtas = 0, usedThreads = 0, usedSmem = 0;
-  int lastShape[3] = {0, 0, 0};
+  // launch-shape cache: the selection below (lookup + occupancy query) only depends on these
+  struct ShapeKey { int feat = -1; uint32_t B = 0, Mpad = 0, countClass = 0; } shapeKey;
+  KernelEntry shapeKe{nullptr, 0, 0, 0, 0};
+  size_t shapeSmem = 0;
+  int shapeOcc = 0;
 };
 
 int fail(rz_ctx_impl* c, int code, const char* fmt, ...) {
@@ -1050,6 +1054,10 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
   KernelEntry ke{nullptr, 0, 0, 0, feat};
   size_t smem = 0;
   int occ = 0;
+  const uint32_t countClass = std::min<uint32_t>(count, 8u);        // shapes are only restricted by count when count < I <= 8
+  const bool cached = c->shapeKe.fn && c->shapeKey.feat == feat && c->shapeKey.B == c->B && c->shapeKey.Mpad == Mpad &&
+                      c->shapeKey.countClass == countClass;
+  if (cached) { ke = c->shapeKe; smem = c->shapeSmem; occ = c->shapeOcc; }
   auto try_shape = [&](int I, int NT, int MINB) -> bool {
     if ((uint32_t)I > count && I > 1) return false;                 // never wider than the instance range
     KernelEntry e = lookup_kernel(feat, I, NT, MINB);
@@ -1062,7 +1070,9 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
     ke = e; smem = sm; occ = o;
     return true;
   };
-  if (c->tuneI || c->tuneThreads) {
+  if (cached) {
+    // nothing to do
+  } else if (c->tuneI || c->tuneThreads) {
     const int I = c->tuneI ? (int)c->tuneI : 2, NT = c->tuneThreads ? (int)c->tuneThreads : 256;
     if (!try_shape(I, NT, (int)c->tuneCtas) && !try_shape(I, NT, 0))
       return fail(c, RZ_ERR_INVALID_ARG, "rz_deform: requested launch shape I=%d threads=%d ctas/SM=%u is not built or does not fit (B=%u)",
@@ -1091,6 +1101,12 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
     if (!ok) return fail(c, RZ_ERR_INVALID_ARG, "rz_deform: no kernel shape fits B=%u (smem limit %zu)", c->B, smemMax);
   }
   if (c->tuneCtas && (int)c->tuneCtas < occ) occ = (int)c->tuneCtas;
+  // (another context may have lowered the limit on the same kernel function: always re-assert it, it is cheap)
+  CU_TRY(c, cudaFuncSetAttribute(ke.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (!cached) {
+    c->shapeKe = ke; c->shapeSmem = smem; c->shapeOcc = occ;
+    c->shapeKey.feat = feat; c->shapeKey.B = c->B; c->shapeKey.Mpad = Mpad; c->shapeKey.countClass = countClass;
+  }
   DeformParams prm;
   memset(&prm, 0, sizeof prm);
   prm.rec0 = reinterpret_cast<const float4*>(c->d_rec0.p);
