@@ -58,6 +58,7 @@ struct DeformParams {
   unsigned long long nrmOffF;          // floats from pos plane to normal plane
   uint32_t V, B, nTiles, K0, Kcount, Mpad;
   uint32_t nGroups, nChunks, tilesPerChunk;
+  uint32_t packedMeta;                 // 1: meta lives in the spare bits of the joint words (B <= 4096), no separate load
   uint32_t posStride, rowStride;       // palette addressing: chunk r of palette row `pos` sits at pos*posStride + r*rowStride bytes
   uint32_t* counter;
 };
@@ -313,7 +314,7 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
         v.r0 = ldg_el(prm.rec0 + p, polLast);
         v.r1 = ldg_el(prm.rec1 + p, polLast);
         v.r2 = ldg_el(prm.rec2 + p, polLast);
-        v.meta = ldg_el(prm.meta + p, polLast);
+        v.meta = prm.packedMeta ? 0u : ldg_el(prm.meta + p, polLast);
       } else {                                                  // the far tiles of a wide pass fall off the chunk
         v.r0 = make_float4(0.f, 0.f, 0.f, 1.f);
         v.r1 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -332,13 +333,21 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
       if (t + NT / kTile < tile1) cur = load_rec(t + NT / kTile);
       if (t + (uint32_t)warp / (kTile / 32) >= tile1) continue;       // warp-uniform: this warp has no tile in the pass
 
-      const uint32_t meta = v.meta;
+      uint32_t jb01 = __float_as_uint(v.r2.z), jb23 = __float_as_uint(v.r2.w);
+      uint32_t meta = v.meta;
+      if (prm.packedMeta) {
+        // 12-bit palette rows + 11 meta bits share the two joint words: saves one LDG (one LSU wavefront) per vertex
+        const uint32_t m11 = (jb01 >> 24) | ((jb23 >> 24) << 8);
+        meta = (m11 & 31u) | (((m11 >> 5) & 7u) << kMetaNinfShift) | ((m11 & 0x100u) ? kMetaValid : 0u) |
+               ((m11 & 0x200u) ? kMetaMorph : 0u) | ((m11 & 0x400u) ? kMetaSdef : 0u);
+        jb01 = (jb01 & 0xFFFu) | (((jb01 >> 12) & 0xFFFu) << 16);
+        jb23 = (jb23 & 0xFFFu) | (((jb23 >> 12) & 0xFFFu) << 16);
+      }
       const bool valid = (meta & kMetaValid) != 0;
       const uint32_t slot = meta & 31u;                           // position among the warp's 32 output vertices
       const int ninf = (int)((meta >> kMetaNinfShift) & 7u);
       const int nmax = __reduce_max_sync(0xffffffffu, ninf);
       const float w0 = v.r0.w, w1 = v.r1.w, w2 = v.r2.x, w3 = v.r2.y;
-      const uint32_t jb01 = __float_as_uint(v.r2.z), jb23 = __float_as_uint(v.r2.w);
       const uint32_t pS = prm.posStride, rS = prm.rowStride, rS2 = 2u * rS;
       const uint32_t j0 = (jb01 & 0xFFFFu) * pS, j1 = (jb01 >> 16) * pS;
       const uint32_t j2 = (jb23 & 0xFFFFu) * pS, j3 = (jb23 >> 16) * pS;

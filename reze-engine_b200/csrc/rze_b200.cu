@@ -77,6 +77,7 @@ struct rz_ctx_impl {
   uint32_t nLevels = 0;
   DevBuf d_skParent, d_skBindT, d_skAppendParent, d_skAppendRatio, d_skLevelBones, d_skLevelStart, d_skChainStart, d_skChainBones;
   bool useChains = false;
+  bool packedMeta = false;
   DevBuf d_twStart, d_twTarget, d_twRest, d_twStartMs, d_twDurMs, d_twActive, d_localRot, d_nowMs;
 
   // per-frame
@@ -293,6 +294,8 @@ int rebuild_tables(rz_ctx_impl* c) {
     return k;
   };
   std::vector<uint16_t> gatherJ;   // filled below, before the first emit_* call
+  const bool packMeta = B <= 4096;  // palette rows fit 12 bits: meta rides in the joint words (deform_kernel.cuh)
+  c->packedMeta = packMeta;
   auto emit_vertex = [&](uint32_t p, uint32_t v, uint32_t slot) {
     const float* x = &c->h_vtx8[(size_t)v * 8];
     const uint8_t* w8 = &c->h_weights[(size_t)v * 4];
@@ -313,7 +316,12 @@ int rebuild_tables(rz_ctx_impl* c) {
     }
     const uint16_t* j = &gatherJ[(size_t)p * 4];
     const uint32_t q0 = c->bonePos[j[0]], q1 = c->bonePos[j[1]], q2 = c->bonePos[j[2]], q3 = c->bonePos[j[3]];   // palette rows
-    const uint32_t j01 = q0 | (q1 << 16), j23 = q2 | (q3 << 16);
+    uint32_t j01 = q0 | (q1 << 16), j23 = q2 | (q3 << 16);
+    if (packMeta) {
+      const uint32_t m11 = (slot & 31u) | (ninf_of(v) << 5) | 0x100u | (mcount[v] ? 0x200u : 0u) | (sdefOf[v] >= 0 ? 0x400u : 0u);
+      j01 = q0 | (q1 << 12) | ((m11 & 0xFFu) << 24);
+      j23 = q2 | (q3 << 12) | ((m11 >> 8) << 24);
+    }
     float j01f, j23f;
     memcpy(&j01f, &j01, 4);
     memcpy(&j23f, &j23, 4);
@@ -330,7 +338,12 @@ int rebuild_tables(rz_ctx_impl* c) {
     rec0[p] = make_float4(0.f, 0.f, 0.f, 1.f);
     rec1[p] = make_float4(0.f, 0.f, 0.f, 0.f);
     const uint16_t* j = &gatherJ[(size_t)p * 4];
-    const uint32_t j01 = c->bonePos[j[0]] | (c->bonePos[j[1]] << 16), j23 = c->bonePos[j[2]] | (c->bonePos[j[3]] << 16);
+    uint32_t j01 = c->bonePos[j[0]] | (c->bonePos[j[1]] << 16), j23 = c->bonePos[j[2]] | (c->bonePos[j[3]] << 16);
+    if (packMeta) {
+      const uint32_t m11 = (slot & 31u) | (1u << 5);
+      j01 = c->bonePos[j[0]] | (c->bonePos[j[1]] << 12) | ((m11 & 0xFFu) << 24);
+      j23 = c->bonePos[j[2]] | (c->bonePos[j[3]] << 12) | ((m11 >> 8) << 24);
+    }
     float j01f, j23f;
     memcpy(&j01f, &j01, 4);
     memcpy(&j23f, &j23, 4);
@@ -1079,7 +1092,7 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
                   I, NT, c->tuneCtas, c->B);
   } else {
     // preference order (measured on B200, profiles/): most resident warps first, then wider instance groups
-    static const int pref[][3] = {{3, 256, 2}, {4, 512, 1}, {2, 512, 2}, {2, 256, 3}, {3, 512, 1}, {2, 256, 2}, {2, 512, 1}, {4, 256, 1},
+    static const int pref[][3] = {{4, 512, 1}, {3, 256, 2}, {2, 512, 2}, {2, 256, 3}, {3, 512, 1}, {2, 256, 2}, {2, 512, 1}, {4, 256, 1},
                                   {1, 256, 4}, {1, 256, 2}, {1, 512, 2}};
     // feature kernels (morph / SDEF / bounds / ...) are compiled for fewer shapes; prefer the ones without register spills
     static const int prefLite[][3] = {{2, 256, 2}, {2, 512, 1}, {4, 512, 1}, {1, 256, 2}};
@@ -1135,6 +1148,7 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
   prm.tilesPerChunk = passesPerChunk * tilesPerPass;
   prm.nChunks = (c->nTiles + prm.tilesPerChunk - 1) / prm.tilesPerChunk;
   prm.counter = reinterpret_cast<uint32_t*>(c->d_counter.p);
+  prm.packedMeta = c->packedMeta ? 1u : 0u;
   prm.posStride = c->layoutMode ? 16u : 48u;
   prm.rowStride = c->layoutMode ? c->B * 16u : 16u;
   const uint32_t nItems = prm.nGroups * prm.nChunks;
@@ -1227,6 +1241,10 @@ int32_t rz_read_skinning(rz_ctx* c, uint16_t* joints, uint8_t* weights) {
       uint32_t j01, j23;
       memcpy(&j01, &rec2[p].z, 4);
       memcpy(&j23, &rec2[p].w, 4);
+      if (c->packedMeta) {
+        j01 = (j01 & 0xFFFu) | (((j01 >> 12) & 0xFFFu) << 16);
+        j23 = (j23 & 0xFFFu) | (((j23 >> 12) & 0xFFFu) << 16);
+      }
       // the device stores palette rows; map them back to the caller's bone ids
       uint16_t dj[4] = {(uint16_t)c->boneAt[j01 & 0xFFFF], (uint16_t)c->boneAt[j01 >> 16], (uint16_t)c->boneAt[j23 & 0xFFFF],
                         (uint16_t)c->boneAt[j23 >> 16]};
