@@ -218,15 +218,18 @@ struct Ctrl {
   uint32_t pad;
 };
 constexpr uint32_t kCtrlBytes = 64;
-constexpr int kStageBufs = 2;
 
 // ------------------------------------------------------------------ the kernel
 // I    : instances evaluated per vertex pass (palettes resident in shared memory)
 // NT   : threads per CTA (multiple of 256)
 // MINB : CTAs per SM the register budget is sized for
 // FEAT : FEAT_* bit set
-template <int I, int NT, int MINB, int FEAT>
+// SB   : instances whose gathers are in flight together (sub-batch; divides I; bounds the register footprint)
+// NB   : staging buffers per warp (2 = double-buffered; 1 when the palettes of a wide group leave no room)
+template <int I, int NT, int MINB, int FEAT, int SB = I, int NB = 2>
 __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm) {
+  static_assert(I % SB == 0, "sub-batch must divide the group");
+  constexpr int kStageBufs = NB;
   constexpr bool MORPH = (FEAT & FEAT_MORPH) != 0;
   constexpr bool SDEF = (FEAT & FEAT_SDEF) != 0;
   constexpr bool BOUNDS = (FEAT & FEAT_BOUNDS) != 0;
@@ -408,37 +411,39 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
       const float2 nx2 = make_float2(vnx, vnx), ny2 = make_float2(vny, vny), nz2 = make_float2(vnz, vnz);
       const float2 w0_2 = make_float2(w0, w0), w1_2 = make_float2(w1, w1), w2_2 = make_float2(w2, w2), w3_2 = make_float2(w3, w3);
 
-      auto body = [&](auto NM) {
+      auto body = [&](auto NM, const int i0) {
         constexpr int NV = decltype(NM)::value;                   // 0: rigid warp with unit weights, else warp-max influence count
         constexpr int NMAX = NV == 0 ? 1 : NV;
         // ---- phase 1: palette gathers of influences 0/1 for all I instances, issued back to back (latency overlaps).
         // No predication: a lane whose weight for influence k is zero carries (set at load time, rze_b200.cu) the joint of
         // an ACTIVE lane of its own warp, so its gather costs no extra shared-memory wavefront (same 16-byte chunk is
         // broadcast) and its FFMA adds an exact 0.
-        float4 a0[I], a1[I], a2[I], b0[I], b1[I], b2[I];
+        float4 a0[SB], a1[SB], a2[SB], b0[SB], b1[SB], b2[SB];
 #pragma unroll
-        for (int i = 0; i < I; ++i) {
+        for (int ii = 0; ii < SB; ++ii) {
+          const int i = i0 + ii;
           if (GPAL) {
             const float4* pal = reinterpret_cast<const float4*>(gpal[i]);
-            a0[i] = pal[j0 / 16]; a1[i] = pal[(j0 + rS) / 16]; a2[i] = pal[(j0 + rS2) / 16];
-            if (NMAX > 1) { b0[i] = pal[j1 / 16]; b1[i] = pal[(j1 + rS) / 16]; b2[i] = pal[(j1 + rS2) / 16]; }
+            a0[ii] = pal[j0 / 16]; a1[ii] = pal[(j0 + rS) / 16]; a2[ii] = pal[(j0 + rS2) / 16];
+            if (NMAX > 1) { b0[ii] = pal[j1 / 16]; b1[ii] = pal[(j1 + rS) / 16]; b2[ii] = pal[(j1 + rS2) / 16]; }
           } else {
             const uint32_t pb = sPal + (uint32_t)i * palBytes;
-            a0[i] = lds128(pb + j0); a1[i] = lds128(pb + j0 + rS); a2[i] = lds128(pb + j0 + rS2);
-            if (NMAX > 1) { b0[i] = lds128(pb + j1); b1[i] = lds128(pb + j1 + rS); b2[i] = lds128(pb + j1 + rS2); }
+            a0[ii] = lds128(pb + j0); a1[ii] = lds128(pb + j0 + rS); a2[ii] = lds128(pb + j0 + rS2);
+            if (NMAX > 1) { b0[ii] = lds128(pb + j1); b1[ii] = lds128(pb + j1 + rS); b2[ii] = lds128(pb + j1 + rS2); }
           }
         }
         // ---- phase 2: blend + transform + staging
 #pragma unroll
-        for (int i = 0; i < I; ++i) {
+        for (int ii = 0; ii < SB; ++ii) {
+          const int i = i0 + ii;
           const float qx = px[MORPH ? i : 0], qy = py[MORPH ? i : 0], qz = pz[MORPH ? i : 0];
           float ox, oy, oz, nx = 0.f, ny = 0.f, nz = 0.f;
           bool done = false;
           if (SDEF && NMAX > 1) {
             if (isSdef) {
               // ---- SDEF: spherical blend of the two bone rotations around C; un-pair the rows first
-              const float4 r0 = make_float4(a0[i].x, a0[i].z, a1[i].x, a1[i].z), r1 = make_float4(a0[i].y, a0[i].w, a1[i].y, a1[i].w), r2 = a2[i];
-              const float4 s0 = make_float4(b0[i].x, b0[i].z, b1[i].x, b1[i].z), s1 = make_float4(b0[i].y, b0[i].w, b1[i].y, b1[i].w), s2 = b2[i];
+              const float4 r0 = make_float4(a0[ii].x, a0[ii].z, a1[ii].x, a1[ii].z), r1 = make_float4(a0[ii].y, a0[ii].w, a1[ii].y, a1[ii].w), r2 = a2[ii];
+              const float4 s0 = make_float4(b0[ii].x, b0[ii].z, b1[ii].x, b1[ii].z), s1 = make_float4(b0[ii].y, b0[ii].w, b1[ii].y, b1[ii].w), s2 = b2[ii];
               const Q4 q = quat_slerp(quat_from_rows(r0, r1, r2), quat_from_rows(s0, s1, s2), w1);
               const float x2 = q.x + q.x, y2 = q.y + q.y, z2 = q.z + q.z;
               const float xx = q.x * x2, xy = q.x * y2, xz = q.x * z2, yy = q.y * y2, yz = q.y * z2, zz = q.z * z2;
@@ -467,9 +472,9 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
           if (!done) {
             // ---- linear blend: M = sum_i w_i M_i (zero weights contribute exactly 0), then one packed mat-vec each
             float4 mA, mB, mC;
-            if (NV == 0) { mA = a0[i]; mB = a1[i]; mC = a2[i]; }          // every lane has the single weight 1.0
-            else { mA = f4_scale(a0[i], w0_2); mB = f4_scale(a1[i], w0_2); mC = f4_scale(a2[i], w0_2); }
-            if (NMAX > 1) { mA = f4_fma(b0[i], w1_2, mA); mB = f4_fma(b1[i], w1_2, mB); mC = f4_fma(b2[i], w1_2, mC); }
+            if (NV == 0) { mA = a0[ii]; mB = a1[ii]; mC = a2[ii]; }          // every lane has the single weight 1.0
+            else { mA = f4_scale(a0[ii], w0_2); mB = f4_scale(a1[ii], w0_2); mC = f4_scale(a2[ii], w0_2); }
+            if (NMAX > 1) { mA = f4_fma(b0[ii], w1_2, mA); mB = f4_fma(b1[ii], w1_2, mB); mC = f4_fma(b2[ii], w1_2, mC); }
             if (NMAX > 2) {
               float4 c0, c1, c2;
               if (GPAL) { const float4* pal = reinterpret_cast<const float4*>(gpal[i]); c0 = pal[j2 / 16]; c1 = pal[(j2 + rS) / 16]; c2 = pal[(j2 + rS2) / 16]; }
@@ -515,11 +520,14 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
         }
       };
       const bool unitW = __all_sync(0xffffffffu, w0 == 1.0f);
-      switch (nmax) {
-        case 1: if (unitW) body(IntC<0>{}); else body(IntC<1>{}); break;
-        case 2: body(IntC<2>{}); break;
-        case 3: body(IntC<3>{}); break;
-        default: body(IntC<4>{}); break;
+#pragma unroll
+      for (int i0 = 0; i0 < I; i0 += SB) {
+        switch (nmax) {
+          case 1: if (unitW) body(IntC<0>{}, i0); else body(IntC<1>{}, i0); break;
+          case 2: body(IntC<2>{}, i0); break;
+          case 3: body(IntC<3>{}, i0); break;
+          default: body(IntC<4>{}, i0); break;
+        }
       }
 
       // ---- drain: this warp's 32 vertices x I instances leave through the TMA (one elected lane)
@@ -552,7 +560,7 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
         }
         __syncwarp();
       }
-      sbuf ^= 1u;
+      if (kStageBufs > 1) sbuf ^= 1u;
     }
 
     if (BOUNDS) {

@@ -3,15 +3,17 @@
 namespace rz {
 struct KernelEntry {
   const void* fn;   // __global__ function pointer (nullptr = shape not compiled for this feature set)
-  int I, NT, MINB;  // instances per group, compute threads (CTA = NT + 32), CTAs/SM the registers are sized for
+  int I, NT, MINB;  // instances per group, threads per CTA, CTAs/SM the registers are sized for
+  int SB, NB;       // gather sub-batch, staging buffers per warp
   int feat;
 };
 // launch shapes (I, NT, MINB).  FULL: the plain BDEF path; LITE: every other feature set.
+// X(I, NT, MINB, SB, NB)
 #define RZ_SHAPES_FULL(X) \
-  X(1, 256, 4) X(2, 256, 3) X(2, 256, 2) X(3, 256, 2) X(4, 256, 1) \
-  X(1, 512, 2) X(2, 512, 2) X(2, 512, 1) X(3, 512, 1) X(4, 512, 1) \
-  X(2, 768, 1) X(3, 768, 1) X(2, 1024, 1) X(3, 1024, 1)
-#define RZ_SHAPES_LITE(X) X(1, 256, 2) X(2, 256, 2) X(2, 512, 1) X(4, 512, 1)
+  X(1, 256, 4, 1, 2) X(2, 256, 3, 2, 2) X(2, 256, 2, 2, 2) X(3, 256, 2, 3, 2) X(4, 256, 1, 4, 2) X(6, 256, 1, 3, 2) \
+  X(1, 512, 2, 1, 2) X(2, 512, 2, 2, 2) X(2, 512, 1, 2, 2) X(3, 512, 1, 3, 2) X(4, 512, 1, 4, 2) X(6, 512, 1, 3, 1) \
+  X(2, 768, 1, 2, 2) X(3, 768, 1, 3, 2) X(2, 1024, 1, 2, 2) X(3, 1024, 1, 3, 2)
+#define RZ_SHAPES_LITE(X) X(1, 256, 2, 1, 2) X(2, 256, 2, 2, 2) X(2, 512, 1, 2, 2) X(4, 512, 1, 4, 2)
 // feature sets compiled (bit meaning: deform_kernel.cuh FEAT_*); keep in sync with build.py
 #define RZ_FEAT_LIST(X) X(0) X(1) X(3) X(4) X(7) X(16) X(19) X(8) X(11) X(15) X(24) X(27)
 #define RZ_DECL(f) KernelEntry lookup_feat_##f(int I, int NT, int MINB);

@@ -103,7 +103,7 @@ struct rz_ctx_impl {
   uint32_t usedI = 0, usedStore = 0, usedCtas = 0, usedThreads = 0, usedSmem = 0;
   // launch-shape cache: the selection below (lookup + occupancy query) only depends on these
   struct ShapeKey { int feat = -1; uint32_t B = 0, Mpad = 0, countClass = 0; } shapeKey;
-  KernelEntry shapeKe{nullptr, 0, 0, 0, 0};
+  KernelEntry shapeKe{nullptr, 0, 0, 0, 0, 0, 0};
   size_t shapeSmem = 0;
   int shapeOcc = 0;
 };
@@ -175,7 +175,7 @@ KernelEntry lookup_kernel(int feat, int I, int NT, int MINB) {
 #undef RZ_CASE
     default: break;
   }
-  KernelEntry none{nullptr, 0, 0, 0, feat};
+  KernelEntry none{nullptr, 0, 0, 0, 0, 0, feat};
   return none;
 }
 
@@ -197,11 +197,11 @@ int resolve_feat(int need) {
   return best;
 }
 
-size_t smem_needed(int I, int NT, int feat, uint32_t B, uint32_t Mpad) {
+size_t smem_needed(int I, int NT, int feat, uint32_t B, uint32_t Mpad, int nbuf = 2) {
   size_t s = kCtrlBytes;
   if (!(feat & FEAT_GPAL)) s += (size_t)I * B * 48;
   if (feat & FEAT_MORPH) s += (size_t)I * Mpad * 4;
-  s += (size_t)kStageBufs * I * ((feat & FEAT_NONRM) ? 1 : 2) * NT * 12;   // warp-private double-buffered staging (pos + normal planes)
+  s += (size_t)nbuf * I * ((feat & FEAT_NONRM) ? 1 : 2) * NT * 12;   // warp-private staging (pos + normal planes)
   return s;
 }
 
@@ -1064,7 +1064,7 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
   if (smem_needed(1, 256, need, c->B, Mpad) > smemMax) need |= FEAT_GPAL;   // palette does not fit: gather from global
   const int feat = resolve_feat(need);
   if (feat < 0) return fail(c, RZ_ERR_INVALID_ARG, "rz_deform: feature combination 0x%x is not built", need);
-  KernelEntry ke{nullptr, 0, 0, 0, feat};
+  KernelEntry ke{nullptr, 0, 0, 0, 0, 0, feat};
   size_t smem = 0;
   int occ = 0;
   const uint32_t countClass = std::min<uint32_t>(count, 8u);        // shapes are only restricted by count when count < I <= 8
@@ -1075,7 +1075,7 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
     if ((uint32_t)I > count && I > 1) return false;                 // never wider than the instance range
     KernelEntry e = lookup_kernel(feat, I, NT, MINB);
     if (!e.fn) return false;
-    const size_t sm = smem_needed(e.I, e.NT, feat, c->B, Mpad);
+    const size_t sm = smem_needed(e.I, e.NT, feat, c->B, Mpad, e.NB);
     if (sm > smemMax) return false;
     if (cudaFuncSetAttribute(e.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) { cudaGetLastError(); return false; }
     int o = 0;
@@ -1092,7 +1092,7 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
                   I, NT, c->tuneCtas, c->B);
   } else {
     // preference order (measured on B200, profiles/): most resident warps first, then wider instance groups
-    static const int pref[][3] = {{4, 512, 1}, {3, 256, 2}, {2, 512, 2}, {2, 256, 3}, {3, 512, 1}, {2, 256, 2}, {2, 512, 1}, {4, 256, 1},
+    static const int pref[][3] = {{6, 512, 1}, {4, 512, 1}, {3, 256, 2}, {2, 512, 2}, {2, 256, 3}, {3, 512, 1}, {2, 256, 2}, {2, 512, 1}, {4, 256, 1},
                                   {1, 256, 4}, {1, 256, 2}, {1, 512, 2}};
     // feature kernels (morph / SDEF / bounds / ...) are compiled for fewer shapes; prefer the ones without register spills
     static const int prefLite[][3] = {{2, 256, 2}, {2, 512, 1}, {4, 512, 1}, {1, 256, 2}};
