@@ -20,12 +20,13 @@ LIB_PATH = os.path.join(_HERE, "lib", "librze_b200.so")
 RZ_FLAG_SDEF = 0x1
 RZ_FLAG_NO_NORMALS = 0x2
 RZ_FLAG_BOUNDS = 0x4
+RZ_FLAG_REORDER_VERTICES = 0x8
 
 EXPORTS = [
     "rz_create", "rz_destroy", "rz_abi_version", "rz_load_mesh", "rz_load_morphs", "rz_load_sdef",
     "rz_set_palettes", "rz_set_palettes_device", "rz_palette_staging", "rz_load_skeleton", "rz_set_local_rotations",
     "rz_set_tweens", "rz_set_instance_clocks", "rz_load_animation", "rz_set_morph_weights", "rz_deform",
-    "rz_sync", "rz_output_device_ptr", "rz_read_instance", "rz_read_bounds", "rz_read_skinning",
+    "rz_sync", "rz_output_device_ptr", "rz_read_instance", "rz_get_vertex_order", "rz_read_bounds", "rz_read_skinning",
     "rz_read_skin_matrices", "rz_get_stats", "rz_last_error",
 ]
 
@@ -53,11 +54,11 @@ class RzStats(C.Structure):
         ("vertexCount", C.c_uint32), ("boneCount", C.c_uint32), ("instanceCount", C.c_uint32), ("paletteCount", C.c_uint32),
         ("morphCount", C.c_uint32), ("morphNnz", C.c_uint32), ("sdefCount", C.c_uint32), ("activeMorphs", C.c_uint32),
         ("instancesPerGroup", C.c_uint32), ("storeMode", C.c_uint32), ("ctas", C.c_uint32), ("threads", C.c_uint32),
-        ("smemBytes", C.c_uint32), ("reserved0", C.c_uint32),
+        ("smemBytes", C.c_uint32), ("fastGatherPermille", C.c_uint32),
     ]
 
     def asdict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved0"}
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 _lib = None
@@ -93,6 +94,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.rz_sync.argtypes = [vp]
     lib.rz_output_device_ptr.argtypes = [vp, P(vp), P(sz), P(sz)]
     lib.rz_read_instance.argtypes = [vp, u32, vp, vp]
+    lib.rz_get_vertex_order.argtypes = [vp, vp]
     lib.rz_read_bounds.argtypes = [vp, u32, u32, vp]
     lib.rz_read_skinning.argtypes = [vp, vp, vp]
     lib.rz_read_skin_matrices.argtypes = [vp, u32, vp]
@@ -292,6 +294,12 @@ class DeformContext:
             nrm = out_nrm if out_nrm is not None else np.empty((self.V, 3), dtype=np.float32)
         self._check(self.lib.rz_read_instance(self.h, inst, _ptr(pos), _ptr(nrm)))
         return pos, nrm
+
+    def vertex_order(self) -> np.ndarray:
+        """order[i] = caller vertex id stored at position i of the device planes."""
+        o = np.empty(self.V, dtype=np.uint32)
+        self._check(self.lib.rz_get_vertex_order(self.h, _ptr(o)))
+        return o
 
     def read_bounds(self, first: int, count: int) -> np.ndarray:
         out = np.empty((count, 6), dtype=np.float32)

@@ -61,13 +61,17 @@ struct rz_ctx_impl {
   // device tables (processing order)
   uint32_t Vp = 0, nTiles = 0;
   std::vector<uint32_t> procToVertex;   // processing index -> caller vertex id (or ~0u for padding)
+  uint64_t packFastSlots = 0, packTotalSlots = 0;   // pair packing: warp x influence-slot gathers on the fast path / all
+  std::vector<uint8_t> procSlotMap;     // [Vp][4] device influence slot holding the caller's influence k (pair packing permutes them)
+  std::vector<uint32_t> vorder, vinv;    // stored position -> caller vertex id and its inverse (identity unless RZ_FLAG_REORDER_VERTICES)
   std::vector<uint32_t> bonePos, boneAt; // palette row of bone b (bank-aware permutation) and its inverse
   DevBuf d_bonePos;
   // experiment knobs (environment RZ_PERM / RZ_COLOR / RZ_LAYOUT, see DESIGN.md "tuning knobs"):
-  //   permMode   1: lanes of a warp sorted by (influence count, bones); 0: natural lane order
+  //   permMode   2: lane PAIRS + influence slots packed so that aligned lane pairs gather the same palette rows (default);
+  //              1: lanes of a warp sorted by (influence count, bones), caller's slot order; 0: natural lane order
   //   colorMode  1: bank-aware palette permutation (8-colouring of the bone co-occurrence graph); 0: identity
   //   layoutMode 0: palette rows of 48 B ([B][3] float4); 1: [3][B] float4 + co-occurrence clustering (measured slower)
-  int permMode = 1, colorMode = 1, layoutMode = 0;       // vertex ordering inside a tile / bank-aware palette permutation
+  int permMode = 2, colorMode = 1, layoutMode = 0;       // vertex ordering inside a tile / bank-aware palette permutation
   DevBuf d_rec0, d_rec1, d_rec2, d_meta, d_wbits, d_mrange, d_ments, d_sdefIdx, d_sdefTab, d_invBind;
   uint32_t morphNnz = 0, sdefActive = 0;
 
@@ -216,17 +220,62 @@ int rebuild_tables(rz_ctx_impl* c) {
   c->nTiles = nTiles;
   c->Vp = Vp;
 
+  // ---- stored vertex order ------------------------------------------------------------------------------------
+  // Default: the caller's order (drop-in: output vertex i == input vertex i).  With RZ_FLAG_REORDER_VERTICES the library
+  // stores vertices sorted by their bone tuple, so that the lanes of a warp (and in particular every aligned lane pair)
+  // gather the SAME palette rows: the shared-memory broadcast fast path then serves almost every gather instruction
+  // (profiles/r01_ubench_lds_row_fetch.txt).  The caller remaps its index buffer once with rz_get_vertex_order().
+  c->vorder.resize(V);
+  c->vinv.resize(V);
+  for (uint32_t v = 0; v < V; ++v) c->vorder[v] = v;
+  if (c->flags & RZ_FLAG_REORDER_VERTICES) {
+    // key = the vertex' SET of influencing bones (non-zero weights, ascending ids): vertices that gather the same rows
+    // become neighbours whatever order their influences are listed in (the slot order is the packer's to choose, below)
+    auto tuple_key = [&](uint32_t v) {
+      const uint8_t* w = &c->h_weights[(size_t)v * 4];
+      const uint16_t* j = &c->h_joints[(size_t)v * 4];
+      uint16_t b[4];
+      uint32_t n = 0;
+      for (uint32_t k = 0; k < 4; ++k) if (w[k]) b[n++] = j[k];
+      if (n == 0) b[n++] = j[0];
+      std::sort(b, b + n);
+      uint64_t key = (uint64_t)n << 60;
+      for (uint32_t k = 0; k < n; ++k) key |= (uint64_t)(b[k] & 0x7FFF) << (45 - 15 * k);
+      return key;
+    };
+    std::vector<uint64_t> keys(V);
+    for (uint32_t v = 0; v < V; ++v) keys[v] = tuple_key(v);
+    std::stable_sort(c->vorder.begin(), c->vorder.end(), [&](uint32_t x, uint32_t y) { return keys[x] < keys[y]; });
+  }
+  for (uint32_t i = 0; i < V; ++i) c->vinv[c->vorder[i]] = i;
+  std::vector<float> vt_s;
+  std::vector<uint16_t> jt_s;
+  std::vector<uint8_t> wt_s;
+  const float* VT = c->h_vtx8.data();
+  const uint16_t* JT = c->h_joints.data();
+  const uint8_t* WT = c->h_weights.data();
+  if (c->flags & RZ_FLAG_REORDER_VERTICES) {
+    vt_s.resize((size_t)V * 8); jt_s.resize((size_t)V * 4); wt_s.resize((size_t)V * 4);
+    for (uint32_t i = 0; i < V; ++i) {
+      const uint32_t v = c->vorder[i];
+      memcpy(&vt_s[(size_t)i * 8], &c->h_vtx8[(size_t)v * 8], 32);
+      memcpy(&jt_s[(size_t)i * 4], &c->h_joints[(size_t)v * 4], 8);
+      memcpy(&wt_s[(size_t)i * 4], &c->h_weights[(size_t)v * 4], 4);
+    }
+    VT = vt_s.data(); JT = jt_s.data(); WT = wt_s.data();
+  }
+
   // vertex-major morph CSR (caller vertex order)
   std::vector<uint32_t> mcount(V, 0), mstart(V + 1, 0);
   const uint32_t nnz = c->M ? c->h_moff[c->M] : 0;
-  for (uint32_t e = 0; e < nnz; ++e) mcount[c->h_mvert[e]]++;
+  for (uint32_t e = 0; e < nnz; ++e) mcount[c->vinv[c->h_mvert[e]]]++;
   for (uint32_t v = 0; v < V; ++v) mstart[v + 1] = mstart[v] + mcount[v];
   std::vector<float4> ments(std::max<uint32_t>(nnz, 1));
   {
     std::vector<uint32_t> fill(mstart.begin(), mstart.end() - 1);
     for (uint32_t m = 0; m < c->M; ++m)
       for (uint32_t e = c->h_moff[m]; e < c->h_moff[m + 1]; ++e) {
-        const uint32_t v = c->h_mvert[e];
+        const uint32_t v = c->vinv[c->h_mvert[e]];
         float4 r;
         r.x = c->h_mdelta[(size_t)e * 3]; r.y = c->h_mdelta[(size_t)e * 3 + 1]; r.z = c->h_mdelta[(size_t)e * 3 + 2];
         memcpy(&r.w, &m, 4);
@@ -241,8 +290,8 @@ int rebuild_tables(rz_ctx_impl* c) {
   c->sdefActive = 0;
   if (c->flags & RZ_FLAG_SDEF) {
     for (size_t n = 0; n < c->h_sdefVert.size(); ++n) {
-      const uint32_t v = c->h_sdefVert[n];
-      const uint8_t* w = &c->h_weights[(size_t)v * 4];
+      const uint32_t v = c->vinv[c->h_sdefVert[n]];
+      const uint8_t* w = &WT[(size_t)v * 4];
       if (w[2] != 0 || w[3] != 0) continue;   // not a two-influence vertex: stays linear
       const float* s = &c->h_sdefVec[n * 9];
       // weights exactly as the kernel derives them
@@ -272,7 +321,7 @@ int rebuild_tables(rz_ctx_impl* c) {
   c->procToVertex.assign(Vp, ~0u);
 
   auto ninf_of = [&](uint32_t v) -> uint32_t {
-    const uint8_t* w = &c->h_weights[(size_t)v * 4];
+    const uint8_t* w = &WT[(size_t)v * 4];
     if ((uint32_t)w[0] + w[1] + w[2] + w[3] == 0) return 1;   // shader rule: sum <= 1e-4 -> (1,0,0,0)
     uint32_t n = 1;
     for (uint32_t k = 0; k < 4; ++k) if (w[k]) n = k + 1;
@@ -284,7 +333,7 @@ int rebuild_tables(rz_ctx_impl* c) {
   // pipe serves per wavefront) are homogeneous: same influence count => whole quarters skip the zero-weight gathers,
   // same bones => same address => no bank conflict.
   auto key2_of = [&](uint32_t v) -> uint64_t {
-    const uint16_t* j = &c->h_joints[(size_t)v * 4];
+    const uint16_t* j = &JT[(size_t)v * 4];
     const uint32_t n = ninf_of(v);
     uint64_t k = (uint64_t)(sdefOf[v] >= 0 ? 1 : 0) << 63 | (uint64_t)n << 60;
     k |= (uint64_t)(j[0] & 0x7FFF) << 45;
@@ -296,17 +345,23 @@ int rebuild_tables(rz_ctx_impl* c) {
   std::vector<uint16_t> gatherJ;   // filled below, before the first emit_* call
   const bool packMeta = B <= 4096;  // palette rows fit 12 bits: meta rides in the joint words (deform_kernel.cuh)
   c->packedMeta = packMeta;
-  auto emit_vertex = [&](uint32_t p, uint32_t v, uint32_t slot) {
-    const float* x = &c->h_vtx8[(size_t)v * 8];
-    const uint8_t* w8 = &c->h_weights[(size_t)v * 4];
-    uint32_t wb;
-    memcpy(&wb, w8, 4);
-    uint32_t meta = slot | (ninf_of(v) << kMetaNinfShift) | kMetaValid;
-    if (mcount[v]) meta |= kMetaMorph;
-    if (sdefOf[v] >= 0) { meta |= kMetaSdef; sdefIdx[p] = (uint32_t)sdefOf[v]; }
-    // weights exactly as the reference's vertex shader derives them (engine.ts:255-258): unorm8 -> f32,
-    // sum, renormalise when the sum exceeds 1e-4 else (1,0,0,0).  IEEE f32 on the host == on the device.
-    float w[4] = {(float)w8[0] / 255.0f, (float)w8[1] / 255.0f, (float)w8[2] / 255.0f, (float)w8[3] / 255.0f};
+
+  // Per processing index p (= warp*32 + lane): the vertex it evaluates, and the influence table the DEVICE sees --
+  // devJ[p][s] bone gathered for influence slot s (kBorrow: weight is zero, any row will do, chosen further down),
+  // devW[p][s] its weight, devN[p] = highest slot with a non-zero weight + 1.
+  constexpr uint16_t kBorrow = 0xFFFFu;
+  std::vector<uint32_t> procVertex(Vp, ~0u), procSlot(Vp, 0);
+  std::vector<uint16_t> devJ((size_t)Vp * 4, kBorrow);
+  std::vector<float> devW((size_t)Vp * 4, 0.f);
+  std::vector<uint8_t> devN(Vp, 1);
+  c->procSlotMap.assign((size_t)Vp * 4, 0);
+  for (uint32_t p = 0; p < Vp; ++p) for (uint32_t k = 0; k < 4; ++k) c->procSlotMap[(size_t)p * 4 + k] = (uint8_t)k;
+
+  // weights exactly as the reference's vertex shader derives them (engine.ts:255-258): unorm8 -> f32, sum in slot order,
+  // renormalise when the sum exceeds 1e-4 else (1,0,0,0).  IEEE f32 on the host == on the device.
+  auto shader_weights = [&](uint32_t v, float w[4]) {
+    const uint8_t* w8 = &WT[(size_t)v * 4];
+    for (int k = 0; k < 4; ++k) w[k] = (float)w8[k] / 255.0f;
     const float wsum = w[0] + w[1] + w[2] + w[3];
     if (wsum > 0.0001f) {
       const float inv = 1.0f / wsum;
@@ -314,56 +369,237 @@ int rebuild_tables(rz_ctx_impl* c) {
     } else {
       w[0] = 1.f; w[1] = w[2] = w[3] = 0.f;
     }
-    const uint16_t* j = &gatherJ[(size_t)p * 4];
-    const uint32_t q0 = c->bonePos[j[0]], q1 = c->bonePos[j[1]], q2 = c->bonePos[j[2]], q3 = c->bonePos[j[3]];   // palette rows
-    uint32_t j01 = q0 | (q1 << 16), j23 = q2 | (q3 << 16);
-    if (packMeta) {
-      const uint32_t m11 = (slot & 31u) | (ninf_of(v) << 5) | 0x100u | (mcount[v] ? 0x200u : 0u) | (sdefOf[v] >= 0 ? 0x400u : 0u);
-      j01 = q0 | (q1 << 12) | ((m11 & 0xFFu) << 24);
-      j23 = q2 | (q3 << 12) | ((m11 >> 8) << 24);
-    }
-    float j01f, j23f;
-    memcpy(&j01f, &j01, 4);
-    memcpy(&j23f, &j23, 4);
-    rec0[p] = make_float4(x[0], x[1], x[2], w[0]);
-    rec1[p] = make_float4(x[3], x[4], x[5], w[1]);
-    rec2[p] = make_float4(w[2], w[3], j01f, j23f);
-    metaArr[p] = meta;
-    wbits[p] = wb;
-    mrange[p] = make_uint2(mstart[v], mcount[v]);
-    c->procToVertex[p] = v;
-  };
-  auto emit_padding = [&](uint32_t p, uint32_t slot) {
-    // a harmless rigid vertex on bone 0, parked on an unused slot of this warp's lane column
-    rec0[p] = make_float4(0.f, 0.f, 0.f, 1.f);
-    rec1[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const uint16_t* j = &gatherJ[(size_t)p * 4];
-    uint32_t j01 = c->bonePos[j[0]] | (c->bonePos[j[1]] << 16), j23 = c->bonePos[j[2]] | (c->bonePos[j[3]] << 16);
-    if (packMeta) {
-      const uint32_t m11 = (slot & 31u) | (1u << 5);
-      j01 = c->bonePos[j[0]] | (c->bonePos[j[1]] << 12) | ((m11 & 0xFFu) << 24);
-      j23 = c->bonePos[j[2]] | (c->bonePos[j[3]] << 12) | ((m11 >> 8) << 24);
-    }
-    float j01f, j23f;
-    memcpy(&j01f, &j01, 4);
-    memcpy(&j23f, &j23, 4);
-    rec2[p] = make_float4(0.f, 0.f, j01f, j23f);
-    metaArr[p] = slot | (1u << kMetaNinfShift);
-    mrange[p] = make_uint2(0u, 0u);
   };
 
-  // Processing order: every warp keeps its 32 CONSECUTIVE output vertices (its results leave as one contiguous
+  // ---- (A) caller's slot order: every warp keeps its 32 CONSECUTIVE output vertices (its results leave as one contiguous
   // 384-byte TMA bulk store per plane), only the lane order inside the warp is chosen: by influence count, then bones.
-  std::vector<uint32_t> procVertex(Vp, ~0u), procSlot(Vp, 0);
-  for (uint32_t w0 = 0; w0 < Vp; w0 += 32) {
+  auto fill_plain = [&](uint32_t w0) {
     uint32_t vs[32];
     uint32_t n = 0;
     for (uint32_t l = 0; l < 32; ++l) if (w0 + l < V) vs[n++] = w0 + l;
     if (classSort) std::stable_sort(vs, vs + n, [&](uint32_t a, uint32_t b2) { return key2_of(a) < key2_of(b2); });
-    uint32_t lane = 0;
-    for (; lane < n; ++lane) { procVertex[w0 + lane] = vs[lane]; procSlot[w0 + lane] = vs[lane] - w0; }
-    for (uint32_t l = n; l < 32; ++l, ++lane) { procVertex[w0 + lane] = ~0u; procSlot[w0 + lane] = l; }
+    for (uint32_t lane = 0; lane < 32; ++lane) {
+      const uint32_t p = w0 + lane;
+      for (uint32_t k = 0; k < 4; ++k) { devJ[(size_t)p * 4 + k] = kBorrow; devW[(size_t)p * 4 + k] = 0.f; c->procSlotMap[(size_t)p * 4 + k] = (uint8_t)k; }
+      if (lane < n) {
+        const uint32_t v = vs[lane];
+        procVertex[p] = v; procSlot[p] = v - w0;
+        float w[4];
+        shader_weights(v, w);
+        const uint32_t ni = ninf_of(v);
+        for (uint32_t k = 0; k < ni; ++k) { devJ[(size_t)p * 4 + k] = JT[(size_t)v * 4 + k]; devW[(size_t)p * 4 + k] = w[k]; }
+        devN[p] = (uint8_t)ni;
+      } else {
+        procVertex[p] = ~0u; procSlot[p] = lane;               // padding: unused output slots n..31 in lane order
+        devW[(size_t)p * 4] = 1.f; devN[p] = 1;
+      }
+    }
+  };
+
+  // ---- (B) pair packing.  A warp-wide gather of one 48-byte palette row per lane costs 6.75 shared-memory cycles when
+  // every ALIGNED LANE PAIR (2l, 2l+1) reads the same row and 12 otherwise -- one mixed pair is enough to lose it
+  // (profiles/r01_ubench_lds_row_fetch.txt), and these gathers are what bounds the kernel.  Three load-time freedoms buy
+  // the fast case without touching the arithmetic of any vertex: which lane evaluates which of the warp's 32 vertices,
+  // in which influence SLOT a vertex keeps each of its (bone, weight) pairs (the blend is a sum), and which row a
+  // zero-weight slot gathers.  For two vertices with bone sets A and B and the warp's slot count N = max |set|, m(A,B) is
+  // the least number of slots in which the two lanes must read different rows (0 iff |A u B| <= N: the lanes then share
+  // one slot list, each with weight 0 where the bone is not its own).  The warp needs a perfect matching of its 32 lanes
+  // minimising the largest m (bottleneck matching: thresholds 0..N, Edmonds' blossom algorithm for each); the mixed slots
+  // of all pairs are then parked in the LAST m* slots, so N - m* gather instructions of the warp run at the fast rate.
+  struct PairMatcher {
+    int n = 32;
+    bool adj[32][32];
+    int match[32], par[32], base[32], q[64];
+    bool used[32], blossom[32];
+    int lca(int a, int b2) {
+      bool seen[32] = {false};
+      for (;;) { a = base[a]; seen[a] = true; if (match[a] < 0) break; a = par[match[a]]; }
+      for (;;) { b2 = base[b2]; if (seen[b2]) return b2; b2 = par[match[b2]]; }
+    }
+    void mark_path(int v, int bb, int child) {
+      while (base[v] != bb) {
+        blossom[base[v]] = blossom[base[match[v]]] = true;
+        par[v] = child; child = match[v]; v = par[match[v]];
+      }
+    }
+    int find_path(int root) {
+      for (int i = 0; i < n; ++i) { used[i] = false; par[i] = -1; base[i] = i; }
+      int qh = 0, qt = 0;
+      used[root] = true; q[qt++] = root;
+      while (qh < qt) {
+        const int v = q[qh++];
+        for (int to = 0; to < n; ++to) {
+          if (!adj[v][to] || base[v] == base[to] || match[v] == to) continue;
+          if (to == root || (match[to] >= 0 && par[match[to]] >= 0)) {
+            const int cb = lca(v, to);
+            for (int i = 0; i < n; ++i) blossom[i] = false;
+            mark_path(v, cb, to); mark_path(to, cb, v);
+            for (int i = 0; i < n; ++i)
+              if (blossom[base[i]]) { base[i] = cb; if (!used[i]) { used[i] = true; q[qt++] = i; } }
+          } else if (par[to] < 0) {
+            par[to] = v;
+            if (match[to] < 0) return to;
+            used[match[to]] = true; q[qt++] = match[to];
+          }
+        }
+      }
+      return -1;
+    }
+    // maximum matching; returns the number of matched pairs
+    int solve() {
+      for (int i = 0; i < n; ++i) match[i] = -1;
+      for (int i = 0; i < n; ++i)                       // greedy start: nearest unmatched neighbour in key order
+        if (match[i] < 0) for (int j = i + 1; j < n; ++j) if (match[j] < 0 && adj[i][j]) { match[i] = j; match[j] = i; break; }
+      for (int i = 0; i < n; ++i)
+        if (match[i] < 0) {
+          int v = find_path(i);
+          while (v >= 0) { const int pv = par[v], ppv = match[pv]; match[v] = pv; match[pv] = v; v = ppv; }
+        }
+      int m = 0;
+      for (int i = 0; i < n; ++i) if (match[i] >= 0) ++m;
+      return m / 2;
+    }
+  };
+  struct LaneSet { uint32_t v; int n; uint16_t b[4]; float w[4]; uint8_t src[4]; uint64_t key; };
+  uint64_t packStat[5] = {0, 0, 0, 0, 0};   // warp-slots: total, fast
+  auto fill_packed = [&](uint32_t w0) -> bool {
+    LaneSet ls[32];
+    int N = 1;
+    for (uint32_t l = 0; l < 32; ++l) {
+      LaneSet& e = ls[l];
+      e.v = (w0 + l < V) ? w0 + l : ~0u;
+      e.n = 0; e.key = 0;
+      if (e.v == ~0u) continue;
+      if (sdefOf[e.v] >= 0) return false;                              // SDEF reads slots 0/1 by position
+      float w[4];
+      shader_weights(e.v, w);
+      for (uint32_t k = 0; k < 4; ++k)
+        if (w[k] != 0.f) {
+          const uint16_t bone = JT[(size_t)e.v * 4 + k];
+          for (int t = 0; t < e.n; ++t) if (e.b[t] == bone) return false;   // a bone listed twice: keep the caller's slots
+          e.b[e.n] = bone; e.w[e.n] = w[k]; e.src[e.n] = (uint8_t)k; ++e.n;
+        }
+      if (e.n == 0) return false;
+      N = std::max(N, e.n);
+      uint16_t sb[4];
+      for (int t = 0; t < e.n; ++t) sb[t] = e.b[t];
+      std::sort(sb, sb + e.n);
+      for (int t = 0; t < e.n; ++t) e.key |= (uint64_t)(sb[t] & 0x7FFF) << (45 - 15 * t);
+    }
+    // lanes in key order (similar sets become neighbours: greedy start of the matcher, homogeneous quarter-warps)
+    int ord[32];
+    for (int i = 0; i < 32; ++i) ord[i] = i;
+    std::stable_sort(ord, ord + 32, [&](int x, int y) {
+      const bool px = ls[x].v == ~0u, py = ls[y].v == ~0u;
+      if (px != py) return py;
+      return ls[x].key < ls[y].key;
+    });
+    auto common = [&](const LaneSet& A, const LaneSet& Bv) { int cc = 0; for (int i = 0; i < A.n; ++i) for (int j = 0; j < Bv.n; ++j) if (A.b[i] == Bv.b[j]) ++cc; return cc; };
+    int mneed[32][32];
+    for (int x = 0; x < 32; ++x)
+      for (int y = x + 1; y < 32; ++y) {
+        const LaneSet &A = ls[ord[x]], &Bv = ls[ord[y]];
+        const int cc = common(A, Bv);
+        int m = 0;
+        for (; m < N; ++m) {
+          const int a = std::max(A.n - m, 0), b2 = std::max(Bv.n - m, 0);
+          const int Lmin = cc >= std::max(a, b2) ? std::max(a, b2) : cc + std::max(a - cc, 0) + std::max(b2 - cc, 0);
+          if (Lmin <= N - m) break;
+        }
+        mneed[x][y] = mneed[y][x] = m;
+      }
+    PairMatcher pm;
+    int mstar = 0;
+    for (; mstar <= N; ++mstar) {
+      for (int x = 0; x < 32; ++x) for (int y = 0; y < 32; ++y) pm.adj[x][y] = x != y && mneed[x][y] <= mstar;
+      if (pm.solve() == 16) break;
+    }
+    if (mstar > N) return false;   // cannot happen (threshold N admits every pair)
+    packStat[0] += (uint64_t)N; packStat[1] += (uint64_t)(N - mstar);
+    const int cap = N - mstar;
+    // bones that many lanes of the warp share go to the low slots everywhere (fewer distinct rows per gather instruction)
+    auto freq = [&](uint16_t bone) { int f = 0; for (int l = 0; l < 32; ++l) for (int t = 0; t < ls[l].n; ++t) if (ls[l].b[t] == bone) ++f; return f; };
+    struct PairOut { int la, lb; uint16_t L[4]; int nL; uint64_t key; };
+    PairOut po[16];
+    int np = 0;
+    for (int x = 0; x < 32; ++x) {
+      const int y = pm.match[x];
+      if (y < x) continue;
+      PairOut& o = po[np++];
+      o.la = ord[x]; o.lb = ord[y]; o.nL = 0; o.key = 0;
+      const LaneSet &A = ls[o.la], &Bv = ls[o.lb];
+      auto inL = [&](uint16_t bone) { for (int t = 0; t < o.nL; ++t) if (o.L[t] == bone) return true; return false; };
+      auto has = [&](const LaneSet& S, uint16_t bone) { for (int t = 0; t < S.n; ++t) if (S.b[t] == bone) return true; return false; };
+      // shared list: common bones first (each one serves both lanes), then whatever either lane cannot park in its m* own slots,
+      // then -- capacity permitting -- the rest (a shared slot is never worse than a private one)
+      for (int t = 0; t < A.n && o.nL < cap; ++t) if (has(Bv, A.b[t])) o.L[o.nL++] = A.b[t];
+      auto outside = [&](const LaneSet& S) { int r = 0; for (int t = 0; t < S.n; ++t) if (!inL(S.b[t])) ++r; return r; };
+      for (int t = 0; t < A.n && outside(A) > mstar && o.nL < cap; ++t) if (!inL(A.b[t])) o.L[o.nL++] = A.b[t];
+      for (int t = 0; t < Bv.n && outside(Bv) > mstar && o.nL < cap; ++t) if (!inL(Bv.b[t])) o.L[o.nL++] = Bv.b[t];
+      if (outside(A) > mstar || outside(Bv) > mstar) return false;   // cannot happen (mneed <= m*)
+      for (int t = 0; t < A.n && o.nL < cap; ++t) if (!inL(A.b[t])) o.L[o.nL++] = A.b[t];
+      for (int t = 0; t < Bv.n && o.nL < cap; ++t) if (!inL(Bv.b[t])) o.L[o.nL++] = Bv.b[t];
+      std::stable_sort(o.L, o.L + o.nL, [&](uint16_t p1, uint16_t p2) { const int f1 = freq(p1), f2 = freq(p2); return f1 != f2 ? f1 > f2 : p1 < p2; });
+      for (int t = 0; t < o.nL; ++t) o.key |= (uint64_t)(o.L[t] & 0x7FFF) << (45 - 15 * t);
+      if (A.v == ~0u && Bv.v == ~0u) o.key = ~0ull;
+    }
+    int pord[16];
+    for (int i = 0; i < 16; ++i) pord[i] = i;
+    std::stable_sort(pord, pord + 16, [&](int x, int y) { return po[x].key < po[y].key; });
+    uint32_t padSlot = 0;
+    bool slotUsed[32] = {false};
+    for (uint32_t l = 0; l < 32; ++l) if (w0 + l < V) slotUsed[l] = true;
+    for (int pi = 0; pi < 16; ++pi) {
+      const PairOut& o = po[pord[pi]];
+      const int lanes[2] = {o.la, o.lb};
+      for (int h = 0; h < 2; ++h) {
+        const LaneSet& S = ls[lanes[h]];
+        const LaneSet& T = ls[lanes[h ^ 1]];
+        const uint32_t p = w0 + (uint32_t)pi * 2 + (uint32_t)h;
+        uint16_t* dj = &devJ[(size_t)p * 4];
+        float* dw = &devW[(size_t)p * 4];
+        uint8_t* sm = &c->procSlotMap[(size_t)p * 4];
+        for (int k = 0; k < 4; ++k) { dj[k] = kBorrow; dw[k] = 0.f; sm[k] = (uint8_t)k; }
+        if (S.v == ~0u) {
+          while (padSlot < 32 && slotUsed[padSlot]) ++padSlot;
+          procVertex[p] = ~0u; procSlot[p] = padSlot; slotUsed[padSlot] = true;
+          // a rigid unit-weight dummy on whatever row its partner reads in slot 0
+          for (int t = 0; t < o.nL; ++t) dj[t] = o.L[t];
+          dw[0] = 1.f; devN[p] = 1;
+          continue;
+        }
+        procVertex[p] = S.v; procSlot[p] = S.v - w0;
+        bool placed[4] = {false, false, false, false};
+        int hi = 0;
+        for (int t = 0; t < o.nL; ++t) {                   // shared slots: the pair's common row, own weight or zero
+          dj[t] = o.L[t];
+          for (int u = 0; u < S.n; ++u) if (S.b[u] == o.L[t]) { dw[t] = S.w[u]; placed[u] = true; sm[S.src[u]] = (uint8_t)t; hi = t + 1; }
+        }
+        int fs = cap;                                       // private slots: the lane's remaining bones
+        for (int u = 0; u < S.n; ++u)
+          if (!placed[u]) { dj[fs] = S.b[u]; dw[fs] = S.w[u]; sm[S.src[u]] = (uint8_t)fs; hi = fs + 1; ++fs; }
+        // leftover private slots mirror the partner's bone there (weight 0): one more shared row for free
+        (void)T;
+        devN[p] = (uint8_t)std::max(hi, 1);
+      }
+    }
+    // private slots still unassigned: take the partner's row when it has one
+    for (uint32_t pi = 0; pi < 16; ++pi)
+      for (int k = 0; k < 4; ++k) {
+        uint16_t& ja = devJ[(size_t)(w0 + 2 * pi) * 4 + k];
+        uint16_t& jb = devJ[(size_t)(w0 + 2 * pi + 1) * 4 + k];
+        if (ja == kBorrow && jb != kBorrow) ja = jb;
+        else if (jb == kBorrow && ja != kBorrow) jb = ja;
+      }
+    // slot-map entries of zero-weight caller slots: point at a device slot that is not one of the vertex' own
+    return true;
+  };
+
+  for (uint32_t w0 = 0; w0 < Vp; w0 += 32) {
+    if (!(c->permMode >= 2 && fill_packed(w0))) fill_plain(w0);
   }
+  c->packFastSlots = packStat[1];
+  c->packTotalSlots = packStat[0];
 
   // ---- bank-aware palette permutation -------------------------------------------------------------------------
   // A warp-wide LDS.128 costs max(2, distinct chunks / 4, 2 x chunks per 16-byte bank group) cycles on sm_100
@@ -379,9 +615,8 @@ int rebuild_tables(rz_ctx_impl* c) {
       for (uint32_t k = 0; k < 4; ++k) {
         seen.clear();
         for (uint32_t l = 0; l < 32; ++l) {
-          const uint32_t v = procVertex[w0 + l];
-          if (v == ~0u || ninf_of(v) <= k) continue;
-          const uint32_t b = c->h_joints[(size_t)v * 4 + k];
+          const uint32_t b = devJ[(size_t)(w0 + l) * 4 + k];
+          if (b == kBorrow) continue;
           if (std::find(seen.begin(), seen.end(), b) == seen.end()) seen.push_back(b);
         }
         for (size_t a = 0; a < seen.size(); ++a)
@@ -454,32 +689,64 @@ int rebuild_tables(rz_ctx_impl* c) {
   c->boneAt.assign(B, 0);
   for (uint32_t b = 0; b < B; ++b) c->boneAt[c->bonePos[b]] = b;
 
-  // joints the kernel gathers: a lane whose weight for influence k is zero borrows the joint of an ACTIVE lane of its
-  // own warp (same quarter-warp if possible), so the unconditional gather adds no shared-memory wavefront.
+  // joints the kernel gathers: a slot still marked kBorrow (zero weight, no partner row) takes the row of an ACTIVE lane
+  // of its own warp (same quarter-warp if possible; both lanes of a pair then pick the same one), so the unconditional
+  // gather adds no shared-memory wavefront.
   gatherJ.assign((size_t)Vp * 4, 0);
   for (uint32_t w0 = 0; w0 < Vp; w0 += 32) {
     for (uint32_t k = 0; k < 4; ++k) {
       int firstWarp = -1, firstQ[4] = {-1, -1, -1, -1};
       for (uint32_t l = 0; l < 32; ++l) {
-        const uint32_t v = procVertex[w0 + l];
-        if (v == ~0u || ninf_of(v) <= k) continue;
+        if (devJ[(size_t)(w0 + l) * 4 + k] == kBorrow) continue;
         if (firstWarp < 0) firstWarp = (int)l;
         if (firstQ[l / 8] < 0) firstQ[l / 8] = (int)l;
       }
       for (uint32_t l = 0; l < 32; ++l) {
-        const uint32_t v = procVertex[w0 + l];
-        const bool active = v != ~0u && ninf_of(v) > k;
-        int src = active ? (int)l : (firstQ[l / 8] >= 0 ? firstQ[l / 8] : firstWarp);
-        uint16_t j = 0;
-        if (src >= 0) j = c->h_joints[(size_t)procVertex[w0 + src] * 4 + k];
-        else if (v != ~0u) j = c->h_joints[(size_t)v * 4 + k];
+        uint16_t j = devJ[(size_t)(w0 + l) * 4 + k];
+        if (j == kBorrow) {
+          const int src = firstQ[l / 8] >= 0 ? firstQ[l / 8] : firstWarp;
+          if (src >= 0) j = devJ[(size_t)(w0 + src) * 4 + k];
+          else j = procVertex[w0 + l] != ~0u ? JT[(size_t)procVertex[w0 + l] * 4 + k] : 0;
+          if (j >= B) j = 0;
+        }
         gatherJ[(size_t)(w0 + l) * 4 + k] = j;
       }
     }
   }
+
   for (uint32_t p = 0; p < Vp; ++p) {
-    if (procVertex[p] != ~0u) emit_vertex(p, procVertex[p], procSlot[p]);
-    else emit_padding(p, procSlot[p]);
+    const uint32_t v = procVertex[p], slot = procSlot[p], ni = devN[p];
+    const uint16_t* j = &gatherJ[(size_t)p * 4];
+    const float* w = &devW[(size_t)p * 4];
+    const uint32_t q0 = c->bonePos[j[0]], q1 = c->bonePos[j[1]], q2 = c->bonePos[j[2]], q3 = c->bonePos[j[3]];   // palette rows
+    const bool real = v != ~0u;
+    const bool hasMorph = real && mcount[v] != 0, hasSdef = real && sdefOf[v] >= 0;
+    uint32_t meta = slot | (ni << kMetaNinfShift) | (real ? kMetaValid : 0u) | (hasMorph ? kMetaMorph : 0u) | (hasSdef ? kMetaSdef : 0u);
+    uint32_t j01 = q0 | (q1 << 16), j23 = q2 | (q3 << 16);
+    if (packMeta) {
+      const uint32_t m11 = (slot & 31u) | (ni << 5) | (real ? 0x100u : 0u) | (hasMorph ? 0x200u : 0u) | (hasSdef ? 0x400u : 0u);
+      j01 = q0 | (q1 << 12) | ((m11 & 0xFFu) << 24);
+      j23 = q2 | (q3 << 12) | ((m11 >> 8) << 24);
+    }
+    float j01f, j23f;
+    memcpy(&j01f, &j01, 4);
+    memcpy(&j23f, &j23, 4);
+    if (real) {
+      const float* x = &VT[(size_t)v * 8];
+      rec0[p] = make_float4(x[0], x[1], x[2], w[0]);
+      rec1[p] = make_float4(x[3], x[4], x[5], w[1]);
+      memcpy(&wbits[p], &WT[(size_t)v * 4], 4);
+      mrange[p] = make_uint2(mstart[v], mcount[v]);
+      if (hasSdef) sdefIdx[p] = (uint32_t)sdefOf[v];
+      c->procToVertex[p] = v;
+    } else {
+      // padding: a harmless rigid vertex parked on an unused output slot of this warp
+      rec0[p] = make_float4(0.f, 0.f, 0.f, w[0]);
+      rec1[p] = make_float4(0.f, 0.f, 0.f, w[1]);
+      mrange[p] = make_uint2(0u, 0u);
+    }
+    rec2[p] = make_float4(w[2], w[3], j01f, j23f);
+    metaArr[p] = meta;
   }
 
   int rc;
@@ -1202,9 +1469,28 @@ int32_t rz_read_instance(rz_ctx* c, uint32_t inst, float* pos3, float* nrm3) {
   if (nrm3 && (c->flags & RZ_FLAG_NO_NORMALS)) return fail(c, RZ_ERR_STATE, "rz_read_instance: context was created with RZ_FLAG_NO_NORMALS");
   CU_TRY(c, cudaSetDevice(c->device));
   const float* src = reinterpret_cast<const float*>(c->d_out.p) + (size_t)inst * c->instStrideF;
+  if (c->flags & RZ_FLAG_REORDER_VERTICES) {
+    // device planes are in the library's stored order: hand them back in the caller's vertex order
+    std::vector<float> tmp((size_t)c->V * 3);
+    for (int plane = 0; plane < 2; ++plane) {
+      float* dst = plane ? nrm3 : pos3;
+      if (!dst) continue;
+      CU_TRY(c, cudaMemcpyAsync(tmp.data(), src + (plane ? c->nrmOffF : 0), (size_t)c->V * 12, cudaMemcpyDeviceToHost, c->stream));
+      CU_TRY(c, cudaStreamSynchronize(c->stream));
+      for (uint32_t i = 0; i < c->V; ++i) memcpy(dst + (size_t)c->vorder[i] * 3, &tmp[(size_t)i * 3], 12);
+    }
+    return RZ_OK;
+  }
   if (pos3) CU_TRY(c, cudaMemcpyAsync(pos3, src, (size_t)c->V * 12, cudaMemcpyDeviceToHost, c->stream));
   if (nrm3) CU_TRY(c, cudaMemcpyAsync(nrm3, src + c->nrmOffF, (size_t)c->V * 12, cudaMemcpyDeviceToHost, c->stream));
   CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return RZ_OK;
+}
+
+int32_t rz_get_vertex_order(rz_ctx* c, uint32_t* order) {
+  if (!c || !order) return fail(c, RZ_ERR_INVALID_ARG, "rz_get_vertex_order: null argument");
+  if (c->V == 0) return fail(c, RZ_ERR_STATE, "rz_get_vertex_order before rz_load_mesh");
+  memcpy(order, c->vorder.data(), (size_t)c->V * 4);
   return RZ_OK;
 }
 
@@ -1235,8 +1521,9 @@ int32_t rz_read_skinning(rz_ctx* c, uint16_t* joints, uint8_t* weights) {
   CU_TRY(c, cudaMemcpyAsync(wb.data(), c->d_wbits.p, (size_t)c->Vp * 4, cudaMemcpyDeviceToHost, c->stream));
   CU_TRY(c, cudaStreamSynchronize(c->stream));
   for (uint32_t p = 0; p < c->Vp; ++p) {
-    const uint32_t v = c->procToVertex[p];
-    if (v == ~0u) continue;
+    const uint32_t sv = c->procToVertex[p];
+    if (sv == ~0u) continue;
+    const uint32_t v = c->vorder[sv];                     // stored position -> caller vertex id
     if (joints) {
       uint32_t j01, j23;
       memcpy(&j01, &rec2[p].z, 4);
@@ -1250,10 +1537,17 @@ int32_t rz_read_skinning(rz_ctx* c, uint16_t* joints, uint8_t* weights) {
                         (uint16_t)c->boneAt[j23 >> 16]};
       // slots beyond the vertex' last non-zero weight hold a borrowed joint on the device (gather coalescing, see
       // rebuild_tables); they never influence the result, report the caller's value there
+      // zero-weight slots hold a borrowed joint on the device and the packer may have moved an influence to another slot
+      // (rebuild_tables); undo both: active influences come from the device table, the rest is the caller's value
       const uint8_t* w8 = reinterpret_cast<const uint8_t*>(&wb[p]);
+      const bool zeroSum = (uint32_t)w8[0] + w8[1] + w8[2] + w8[3] == 0;
+      const bool packed = c->permMode >= 2;
       uint32_t n = 1;
-      if ((uint32_t)w8[0] + w8[1] + w8[2] + w8[3] != 0) for (uint32_t k = 0; k < 4; ++k) if (w8[k]) n = k + 1;
-      for (uint32_t k = 0; k < 4; ++k) joints[(size_t)v * 4 + k] = k < n ? dj[k] : c->h_joints[(size_t)v * 4 + k];
+      if (!zeroSum) for (uint32_t k = 0; k < 4; ++k) if (w8[k]) n = k + 1;
+      for (uint32_t k = 0; k < 4; ++k) {
+        const bool fromDevice = packed ? (w8[k] != 0 || (zeroSum && k == 0)) && k < n : k < n;
+        joints[(size_t)v * 4 + k] = fromDevice ? dj[c->procSlotMap[(size_t)p * 4 + k]] : c->h_joints[(size_t)v * 4 + k];
+      }
     }
     if (weights) memcpy(&weights[(size_t)v * 4], &wb[p], 4);
   }
@@ -1311,6 +1605,7 @@ int32_t rz_get_stats(rz_ctx* c, rz_stats* out) {
   out->morphCount = c->M; out->morphNnz = c->morphNnz; out->sdefCount = c->sdefActive; out->activeMorphs = c->Mact;
   out->instancesPerGroup = c->usedI; out->storeMode = c->usedStore; out->ctas = c->usedCtas; out->threads = c->usedThreads;
   out->smemBytes = c->usedSmem;
+  out->fastGatherPermille = c->packTotalSlots ? (uint32_t)(c->packFastSlots * 1000 / c->packTotalSlots) : 0u;
   return RZ_OK;
 }
 

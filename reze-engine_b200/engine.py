@@ -64,7 +64,7 @@ class ManualClock:
 class Engine:
     def __init__(self, canvas=None, options: Optional[dict] = None, *, instances: int = 1, device: int = 0,
                  clock: Optional[Callable[[], float]] = None, sdef: bool = False, bounds: bool = False, stream: int = 0,
-                 gpu_pose: bool = False, crowd: bool = False):
+                 gpu_pose: bool = False, crowd: bool = False, reorder_vertices: bool = False):
         o = options or {}
         # EngineOptions (engine.ts:8-14): kept so existing call sites construct unchanged; they only
         # parameterise passes this repo does not replace.
@@ -76,7 +76,9 @@ class Engine:
         self.instances = int(instances)
         self.device = device
         self.clock = clock or (lambda: time.perf_counter() * 1000.0)
-        self._flags = (capi.RZ_FLAG_SDEF if sdef else 0) | (capi.RZ_FLAG_BOUNDS if bounds else 0)
+        # reorder_vertices: the device planes store vertices grouped by bone tuple (faster blend); draw with deviceIndexBuffer()
+        self._flags = ((capi.RZ_FLAG_SDEF if sdef else 0) | (capi.RZ_FLAG_BOUNDS if bounds else 0)
+                       | (capi.RZ_FLAG_REORDER_VERTICES if reorder_vertices else 0))
         self._stream = stream
         self.gpu_pose = gpu_pose or crowd   # walk the bone hierarchy on the GPU (rz_set_local_rotations) instead of in Model
         # crowd mode: ONE shared skeleton runtime + animation clip, every instance plays it at its own clock offset; tweens /
@@ -400,6 +402,17 @@ class Engine:
         return EngineStats(**self._stats.__dict__)
 
     # ---- results (the reference hands these straight to the rasteriser) ---------------------------
+    def deviceIndexBuffer(self) -> np.ndarray:
+        """The model's triangle list (Model.getIndices(), engine.ts:1762-1771 uploads it as the index buffer) re-expressed
+        against the device planes: identical to getIndices() unless reorder_vertices was requested."""
+        idx = np.asarray(self.currentModel.getIndices(), np.uint32)
+        if not (self._flags & capi.RZ_FLAG_REORDER_VERTICES):
+            return idx
+        order = self.ctx.vertex_order()
+        inv = np.empty_like(order)
+        inv[order] = np.arange(order.size, dtype=np.uint32)
+        return inv[idx]
+
     def readSkinned(self, instance: int = 0):
         """Skinned positions and normals of one instance, [V,3] float32 each."""
         return self.ctx.read_instance(instance)

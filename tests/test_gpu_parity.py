@@ -171,6 +171,37 @@ def test_bounds_and_positions_only(rzlib, orc, wl_small):
             assert gn is None and rel_err(gp, rp) <= TOL
 
 
+def test_reordered_vertex_storage_is_transparent_to_host_readers(rzlib, orc, wl_small):
+    """RZ_FLAG_REORDER_VERTICES: device planes hold vertices sorted by bone tuple; host reads and integer tables stay in
+    caller order, the order table is a permutation, morphs + SDEF keep following their vertices."""
+    import torch
+    wl = wl_small
+    K = 5
+    rng = np.random.default_rng(14)
+    world = synth.make_palettes(wl.bones, K, rng)
+    dense = rng.uniform(0, 1, (K, wl.morphs.count)).astype(np.float32)
+    with capi.DeformContext(max_instances=K, flags=capi.RZ_FLAG_REORDER_VERTICES | capi.RZ_FLAG_SDEF) as ctx:
+        ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
+        ctx.load_morphs(wl.morphs.offsets, wl.morphs.vertexIndex, wl.morphs.delta)
+        ctx.load_sdef(wl.sdef.vertexIndex, wl.sdef.c_r0_r1)
+        order = ctx.vertex_order()
+        assert sorted(order.tolist()) == list(range(wl.V)) and not np.array_equal(order, np.arange(wl.V))
+        j, w = ctx.read_skinning()
+        assert np.array_equal(j, wl.joints.reshape(-1)) and np.array_equal(w, wl.weights.reshape(-1))
+        ctx.set_palettes(world)
+        ctx.set_morph_weights(dense, np.arange(wl.morphs.count), K=K)
+        ctx.deform()
+        check_all(orc, ctx, wl, world, None, K, morphW=dense, sdef=True)
+        # the device plane really is permuted: position i of the plane is caller vertex order[i]
+        base, stride, noff = ctx.output_device_ptr()
+        gp, _ = ctx.read_instance(2)
+        class _Dev:   # view the library-owned plane through the CUDA array interface
+            __cuda_array_interface__ = {"shape": (wl.V, 3), "typestr": "<f4", "data": (base + 2 * stride, False), "version": 2}
+        ctx.sync()
+        plane = torch.as_tensor(_Dev(), device="cuda").cpu().numpy()
+        assert np.array_equal(plane, gp[order])
+
+
 def test_sub_range_deform_and_device_palettes(rzlib, orc, wl_small):
     import torch
     wl = wl_small
@@ -443,6 +474,28 @@ def _bones_from(z):
                           appendParentIndex=None if ap < 0 and not bool(z["appendRotate"][i]) and not bool(z["appendMove"][i]) else ap,
                           appendRatio=None if np.isnan(ar) else ar, appendRotate=bool(z["appendRotate"][i]), appendMove=bool(z["appendMove"][i])))
     return bones
+
+
+def test_engine_reordered_storage_draws_the_same_triangles(rzlib, tmp_path):
+    """Engine(reorder_vertices=True): same host-visible result as the default engine; the remapped index buffer addresses the
+    permuted device planes so every triangle corner lands on the same skinned position."""
+    rng = np.random.default_rng(47)
+    data, *_ = random_pmx(rng, V=900, B=14, n_morph=2, with_sdef=True)
+    (tmp_path / "m.pmx").write_bytes(data)
+    outs = []
+    for reorder in (False, True):
+        eng = Engine(None, None, instances=2, clock=ManualClock(), sdef=True, reorder_vertices=reorder).init()
+        model = eng.loadModel(str(tmp_path / "m.pmx"))
+        eng.rotateBones(["骨1", "骨3"], [Quat.fromEuler(0.2, -0.4, 0.1), Quat.fromEuler(-0.3, 0.1, 0.5)], 0)
+        eng.render()
+        pos, nrm = eng.readSkinned(1)
+        didx = eng.deviceIndexBuffer()
+        order = eng.ctx.vertex_order()
+        assert np.array_equal(order[didx], np.asarray(model.getIndices(), np.uint32))
+        outs.append((pos, nrm, order))
+        eng.dispose()
+    assert np.array_equal(outs[0][2], np.arange(900)) and not np.array_equal(outs[1][2], np.arange(900))
+    assert rel_err(outs[1][0], outs[0][0]) <= 2e-6 and rel_err(outs[1][1], outs[0][1]) <= 2e-6
 
 
 @pytest.mark.parametrize("key", ["serqet", "serqet2"])

@@ -22,11 +22,20 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--shapes", default="1:256:4,2:256:3,2:256:2,3:256:2,4:256:1,1:512:2,2:512:2,2:512:1,3:512:1,4:512:1,2:768:1,3:768:1,2:1024:1,3:1024:1")
     ap.add_argument("--chunks", default="0")
+    ap.add_argument("--pair-coherent", type=int, default=0, help="experiment: make groups of N consecutive vertices share joints (upper bound of lane packing)")
+    ap.add_argument("--flags", type=lambda x: int(x, 0), default=0, help="rz_config.flags, e.g. 0x8 = RZ_FLAG_REORDER_VERTICES")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.jsonl"))
     a = ap.parse_args()
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     V, B, K = a.verts, a.bones, a.instances
     wl = synth.make_workload(V, B)
+    if a.pair_coherent > 1:
+        g = a.pair_coherent
+        n = (V // g) * g
+        J = wl.joints[:n].reshape(-1, g, 4)
+        Wt = wl.weights[:n].reshape(-1, g, 4)
+        J[:, 1:, :] = J[:, :1, :]
+        Wt[:, 1:, :] = Wt[:, :1, :]
     P = min(K, 1024)
     world = synth.make_palettes(wl.bones, P, np.random.default_rng(1))
     dw = torch.from_numpy(world).cuda()
@@ -40,7 +49,7 @@ def main():
         st = 2
         try:
             ctx = capi.DeformContext(max_instances=K, stream=stream.cuda_stream, instances_per_group=I, threads=nt,
-                                     ctas_per_sm=ctas, chunks=chunks)
+                                     ctas_per_sm=ctas, chunks=chunks, flags=a.flags)
             ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
             ctx.set_palettes_device(dw.data_ptr(), P, i2p.data_ptr(), K)
             for _ in range(2):
@@ -56,7 +65,7 @@ def main():
             ctx.close()
             med = float(np.median(ms))
             row = dict(I=s["instancesPerGroup"], threads=s["threads"], store=s["storeMode"], ctas=s["ctas"], smem=s["smemBytes"], req=[I, nt, st, ctas, chunks],
-                       ms=med, ms_min=float(min(ms)), gverts=K * V / med / 1e6, gbs=s["algorithmicBytes"] / med / 1e6)
+                       ms=med, ms_min=float(min(ms)), flags=a.flags, fast_gathers=s["fastGatherPermille"] / 1000, perm=os.environ.get("RZ_PERM", "default"), gverts=K * V / med / 1e6, gbs=s["algorithmicBytes"] / med / 1e6)
         except Exception as e:  # noqa: BLE001
             row = dict(req=[I, nt, st, ctas, chunks], error=str(e))
         rows.append(row)
