@@ -157,6 +157,15 @@ int32_t rz_output_device_ptr(rz_ctx* ctx, void** base, size_t* instanceStride, s
 int32_t rz_read_instance(rz_ctx* ctx, uint32_t inst, float* pos3 /* 3V or NULL */, float* nrm3 /* 3V or NULL */);
 /* order[i] = caller vertex id stored at position i of the device planes (identity unless RZ_FLAG_REORDER_VERTICES) */
 int32_t rz_get_vertex_order(rz_ctx* ctx, uint32_t* order /* V */);
+
+/* ---- diagnostics: the load-time lane / influence-slot plan rz_load_mesh applies (pair packing), computed on
+ * the host for the given tables; needs no context and no device (CPU tests, tooling).  Vp = V rounded up to 256.
+ * mode: 0 natural lane order, 1 lanes sorted, 2 pair packing (the library default).
+ * laneVertex [Vp]: vertex evaluated by warp*32+lane (0xFFFFFFFF = padding); laneJoints / laneWeights [Vp*4]: the
+ * influence table the kernel sees; stats [27]: fast, total gather instructions of packed warps, then the 5x5 histogram
+ * of packed warps by [slot count N][mixed slots m].  Any output may be NULL. */
+int32_t rz_plan_lanes(const uint16_t* joints, const uint8_t* weights, uint32_t V, uint32_t B, uint32_t mode,
+                      uint32_t* laneVertex, uint16_t* laneJoints, float* laneWeights, uint64_t* stats);
 int32_t rz_read_bounds(rz_ctx* ctx, uint32_t firstInstance, uint32_t count, float* minmax6 /* 6*count */);
 /* bit-exact integer view of the tables the kernel consumes, mapped back to caller order (parity tests) */
 int32_t rz_read_skinning(rz_ctx* ctx, uint16_t* joints /* 4V */, uint8_t* weights /* 4V */);

@@ -26,7 +26,7 @@ EXPORTS = [
     "rz_create", "rz_destroy", "rz_abi_version", "rz_load_mesh", "rz_load_morphs", "rz_load_sdef",
     "rz_set_palettes", "rz_set_palettes_device", "rz_palette_staging", "rz_load_skeleton", "rz_set_local_rotations",
     "rz_set_tweens", "rz_set_instance_clocks", "rz_load_animation", "rz_set_morph_weights", "rz_deform",
-    "rz_sync", "rz_output_device_ptr", "rz_read_instance", "rz_get_vertex_order", "rz_read_bounds", "rz_read_skinning",
+    "rz_sync", "rz_output_device_ptr", "rz_read_instance", "rz_get_vertex_order", "rz_plan_lanes", "rz_read_bounds", "rz_read_skinning",
     "rz_read_skin_matrices", "rz_get_stats", "rz_last_error",
 ]
 
@@ -95,6 +95,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.rz_output_device_ptr.argtypes = [vp, P(vp), P(sz), P(sz)]
     lib.rz_read_instance.argtypes = [vp, u32, vp, vp]
     lib.rz_get_vertex_order.argtypes = [vp, vp]
+    lib.rz_plan_lanes.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp, vp]
     lib.rz_read_bounds.argtypes = [vp, u32, u32, vp]
     lib.rz_read_skinning.argtypes = [vp, vp, vp]
     lib.rz_read_skin_matrices.argtypes = [vp, u32, vp]
@@ -116,6 +117,23 @@ def _ptr(a: Optional[np.ndarray]):
 
 def _arr(a, dtype) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=dtype)
+
+
+def plan_lanes(joints, weights, B: int, mode: int = 2, lib: Optional[C.CDLL] = None) -> dict:
+    """rz_plan_lanes: the load-time lane / influence-slot plan for a skinning table (host only, no device needed)."""
+    lib = lib or load_library()
+    j, w = _arr(joints, np.uint16).reshape(-1, 4), _arr(weights, np.uint8).reshape(-1, 4)
+    V = j.shape[0]
+    Vp = (V + 255) // 256 * 256
+    lane_vertex = np.empty(Vp, np.uint32)
+    lane_joints = np.empty((Vp, 4), np.uint16)
+    lane_weights = np.empty((Vp, 4), np.float32)
+    stats = np.zeros(27, np.uint64)
+    st = lib.rz_plan_lanes(_ptr(j), _ptr(w), V, B, mode, _ptr(lane_vertex), _ptr(lane_joints), _ptr(lane_weights), _ptr(stats))
+    if st != 0:
+        raise RzError(st, lib.rz_last_error(None).decode("utf-8", "replace"))
+    return {"laneVertex": lane_vertex, "laneJoints": lane_joints, "laneWeights": lane_weights, "fast": int(stats[0]), "total": int(stats[1]),
+            "hist": stats[2:].reshape(5, 5).astype(np.int64)}
 
 
 class DeformContext:

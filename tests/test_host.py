@@ -169,6 +169,59 @@ def test_capi_exports_every_declared_symbol(rzlib):
     assert C.sizeof(capi.RzConfig) == 56 and C.sizeof(capi.RzStats) == 128
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_lane_plan_preserves_every_influence_and_packs_pairs(rzlib, mode):
+    """rz_plan_lanes (host only): whatever lane / slot a (bone, weight) pair ends up in, every vertex keeps exactly its
+    shader-normalised non-zero influences (engine.ts:255-258); zero-weight slots stay in range; the fast-path count the
+    library reports is really there (aligned lane pairs gather the same row in those slots)."""
+    from reze_engine_b200 import capi
+    wl = synth.make_workload(5000, 96, seed=5)
+    J, W = wl.joints.copy(), wl.weights.copy()
+    W[7] = 0                                   # weight sum 0 -> (1,0,0,0) on joint 0 of the vertex
+    J[11], W[11] = (3, 3, 9, 0), (100, 55, 100, 0)   # a bone listed twice keeps the caller's slots
+    W[13] = (0, 200, 0, 55)                    # interior zero weights
+    V, B = J.shape[0], 96
+    plan = capi.plan_lanes(J, W, B, mode)
+    lv, lj, lw = plan["laneVertex"], plan["laneJoints"], plan["laneWeights"]
+    Vp = lv.size
+    assert Vp % 256 == 0 and Vp >= V and lj.max() < B
+    real = lv != 0xFFFFFFFF
+    assert np.array_equal(np.sort(lv[real]), np.arange(V))
+    for w0 in range(0, Vp, 32):                # a warp owns 32 consecutive vertices
+        mine = lv[w0:w0 + 32]
+        assert set(mine[mine != 0xFFFFFFFF].tolist()) == set(range(w0, min(w0 + 32, V)))
+    wf = W.astype(np.float32) / np.float32(255.0)
+    ssum = (wf[:, 0] + wf[:, 1]) + wf[:, 2] + wf[:, 3]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        norm = np.where(ssum[:, None] > 1e-4, wf * (np.float32(1.0) / ssum)[:, None], np.array([1, 0, 0, 0], np.float32)).astype(np.float32)
+    for p in np.nonzero(real)[0]:
+        v = int(lv[p])
+        want = sorted((int(J[v, k]), float(norm[v, k])) for k in range(4) if norm[v, k] != 0)
+        got = sorted((int(lj[p, s]), float(lw[p, s])) for s in range(4) if lw[p, s] != 0)
+        assert want == got, (p, v, want, got)
+        if mode < 2:
+            assert all(lw[p, k] == norm[v, k] for k in range(4))
+    pad = ~real
+    assert np.all(lw[pad, 0] == 1.0) and np.all(lw[pad, 1:] == 0.0)
+    # fast-path accounting
+    coherent = 0
+    for w0 in range(0, Vp, 32):
+        n = int(max(1, max(int(np.max(np.nonzero(lw[p])[0]) + 1) for p in range(w0, w0 + 32))))
+        for s in range(n):
+            coherent += bool(np.all(lj[w0:w0 + 32:2, s] == lj[w0 + 1:w0 + 32:2, s]))
+    if mode == 2:
+        assert plan["total"] > 0 and coherent >= plan["fast"] > 0.5 * plan["total"]
+        assert plan["hist"].sum() > 0
+    else:
+        assert plan["total"] == 0
+
+
+def test_lane_plan_rejects_bad_tables(rzlib):
+    from reze_engine_b200 import capi
+    with pytest.raises(capi.RzError):
+        capi.plan_lanes(np.full((4, 4), 9, np.uint16), np.full((4, 4), 60, np.uint8), B=4)
+
+
 def test_no_device_fails_loudly_never_falls_back(rzlib):
     import torch
     if torch.cuda.is_available():
