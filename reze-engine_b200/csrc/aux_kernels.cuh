@@ -36,6 +36,21 @@ __global__ void skin_matrices_kernel(const float4* __restrict__ world, const flo
   }
 }
 
+// quat[p][row] = rotation part of skin[p][row] as a quaternion (math.ts:406-448 Mat4.toQuatFromArray, via
+// deform_kernel.cuh quat_from_rows).  Feeds the SDEF dense phase: the deform kernel slerps these instead of converting
+// two matrices per SDEF vertex-instance.  One thread per (palette, palette row).
+__global__ void skin_quats_kernel(const float4* __restrict__ skin, float4* __restrict__ quat, uint32_t P, uint32_t B, uint32_t soa) {
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P * B) return;
+  const uint32_t row = idx % B;
+  float4 cA, cB, cC;
+  if (soa) { const size_t pb = (size_t)(idx - row) * 3; cA = skin[pb + row]; cB = skin[pb + B + row]; cC = skin[pb + 2 * (size_t)B + row]; }
+  else { cA = skin[(size_t)idx * 3]; cB = skin[(size_t)idx * 3 + 1]; cC = skin[(size_t)idx * 3 + 2]; }
+  // un-pair (deform_kernel.cuh kRowF4)
+  const Q4 q = quat_from_rows(make_float4(cA.x, cA.z, cB.x, cB.z), make_float4(cA.y, cA.w, cB.y, cB.w), cC);
+  quat[idx] = make_float4(q.x, q.y, q.z, q.w);
+}
+
 // dense per-instance morph weights: dense[k][m] = 0, dense[k][activeIds[a]] += w[k][a]
 __global__ void morph_weights_kernel(const float* __restrict__ w, const uint32_t* __restrict__ ids, float* __restrict__ dense,
                                      uint32_t K, uint32_t Mact, uint32_t Mpad) {

@@ -47,9 +47,10 @@ struct DeformParams {
   const uint32_t* __restrict__ meta;   // [Vp] slot | ninf | flags
   const uint2*  __restrict__ mrange;   // [Vp] (first entry, count) into ments
   const float4* __restrict__ ments;    // [nnz] dx,dy,dz, morph id bits
-  const uint32_t* __restrict__ sdefIdx;// [Vp] index into sdefTab (valid when kMetaSdef)
-  const float4* __restrict__ sdefTab;  // [nSdef*3]: (C.xyz,c0.x) (c0.yz,c1.xy) (c1.z,0,0,0)
+  const uint32_t* __restrict__ sdefIdx;// [Vp] word of lane l = descriptor of the l-th SDEF vertex of its warp: table index | output slot << 24 (~0u: none)
+  const float4* __restrict__ sdefTab;  // [nSdef*3]: (C.xyz,c0.x) (c0.yz,c1.xy) (c1.z, w0, w1, palette rows j0 | j1 << 16)
   const float*  __restrict__ skin;     // [P][B][12]
+  const float4* __restrict__ quat;     // [P][B] rotation of each skin matrix as a quaternion (SDEF only; skin_quats_kernel)
   const uint32_t* __restrict__ inst2pal; // [K] or nullptr (identity)
   const float*  __restrict__ mweights; // dense [K][Mpad]
   float* __restrict__ out;
@@ -133,6 +134,11 @@ __device__ __forceinline__ uint32_t ldg_el(const uint32_t* p, uint64_t pol) {
   asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
   return r;
 }
+__device__ __forceinline__ uint2 ldg_el(const uint2* p, uint64_t pol) {
+  uint2 r;
+  asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(pol));
+  return r;
+}
 __device__ __forceinline__ float4 lds128(uint32_t a) {
   float4 r;
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a));
@@ -188,6 +194,17 @@ __device__ __forceinline__ Q4 quat_from_rows(float4 r0, float4 r1, float4 r2) {
   const float inv = 1.0f / sqrtf(x * x + y * y + z * z + w * w);
   return Q4{x * inv, y * inv, z * inv, w * inv};
 }
+// sin(y) for 0 <= y <= pi/2: y * (1 + z*P(z)), z = y^2, Taylor through y^13 (truncation 7e-10 at pi/2)
+__device__ __forceinline__ float sin_0_halfpi(float y) {
+  const float z = y * y;
+  float p = 1.6059044e-10f;
+  p = fmaf(p, z, -2.5052108e-08f);
+  p = fmaf(p, z, 2.7557319e-06f);
+  p = fmaf(p, z, -1.9841270e-04f);
+  p = fmaf(p, z, 8.3333333e-03f);
+  p = fmaf(p, z, -1.6666667e-01f);
+  return fmaf(y * z, p, y);
+}
 __device__ __forceinline__ Q4 quat_slerp(Q4 a, Q4 b, float t) {
   float c = a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
   if (c < 0.f) { c = -c; b.x = -b.x; b.y = -b.y; b.z = -b.z; b.w = -b.w; }
@@ -196,10 +213,11 @@ __device__ __forceinline__ Q4 quat_slerp(Q4 a, Q4 b, float t) {
     const float inv = 1.0f / sqrtf(x * x + y * y + z * z + w * w);
     return Q4{x * inv, y * inv, z * inv, w * inv};
   }
-  // precise sinf on purpose: near the 0.9995 threshold th0 ~ 0.03 rad and __sinf's absolute error (2^-21.4) would be a
-  // 1e-5 RELATIVE error of s0/s1 (measured: 2.2e-5 on config 3), i.e. outside the parity tolerance
-  const float th0 = acosf(c), s = sinf(th0), th = th0 * t;
-  const float s0 = sinf(th0 - th) / s, s1 = sinf(th) / s;
+  // every sine argument lies in [0, pi/2] here (0 <= c <= 0.9995, 0 <= t <= 1).  __sinf is not an option: near the 0.9995
+  // threshold th0 ~ 0.03 rad and its absolute error (2^-21.4) would be a 1e-5 RELATIVE error of s0/s1 (measured: 2.2e-5 on
+  // config 3), outside the parity tolerance; sin_0_halfpi keeps ~1e-7 relative without sinf's range-reduction slow path.
+  const float th0 = acosf(c), rs = 1.0f / sin_0_halfpi(th0), th = th0 * t;
+  const float s0 = sin_0_halfpi(th0 - th) * rs, s1 = sin_0_halfpi(th) * rs;
   return Q4{s0 * a.x + s1 * b.x, s0 * a.y + s1 * b.y, s0 * a.z + s1 * b.z, s0 * a.w + s1 * b.w};
 }
 
@@ -209,6 +227,8 @@ template <int N> struct IntC { static constexpr int value = N; };
 struct VRec {
   float4 r0, r1, r2;
   uint32_t meta;
+  uint32_t sdesc;   // SDEF: descriptor of the lane-th SDEF vertex of this warp (~0u: none)
+  uint2 mr;         // MORPH: (first entry, count) of this lane's vertex
 };
 
 // shared-memory control block at the start of dynamic smem; data starts at byte kCtrlBytes
@@ -249,11 +269,13 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
   const uint32_t palBytes = GPAL ? 0u : B * 48u;
   const uint32_t sMw = sPal + (uint32_t)I * palBytes;
   const uint32_t mwBytes = MORPH ? prm.Mpad * 4u : 0u;
+  const uint32_t sQuat = sMw + (uint32_t)I * mwBytes;               // [I][B] float4 quaternions (SDEF, palette in smem)
+  const uint32_t quatBytes = (SDEF && !GPAL) ? B * 16u : 0u;
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform by construction: TMA operands stay in uniform registers
   // warp-private staging: [kStageBufs][I][PLANES][32*3 floats], laid out exactly like 32 vertices of the output planes
-  const uint32_t sStageW = sMw + (uint32_t)I * mwBytes + (uint32_t)warp * (kStageBufs * kBufB);
+  const uint32_t sStageW = sQuat + (uint32_t)I * quatBytes + (uint32_t)warp * (kStageBufs * kBufB);
 
   if (tid == 0) {
     mbar_init(palBar, 1);
@@ -289,10 +311,12 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
     }
     if (!GPAL || MORPH) {
       if (tid == 0) {
-        mbar_expect_tx(palBar, (uint32_t)I * (palBytes + mwBytes));
+        mbar_expect_tx(palBar, (uint32_t)I * (palBytes + mwBytes + quatBytes));
 #pragma unroll
         for (int i = 0; i < I; ++i) {
           if (!GPAL) bulk_g2s(sPal + (uint32_t)i * palBytes, gpal[i], palBytes, palBar, polLast);
+          if (SDEF && !GPAL)   // same palette index as gpal[i]: (gpal[i] - skin) / 12 floats = palette * B rows
+            bulk_g2s(sQuat + (uint32_t)i * quatBytes, prm.quat + (size_t)(gpal[i] - prm.skin) / 12, quatBytes, palBar, polLast);
           if (MORPH) {
             const uint32_t k = kBase + min((uint32_t)i, nInst - 1);
             bulk_g2s(sMw + (uint32_t)i * mwBytes, prm.mweights + (size_t)k * prm.Mpad, mwBytes, palBar, polLast);
@@ -318,11 +342,15 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
         v.r1 = ldg_el(prm.rec1 + p, polLast);
         v.r2 = ldg_el(prm.rec2 + p, polLast);
         v.meta = prm.packedMeta ? 0u : ldg_el(prm.meta + p, polLast);
+        v.sdesc = SDEF ? ldg_el(prm.sdefIdx + p, polLast) : ~0u;
+        v.mr = MORPH ? ldg_el(prm.mrange + p, polLast) : make_uint2(0u, 0u);
       } else {                                                  // the far tiles of a wide pass fall off the chunk
         v.r0 = make_float4(0.f, 0.f, 0.f, 1.f);
         v.r1 = make_float4(0.f, 0.f, 0.f, 0.f);
         v.r2 = make_float4(0.f, 0.f, 0.f, 0.f);
         v.meta = (uint32_t)lane | (1u << kMetaNinfShift);
+        v.sdesc = ~0u;
+        v.mr = make_uint2(0u, 0u);
       }
       return v;
     };
@@ -365,7 +393,7 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
       for (int i = 0; i < (MORPH ? I : 1); ++i) { px[i] = v.r0.x; py[i] = v.r0.y; pz[i] = v.r0.z; }
       if (MORPH) {
         if (meta & kMetaMorph) {
-          const uint2 mr = __ldg(prm.mrange + (size_t)t * kTile + tid);
+          const uint2 mr = v.mr;                                   // prefetched with the record: one L2 round trip less
           // entries of one vertex are contiguous: fetch 4 at a time so their L2 latencies overlap (the loop is a
           // dependent chain otherwise: ~20 entries on a face vertex x one round trip each)
           const uint32_t eEnd = mr.x + mr.y;
@@ -388,16 +416,23 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
         }
       }
 
+      // ---- SDEF runs as a DENSE second phase (after the linear pass, below): the warp's SDEF vertices x I instances are
+      // spread over the lanes as (vertex, instance) pairs, so the spherical blend costs one pass per 32 pairs instead of
+      // one predicated pass per instance whenever any lane is SDEF.  Owner lanes only park (p~, n) in their staging slots.
+      // The pair -> table mapping is static: lane l's descriptor word describes the l-th SDEF vertex of this warp, and
+      // the records of round 0 are fetched here, ahead of the palette gathers, so the L2 latency overlaps the linear pass.
       const bool isSdef = SDEF && (meta & kMetaSdef);
-      float sC[3] = {0.f, 0.f, 0.f}, sc0[3] = {0.f, 0.f, 0.f}, sc1[3] = {0.f, 0.f, 0.f};
+      uint32_t sdCount = 0, sdW = ~0u;
+      float4 sT0 = make_float4(0.f, 0.f, 0.f, 0.f), sT1 = sT0, sT2 = sT0;
       if (SDEF) {
-        if (isSdef) {
-          const uint32_t si = __ldg(prm.sdefIdx + (size_t)t * kTile + tid);
-          const float4 t0 = __ldg(prm.sdefTab + (size_t)si * 3), t1 = __ldg(prm.sdefTab + (size_t)si * 3 + 1),
-                       t2 = __ldg(prm.sdefTab + (size_t)si * 3 + 2);
-          sC[0] = t0.x; sC[1] = t0.y; sC[2] = t0.z;
-          sc0[0] = t0.w; sc0[1] = t1.x; sc0[2] = t1.y;
-          sc1[0] = t1.z; sc1[1] = t1.w; sc1[2] = t2.x;
+        sdCount = (uint32_t)__popc(__ballot_sync(0xffffffffu, v.sdesc != ~0u));
+        if (sdCount) {
+          const uint32_t r = (uint32_t)lane / (uint32_t)I;
+          sdW = __shfl_sync(0xffffffffu, v.sdesc, (int)r);
+          if (r < sdCount) {
+            const float4* e = prm.sdefTab + (size_t)(sdW & 0xFFFFFFu) * 3;
+            sT0 = __ldg(e); sT1 = __ldg(e + 1); sT2 = __ldg(e + 2);
+          }
         }
       }
 
@@ -438,38 +473,7 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
           const int i = i0 + ii;
           const float qx = px[MORPH ? i : 0], qy = py[MORPH ? i : 0], qz = pz[MORPH ? i : 0];
           float ox, oy, oz, nx = 0.f, ny = 0.f, nz = 0.f;
-          bool done = false;
-          if (SDEF && NMAX > 1) {
-            if (isSdef) {
-              // ---- SDEF: spherical blend of the two bone rotations around C; un-pair the rows first
-              const float4 r0 = make_float4(a0[ii].x, a0[ii].z, a1[ii].x, a1[ii].z), r1 = make_float4(a0[ii].y, a0[ii].w, a1[ii].y, a1[ii].w), r2 = a2[ii];
-              const float4 s0 = make_float4(b0[ii].x, b0[ii].z, b1[ii].x, b1[ii].z), s1 = make_float4(b0[ii].y, b0[ii].w, b1[ii].y, b1[ii].w), s2 = b2[ii];
-              const Q4 q = quat_slerp(quat_from_rows(r0, r1, r2), quat_from_rows(s0, s1, s2), w1);
-              const float x2 = q.x + q.x, y2 = q.y + q.y, z2 = q.z + q.z;
-              const float xx = q.x * x2, xy = q.x * y2, xz = q.x * z2, yy = q.y * y2, yz = q.y * z2, zz = q.z * z2;
-              const float wx = q.w * x2, wy = q.w * y2, wz = q.w * z2;
-              const float R00 = 1.f - (yy + zz), R01 = xy - wz, R02 = xz + wy;
-              const float R10 = xy + wz, R11 = 1.f - (xx + zz), R12 = yz - wx;
-              const float R20 = xz - wy, R21 = yz + wx, R22 = 1.f - (xx + yy);
-              const float dx = qx - sC[0], dy = qy - sC[1], dz = qz - sC[2];
-              const float e0x = fmaf(r0.x, sc0[0], fmaf(r0.y, sc0[1], fmaf(r0.z, sc0[2], r0.w)));
-              const float e0y = fmaf(r1.x, sc0[0], fmaf(r1.y, sc0[1], fmaf(r1.z, sc0[2], r1.w)));
-              const float e0z = fmaf(r2.x, sc0[0], fmaf(r2.y, sc0[1], fmaf(r2.z, sc0[2], r2.w)));
-              const float e1x = fmaf(s0.x, sc1[0], fmaf(s0.y, sc1[1], fmaf(s0.z, sc1[2], s0.w)));
-              const float e1y = fmaf(s1.x, sc1[0], fmaf(s1.y, sc1[1], fmaf(s1.z, sc1[2], s1.w)));
-              const float e1z = fmaf(s2.x, sc1[0], fmaf(s2.y, sc1[1], fmaf(s2.z, sc1[2], s2.w)));
-              ox = fmaf(R00, dx, fmaf(R01, dy, R02 * dz)) + w0 * e0x + w1 * e1x;
-              oy = fmaf(R10, dx, fmaf(R11, dy, R12 * dz)) + w0 * e0y + w1 * e1y;
-              oz = fmaf(R20, dx, fmaf(R21, dy, R22 * dz)) + w0 * e0z + w1 * e1z;
-              if (NRM) {
-                nx = fmaf(R00, vnx, fmaf(R01, vny, R02 * vnz));
-                ny = fmaf(R10, vnx, fmaf(R11, vny, R12 * vnz));
-                nz = fmaf(R20, vnx, fmaf(R21, vny, R22 * vnz));
-              }
-              done = true;
-            }
-          }
-          if (!done) {
+          {
             // ---- linear blend: M = sum_i w_i M_i (zero weights contribute exactly 0), then one packed mat-vec each
             float4 mA, mB, mC;
             if (NV == 0) { mA = a0[ii]; mB = a1[ii]; mC = a2[ii]; }          // every lane has the single weight 1.0
@@ -505,8 +509,11 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
             const float rl = l2 > 0.f ? rsqrtf(l2) : 0.f;        // normalize(0) := 0 (SURVEY 8c edge case)
             nx *= rl; ny *= rl; nz *= rl;
           }
+          if (SDEF) {
+            if (isSdef) { ox = qx; oy = qy; oz = qz; nx = vnx; ny = vny; nz = vnz; }   // parked for the dense phase
+          }
           if (BOUNDS) {
-            if (valid) {
+            if (valid && !isSdef) {
               bmin[i][0] = fminf(bmin[i][0], ox); bmax[i][0] = fmaxf(bmax[i][0], ox);
               bmin[i][1] = fminf(bmin[i][1], oy); bmax[i][1] = fmaxf(bmax[i][1], oy);
               bmin[i][2] = fminf(bmin[i][2], oz); bmax[i][2] = fmaxf(bmax[i][2], oz);
@@ -527,6 +534,89 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
           case 2: body(IntC<2>{}, i0); break;
           case 3: body(IntC<3>{}, i0); break;
           default: body(IntC<4>{}, i0); break;
+        }
+      }
+
+      // ---- SDEF dense phase: pos' = R(q)·(p~ - C) + w0·(M0·c0) + w1·(M1·c1), n' = normalize(R(q)·n),
+      //      q = slerp(quat(M0), quat(M1), w1).  quat(M) comes from the per-palette table (skin_quats_kernel: same
+      //      math.ts:406-448 formula, evaluated once per bone instead of once per vertex-instance).
+      if (SDEF) {
+        if (sdCount) {                                            // warp-uniform
+          __syncwarp();                                           // the owners' parked (p~, n) are visible
+          for (uint32_t base = 0; base < sdCount * (uint32_t)I; base += 32u) {
+            const uint32_t pp = base + (uint32_t)lane;
+            const uint32_t r = pp / (uint32_t)I, i = pp - r * (uint32_t)I;
+            uint32_t w = sdW;
+            float4 t0 = sT0, t1 = sT1, t2 = sT2;
+            if (base) {                                           // rare: more than 32/I SDEF vertices in this warp
+              w = __shfl_sync(0xffffffffu, v.sdesc, (int)(r & 31u));
+              if (r < sdCount) {
+                const float4* e = prm.sdefTab + (size_t)(w & 0xFFFFFFu) * 3;
+                t0 = __ldg(e); t1 = __ldg(e + 1); t2 = __ldg(e + 2);
+              }
+            }
+            if (r < sdCount) {
+              const uint32_t sa = stg + i * kInstB + (w >> 24) * 12u;
+              const float qx = lds32(sa), qy = lds32(sa + 4), qz = lds32(sa + 8);
+              const uint32_t jj = __float_as_uint(t2.w);
+              const uint32_t r0p = jj & 0xFFFFu, r1p = jj >> 16;                 // palette rows of the two bones
+              const float sw0 = t2.y, sw1 = t2.z;
+              float4 a0, a1, a2, b0, b1, b2, qa, qb;
+              if (GPAL) {
+                const uint32_t k = kBase + min(i, nInst - 1);
+                const uint32_t pidx = prm.inst2pal ? __ldg(prm.inst2pal + k) : k;
+                const float4* pal = reinterpret_cast<const float4*>(prm.skin + (size_t)pidx * B * 12);
+                a0 = pal[(r0p * pS) / 16]; a1 = pal[(r0p * pS + rS) / 16]; a2 = pal[(r0p * pS + rS2) / 16];
+                b0 = pal[(r1p * pS) / 16]; b1 = pal[(r1p * pS + rS) / 16]; b2 = pal[(r1p * pS + rS2) / 16];
+                qa = __ldg(prm.quat + (size_t)pidx * B + r0p); qb = __ldg(prm.quat + (size_t)pidx * B + r1p);
+              } else {
+                const uint32_t pb = sPal + i * palBytes, qbase = sQuat + i * quatBytes;
+                a0 = lds128(pb + r0p * pS); a1 = lds128(pb + r0p * pS + rS); a2 = lds128(pb + r0p * pS + rS2);
+                b0 = lds128(pb + r1p * pS); b1 = lds128(pb + r1p * pS + rS); b2 = lds128(pb + r1p * pS + rS2);
+                qa = lds128(qbase + r0p * 16u); qb = lds128(qbase + r1p * 16u);
+              }
+              // un-pair the rows (kRowF4): r* = rows of M0, s* = rows of M1
+              const float4 r0 = make_float4(a0.x, a0.z, a1.x, a1.z), r1 = make_float4(a0.y, a0.w, a1.y, a1.w), r2 = a2;
+              const float4 s0 = make_float4(b0.x, b0.z, b1.x, b1.z), s1 = make_float4(b0.y, b0.w, b1.y, b1.w), s2 = b2;
+              const Q4 q = quat_slerp(Q4{qa.x, qa.y, qa.z, qa.w}, Q4{qb.x, qb.y, qb.z, qb.w}, sw1);
+              const float x2 = q.x + q.x, y2 = q.y + q.y, z2 = q.z + q.z;
+              const float xx = q.x * x2, xy = q.x * y2, xz = q.x * z2, yy = q.y * y2, yz = q.y * z2, zz = q.z * z2;
+              const float wx = q.w * x2, wy = q.w * y2, wz = q.w * z2;
+              const float R00 = 1.f - (yy + zz), R01 = xy - wz, R02 = xz + wy;
+              const float R10 = xy + wz, R11 = 1.f - (xx + zz), R12 = yz - wx;
+              const float R20 = xz - wy, R21 = yz + wx, R22 = 1.f - (xx + yy);
+              const float dx = qx - t0.x, dy = qy - t0.y, dz = qz - t0.z;
+              const float c0x = t0.w, c0y = t1.x, c0z = t1.y, c1x = t1.z, c1y = t1.w, c1z = t2.x;
+              const float e0x = fmaf(r0.x, c0x, fmaf(r0.y, c0y, fmaf(r0.z, c0z, r0.w)));
+              const float e0y = fmaf(r1.x, c0x, fmaf(r1.y, c0y, fmaf(r1.z, c0z, r1.w)));
+              const float e0z = fmaf(r2.x, c0x, fmaf(r2.y, c0y, fmaf(r2.z, c0z, r2.w)));
+              const float e1x = fmaf(s0.x, c1x, fmaf(s0.y, c1y, fmaf(s0.z, c1z, s0.w)));
+              const float e1y = fmaf(s1.x, c1x, fmaf(s1.y, c1y, fmaf(s1.z, c1z, s1.w)));
+              const float e1z = fmaf(s2.x, c1x, fmaf(s2.y, c1y, fmaf(s2.z, c1z, s2.w)));
+              const float ox = fmaf(R00, dx, fmaf(R01, dy, R02 * dz)) + sw0 * e0x + sw1 * e1x;
+              const float oy = fmaf(R10, dx, fmaf(R11, dy, R12 * dz)) + sw0 * e0y + sw1 * e1y;
+              const float oz = fmaf(R20, dx, fmaf(R21, dy, R22 * dz)) + sw0 * e0z + sw1 * e1z;
+              sts3(sa, ox, oy, oz);
+              if (NRM) {
+                const float vx = lds32(sa + kPlaneB), vy = lds32(sa + kPlaneB + 4), vz = lds32(sa + kPlaneB + 8);
+                float nx = fmaf(R00, vx, fmaf(R01, vy, R02 * vz));
+                float ny = fmaf(R10, vx, fmaf(R11, vy, R12 * vz));
+                float nz = fmaf(R20, vx, fmaf(R21, vy, R22 * vz));
+                const float l2 = fmaf(nx, nx, fmaf(ny, ny, nz * nz));
+                const float rl = l2 > 0.f ? rsqrtf(l2) : 0.f;
+                sts3(sa + kPlaneB, nx * rl, ny * rl, nz * rl);
+              }
+              if (BOUNDS) {
+#pragma unroll
+                for (int ii = 0; ii < I; ++ii)
+                  if ((uint32_t)ii == i) {
+                    bmin[ii][0] = fminf(bmin[ii][0], ox); bmax[ii][0] = fmaxf(bmax[ii][0], ox);
+                    bmin[ii][1] = fminf(bmin[ii][1], oy); bmax[ii][1] = fmaxf(bmax[ii][1], oy);
+                    bmin[ii][2] = fminf(bmin[ii][2], oz); bmax[ii][2] = fmaxf(bmax[ii][2], oz);
+                  }
+              }
+            }
+          }
         }
       }
 

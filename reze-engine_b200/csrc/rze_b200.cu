@@ -87,6 +87,7 @@ struct rz_ctx_impl {
 
   // per-frame
   uint32_t P = 0, K = 0;
+  DevBuf d_quat;
   DevBuf d_world, d_skin, d_inst2pal, d_mwIn, d_mwIds, d_mwDense, d_out, d_bounds, d_counter;
   bool haveInst2pal = false, palettesSet = false;
   uint32_t Mact = 0, Mpad = 4;
@@ -206,6 +207,7 @@ size_t smem_needed(int I, int NT, int feat, uint32_t B, uint32_t Mpad, int nbuf 
   size_t s = kCtrlBytes;
   if (!(feat & FEAT_GPAL)) s += (size_t)I * B * 48;
   if (feat & FEAT_MORPH) s += (size_t)I * Mpad * 4;
+  if ((feat & FEAT_SDEF) && !(feat & FEAT_GPAL)) s += (size_t)I * B * 16;   // per-bone quaternions
   s += (size_t)nbuf * I * ((feat & FEAT_NONRM) ? 1 : 2) * NT * 12;   // warp-private staging (pos + normal planes)
   return s;
 }
@@ -285,8 +287,9 @@ int rebuild_tables(rz_ctx_impl* c) {
   }
   c->morphNnz = nnz;
 
-  // SDEF table (only when enabled)
-  std::vector<int32_t> sdefOf(V, -1);
+  // SDEF (only when enabled): which vertices take the spherical path.  The table itself needs the palette rows and is
+  // built further down, after the bank-aware permutation.
+  std::vector<int32_t> sdefOf(V, -1);     // stored vertex -> record n of the caller's rz_load_sdef arrays
   std::vector<float4> sdefTab;
   c->sdefActive = 0;
   if (c->flags & RZ_FLAG_SDEF) {
@@ -294,25 +297,8 @@ int rebuild_tables(rz_ctx_impl* c) {
       const uint32_t v = c->vinv[c->h_sdefVert[n]];
       const uint8_t* w = &WT[(size_t)v * 4];
       if (w[2] != 0 || w[3] != 0) continue;   // not a two-influence vertex: stays linear
-      const float* s = &c->h_sdefVec[n * 9];
-      // weights exactly as the kernel derives them
-      float w0 = (float)w[0] / 255.0f, w1 = (float)w[1] / 255.0f;
-      const float ws = w0 + w1 + 0.f + 0.f;
-      if (ws > 0.0001f) { const float inv = 1.0f / ws; w0 *= inv; w1 *= inv; } else { w0 = 1.f; w1 = 0.f; }
-      float C[3] = {s[0], s[1], s[2]}, c0[3], c1[3];
-      for (int k = 0; k < 3; ++k) {
-        const float R0 = s[3 + k], R1 = s[6 + k];
-        const float rw = w0 * R0 + w1 * R1;
-        const float r0 = C[k] + R0 - rw, r1 = C[k] + R1 - rw;
-        c0[k] = (C[k] + r0) * 0.5f;
-        c1[k] = (C[k] + r1) * 0.5f;
+      sdefOf[v] = (int32_t)n;
       }
-      sdefOf[v] = (int32_t)(sdefTab.size() / 3);
-      sdefTab.push_back(make_float4(C[0], C[1], C[2], c0[0]));
-      sdefTab.push_back(make_float4(c0[1], c0[2], c1[0], c1[1]));
-      sdefTab.push_back(make_float4(c1[2], 0.f, 0.f, 0.f));
-      c->sdefActive++;
-    }
   }
 
   std::vector<float4> rec0(Vp), rec1(Vp), rec2(Vp);
@@ -327,9 +313,9 @@ int rebuild_tables(rz_ctx_impl* c) {
   // which lane evaluates which vertex, and the influence table the device sees (lane_plan.h: pair packing)
   LanePlan plan;
   {
-    std::vector<uint8_t> isSdef(V, 0);
-    for (uint32_t v = 0; v < V; ++v) isSdef[v] = sdefOf[v] >= 0;
-    plan_lanes(JT, WT, isSdef.data(), V, B, kTile, c->permMode, plan);
+    // SDEF vertices are planned like any other: their spherical blend runs in the kernel's dense phase from the table
+    // below (own bone rows + weights), so the linear slots are the packer's to arrange
+    plan_lanes(JT, WT, nullptr, V, B, kTile, c->permMode, plan);
   }
   const std::vector<uint32_t>& procVertex = plan.procVertex;
   const std::vector<uint32_t>& procSlot = plan.procSlot;
@@ -427,6 +413,48 @@ int rebuild_tables(rz_ctx_impl* c) {
   c->boneAt.assign(B, 0);
   for (uint32_t b = 0; b < B; ++b) c->boneAt[c->bonePos[b]] = b;
 
+  // ---- SDEF table (36 B of vectors + weights + palette rows per vertex) and the per-warp descriptor list: word l of a
+  // warp describes the l-th SDEF vertex among the warp's 32 outputs (table index | output slot << 24), ~0u beyond
+  if (c->flags & RZ_FLAG_SDEF) {
+    std::vector<int32_t> recOf(V, -1);
+    for (uint32_t v = 0; v < V; ++v) {
+      if (sdefOf[v] < 0) continue;
+      const size_t n = (size_t)sdefOf[v];
+      const uint8_t* w = &WT[(size_t)v * 4];
+      const float* s = &c->h_sdefVec[n * 9];
+      // weights exactly as the kernel derives them
+      float w0 = (float)w[0] / 255.0f, w1 = (float)w[1] / 255.0f;
+      const float ws = w0 + w1 + 0.f + 0.f;
+      if (ws > 0.0001f) { const float inv = 1.0f / ws; w0 *= inv; w1 *= inv; } else { w0 = 1.f; w1 = 0.f; }
+      float C[3] = {s[0], s[1], s[2]}, c0[3], c1[3];
+      for (int k = 0; k < 3; ++k) {
+        const float R0 = s[3 + k], R1 = s[6 + k];
+        const float rw = w0 * R0 + w1 * R1;
+        const float r0 = C[k] + R0 - rw, r1 = C[k] + R1 - rw;
+        c0[k] = (C[k] + r0) * 0.5f;
+        c1[k] = (C[k] + r1) * 0.5f;
+      }
+      const uint32_t rows = c->bonePos[JT[(size_t)v * 4]] | (c->bonePos[JT[(size_t)v * 4 + 1]] << 16);
+      float rowsF;
+      memcpy(&rowsF, &rows, 4);
+      recOf[v] = (int32_t)(sdefTab.size() / 3);
+      sdefTab.push_back(make_float4(C[0], C[1], C[2], c0[0]));
+      sdefTab.push_back(make_float4(c0[1], c0[2], c1[0], c1[1]));
+      sdefTab.push_back(make_float4(c1[2], w0, w1, rowsF));
+      c->sdefActive++;
+    }
+    if (sdefTab.size() / 3 >= (1u << 24)) return fail(c, RZ_ERR_INVALID_ARG, "rz_load_sdef: more than 2^24 SDEF vertices");
+    std::fill(sdefIdx.begin(), sdefIdx.end(), ~0u);
+    for (uint32_t w0 = 0; w0 < Vp; w0 += 32) {
+      uint32_t n = 0;
+      for (uint32_t l = 0; l < 32; ++l) {
+        const uint32_t v = procVertex[w0 + l];
+        if (v == ~0u || recOf[v] < 0) continue;
+        sdefIdx[w0 + n++] = (uint32_t)recOf[v] | (procSlot[w0 + l] << 24);
+      }
+    }
+  }
+
   for (uint32_t p = 0; p < Vp; ++p) {
     const uint32_t v = procVertex[p], slot = procSlot[p], ni = devN[p];
     const uint16_t* j = &gatherJ[(size_t)p * 4];
@@ -450,7 +478,6 @@ int rebuild_tables(rz_ctx_impl* c) {
       rec1[p] = make_float4(x[3], x[4], x[5], w[1]);
       memcpy(&wbits[p], &WT[(size_t)v * 4], 4);
       mrange[p] = make_uint2(mstart[v], mcount[v]);
-      if (hasSdef) sdefIdx[p] = (uint32_t)sdefOf[v];
       c->procToVertex[p] = v;
     } else {
       // padding: a harmless rigid vertex parked on an unused output slot of this warp
@@ -1111,6 +1138,7 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
   prm.sdefIdx = reinterpret_cast<const uint32_t*>(c->d_sdefIdx.p);
   prm.sdefTab = reinterpret_cast<const float4*>(c->d_sdefTab.p);
   prm.skin = reinterpret_cast<const float*>(c->d_skin.p);
+  prm.quat = reinterpret_cast<const float4*>(c->d_quat.p);
   prm.inst2pal = c->haveInst2pal ? reinterpret_cast<const uint32_t*>(c->d_inst2pal.p) : nullptr;
   prm.mweights = reinterpret_cast<const float*>(c->d_mwDense.p);
   prm.out = reinterpret_cast<float*>(c->d_out.p);
@@ -1134,8 +1162,19 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
   const uint32_t nItems = prm.nGroups * prm.nChunks;
   grid = std::min(grid, nItems);
 
+  if (feat & FEAT_SDEF) {
+    if ((rc = dev_reserve(c, c->d_quat, (size_t)c->P * c->B * 16))) return rc;
+    prm.quat = reinterpret_cast<const float4*>(c->d_quat.p);
+  }
   CU_TRY(c, cudaEventRecord(c->evStart, c->stream));
   CU_TRY(c, cudaMemsetAsync(c->d_counter.p, 0, 4, c->stream));
+  if (feat & FEAT_SDEF) {
+    // rotation of every skin matrix as a quaternion, once per (palette, bone) instead of once per SDEF vertex-instance
+    const uint32_t n = c->P * c->B;
+    skin_quats_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(reinterpret_cast<const float4*>(c->d_skin.p),
+                                                               reinterpret_cast<float4*>(c->d_quat.p), c->P, c->B, c->layoutMode ? 1u : 0u);
+    c->launches++;
+  }
   if (feat & FEAT_BOUNDS) {
     bounds_reset_kernel<<<(count * 6 + 127) / 128, 128, 0, c->stream>>>(reinterpret_cast<int*>(c->d_bounds.p) + (size_t)first * 6, count * 6);
     c->launches++;
