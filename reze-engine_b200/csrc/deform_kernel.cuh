@@ -27,6 +27,8 @@
 namespace rz {
 
 constexpr int kTile = 256;          // vertices per preprocessing tile (permutation unit)
+constexpr int kMorphPF = 4;         // morph entries of a vertex fetched one pass ahead
+constexpr int kMorphBatch = 8;      // further entries per L2 round trip
 constexpr int kRowF4 = 3;           // float4 per bone.  PAIR LAYOUT of the 3x4 skin matrix m[row][col] (48 B):
                                     //   A = (m00,m10,m01,m11)  B = (m02,m12,m03,m13)  C = (m20,m21,m22,m23)
                                     // rows 0/1 are interleaved so that (x,y) of a transformed point come out of one FFMA2
@@ -45,8 +47,8 @@ struct DeformParams {
   const float4* __restrict__ rec1;     // [Vp] nx,ny,nz, w1
   const float4* __restrict__ rec2;     // [Vp] w2, w3, joints01 bits, joints23 bits
   const uint32_t* __restrict__ meta;   // [Vp] slot | ninf | flags
-  const uint2*  __restrict__ mrange;   // [Vp] (first entry, count) into ments
-  const float4* __restrict__ ments;    // [nnz] dx,dy,dz, morph id bits
+  const uint2*  __restrict__ mrange;   // [Vp/32] per warp: (first entry, depth) into ments
+  const float4* __restrict__ ments;    // lane-interleaved per warp: entry u of lane l at first + u*32 + l = (dx,dy,dz, morph id bits); padding = zeros
   const uint32_t* __restrict__ sdefIdx;// [Vp] word of lane l = descriptor of the l-th SDEF vertex of its warp: table index | output slot << 24 (~0u: none)
   const float4* __restrict__ sdefTab;  // [nSdef*3]: (C.xyz,c0.x) (c0.yz,c1.xy) (c1.z, w0, w1, palette rows j0 | j1 << 16)
   const float*  __restrict__ skin;     // [P][B][12]
@@ -61,6 +63,7 @@ struct DeformParams {
   uint32_t nGroups, nChunks, tilesPerChunk;
   uint32_t packedMeta;                 // 1: meta lives in the spare bits of the joint words (B <= 4096), no separate load
   uint32_t posStride, rowStride;       // palette addressing: chunk r of palette row `pos` sits at pos*posStride + r*rowStride bytes
+  const uint32_t* __restrict__ chunkTab; // [nChunks+1] tile boundaries of cost-balanced chunks, or nullptr (uniform tilesPerChunk)
   uint32_t* counter;
 };
 
@@ -210,13 +213,13 @@ __device__ __forceinline__ Q4 quat_slerp(Q4 a, Q4 b, float t) {
   if (c < 0.f) { c = -c; b.x = -b.x; b.y = -b.y; b.z = -b.z; b.w = -b.w; }
   if (c > 0.9995f) {
     const float x = a.x + t * (b.x - a.x), y = a.y + t * (b.y - a.y), z = a.z + t * (b.z - a.z), w = a.w + t * (b.w - a.w);
-    const float inv = 1.0f / sqrtf(x * x + y * y + z * z + w * w);
+    const float inv = rsqrtf(x * x + y * y + z * z + w * w);        // 2 ulp, far inside the parity tolerance
     return Q4{x * inv, y * inv, z * inv, w * inv};
   }
   // every sine argument lies in [0, pi/2] here (0 <= c <= 0.9995, 0 <= t <= 1).  __sinf is not an option: near the 0.9995
   // threshold th0 ~ 0.03 rad and its absolute error (2^-21.4) would be a 1e-5 RELATIVE error of s0/s1 (measured: 2.2e-5 on
   // config 3), outside the parity tolerance; sin_0_halfpi keeps ~1e-7 relative without sinf's range-reduction slow path.
-  const float th0 = acosf(c), rs = 1.0f / sin_0_halfpi(th0), th = th0 * t;
+  const float th0 = acosf(c), rs = __fdividef(1.0f, sin_0_halfpi(th0)), th = th0 * t;
   const float s0 = sin_0_halfpi(th0 - th) * rs, s1 = sin_0_halfpi(th) * rs;
   return Q4{s0 * a.x + s1 * b.x, s0 * a.y + s1 * b.y, s0 * a.z + s1 * b.z, s0 * a.w + s1 * b.w};
 }
@@ -228,7 +231,7 @@ struct VRec {
   float4 r0, r1, r2;
   uint32_t meta;
   uint32_t sdesc;   // SDEF: descriptor of the lane-th SDEF vertex of this warp (~0u: none)
-  uint2 mr;         // MORPH: (first entry, count) of this lane's vertex
+  uint2 mr;         // MORPH: (first entry, depth) of this warp's lane-interleaved morph entries (warp-uniform)
 };
 
 // shared-memory control block at the start of dynamic smem; data starts at byte kCtrlBytes
@@ -297,8 +300,8 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
     const uint32_t chunk = item - g * prm.nChunks;
     const uint32_t kBase = prm.K0 + g * I;                       // first instance of this group
     const uint32_t nInst = min((uint32_t)I, prm.K0 + prm.Kcount - kBase);
-    const uint32_t tile0 = chunk * prm.tilesPerChunk;
-    const uint32_t tile1 = min(prm.nTiles, tile0 + prm.tilesPerChunk);
+    const uint32_t tile0 = prm.chunkTab ? __ldg(prm.chunkTab + chunk) : chunk * prm.tilesPerChunk;
+    const uint32_t tile1 = prm.chunkTab ? __ldg(prm.chunkTab + chunk + 1) : min(prm.nTiles, tile0 + prm.tilesPerChunk);
     float* const outItem = prm.out + (size_t)kBase * prm.instStrideF;   // pos plane of the group's first instance
 
     // ---- stage the palettes (+ morph weights) of the I instances: TMA bulk copies on one mbarrier
@@ -343,7 +346,7 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
         v.r2 = ldg_el(prm.rec2 + p, polLast);
         v.meta = prm.packedMeta ? 0u : ldg_el(prm.meta + p, polLast);
         v.sdesc = SDEF ? ldg_el(prm.sdefIdx + p, polLast) : ~0u;
-        v.mr = MORPH ? ldg_el(prm.mrange + p, polLast) : make_uint2(0u, 0u);
+        v.mr = MORPH ? ldg_el(prm.mrange + p / 32u, polLast) : make_uint2(0u, 0u);
       } else {                                                  // the far tiles of a wide pass fall off the chunk
         v.r0 = make_float4(0.f, 0.f, 0.f, 1.f);
         v.r1 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -355,12 +358,26 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
       return v;
     };
     VRec cur = load_rec(tile0);
+    // first kMorphPF morph entries of a record's vertex; fetched one pass ahead so that the dependent chain
+    // record -> entries -> weights costs one L2 round trip less per pass
+    float4 pf[MORPH ? kMorphPF : 1];
+    auto load_pf = [&](const VRec& r) {
+#pragma unroll
+      for (int u = 0; u < kMorphPF; ++u)
+        pf[u] = ((uint32_t)u < r.mr.y) ? ldg_el(prm.ments + r.mr.x + (uint32_t)u * 32u + (uint32_t)lane, polLast) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
 
     if (!GPAL || MORPH) mbar_wait(palBar, palPhase);
     palPhase ^= 1u;
+    if (MORPH) load_pf(cur);
 
     for (uint32_t t = tile0; t < tile1; t += NT / kTile) {
       const VRec v = cur;
+      float4 pfv[MORPH ? kMorphPF : 1];
+      if (MORPH) {
+#pragma unroll
+        for (int u = 0; u < kMorphPF; ++u) pfv[u] = pf[u];
+      }
       if (t + NT / kTile < tile1) cur = load_rec(t + NT / kTile);
       if (t + (uint32_t)warp / (kTile / 32) >= tile1) continue;       // warp-uniform: this warp has no tile in the pass
 
@@ -392,26 +409,28 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
 #pragma unroll
       for (int i = 0; i < (MORPH ? I : 1); ++i) { px[i] = v.r0.x; py[i] = v.r0.y; pz[i] = v.r0.z; }
       if (MORPH) {
-        if (meta & kMetaMorph) {
-          const uint2 mr = v.mr;                                   // prefetched with the record: one L2 round trip less
-          // entries of one vertex are contiguous: fetch 4 at a time so their L2 latencies overlap (the loop is a
-          // dependent chain otherwise: ~20 entries on a face vertex x one round trip each)
-          const uint32_t eEnd = mr.x + mr.y;
-          for (uint32_t e = mr.x; e < eEnd; e += 4) {
-            float4 d[4];
+        const uint2 mr = v.mr;                                     // prefetched with the record
+        if (mr.y) {
+          auto apply = [&](const float4 d) {
+            const uint32_t m = __float_as_uint(d.w);               // padded entries: delta 0, morph 0
 #pragma unroll
-            for (int u = 0; u < 4; ++u) d[u] = (e + u < eEnd) ? __ldg(prm.ments + e + u) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const uint32_t m = __float_as_uint(d[u].w);          // padded entries: delta 0, morph 0
-#pragma unroll
-              for (int i = 0; i < I; ++i) {
-                const float wgt = lds32(sMw + ((uint32_t)i * prm.Mpad + m) * 4u);
-                px[i] = fmaf(wgt, d[u].x, px[i]);
-                py[i] = fmaf(wgt, d[u].y, py[i]);
-                pz[i] = fmaf(wgt, d[u].z, pz[i]);
-              }
+            for (int i = 0; i < I; ++i) {
+              const float wgt = lds32(sMw + ((uint32_t)i * prm.Mpad + m) * 4u);
+              px[i] = fmaf(wgt, d.x, px[i]);
+              py[i] = fmaf(wgt, d.y, py[i]);
+              pz[i] = fmaf(wgt, d.z, pz[i]);
             }
+          };
+#pragma unroll
+          for (int u = 0; u < kMorphPF; ++u) apply(pfv[u]);
+          // the rest kMorphBatch depth steps at a time so their L2 latencies overlap; the bound is warp-uniform
+          const float4* ep = prm.ments + mr.x + (uint32_t)lane;
+          for (uint32_t u0 = kMorphPF; u0 < mr.y; u0 += kMorphBatch) {
+            float4 d[kMorphBatch];
+#pragma unroll
+            for (int u = 0; u < kMorphBatch; ++u) d[u] = (u0 + u < mr.y) ? ldg_el(ep + (size_t)(u0 + u) * 32u, polLast) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < kMorphBatch; ++u) apply(d[u]);
           }
         }
       }
@@ -651,6 +670,9 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
         __syncwarp();
       }
       if (kStageBufs > 1) sbuf ^= 1u;
+      if (MORPH) {
+        if (t + NT / kTile < tile1) load_pf(cur);                  // cur's record has landed by now
+      }
     }
 
     if (BOUNDS) {

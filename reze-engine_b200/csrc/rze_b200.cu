@@ -75,6 +75,10 @@ struct rz_ctx_impl {
   int permMode = 2, colorMode = 1, layoutMode = 0;       // vertex ordering inside a tile / bank-aware palette permutation
   DevBuf d_rec0, d_rec1, d_rec2, d_meta, d_wbits, d_mrange, d_ments, d_sdefIdx, d_sdefTab, d_invBind;
   uint32_t morphNnz = 0, sdefActive = 0;
+  std::vector<uint32_t> tileMorphMax;     // [nTiles] most morph entries on one vertex of the tile (chunk balancing)
+  DevBuf d_chunkTab;
+  struct ChunkKey { uint32_t tilesPerPass = 0, target = 0; } chunkKey;
+  uint32_t chunkCount = 0;
 
   // skeleton for GPU pose evaluation
   bool haveSkeleton = false, haveTweens = false, haveAnimation = false;
@@ -286,6 +290,10 @@ int rebuild_tables(rz_ctx_impl* c) {
       }
   }
   c->morphNnz = nnz;
+  c->tileMorphMax.assign(nTiles, 0);
+  for (uint32_t v = 0; v < V; ++v) c->tileMorphMax[v / kTile] = std::max(c->tileMorphMax[v / kTile], mcount[v]);
+  c->chunkKey = {};
+  // (the per-vertex lists above are re-laid out per warp once the lane plan is known, see `mell` below)
 
   // SDEF (only when enabled): which vertices take the spherical path.  The table itself needs the palette rows and is
   // built further down, after the bank-aware permutation.
@@ -303,7 +311,8 @@ int rebuild_tables(rz_ctx_impl* c) {
 
   std::vector<float4> rec0(Vp), rec1(Vp), rec2(Vp);
   std::vector<uint32_t> metaArr(Vp), wbits(Vp, 0);
-  std::vector<uint2> mrange(Vp);
+  std::vector<uint2> mrange(Vp / 32);     // per warp: (first entry, depth) of its lane-interleaved morph entries
+  std::vector<float4> mell;
   std::vector<uint32_t> sdefIdx(Vp, 0);
   c->procToVertex.assign(Vp, ~0u);
 
@@ -477,17 +486,34 @@ int rebuild_tables(rz_ctx_impl* c) {
       rec0[p] = make_float4(x[0], x[1], x[2], w[0]);
       rec1[p] = make_float4(x[3], x[4], x[5], w[1]);
       memcpy(&wbits[p], &WT[(size_t)v * 4], 4);
-      mrange[p] = make_uint2(mstart[v], mcount[v]);
       c->procToVertex[p] = v;
     } else {
       // padding: a harmless rigid vertex parked on an unused output slot of this warp
       rec0[p] = make_float4(0.f, 0.f, 0.f, w[0]);
       rec1[p] = make_float4(0.f, 0.f, 0.f, w[1]);
-      mrange[p] = make_uint2(0u, 0u);
     }
     rec2[p] = make_float4(w[2], w[3], j01f, j23f);
     metaArr[p] = meta;
   }
+
+  // ---- morph entries, lane-interleaved per warp (ELL): entry u of lane l sits at first + u*32 + l, padded with
+  // (delta 0, morph 0) up to the deepest vertex of the warp.  One LDG.128 per depth step is then a single coalesced
+  // 512-byte request for the warp instead of 32 scattered 16-byte ones (the L1 tag stage serialises those: measured
+  // +0.16 ms on config 3), and the loop bound is warp-uniform.  Within a lane the entries keep PMX morph order.
+  for (uint32_t w0 = 0; w0 < Vp; w0 += 32) {
+    uint32_t deep = 0;
+    for (uint32_t l = 0; l < 32; ++l) { const uint32_t v = procVertex[w0 + l]; if (v != ~0u) deep = std::max(deep, mcount[v]); }
+    const uint32_t first = (uint32_t)mell.size();
+    mrange[w0 / 32] = make_uint2(first, deep);
+    if (!deep) continue;
+    mell.resize((size_t)first + (size_t)deep * 32, make_float4(0.f, 0.f, 0.f, 0.f));
+    for (uint32_t l = 0; l < 32; ++l) {
+      const uint32_t v = procVertex[w0 + l];
+      if (v == ~0u) continue;
+      for (uint32_t u = 0; u < mcount[v]; ++u) mell[(size_t)first + (size_t)u * 32 + l] = ments[mstart[v] + u];
+    }
+  }
+  if (mell.empty()) mell.push_back(make_float4(0.f, 0.f, 0.f, 0.f));
 
   int rc;
   if ((rc = dev_reserve(c, c->d_rec0, (size_t)Vp * 16))) return rc;
@@ -495,8 +521,8 @@ int rebuild_tables(rz_ctx_impl* c) {
   if ((rc = dev_reserve(c, c->d_rec2, (size_t)Vp * 16))) return rc;
   if ((rc = dev_reserve(c, c->d_meta, (size_t)Vp * 4))) return rc;
   if ((rc = dev_reserve(c, c->d_wbits, (size_t)Vp * 4))) return rc;
-  if ((rc = dev_reserve(c, c->d_mrange, (size_t)Vp * 8))) return rc;
-  if ((rc = dev_reserve(c, c->d_ments, ments.size() * 16))) return rc;
+  if ((rc = dev_reserve(c, c->d_mrange, (size_t)(Vp / 32) * 8))) return rc;
+  if ((rc = dev_reserve(c, c->d_ments, mell.size() * 16))) return rc;
   if ((rc = dev_reserve(c, c->d_sdefIdx, (size_t)Vp * 4))) return rc;
   if ((rc = dev_reserve(c, c->d_sdefTab, std::max<size_t>(sdefTab.size(), 3) * 16))) return rc;
   if ((rc = dev_reserve(c, c->d_invBind, (size_t)B * 64))) return rc;
@@ -506,8 +532,8 @@ int rebuild_tables(rz_ctx_impl* c) {
   CU_TRY(c, cudaMemcpyAsync(c->d_rec2.p, rec2.data(), (size_t)Vp * 16, cudaMemcpyHostToDevice, c->stream));
   CU_TRY(c, cudaMemcpyAsync(c->d_meta.p, metaArr.data(), (size_t)Vp * 4, cudaMemcpyHostToDevice, c->stream));
   CU_TRY(c, cudaMemcpyAsync(c->d_wbits.p, wbits.data(), (size_t)Vp * 4, cudaMemcpyHostToDevice, c->stream));
-  CU_TRY(c, cudaMemcpyAsync(c->d_mrange.p, mrange.data(), (size_t)Vp * 8, cudaMemcpyHostToDevice, c->stream));
-  CU_TRY(c, cudaMemcpyAsync(c->d_ments.p, ments.data(), ments.size() * 16, cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(c->d_mrange.p, mrange.data(), (size_t)(Vp / 32) * 8, cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(c->d_ments.p, mell.data(), mell.size() * 16, cudaMemcpyHostToDevice, c->stream));
   CU_TRY(c, cudaMemcpyAsync(c->d_sdefIdx.p, sdefIdx.data(), (size_t)Vp * 4, cudaMemcpyHostToDevice, c->stream));
   if (!sdefTab.empty())
     CU_TRY(c, cudaMemcpyAsync(c->d_sdefTab.p, sdefTab.data(), sdefTab.size() * 16, cudaMemcpyHostToDevice, c->stream));
@@ -1101,8 +1127,10 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
     // preference order (measured on B200, profiles/): most resident warps first, then wider instance groups
     static const int pref[][3] = {{6, 512, 1}, {4, 512, 1}, {3, 256, 2}, {2, 512, 2}, {2, 256, 3}, {3, 512, 1}, {2, 256, 2}, {2, 512, 1}, {4, 256, 1},
                                   {1, 256, 4}, {1, 256, 2}, {1, 512, 2}};
-    // feature kernels (morph / SDEF / bounds / ...) are compiled for fewer shapes; prefer the ones without register spills
-    static const int prefLite[][3] = {{2, 256, 2}, {2, 512, 1}, {4, 512, 1}, {1, 256, 2}};
+    // feature kernels (morph / SDEF / bounds / ...) are compiled for fewer shapes
+    // (measured on config 3, profiles/r01_config3_split_*.jsonl: the wide group wins despite a few spilled registers --
+    // more (vertex, instance) pairs per SDEF dense pass, morph entries fetched once per 4 instances)
+    static const int prefLite[][3] = {{4, 512, 1}, {2, 256, 2}, {2, 512, 1}, {1, 256, 2}};
     bool ok = false;
     if (feat != 0) {
       for (const auto& p : prefLite) if (try_shape(p[0], p[1], p[2])) { ok = true; break; }
@@ -1155,6 +1183,39 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
   const uint32_t passesPerChunk = (nPasses + nChunks - 1) / nChunks;
   prm.tilesPerChunk = passesPerChunk * tilesPerPass;
   prm.nChunks = (c->nTiles + prm.tilesPerChunk - 1) / prm.tilesPerChunk;
+  if ((feat & FEAT_MORPH) && c->morphNnz && nChunks > 1) {
+    // Morph passes are latency chains (record -> entries -> weights: one L2 round trip per kMorphBatch entries of the
+    // deepest vertex), several times longer than a plain pass, and PMX morphs cluster on the face: uniform chunks would
+    // leave a few very long items (measured: +70 % on config 3).  Chunk boundaries are placed so that every item carries
+    // the same estimated time instead; the table only depends on the launch shape and is cached.
+    if (c->chunkKey.tilesPerPass != tilesPerPass || c->chunkKey.target != nChunks || !c->d_chunkTab.p) {
+      std::vector<float> cost(nPasses);
+      double total = 0;
+      for (uint32_t p = 0; p < nPasses; ++p) {
+        uint32_t deep = 0;
+        for (uint32_t t = p * tilesPerPass; t < std::min(c->nTiles, (p + 1) * tilesPerPass); ++t) deep = std::max(deep, c->tileMorphMax[t]);
+        const uint32_t trips = deep > (uint32_t)kMorphPF ? (deep - kMorphPF + kMorphBatch - 1) / kMorphBatch : 0;
+        static const float tripCost = getenv("RZ_MORPH_TRIP_COST") ? (float)atof(getenv("RZ_MORPH_TRIP_COST")) : 0.5f;
+        cost[p] = 1.0f + (deep ? 0.25f : 0.f) + tripCost * (float)trips;   // in plain passes; an L2 round trip ~ half a pass
+        total += cost[p];
+      }
+      std::vector<uint32_t> tab;
+      tab.push_back(0);
+      double acc = 0;
+      for (uint32_t p = 0; p < nPasses; ++p) {
+        acc += cost[p];
+        if (acc >= total * (double)tab.size() / (double)nChunks && p + 1 < nPasses) tab.push_back((p + 1) * tilesPerPass);
+      }
+      tab.push_back(c->nTiles);
+      if ((rc = dev_reserve(c, c->d_chunkTab, tab.size() * 4))) return rc;
+      CU_TRY(c, cudaMemcpyAsync(c->d_chunkTab.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, c->stream));
+      CU_TRY(c, cudaStreamSynchronize(c->stream));                  // once per launch shape; `tab` goes out of scope
+      c->chunkKey.tilesPerPass = tilesPerPass; c->chunkKey.target = nChunks;
+      c->chunkCount = (uint32_t)tab.size() - 1;
+    }
+    prm.chunkTab = reinterpret_cast<const uint32_t*>(c->d_chunkTab.p);
+    prm.nChunks = c->chunkCount;
+  }
   prm.counter = reinterpret_cast<uint32_t*>(c->d_counter.p);
   prm.packedMeta = c->packedMeta ? 1u : 0u;
   prm.posStride = c->layoutMode ? 16u : 48u;

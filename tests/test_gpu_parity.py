@@ -148,6 +148,94 @@ def test_sdef_on_and_compat_off(rzlib, orc, wl_small):
         check_all(orc, ctx, wl, world, None, K, sdef=False)
 
 
+def _all_sdef(wl, rng):
+    """Every vertex that may be SDEF (third and fourth weight zero) becomes SDEF: up to 32 per warp, so the kernel's dense
+    phase needs several rounds per pass (32 / I pairs fit one round)."""
+    W = wl.weights.reshape(-1, 4)
+    idx = np.nonzero((W[:, 2] == 0) & (W[:, 3] == 0))[0].astype(np.uint32)
+    pos = wl.vtx8.reshape(-1, 8)[idx, :3]
+    C = pos + rng.normal(0, 0.1, pos.shape)
+    vec = np.concatenate([C, C + rng.normal(0, 0.2, pos.shape), C - rng.normal(0, 0.2, pos.shape)], axis=1).astype(np.float32)
+    return idx, vec
+
+
+@pytest.mark.parametrize("I,nt", [(1, 256), (2, 256), (2, 512), (4, 512)])
+def test_sdef_dense_phase_many_rounds_and_feature_sets(rzlib, orc, wl_small, I, nt):
+    wl = wl_small
+    K = 5                                           # partial last group for I = 2, 4
+    rng = np.random.default_rng(50 + I)
+    world = synth.make_palettes(wl.bones, K, rng)
+    world[1] = world[0]                             # two instances, one pose
+    dense = rng.uniform(0, 1, (K, wl.morphs.count)).astype(np.float32)
+    dense[1] = dense[0]
+    idx, vec = _all_sdef(wl, rng)
+    assert idx.size > wl.V // 2
+    sd = (idx, vec)
+    for flags in (0, capi.RZ_FLAG_BOUNDS, capi.RZ_FLAG_NO_NORMALS):
+        with capi.DeformContext(max_instances=K, flags=capi.RZ_FLAG_SDEF | flags, instances_per_group=I, threads=nt) as ctx:
+            ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
+            ctx.load_sdef(idx, vec)
+            ctx.load_morphs(wl.morphs.offsets, wl.morphs.vertexIndex, wl.morphs.delta)
+            ctx.set_palettes(world)
+            ctx.set_morph_weights(dense, np.arange(wl.morphs.count), K=K)
+            ctx.deform()
+            s = ctx.stats()
+            assert (s["instancesPerGroup"], s["threads"], s["sdefCount"]) == (I, nt, idx.size)
+            for k in range(K):
+                rp, rn = orc.deform(wl.vtx8, wl.joints, wl.weights, orc.skin_matrices(world[k], wl.invBind),
+                                    morph=(wl.morphs.offsets, wl.morphs.vertexIndex, wl.morphs.delta), morphW=dense[k], sdef=sd)
+                gp, gn = ctx.read_instance(k, normals=not (flags & capi.RZ_FLAG_NO_NORMALS))
+                assert rel_err(gp, rp) <= TOL, (flags, k, rel_err(gp, rp))
+                if gn is not None:
+                    assert rel_err(gn, rn) <= TOL, (flags, k, rel_err(gn, rn))
+                if flags & capi.RZ_FLAG_BOUNDS:
+                    bb = ctx.read_bounds(k, 1)[0]
+                    assert np.array_equal(bb[:3], gp.min(axis=0)) and np.array_equal(bb[3:], gp.max(axis=0))
+            a, b = ctx.read_instance(0, normals=False), ctx.read_instance(1, normals=False)
+            assert np.array_equal(a[0], b[0])
+
+
+def test_sdef_edge_cases(rzlib, orc):
+    """Bind pose (all quaternions equal: the lerp branch of slerp), one-bone SDEF records, the same bone twice, and the
+    palette-in-global path (B too large for shared memory)."""
+    rng = np.random.default_rng(61)
+    wl = synth.make_workload(2000, 24, seed=61, sdef=True)
+    W = wl.weights.reshape(-1, 4).copy()
+    J = wl.joints.reshape(-1, 4).copy()
+    idx, vec = _all_sdef(wl, rng)
+    W[idx[0]] = [255, 0, 0, 0]                      # w1 = 0: slerp at t = 0
+    W[idx[1]] = [0, 255, 0, 0]                      # w0 = 0
+    J[idx[2], 1] = J[idx[2], 0]                     # the same bone in both slots
+    wl.weights, wl.joints = W, J
+    ident = np.tile(np.eye(4, dtype=np.float32).T.reshape(1, 1, 16), (1, wl.B, 1))
+    bind = ident.copy()
+    bind[0, :, 12:15] = -wl.invBind.reshape(-1, 16)[:, 12:15]        # world = inverse of the (pure translation) inverse bind
+    world = np.concatenate([bind, synth.make_palettes(wl.bones, 2, rng)], axis=0)
+    with capi.DeformContext(max_instances=3, flags=capi.RZ_FLAG_SDEF) as ctx:
+        ctx.load_mesh(wl.vtx8, J, W, wl.invBind)
+        ctx.load_sdef(idx, vec)
+        ctx.set_palettes(world)
+        ctx.deform()
+        for k in range(3):
+            rp, rn = orc.deform(wl.vtx8, J, W, orc.skin_matrices(world[k], wl.invBind), sdef=(idx, vec))
+            gp, gn = ctx.read_instance(k)
+            assert rel_err(gp, rp) <= TOL and rel_err(gn, rn) <= TOL, (k, rel_err(gp, rp), rel_err(gn, rn))
+        gp, _ = ctx.read_instance(0)                # bind pose: SDEF is the identity too
+        assert np.abs(gp - wl.vtx8.reshape(-1, 8)[:, :3]).max() <= 2e-5
+    big = synth.make_workload(3000, 6000, seed=78)
+    idx, vec = _all_sdef(big, rng)
+    world = synth.make_palettes(big.bones, 3, rng)
+    with capi.DeformContext(max_instances=3, flags=capi.RZ_FLAG_SDEF) as ctx:
+        ctx.load_mesh(big.vtx8, big.joints, big.weights, big.invBind)
+        ctx.load_sdef(idx, vec)
+        ctx.set_palettes(world, np.array([2, 0, 1], np.uint32))
+        ctx.deform()
+        for k, p in enumerate((2, 0, 1)):
+            rp, rn = orc.deform(big.vtx8, big.joints, big.weights, orc.skin_matrices(world[p], big.invBind), sdef=(idx, vec))
+            gp, gn = ctx.read_instance(k)
+            assert rel_err(gp, rp) <= TOL and rel_err(gn, rn) <= TOL, (k, rel_err(gp, rp), rel_err(gn, rn))
+
+
 def test_bounds_and_positions_only(rzlib, orc, wl_small):
     wl = wl_small
     K = 9

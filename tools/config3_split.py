@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--iters", type=int, default=8)
     ap.add_argument("--shapes", default="0:0:0,2:256:2,2:512:1,4:512:1,1:256:2")
     ap.add_argument("--variants", default="plain,morph,sdef,both")
+    ap.add_argument("--chunks", default="0", help="comma list of rz_config.tune_chunks values (0 = library default)")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "config3_split.jsonl"))
     a = ap.parse_args()
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
@@ -39,12 +40,12 @@ def main():
     for variant in a.variants.split(","):
         morph = variant in ("morph", "both")
         sdef = variant in ("sdef", "both")
-        for sh in a.shapes.split(","):
+        for sh, chunks in [(x, int(y)) for x in a.shapes.split(",") for y in a.chunks.split(",")]:
             I, nt, ctas = (int(x) for x in sh.split(":"))
-            row = dict(variant=variant, req=[I, nt, ctas])
+            row = dict(variant=variant, req=[I, nt, ctas, chunks])
             try:
                 with capi.DeformContext(max_instances=K, stream=stream.cuda_stream, flags=capi.RZ_FLAG_SDEF if sdef else 0,
-                                        instances_per_group=I, threads=nt, ctas_per_sm=ctas) as ctx:
+                                        instances_per_group=I, threads=nt, ctas_per_sm=ctas, chunks=chunks) as ctx:
                     ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
                     if morph:
                         ctx.load_morphs(wl.morphs.offsets, wl.morphs.vertexIndex, wl.morphs.delta)
