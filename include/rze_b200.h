@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RZE_B200_ABI_VERSION 1
+#define RZE_B200_ABI_VERSION 2
 
 typedef struct rz_ctx rz_ctx;
 
@@ -46,6 +46,16 @@ typedef enum rz_status {
 #define RZ_FLAG_REORDER_VERTICES 0x8u /* opt-in: the device planes store vertices sorted by bone tuple (like a vertex-cache
                                      optimiser reorders a mesh); ~20 % faster.  rz_get_vertex_order() gives the order so the
                                      caller can remap its index buffer once; rz_read_instance still returns caller order */
+
+#define RZ_FLAG_OUTLINE     0x10u /* fused consumer: a third plane per instance with the outline hull position
+                                     pos' + normalize(n') * edgeSize * 0.01 — what the reference's outline vertex shader
+                                     feeds the rasteriser (engine.ts:431-463, expansion 458-461); edgeSize per vertex from
+                                     rz_load_edge_size (0 = no outline: hull == pos') */
+#define RZ_FLAG_INTERLEAVED 0x20u /* fused consumer: the result leaves as ONE stream of 8 f32 per vertex
+                                     [x,y,z,nx,ny,nz,u,v] per instance — the reference's own vertex-buffer layout
+                                     (arrayStride 32, engine.ts:340-347; model.ts:196-200), so an unmodified pipeline can
+                                     draw instance k with an identity palette.  uv is passed through from rz_load_mesh.
+                                     Not combinable with RZ_FLAG_NO_NORMALS / RZ_FLAG_OUTLINE */
 
 typedef struct rz_config {
   uint32_t struct_size;    /* sizeof(rz_config), for forward compatibility */
@@ -104,6 +114,11 @@ int32_t rz_load_morphs(rz_ctx* ctx, const uint32_t* morphOffsets /* M+1 */, cons
  * Only used when RZ_FLAG_SDEF is set; the vertex must carry exactly two influences. */
 int32_t rz_load_sdef(rz_ctx* ctx, const uint32_t* vertIdx /* n */, const float* c_r0_r1 /* 9*n */, uint32_t n);
 
+/* Outline width per vertex for RZ_FLAG_OUTLINE: Material.edgeSize (model.ts:24, uploaded at engine.ts:2030) of the
+ * material the vertex is drawn with when that material has an outline ((edgeFlag & 0x10) && edgeSize > 0,
+ * engine.ts:2024), else 0.  NULL resets every vertex to 0.  The 0.01 scale factor of engine.ts:459 is applied here. */
+int32_t rz_load_edge_size(rz_ctx* ctx, const float* edgeSize /* V or NULL */);
+
 /* ---- per frame: replaces queue.writeBuffer(worldMatrixBuffer) + computeSkinMatrices
  * (engine.ts:2383-2402, shader engine.ts:920-929) ----
  * world : P x B x 16 f32 column-major, exactly Model.getBoneWorldMatrices() (model.ts:317-319), P palettes.
@@ -154,7 +169,26 @@ int32_t rz_sync(rz_ctx* ctx);
  * Device layout per instance k: pos plane V x 3 f32 at  base + k*instanceStride,
  *                               nrm plane V x 3 f32 at  base + k*instanceStride + normalOffset.  */
 int32_t rz_output_device_ptr(rz_ctx* ctx, void** base, size_t* instanceStride, size_t* normalOffset);
+/* Full description of the device result (all sizes in bytes).  Attribute a of vertex i of instance k lives at
+ * base + k*instanceStride + aOffset + i*vertexStride.  Planar (default): vertexStride 12, one plane per attribute.
+ * RZ_FLAG_INTERLEAVED: vertexStride 32, offsets 0 / 12 / 24 inside the vertex.  An attribute that is not produced has
+ * offset RZ_NO_ATTRIBUTE. */
+#define RZ_NO_ATTRIBUTE ((size_t)-1)
+typedef struct rz_output_layout {
+  void*  base;
+  size_t instanceStride;
+  size_t vertexStride;
+  size_t positionOffset;   /* always 0 */
+  size_t normalOffset;     /* RZ_NO_ATTRIBUTE with RZ_FLAG_NO_NORMALS */
+  size_t hullOffset;       /* outline hull plane, RZ_FLAG_OUTLINE only */
+  size_t uvOffset;         /* RZ_FLAG_INTERLEAVED only */
+} rz_output_layout;
+int32_t rz_get_output_layout(rz_ctx* ctx, rz_output_layout* out);
 int32_t rz_read_instance(rz_ctx* ctx, uint32_t inst, float* pos3 /* 3V or NULL */, float* nrm3 /* 3V or NULL */);
+/* outline hull positions of one instance (RZ_FLAG_OUTLINE), caller vertex order */
+int32_t rz_read_outline(rz_ctx* ctx, uint32_t inst, float* hull3 /* 3V */);
+/* the interleaved stream of one instance (RZ_FLAG_INTERLEAVED), caller vertex order: 8 f32 per vertex */
+int32_t rz_read_interleaved(rz_ctx* ctx, uint32_t inst, float* vtx8 /* 8V */);
 /* order[i] = caller vertex id stored at position i of the device planes (identity unless RZ_FLAG_REORDER_VERTICES) */
 int32_t rz_get_vertex_order(rz_ctx* ctx, uint32_t* order /* V */);
 

@@ -51,6 +51,23 @@ def skin_matrices(world: np.ndarray, invBind: np.ndarray, dtype=np.float32) -> n
     return out
 
 
+def outline_hull(pos: np.ndarray, nrm: np.ndarray, edge_size) -> np.ndarray:
+    """The outline vertex shader's expansion (engine.ts:458-461), on the blend's outputs:
+        expandedPos = worldPos + worldNormal * material.edgeSize * scaleFactor,   scaleFactor = 0.01
+    f32, evaluated left to right like the WGSL expression.  edge_size: [V] Material.edgeSize per vertex (0 = none)."""
+    pos = np.asarray(pos, np.float32)
+    nrm = np.asarray(nrm, np.float32)
+    e = np.asarray(edge_size, np.float32).reshape(-1, 1)
+    return (pos + (nrm * e) * np.float32(0.01)).astype(np.float32)
+
+
+def interleaved(pos: np.ndarray, nrm: np.ndarray, vtx8: np.ndarray) -> np.ndarray:
+    """[V,8] = [pos', nrm', uv]: the reference's vertex-buffer record (model.ts:196-200, arrayStride 32 at
+    engine.ts:340-347) holding the blend's outputs (engine.ts:270-273: uv is passed through)."""
+    uv = np.asarray(vtx8, np.float32).reshape(-1, 8)[:, 6:8]
+    return np.concatenate([np.asarray(pos, np.float32), np.asarray(nrm, np.float32), uv], axis=1)
+
+
 def vertex_major_morphs(V: int, offsets, vertIdx, delta3):
     """morph-major CSR -> vertex-major (start[V+1], morphId[nnz], delta[nnz,3]) keeping PMX morph order."""
     offsets = np.asarray(offsets, np.int64)

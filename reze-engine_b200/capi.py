@@ -21,6 +21,9 @@ RZ_FLAG_SDEF = 0x1
 RZ_FLAG_NO_NORMALS = 0x2
 RZ_FLAG_BOUNDS = 0x4
 RZ_FLAG_REORDER_VERTICES = 0x8
+RZ_FLAG_OUTLINE = 0x10
+RZ_FLAG_INTERLEAVED = 0x20
+RZ_NO_ATTRIBUTE = (1 << (8 * C.sizeof(C.c_size_t))) - 1
 
 EXPORTS = [
     "rz_create", "rz_destroy", "rz_abi_version", "rz_load_mesh", "rz_load_morphs", "rz_load_sdef",
@@ -28,6 +31,7 @@ EXPORTS = [
     "rz_set_tweens", "rz_set_instance_clocks", "rz_load_animation", "rz_set_morph_weights", "rz_deform",
     "rz_sync", "rz_output_device_ptr", "rz_read_instance", "rz_get_vertex_order", "rz_plan_lanes", "rz_read_bounds", "rz_read_skinning",
     "rz_read_skin_matrices", "rz_get_stats", "rz_last_error",
+    "rz_load_edge_size", "rz_get_output_layout", "rz_read_outline", "rz_read_interleaved",
 ]
 
 
@@ -59,6 +63,11 @@ class RzStats(C.Structure):
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class RzOutputLayout(C.Structure):
+    _fields_ = [("base", C.c_void_p), ("instanceStride", C.c_size_t), ("vertexStride", C.c_size_t), ("positionOffset", C.c_size_t),
+                ("normalOffset", C.c_size_t), ("hullOffset", C.c_size_t), ("uvOffset", C.c_size_t)]
 
 
 _lib = None
@@ -94,6 +103,10 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.rz_sync.argtypes = [vp]
     lib.rz_output_device_ptr.argtypes = [vp, P(vp), P(sz), P(sz)]
     lib.rz_read_instance.argtypes = [vp, u32, vp, vp]
+    lib.rz_load_edge_size.argtypes = [vp, vp]
+    lib.rz_get_output_layout.argtypes = [vp, P(RzOutputLayout)]
+    lib.rz_read_outline.argtypes = [vp, u32, vp]
+    lib.rz_read_interleaved.argtypes = [vp, u32, vp]
     lib.rz_get_vertex_order.argtypes = [vp, vp]
     lib.rz_plan_lanes.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp, vp]
     lib.rz_read_bounds.argtypes = [vp, u32, u32, vp]
@@ -312,6 +325,30 @@ class DeformContext:
             nrm = out_nrm if out_nrm is not None else np.empty((self.V, 3), dtype=np.float32)
         self._check(self.lib.rz_read_instance(self.h, inst, _ptr(pos), _ptr(nrm)))
         return pos, nrm
+
+    def load_edge_size(self, edge_size):
+        """Per-vertex Material.edgeSize (0 = no outline) for RZ_FLAG_OUTLINE; None resets to zero."""
+        e = None if edge_size is None else _arr(edge_size, np.float32).reshape(-1)
+        if e is not None and e.size != self.V:
+            raise ValueError("edge_size must hold one entry per vertex")
+        self._check(self.lib.rz_load_edge_size(self.h, _ptr(e)))
+
+    def output_layout(self) -> dict:
+        lay = RzOutputLayout()
+        self._check(self.lib.rz_get_output_layout(self.h, C.byref(lay)))
+        return {k: getattr(lay, k) for k, _ in lay._fields_}
+
+    def read_outline(self, inst: int) -> np.ndarray:
+        """Outline hull positions pos' + n' * edgeSize * 0.01 of one instance, [V,3] float32 (RZ_FLAG_OUTLINE)."""
+        out = np.empty((self.V, 3), dtype=np.float32)
+        self._check(self.lib.rz_read_outline(self.h, inst, _ptr(out)))
+        return out
+
+    def read_interleaved(self, inst: int) -> np.ndarray:
+        """The [x,y,z,nx,ny,nz,u,v] stream of one instance, [V,8] float32 (RZ_FLAG_INTERLEAVED)."""
+        out = np.empty((self.V, 8), dtype=np.float32)
+        self._check(self.lib.rz_read_interleaved(self.h, inst, _ptr(out)))
+        return out
 
     def vertex_order(self) -> np.ndarray:
         """order[i] = caller vertex id stored at position i of the device planes."""

@@ -40,7 +40,9 @@ constexpr uint32_t kMetaValid = 1u << 13;
 constexpr uint32_t kMetaMorph = 1u << 14;
 constexpr uint32_t kMetaSdef  = 1u << 15;
 
-enum : int { FEAT_MORPH = 1, FEAT_SDEF = 2, FEAT_BOUNDS = 4, FEAT_GPAL = 8, FEAT_NONRM = 16 };
+enum : int { FEAT_MORPH = 1, FEAT_SDEF = 2, FEAT_BOUNDS = 4, FEAT_GPAL = 8, FEAT_NONRM = 16,
+              FEAT_HULL = 32,   // third output plane: outline hull pos' + n^' * edgeScale[v]   (engine.ts:458-461)
+              FEAT_ILV = 64 };  // one interleaved 32-byte [pos, nrm, uv] stream per instance   (engine.ts:340-347 vertex stride)
 
 struct DeformParams {
   const float4* __restrict__ rec0;     // [Vp] px,py,pz, w0      (weights already normalised like engine.ts:255-258)
@@ -55,10 +57,13 @@ struct DeformParams {
   const float4* __restrict__ quat;     // [P][B] rotation of each skin matrix as a quaternion (SDEF only; skin_quats_kernel)
   const uint32_t* __restrict__ inst2pal; // [K] or nullptr (identity)
   const float*  __restrict__ mweights; // dense [K][Mpad]
+  const float* __restrict__ edge;      // [Vp] outline offset of the lane's vertex = material edgeSize * 0.01 (FEAT_HULL)
+  const float2* __restrict__ uv;       // [Vp] texture coordinates of the lane's vertex, passed through (FEAT_ILV)
   float* __restrict__ out;
   float* __restrict__ bounds;          // [K][6] as ordered ints, or nullptr
   unsigned long long instStrideF;      // floats between instances
   unsigned long long nrmOffF;          // floats from pos plane to normal plane
+  unsigned long long hullOffF;         // floats from pos plane to outline-hull plane (FEAT_HULL)
   uint32_t V, B, nTiles, K0, Kcount, Mpad;
   uint32_t nGroups, nChunks, tilesPerChunk;
   uint32_t packedMeta;                 // 1: meta lives in the spare bits of the joint words (B <= 4096), no separate load
@@ -155,6 +160,9 @@ __device__ __forceinline__ float lds32(uint32_t a) {
 __device__ __forceinline__ void sts3(uint32_t a, float x, float y, float z) {
   asm volatile("st.shared.f32 [%0], %1;\n\tst.shared.f32 [%0+4], %2;\n\tst.shared.f32 [%0+8], %3;" ::"r"(a), "f"(x), "f"(y), "f"(z) : "memory");
 }
+__device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
 __device__ __forceinline__ void st_cs(float* p, float v) { asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
 
 // Blackwell packed FP32 (FFMA2 / FMUL2: two fp32 lanes per instruction).  The blend of 3x4 matrices is element-wise,
@@ -232,6 +240,8 @@ struct VRec {
   uint32_t meta;
   uint32_t sdesc;   // SDEF: descriptor of the lane-th SDEF vertex of this warp (~0u: none)
   uint2 mr;         // MORPH: (first entry, depth) of this warp's lane-interleaved morph entries (warp-uniform)
+  float edge;       // HULL: outline offset along the skinned normal
+  float2 uv;        // ILV: texture coordinates (passed through)
 };
 
 // shared-memory control block at the start of dynamic smem; data starts at byte kCtrlBytes
@@ -258,8 +268,14 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
   constexpr bool BOUNDS = (FEAT & FEAT_BOUNDS) != 0;
   constexpr bool GPAL = (FEAT & FEAT_GPAL) != 0;      // palette too large for smem: gather from global/L1
   constexpr bool NRM = (FEAT & FEAT_NONRM) == 0;
-  constexpr int PLANES = NRM ? 2 : 1;
-  constexpr uint32_t kPlaneB = 32 * 12;                // bytes of one warp-private staging plane (32 vertices x float3)
+  constexpr bool HULL = (FEAT & FEAT_HULL) != 0;
+  constexpr bool ILV = (FEAT & FEAT_ILV) != 0;
+  static_assert(!(HULL && !NRM) && !(ILV && !NRM) && !(HULL && ILV), "hull / interleaved output need normals; one layout at a time");
+  constexpr int PLANES = ILV ? 1 : (NRM ? 2 : 1) + (HULL ? 1 : 0);
+  constexpr uint32_t kVtxB = ILV ? 32u : 12u;          // bytes per vertex of a staging plane
+  constexpr uint32_t kPlaneB = 32 * kVtxB;             // bytes of one warp-private staging plane (32 vertices)
+  constexpr uint32_t kNrmO = ILV ? 12u : kPlaneB;      // normal of a vertex relative to its position
+  constexpr uint32_t kHullO = 2 * kPlaneB;             // outline hull position relative to its position (HULL)
   constexpr uint32_t kInstB = PLANES * kPlaneB;        // one instance of one warp
   constexpr uint32_t kBufB = I * kInstB;               // one staging buffer of one warp
 
@@ -347,6 +363,8 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
         v.meta = prm.packedMeta ? 0u : ldg_el(prm.meta + p, polLast);
         v.sdesc = SDEF ? ldg_el(prm.sdefIdx + p, polLast) : ~0u;
         v.mr = MORPH ? ldg_el(prm.mrange + p / 32u, polLast) : make_uint2(0u, 0u);
+        v.edge = HULL ? __ldg(prm.edge + p) : 0.f;
+        v.uv = ILV ? __ldg(prm.uv + p) : make_float2(0.f, 0.f);
       } else {                                                  // the far tiles of a wide pass fall off the chunk
         v.r0 = make_float4(0.f, 0.f, 0.f, 1.f);
         v.r1 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -354,6 +372,8 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
         v.meta = (uint32_t)lane | (1u << kMetaNinfShift);
         v.sdesc = ~0u;
         v.mr = make_uint2(0u, 0u);
+        v.edge = 0.f;
+        v.uv = make_float2(0.f, 0.f);
       }
       return v;
     };
@@ -402,7 +422,7 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
       const float vnx = v.r1.x, vny = v.r1.y, vnz = v.r1.z;
       const uint32_t warpVtx0 = t * kTile + (uint32_t)warp * 32u;        // first output vertex of this warp (uniform)
       const uint32_t nWarpVerts = min(32u, prm.V - min(prm.V, warpVtx0));
-      const uint32_t nAligned = nWarpVerts & ~3u;                 // bulk sizes must be multiples of 16 B
+      const uint32_t nAligned = ILV ? nWarpVerts : (nWarpVerts & ~3u);   // bulk sizes must be multiples of 16 B
 
       // ---- morph accumulation: p~ = p + sum_m w[k][m] * delta_m[v]   (model space, before skinning)
       float px[MORPH ? I : 1], py[MORPH ? I : 1], pz[MORPH ? I : 1];
@@ -459,7 +479,7 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
       if (elect_one()) bulk_wait_read<kStageBufs - 1>();
       __syncwarp();
       const uint32_t stg = sStageW + sbuf * kBufB;
-      const uint32_t stgLane = stg + slot * 12u;
+      const uint32_t stgLane = stg + slot * kVtxB;
 
       // splats for the packed mat-vec (once per vertex unless morphing moves the position per instance)
       const float2 nx2 = make_float2(vnx, vnx), ny2 = make_float2(vny, vny), nz2 = make_float2(vnz, vnz);
@@ -540,8 +560,18 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
           }
           {
             const uint32_t sa = stgLane + (uint32_t)i * kInstB;
-            sts3(sa, ox, oy, oz);
-            if (NRM) sts3(sa + kPlaneB, nx, ny, nz);
+            if (ILV) {
+              sts128(sa, ox, oy, oz, nx);
+              sts128(sa + 16u, ny, nz, v.uv.x, v.uv.y);
+            } else {
+              sts3(sa, ox, oy, oz);
+              if (NRM) sts3(sa + kNrmO, nx, ny, nz);
+              if (HULL) {
+                // MMD inverted hull: pos' + n^' * edgeSize * 0.01 (engine.ts:458-461); SDEF owners park the offset instead
+                if (SDEF && isSdef) sts3(sa + kHullO, v.edge, 0.f, 0.f);
+                else sts3(sa + kHullO, fmaf(nx, v.edge, ox), fmaf(ny, v.edge, oy), fmaf(nz, v.edge, oz));
+              }
+            }
           }
         }
       };
@@ -575,7 +605,7 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
               }
             }
             if (r < sdCount) {
-              const uint32_t sa = stg + i * kInstB + (w >> 24) * 12u;
+              const uint32_t sa = stg + i * kInstB + (w >> 24) * kVtxB;
               const float qx = lds32(sa), qy = lds32(sa + 4), qz = lds32(sa + 8);
               const uint32_t jj = __float_as_uint(t2.w);
               const uint32_t r0p = jj & 0xFFFFu, r1p = jj >> 16;                 // palette rows of the two bones
@@ -617,13 +647,18 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
               const float oz = fmaf(R20, dx, fmaf(R21, dy, R22 * dz)) + sw0 * e0z + sw1 * e1z;
               sts3(sa, ox, oy, oz);
               if (NRM) {
-                const float vx = lds32(sa + kPlaneB), vy = lds32(sa + kPlaneB + 4), vz = lds32(sa + kPlaneB + 8);
+                const float vx = lds32(sa + kNrmO), vy = lds32(sa + kNrmO + 4), vz = lds32(sa + kNrmO + 8);
                 float nx = fmaf(R00, vx, fmaf(R01, vy, R02 * vz));
                 float ny = fmaf(R10, vx, fmaf(R11, vy, R12 * vz));
                 float nz = fmaf(R20, vx, fmaf(R21, vy, R22 * vz));
                 const float l2 = fmaf(nx, nx, fmaf(ny, ny, nz * nz));
                 const float rl = l2 > 0.f ? rsqrtf(l2) : 0.f;
-                sts3(sa + kPlaneB, nx * rl, ny * rl, nz * rl);
+                nx *= rl; ny *= rl; nz *= rl;
+                sts3(sa + kNrmO, nx, ny, nz);
+                if (HULL) {
+                  const float eg = lds32(sa + kHullO);              // parked by the owner lane
+                  sts3(sa + kHullO, fmaf(nx, eg, ox), fmaf(ny, eg, oy), fmaf(nz, eg, oz));
+                }
               }
               if (BOUNDS) {
 #pragma unroll
@@ -644,12 +679,13 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
       __syncwarp();
       if (elect_one()) {
         if (nAligned) {
-          float* dst = outItem + (size_t)warpVtx0 * 3;
+          float* dst = outItem + (size_t)warpVtx0 * (kVtxB / 4u);
 #pragma unroll
           for (int i = 0; i < I; ++i) {
             if ((uint32_t)i < nInst) {
-              bulk_s2g(dst, stg + (uint32_t)i * kInstB, nAligned * 12u, polFirst);
-              if (NRM) bulk_s2g(dst + prm.nrmOffF, stg + (uint32_t)i * kInstB + kPlaneB, nAligned * 12u, polFirst);
+              bulk_s2g(dst, stg + (uint32_t)i * kInstB, nAligned * kVtxB, polFirst);
+              if (NRM && !ILV) bulk_s2g(dst + prm.nrmOffF, stg + (uint32_t)i * kInstB + kPlaneB, nAligned * 12u, polFirst);
+              if (HULL) bulk_s2g(dst + prm.hullOffF, stg + (uint32_t)i * kInstB + kHullO, nAligned * 12u, polFirst);
             }
             dst += prm.instStrideF;
           }
@@ -665,6 +701,7 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
             float* dst = outItem + (size_t)i * prm.instStrideF + (size_t)warpVtx0 * 3 + o;
             st_cs(dst, lds32(stg + i * kInstB + o * 4u));
             if (NRM) st_cs(dst + prm.nrmOffF, lds32(stg + i * kInstB + kPlaneB + o * 4u));
+            if (HULL) st_cs(dst + prm.hullOffF, lds32(stg + i * kInstB + kHullO + o * 4u));
           }
         }
         __syncwarp();

@@ -57,6 +57,9 @@ struct rz_ctx_impl {
   std::vector<float> h_mdelta;
   std::vector<uint32_t> h_sdefVert;
   std::vector<float> h_sdefVec;
+  std::vector<float> h_edgeSize;          // [V] Material.edgeSize per vertex (RZ_FLAG_OUTLINE), empty = all zero
+  DevBuf d_edge, d_uv;
+  size_t hullOffF = 0;
   bool tablesDirty = true;
 
   // device tables (processing order)
@@ -197,7 +200,7 @@ int resolve_feat(int need) {
 #undef RZ_V
   };
   int best = -1, bestBits = 99;
-  const int exact = FEAT_GPAL | FEAT_NONRM;
+  const int exact = FEAT_GPAL | FEAT_NONRM | FEAT_HULL | FEAT_ILV;
   for (int cnd : compiled) {
     if ((cnd & need) != need) continue;
     if ((cnd & exact) != (need & exact)) continue;
@@ -212,7 +215,8 @@ size_t smem_needed(int I, int NT, int feat, uint32_t B, uint32_t Mpad, int nbuf 
   if (!(feat & FEAT_GPAL)) s += (size_t)I * B * 48;
   if (feat & FEAT_MORPH) s += (size_t)I * Mpad * 4;
   if ((feat & FEAT_SDEF) && !(feat & FEAT_GPAL)) s += (size_t)I * B * 16;   // per-bone quaternions
-  s += (size_t)nbuf * I * ((feat & FEAT_NONRM) ? 1 : 2) * NT * 12;   // warp-private staging (pos + normal planes)
+  const size_t vtxBytes = (feat & FEAT_ILV) ? 32 : (((feat & FEAT_NONRM) ? 1 : 2) + ((feat & FEAT_HULL) ? 1 : 0)) * 12;
+  s += (size_t)nbuf * I * NT * vtxBytes;                                // warp-private staging, laid out like the output
   return s;
 }
 
@@ -311,6 +315,8 @@ int rebuild_tables(rz_ctx_impl* c) {
 
   std::vector<float4> rec0(Vp), rec1(Vp), rec2(Vp);
   std::vector<uint32_t> metaArr(Vp), wbits(Vp, 0);
+  std::vector<float> edgeArr((c->flags & RZ_FLAG_OUTLINE) ? Vp : 0, 0.f);
+  std::vector<float2> uvArr((c->flags & RZ_FLAG_INTERLEAVED) ? Vp : 0, make_float2(0.f, 0.f));
   std::vector<uint2> mrange(Vp / 32);     // per warp: (first entry, depth) of its lane-interleaved morph entries
   std::vector<float4> mell;
   std::vector<uint32_t> sdefIdx(Vp, 0);
@@ -486,6 +492,9 @@ int rebuild_tables(rz_ctx_impl* c) {
       rec0[p] = make_float4(x[0], x[1], x[2], w[0]);
       rec1[p] = make_float4(x[3], x[4], x[5], w[1]);
       memcpy(&wbits[p], &WT[(size_t)v * 4], 4);
+      // engine.ts:459-460: worldNormal * material.edgeSize * scaleFactor, scaleFactor = 0.01
+      if (!edgeArr.empty() && !c->h_edgeSize.empty()) edgeArr[p] = c->h_edgeSize[c->vorder[v]] * 0.01f;
+      if (!uvArr.empty()) uvArr[p] = make_float2(x[6], x[7]);
       c->procToVertex[p] = v;
     } else {
       // padding: a harmless rigid vertex parked on an unused output slot of this warp
@@ -539,12 +548,23 @@ int rebuild_tables(rz_ctx_impl* c) {
     CU_TRY(c, cudaMemcpyAsync(c->d_sdefTab.p, sdefTab.data(), sdefTab.size() * 16, cudaMemcpyHostToDevice, c->stream));
   CU_TRY(c, cudaMemcpyAsync(c->d_invBind.p, c->h_invBind.data(), (size_t)B * 64, cudaMemcpyHostToDevice, c->stream));
   CU_TRY(c, cudaMemcpyAsync(c->d_bonePos.p, c->bonePos.data(), (size_t)B * 4, cudaMemcpyHostToDevice, c->stream));
+  if (!edgeArr.empty()) {
+    if ((rc = dev_reserve(c, c->d_edge, (size_t)Vp * 4))) return rc;
+    CU_TRY(c, cudaMemcpyAsync(c->d_edge.p, edgeArr.data(), (size_t)Vp * 4, cudaMemcpyHostToDevice, c->stream));
+  }
+  if (!uvArr.empty()) {
+    if ((rc = dev_reserve(c, c->d_uv, (size_t)Vp * 8))) return rc;
+    CU_TRY(c, cudaMemcpyAsync(c->d_uv.p, uvArr.data(), (size_t)Vp * 8, cudaMemcpyHostToDevice, c->stream));
+  }
   CU_TRY(c, cudaStreamSynchronize(c->stream));   // the std::vectors above go out of scope
 
   // output planes: pos plane then normal plane, both 16-byte aligned (TMA bulk stores)
   const bool nrm = !(c->flags & RZ_FLAG_NO_NORMALS);
   c->nrmOffF = align_up((size_t)V * 3, 4);
   c->instStrideF = nrm ? 2 * c->nrmOffF : c->nrmOffF;
+  c->hullOffF = 0;
+  if (c->flags & RZ_FLAG_OUTLINE) { c->hullOffF = 2 * c->nrmOffF; c->instStrideF = 3 * c->nrmOffF; }
+  if (c->flags & RZ_FLAG_INTERLEAVED) { c->nrmOffF = 3; c->instStrideF = (size_t)V * 8; }   // one stream of 8 f32 per vertex
   if ((rc = dev_reserve(c, c->d_out, (size_t)c->maxK * c->instStrideF * 4))) return rc;
   if (c->flags & RZ_FLAG_BOUNDS)
     if ((rc = dev_reserve(c, c->d_bounds, (size_t)c->maxK * 24))) return rc;
@@ -588,6 +608,10 @@ int32_t rz_create(const rz_config* cfg, rz_ctx** out) {
   if (cfg->device < 0 || cfg->device >= ndev)
     return fail(nullptr, RZ_ERR_INVALID_ARG, "device %d out of range (have %d)", cfg->device, ndev);
   if (cfg->max_instances == 0) return fail(nullptr, RZ_ERR_INVALID_ARG, "max_instances must be >= 1");
+  if ((cfg->flags & RZ_FLAG_NO_NORMALS) && (cfg->flags & (RZ_FLAG_OUTLINE | RZ_FLAG_INTERLEAVED)))
+    return fail(nullptr, RZ_ERR_INVALID_ARG, "RZ_FLAG_NO_NORMALS cannot be combined with RZ_FLAG_OUTLINE / RZ_FLAG_INTERLEAVED (both need the normal)");
+  if ((cfg->flags & RZ_FLAG_OUTLINE) && (cfg->flags & RZ_FLAG_INTERLEAVED))
+    return fail(nullptr, RZ_ERR_INVALID_ARG, "RZ_FLAG_OUTLINE and RZ_FLAG_INTERLEAVED are separate output layouts: pick one");
   CU_TRY(nullptr, cudaSetDevice(cfg->device));
   cudaDeviceProp prop;
   CU_TRY(nullptr, cudaGetDeviceProperties(&prop, cfg->device));
@@ -638,7 +662,7 @@ int32_t rz_destroy(rz_ctx* c) {
                     &c->d_invBind, &c->d_bonePos, &c->d_world, &c->d_skin, &c->d_inst2pal, &c->d_mwIn, &c->d_mwIds, &c->d_mwDense,
                     &c->d_out, &c->d_bounds, &c->d_counter, &c->d_skParent, &c->d_skBindT, &c->d_skAppendParent, &c->d_skAppendRatio,
                     &c->d_skLevelBones, &c->d_skLevelStart, &c->d_skChainStart, &c->d_skChainBones, &c->d_twStart, &c->d_twTarget, &c->d_twRest, &c->d_twStartMs, &c->d_twDurMs,
-                    &c->d_twActive, &c->d_localRot, &c->d_nowMs, &c->d_trStart, &c->d_trMs, &c->d_trQ};
+                    &c->d_twActive, &c->d_localRot, &c->d_nowMs, &c->d_trStart, &c->d_trMs, &c->d_trQ, &c->d_quat, &c->d_chunkTab, &c->d_edge, &c->d_uv};
   for (DevBuf* b : bufs) dev_free(c, *b);
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->h_small) cudaFreeHost(c->h_small);
@@ -667,6 +691,7 @@ int32_t rz_load_mesh(rz_ctx* c, const float* vtx8, const uint16_t* joints, const
   c->M = 0;
   c->h_moff.clear(); c->h_mvert.clear(); c->h_mdelta.clear();
   c->h_sdefVert.clear(); c->h_sdefVec.clear();
+  c->h_edgeSize.clear();
   c->palettesSet = false;
   c->haveSkeleton = false;
   c->haveTweens = false;
@@ -1089,6 +1114,8 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
   if ((c->flags & RZ_FLAG_SDEF) && c->sdefActive) need |= FEAT_SDEF;
   if (c->flags & RZ_FLAG_BOUNDS) need |= FEAT_BOUNDS;
   if (c->flags & RZ_FLAG_NO_NORMALS) need |= FEAT_NONRM;
+  if (c->flags & RZ_FLAG_OUTLINE) need |= FEAT_HULL;
+  if (c->flags & RZ_FLAG_INTERLEAVED) need |= FEAT_ILV;
   if ((rc = ensure_dense_weights(c))) return rc;
   const uint32_t Mpad = c->Mpad;
 
@@ -1096,7 +1123,9 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
   const size_t smemMax = (size_t)c->maxSmemOptin;
   if (smem_needed(1, 256, need, c->B, Mpad) > smemMax) need |= FEAT_GPAL;   // palette does not fit: gather from global
   const int feat = resolve_feat(need);
-  if (feat < 0) return fail(c, RZ_ERR_INVALID_ARG, "rz_deform: feature combination 0x%x is not built", need);
+  if (feat < 0)
+    return fail(c, RZ_ERR_INVALID_ARG, "rz_deform: feature combination 0x%x is not built%s", need,
+                (need & FEAT_GPAL) && (need & (FEAT_HULL | FEAT_ILV)) ? " (outline / interleaved output need the palette in shared memory: B too large)" : "");
   KernelEntry ke{nullptr, 0, 0, 0, 0, 0, feat};
   size_t smem = 0;
   int occ = 0;
@@ -1169,6 +1198,9 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
   prm.quat = reinterpret_cast<const float4*>(c->d_quat.p);
   prm.inst2pal = c->haveInst2pal ? reinterpret_cast<const uint32_t*>(c->d_inst2pal.p) : nullptr;
   prm.mweights = reinterpret_cast<const float*>(c->d_mwDense.p);
+  prm.edge = reinterpret_cast<const float*>(c->d_edge.p);
+  prm.uv = reinterpret_cast<const float2*>(c->d_uv.p);
+  prm.hullOffF = c->hullOffF;
   prm.out = reinterpret_cast<float*>(c->d_out.p);
   prm.bounds = reinterpret_cast<float*>(c->d_bounds.p);
   prm.instStrideF = c->instStrideF;
@@ -1249,8 +1281,10 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
   c->usedI = ke.I; c->usedStore = 2; c->usedCtas = grid; c->usedThreads = ke.NT; c->usedSmem = (uint32_t)smem;
   c->lastVerts = (uint64_t)count * c->V;
   // compulsory DRAM bytes: outputs + mesh + palettes + invBind + morph entries/weights + sdef records
-  const double planes = (feat & FEAT_NONRM) ? 1.0 : 2.0;
-  c->lastAlgBytes = (double)count * c->V * 12.0 * planes + (double)c->V * 36.0 + (double)c->P * c->B * 64.0 + (double)c->B * 64.0 +
+  // (fused consumers add their own compulsory bytes: +12 B per vertex-instance for the hull plane, 32 B instead of 24 B
+  //  for the interleaved stream, +4 / +8 B per vertex for the edge sizes / texture coordinates read)
+  const double planes = (feat & FEAT_ILV) ? 32.0 / 12.0 : ((feat & FEAT_NONRM) ? 1.0 : 2.0) + ((feat & FEAT_HULL) ? 1.0 : 0.0);
+  c->lastAlgBytes = (double)count * c->V * 12.0 * planes + ((feat & FEAT_HULL) ? 4.0 * c->V : 0.0) + ((feat & FEAT_ILV) ? 8.0 * c->V : 0.0) + (double)c->V * 36.0 + (double)c->P * c->B * 64.0 + (double)c->B * 64.0 +
                     ((feat & FEAT_MORPH) ? (double)c->morphNnz * 16.0 + (double)count * c->Mact * 4.0 : 0.0) +
                     ((feat & FEAT_SDEF) ? (double)c->sdefActive * 36.0 : 0.0);
   const double now = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -1271,8 +1305,78 @@ int32_t rz_output_device_ptr(rz_ctx* c, void** base, size_t* stride, size_t* nrm
   if (c->V == 0) return fail(c, RZ_ERR_STATE, "rz_output_device_ptr before rz_load_mesh");
   *base = c->d_out.p;
   if (stride) *stride = c->instStrideF * 4;
-  if (nrmOff) *nrmOff = (c->flags & RZ_FLAG_NO_NORMALS) ? 0 : c->nrmOffF * 4;
+  if (nrmOff) *nrmOff = (c->flags & RZ_FLAG_NO_NORMALS) ? 0 : c->nrmOffF * 4;   // (interleaved: 12, see rz_get_output_layout)
   return RZ_OK;
+}
+
+// one interleaved instance (RZ_FLAG_INTERLEAVED) to the host in CALLER vertex order, 8 floats per vertex
+static int fetch_interleaved(rz_ctx* c, uint32_t inst, std::vector<float>& tmp) {
+  tmp.resize((size_t)c->V * 8);
+  const float* src = reinterpret_cast<const float*>(c->d_out.p) + (size_t)inst * c->instStrideF;
+  CU_TRY(c, cudaMemcpyAsync(tmp.data(), src, (size_t)c->V * 32, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  if (c->flags & RZ_FLAG_REORDER_VERTICES) {
+    std::vector<float> t2((size_t)c->V * 8);
+    for (uint32_t i = 0; i < c->V; ++i) memcpy(&t2[(size_t)c->vorder[i] * 8], &tmp[(size_t)i * 8], 32);
+    tmp.swap(t2);
+  }
+  return RZ_OK;
+}
+
+int32_t rz_read_interleaved(rz_ctx* c, uint32_t inst, float* vtx8) {
+  if (!c || !vtx8) return fail(c, RZ_ERR_INVALID_ARG, "rz_read_interleaved: null argument");
+  if (c->V == 0) return fail(c, RZ_ERR_STATE, "rz_read_interleaved before rz_load_mesh");
+  if (!(c->flags & RZ_FLAG_INTERLEAVED)) return fail(c, RZ_ERR_STATE, "rz_read_interleaved: context was created without RZ_FLAG_INTERLEAVED");
+  if (inst >= c->maxK) return fail(c, RZ_ERR_INVALID_ARG, "rz_read_interleaved: instance %u >= max_instances %u", inst, c->maxK);
+  CU_TRY(c, cudaSetDevice(c->device));
+  std::vector<float> tmp;
+  int rc;
+  if ((rc = fetch_interleaved(c, inst, tmp))) return rc;
+  memcpy(vtx8, tmp.data(), (size_t)c->V * 32);
+  return RZ_OK;
+}
+
+int32_t rz_read_outline(rz_ctx* c, uint32_t inst, float* hull3) {
+  if (!c || !hull3) return fail(c, RZ_ERR_INVALID_ARG, "rz_read_outline: null argument");
+  if (c->V == 0) return fail(c, RZ_ERR_STATE, "rz_read_outline before rz_load_mesh");
+  if (!(c->flags & RZ_FLAG_OUTLINE)) return fail(c, RZ_ERR_STATE, "rz_read_outline: context was created without RZ_FLAG_OUTLINE");
+  if (inst >= c->maxK) return fail(c, RZ_ERR_INVALID_ARG, "rz_read_outline: instance %u >= max_instances %u", inst, c->maxK);
+  CU_TRY(c, cudaSetDevice(c->device));
+  const float* src = reinterpret_cast<const float*>(c->d_out.p) + (size_t)inst * c->instStrideF + c->hullOffF;
+  if (c->flags & RZ_FLAG_REORDER_VERTICES) {
+    std::vector<float> tmp((size_t)c->V * 3);
+    CU_TRY(c, cudaMemcpyAsync(tmp.data(), src, (size_t)c->V * 12, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    for (uint32_t i = 0; i < c->V; ++i) memcpy(hull3 + (size_t)c->vorder[i] * 3, &tmp[(size_t)i * 3], 12);
+    return RZ_OK;
+  }
+  CU_TRY(c, cudaMemcpyAsync(hull3, src, (size_t)c->V * 12, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return RZ_OK;
+}
+
+int32_t rz_get_output_layout(rz_ctx* c, rz_output_layout* out) {
+  if (!c || !out) return fail(c, RZ_ERR_INVALID_ARG, "rz_get_output_layout: null argument");
+  if (c->V == 0) return fail(c, RZ_ERR_STATE, "rz_get_output_layout before rz_load_mesh");
+  const bool ilv = (c->flags & RZ_FLAG_INTERLEAVED) != 0;
+  out->base = c->d_out.p;
+  out->instanceStride = c->instStrideF * 4;
+  out->vertexStride = ilv ? 32 : 12;
+  out->positionOffset = 0;
+  out->normalOffset = (c->flags & RZ_FLAG_NO_NORMALS) ? RZ_NO_ATTRIBUTE : c->nrmOffF * 4;
+  out->hullOffset = (c->flags & RZ_FLAG_OUTLINE) ? c->hullOffF * 4 : RZ_NO_ATTRIBUTE;
+  out->uvOffset = ilv ? 24 : RZ_NO_ATTRIBUTE;
+  return RZ_OK;
+}
+
+int32_t rz_load_edge_size(rz_ctx* c, const float* edgeSize) {
+  if (!c) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_load_edge_size: null ctx");
+  if (c->V == 0) return fail(c, RZ_ERR_STATE, "rz_load_edge_size before rz_load_mesh");
+  if (!(c->flags & RZ_FLAG_OUTLINE)) return fail(c, RZ_ERR_STATE, "rz_load_edge_size: context was created without RZ_FLAG_OUTLINE");
+  CU_TRY(c, cudaSetDevice(c->device));
+  if (edgeSize) c->h_edgeSize.assign(edgeSize, edgeSize + c->V); else c->h_edgeSize.clear();
+  c->tablesDirty = true;
+  return rebuild_tables(c);
 }
 
 int32_t rz_read_instance(rz_ctx* c, uint32_t inst, float* pos3, float* nrm3) {
@@ -1281,6 +1385,16 @@ int32_t rz_read_instance(rz_ctx* c, uint32_t inst, float* pos3, float* nrm3) {
   if (inst >= c->maxK) return fail(c, RZ_ERR_INVALID_ARG, "rz_read_instance: instance %u >= max_instances %u", inst, c->maxK);
   if (nrm3 && (c->flags & RZ_FLAG_NO_NORMALS)) return fail(c, RZ_ERR_STATE, "rz_read_instance: context was created with RZ_FLAG_NO_NORMALS");
   CU_TRY(c, cudaSetDevice(c->device));
+  if (c->flags & RZ_FLAG_INTERLEAVED) {
+    std::vector<float> tmp;
+    int rc;
+    if ((rc = fetch_interleaved(c, inst, tmp))) return rc;
+    for (uint32_t i = 0; i < c->V; ++i) {
+      if (pos3) memcpy(pos3 + (size_t)i * 3, &tmp[(size_t)i * 8], 12);
+      if (nrm3) memcpy(nrm3 + (size_t)i * 3, &tmp[(size_t)i * 8 + 3], 12);
+    }
+    return RZ_OK;
+  }
   const float* src = reinterpret_cast<const float*>(c->d_out.p) + (size_t)inst * c->instStrideF;
   if (c->flags & RZ_FLAG_REORDER_VERTICES) {
     // device planes are in the library's stored order: hand them back in the caller's vertex order

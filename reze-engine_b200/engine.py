@@ -64,7 +64,8 @@ class ManualClock:
 class Engine:
     def __init__(self, canvas=None, options: Optional[dict] = None, *, instances: int = 1, device: int = 0,
                  clock: Optional[Callable[[], float]] = None, sdef: bool = False, bounds: bool = False, stream: int = 0,
-                 gpu_pose: bool = False, crowd: bool = False, reorder_vertices: bool = False):
+                 gpu_pose: bool = False, crowd: bool = False, reorder_vertices: bool = False, outline: bool = False,
+                 interleaved: bool = False):
         o = options or {}
         # EngineOptions (engine.ts:8-14): kept so existing call sites construct unchanged; they only
         # parameterise passes this repo does not replace.
@@ -78,7 +79,10 @@ class Engine:
         self.clock = clock or (lambda: time.perf_counter() * 1000.0)
         # reorder_vertices: the device planes store vertices grouped by bone tuple (faster blend); draw with deviceIndexBuffer()
         self._flags = ((capi.RZ_FLAG_SDEF if sdef else 0) | (capi.RZ_FLAG_BOUNDS if bounds else 0)
-                       | (capi.RZ_FLAG_REORDER_VERTICES if reorder_vertices else 0))
+                       | (capi.RZ_FLAG_REORDER_VERTICES if reorder_vertices else 0)
+                       # fused consumers of the skinned stream: the outline pass' hull positions
+                       # (engine.ts:431-463) as a third plane / the result in the reference's 32-byte vertex layout
+                       | (capi.RZ_FLAG_OUTLINE if outline else 0) | (capi.RZ_FLAG_INTERLEAVED if interleaved else 0))
         self._stream = stream
         self.gpu_pose = gpu_pose or crowd   # walk the bone hierarchy on the GPU (rz_set_local_rotations) instead of in Model
         # crowd mode: ONE shared skeleton runtime + animation clip, every instance plays it at its own clock offset; tweens /
@@ -159,6 +163,8 @@ class Engine:
             self.ctx.load_morphs(model.morphs.offsets, model.morphs.vertexIndex, model.morphs.delta)
         if model.sdef.vertexIndex.size:
             self.ctx.load_sdef(model.sdef.vertexIndex, model.sdef.c_r0_r1)
+        if self._flags & capi.RZ_FLAG_OUTLINE:
+            self.ctx.load_edge_size(self.vertexEdgeSizes(model))
         self._world_stage = self.ctx.palette_staging(self.instances)
         if self.gpu_pose:
             self.ctx.load_skeleton(model.getSkeleton().bones)
@@ -412,6 +418,31 @@ class Engine:
         inv = np.empty_like(order)
         inv[order] = np.arange(order.size, dtype=np.uint32)
         return inv[idx]
+
+    @staticmethod
+    def vertexEdgeSizes(model: Model) -> np.ndarray:
+        """Material.edgeSize per vertex: the reference draws the outline of material m over m's slice of the index buffer
+        when (edgeFlag & 0x10) and edgeSize > 0 (engine.ts:2016-2046), expanding by material.edgeSize (engine.ts:458-461).
+        A vertex shared by two outlined materials takes the larger size."""
+        idx = np.asarray(model.getIndices(), np.int64)
+        edge = np.zeros(model.getVertexCount(), np.float32)
+        start = 0
+        for m in model.getMaterials():
+            get = m.get if isinstance(m, dict) else (lambda k, _m=m: getattr(_m, k))
+            n = int(get("vertexCount"))
+            if (int(get("edgeFlag")) & 0x10) and float(get("edgeSize")) > 0:
+                sl = idx[start:start + n]
+                edge[sl] = np.maximum(edge[sl], np.float32(get("edgeSize")))
+            start += n
+        return edge
+
+    def readOutline(self, instance: int = 0) -> np.ndarray:
+        """Outline hull positions of one instance (Engine(outline=True)), [V,3] float32."""
+        return self.ctx.read_outline(instance)
+
+    def readInterleaved(self, instance: int = 0) -> np.ndarray:
+        """One instance in the reference's vertex-buffer layout [x,y,z,nx,ny,nz,u,v] (Engine(interleaved=True))."""
+        return self.ctx.read_interleaved(instance)
 
     def readSkinned(self, instance: int = 0):
         """Skinned positions and normals of one instance, [V,3] float32 each."""

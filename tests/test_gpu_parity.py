@@ -236,6 +236,91 @@ def test_sdef_edge_cases(rzlib, orc):
             assert rel_err(gp, rp) <= TOL and rel_err(gn, rn) <= TOL, (k, rel_err(gp, rp), rel_err(gn, rn))
 
 
+@pytest.mark.parametrize("full", [False, True])
+def test_outline_hull_plane(rzlib, orc, wl_small, full):
+    """RZ_FLAG_OUTLINE: third plane = pos' + n' * edgeSize * 0.01 (engine.ts:458-461), fused into the deform pass; plain and with
+    morphs + SDEF + bounds; positions / normals are untouched by the extra plane."""
+    wl = wl_small
+    K = 5
+    rng = np.random.default_rng(70)
+    world = synth.make_palettes(wl.bones, K, rng)
+    edge = np.where(rng.uniform(size=wl.V) < 0.7, rng.uniform(0.2, 2.0, wl.V), 0.0).astype(np.float32)
+    dense = rng.uniform(0, 1, (K, wl.morphs.count)).astype(np.float32) if full else None
+    flags = capi.RZ_FLAG_OUTLINE | ((capi.RZ_FLAG_SDEF | capi.RZ_FLAG_BOUNDS) if full else 0)
+    for I, nt in ((0, 0), (1, 256), (2, 512)):
+        with capi.DeformContext(max_instances=K, flags=flags, instances_per_group=I, threads=nt) as ctx:
+            ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
+            if full:
+                ctx.load_morphs(wl.morphs.offsets, wl.morphs.vertexIndex, wl.morphs.delta)
+                ctx.load_sdef(wl.sdef.vertexIndex, wl.sdef.c_r0_r1)
+            ctx.set_palettes(world)
+            if full:
+                ctx.set_morph_weights(dense, np.arange(wl.morphs.count), K=K)
+            ctx.deform()                                    # no edge sizes loaded: hull == pos'
+            gp, _ = ctx.read_instance(2)
+            assert np.array_equal(ctx.read_outline(2), gp)
+            ctx.load_edge_size(edge)
+            ctx.deform()
+            lay = ctx.output_layout()
+            assert lay["vertexStride"] == 12 and lay["hullOffset"] == 2 * lay["normalOffset"] and lay["uvOffset"] == capi.RZ_NO_ATTRIBUTE
+            assert lay["instanceStride"] >= 3 * wl.V * 12
+            for k in range(K):
+                rp, rn = oracle_instance(orc, wl, world[k], None if dense is None else dense[k], sdef=full)
+                gp, gn = ctx.read_instance(k)
+                gh = ctx.read_outline(k)
+                assert rel_err(gp, rp) <= TOL and rel_err(gn, rn) <= TOL
+                assert rel_err(gh, orc.outline_hull(rp, rn, edge)) <= TOL, (k, rel_err(gh, orc.outline_hull(rp, rn, edge)))
+                # against its own position / normal the hull is exact up to one fma rounding
+                assert np.abs(gh - (gp + gn * (edge * np.float32(0.01))[:, None])).max() <= 4e-6
+                assert np.array_equal(gh[edge == 0], gp[edge == 0])
+    with pytest.raises(capi.RzError):
+        capi.DeformContext(max_instances=1, flags=capi.RZ_FLAG_OUTLINE | capi.RZ_FLAG_NO_NORMALS)
+    with pytest.raises(capi.RzError):
+        capi.DeformContext(max_instances=1, flags=capi.RZ_FLAG_OUTLINE | capi.RZ_FLAG_INTERLEAVED)
+
+
+@pytest.mark.parametrize("full", [False, True])
+def test_interleaved_vertex_stream(rzlib, orc, wl_small, full):
+    """RZ_FLAG_INTERLEAVED: the result leaves in the reference's vertex-buffer layout (8 f32 per vertex, engine.ts:340-347):
+    bit-identical to the planar result, uv passed through; ragged vertex counts included."""
+    rng = np.random.default_rng(71)
+    for V in (wl_small.V, 1001, 33):
+        wl = wl_small if V == wl_small.V else synth.make_workload(V, 20, M=4, sdef=True, seed=V)
+        K = 5
+        world = synth.make_palettes(wl.bones, K, rng)
+        dense = rng.uniform(0, 1, (K, wl.morphs.count)).astype(np.float32) if full else None
+        extra = (capi.RZ_FLAG_SDEF | capi.RZ_FLAG_BOUNDS) if full else 0
+        outs = {}
+        for flags in (0, capi.RZ_FLAG_INTERLEAVED):
+            with capi.DeformContext(max_instances=K, flags=flags | extra, instances_per_group=2, threads=256) as ctx:
+                ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
+                if full:
+                    ctx.load_morphs(wl.morphs.offsets, wl.morphs.vertexIndex, wl.morphs.delta)
+                    ctx.load_sdef(wl.sdef.vertexIndex, wl.sdef.c_r0_r1)
+                ctx.set_palettes(world)
+                if full:
+                    ctx.set_morph_weights(dense, np.arange(wl.morphs.count), K=K)
+                ctx.deform()
+                outs[flags] = [ctx.read_instance(k) for k in range(K)]
+                if flags:
+                    lay = ctx.output_layout()
+                    assert (lay["vertexStride"], lay["normalOffset"], lay["uvOffset"], lay["instanceStride"]) == (32, 12, 24, wl.V * 32)
+                    for k in range(K):
+                        st = ctx.read_interleaved(k)
+                        rp, rn = oracle_instance(orc, wl, world[k], None if dense is None else dense[k], sdef=full)
+                        ref = orc.interleaved(rp, rn, wl.vtx8)
+                        assert rel_err(st[:, :3], ref[:, :3]) <= TOL and rel_err(st[:, 3:6], ref[:, 3:6]) <= TOL
+                        assert np.array_equal(st[:, 6:], ref[:, 6:])                      # uv: bit-exact pass-through
+                        assert np.array_equal(st[:, :3], outs[flags][k][0]) and np.array_equal(st[:, 3:6], outs[flags][k][1])
+                    if full:
+                        bb = ctx.read_bounds(0, K)
+                        for k in range(K):
+                            assert np.array_equal(bb[k, :3], outs[flags][k][0].min(axis=0))
+        for k in range(K):                                                                 # same arithmetic, different layout
+            assert np.array_equal(outs[0][k][0], outs[capi.RZ_FLAG_INTERLEAVED][k][0])
+            assert np.array_equal(outs[0][k][1], outs[capi.RZ_FLAG_INTERLEAVED][k][1])
+
+
 def test_bounds_and_positions_only(rzlib, orc, wl_small):
     wl = wl_small
     K = 9

@@ -164,7 +164,7 @@ def test_capi_exports_every_declared_symbol(rzlib):
     assert declared == set(capi.EXPORTS)
     for name in declared:
         assert hasattr(rzlib, name), name
-    assert rzlib.rz_abi_version() == 1
+    assert rzlib.rz_abi_version() == 2
     import ctypes as C
     assert C.sizeof(capi.RzConfig) == 56 and C.sizeof(capi.RzStats) == 128
 
