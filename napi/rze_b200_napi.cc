@@ -190,6 +190,67 @@ napi_value ReadInstance(napi_env env, napi_callback_info info) {
   return nullptr;
 }
 
+// loadEdgeSize(ctx, Float32Array|null edgeSize /*V: Material.edgeSize of the material drawing the vertex, 0 = no outline*/)
+napi_value LoadEdgeSize(napi_env env, napi_callback_info info) {
+  size_t argc = 2;
+  napi_value a[2];
+  NAPI_OK(env, napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+  rz_ctx* c = unwrap(env, a[0]);
+  napi_valuetype vt;
+  napi_typeof(env, a[1], &vt);
+  size_t n = 0;
+  const float* e = (vt == napi_null || vt == napi_undefined) ? nullptr : typed<float>(env, a[1], &n, napi_float32_array);
+  if (c) check(env, c, rz_load_edge_size(c, e));
+  return nullptr;
+}
+
+// readOutline(ctx, inst, Float32Array hull /*3V*/): the outline pass' expanded positions (engine.ts:458-461), RZ_FLAG_OUTLINE
+napi_value ReadOutline(napi_env env, napi_callback_info info) {
+  size_t argc = 3;
+  napi_value a[3];
+  NAPI_OK(env, napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+  rz_ctx* c = unwrap(env, a[0]);
+  size_t n = 0;
+  float* hull = typed<float>(env, a[2], &n, napi_float32_array);
+  if (c && hull) check(env, c, rz_read_outline(c, u32(env, a[1]), hull));
+  return nullptr;
+}
+
+// readInterleaved(ctx, inst, Float32Array vtx8 /*8V*/): one instance in the reference's vertex-buffer layout, RZ_FLAG_INTERLEAVED
+napi_value ReadInterleaved(napi_env env, napi_callback_info info) {
+  size_t argc = 3;
+  napi_value a[3];
+  NAPI_OK(env, napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+  rz_ctx* c = unwrap(env, a[0]);
+  size_t n = 0;
+  float* v = typed<float>(env, a[2], &n, napi_float32_array);
+  if (c && v) check(env, c, rz_read_interleaved(c, u32(env, a[1]), v));
+  return nullptr;
+}
+
+// getOutputLayout(ctx) -> {base: BigInt device pointer, instanceStride, vertexStride, positionOffset, normalOffset, hullOffset, uvOffset}
+//   (bytes; an attribute that is not produced is -1) — for zero-copy consumers (CUDA / Vulkan interop)
+napi_value GetOutputLayout(napi_env env, napi_callback_info info) {
+  size_t argc = 1;
+  napi_value a[1];
+  NAPI_OK(env, napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+  rz_ctx* c = unwrap(env, a[0]);
+  rz_output_layout l;
+  if (!c || !check(env, c, rz_get_output_layout(c, &l))) return nullptr;
+  napi_value o, base;
+  NAPI_OK(env, napi_create_object(env, &o));
+  napi_create_bigint_uint64(env, (uint64_t)(uintptr_t)l.base, &base);
+  napi_set_named_property(env, o, "base", base);
+  auto put = [&](const char* k, size_t v) {
+    napi_value n;
+    napi_create_double(env, v == RZ_NO_ATTRIBUTE ? -1.0 : (double)v, &n);
+    napi_set_named_property(env, o, k, n);
+  };
+  put("instanceStride", l.instanceStride); put("vertexStride", l.vertexStride); put("positionOffset", l.positionOffset);
+  put("normalOffset", l.normalOffset); put("hullOffset", l.hullOffset); put("uvOffset", l.uvOffset);
+  return o;
+}
+
 // getStats(ctx) -> {fps, frameTime, gpuMemory, vertsPerSec, achievedGBs}  (EngineStats, engine.ts:16-20 + additions)
 napi_value GetStats(napi_env env, napi_callback_info info) {
   size_t argc = 1;
@@ -222,6 +283,10 @@ napi_value Init(napi_env env, napi_value exports) {
       {"sync", nullptr, Sync, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"readInstance", nullptr, ReadInstance, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"getStats", nullptr, GetStats, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"loadEdgeSize", nullptr, LoadEdgeSize, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"readOutline", nullptr, ReadOutline, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"readInterleaved", nullptr, ReadInterleaved, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"getOutputLayout", nullptr, GetOutputLayout, nullptr, nullptr, nullptr, napi_default, nullptr},
   };
   napi_define_properties(env, exports, sizeof d / sizeof d[0], d);
   return exports;

@@ -157,6 +157,32 @@ def test_oracle_morph_and_sdef_reduce_to_pinned_path(orc):
     assert rel_err(sd[0], lin[0]) < 5e-6 and rel_err(sd[1], lin[1]) < 5e-6
 
 
+def test_vertex_edge_sizes_follow_the_outline_draw_rule(orc):
+    """Engine.vertexEdgeSizes: a vertex takes Material.edgeSize of the material slice of the index buffer that draws it, only
+    when that material is outlined ((edgeFlag & 0x10) and edgeSize > 0, engine.ts:2024); the oracle's hull follows
+    engine.ts:458-461 term by term."""
+    from reze_engine_b200 import Engine
+    from reze_engine_b200.model import Bone, Model, Skeleton, Skinning
+    V = 12
+    vtx = np.zeros((V, 8), np.float32)
+    idx = np.array([0, 1, 2, 3, 4, 5, 5, 6, 7, 8, 9, 10], np.uint32)            # vertex 11 is drawn by nothing, 5 by two materials
+    mats = [dict(vertexCount=3, edgeFlag=0x10, edgeSize=1.5), dict(vertexCount=3, edgeFlag=0x00, edgeSize=2.0),
+            dict(vertexCount=3, edgeFlag=0x10, edgeSize=0.5), dict(vertexCount=3, edgeFlag=0x10, edgeSize=0.0)]
+    bones = [Bone(name="root", parentIndex=-1, bindTranslation=[0.0, 0.0, 0.0])]
+    sk = Skeleton(bones=bones, inverseBindMatrices=np.tile(np.eye(4, dtype=np.float32).reshape(1, 16), (1, 1)))
+    skin = Skinning(joints=np.zeros(V * 4, np.uint16), weights=np.tile(np.array([255, 0, 0, 0], np.uint8), V))
+    model = Model(vtx.reshape(-1), idx, [], mats, sk, skin)
+    e = Engine.vertexEdgeSizes(model)
+    assert e.dtype == np.float32 and e.tolist() == [1.5, 1.5, 1.5, 0, 0, 0.5, 0.5, 0.5, 0, 0, 0, 0]
+    pos = np.arange(V * 3, dtype=np.float32).reshape(V, 3)
+    nrm = np.tile(np.array([0.0, 0.6, 0.8], np.float32), (V, 1))
+    hull = orc.outline_hull(pos, nrm, e)
+    assert hull.dtype == np.float32 and np.array_equal(hull[3], pos[3])
+    assert np.allclose(hull[0] - pos[0], [0, 0.009, 0.012], atol=1e-6)
+    st = orc.interleaved(pos, nrm, vtx)
+    assert st.shape == (V, 8) and np.array_equal(st[:, :3], pos) and np.array_equal(st[:, 6:], vtx[:, 6:])
+
+
 def test_capi_exports_every_declared_symbol(rzlib):
     from reze_engine_b200 import capi
     hdr = open(os.path.join(ROOT, "include", "rze_b200.h")).read()

@@ -21,6 +21,8 @@ export type EngineOptions = {
   instances?: number        // new: crowd size K (default 1)
   device?: number           // new: CUDA device ordinal (one process per GPU)
   sdef?: boolean            // new: evaluate SDEF spherically instead of as BDEF2
+  outline?: boolean         // new: also produce the outline pass' hull positions (engine.ts:458-461) as a third plane
+  interleaved?: boolean     // new: result in the reference's own 32-byte vertex layout [pos, nrm, uv] (engine.ts:340-347)
   clock?: () => number      // new: replaces performance.now() (model.ts:160,249) for reproducible playback
 }
 export interface EngineStats { fps: number; frameTime: number; gpuMemory: number; vertsPerSec?: number; achievedGBs?: number }
@@ -41,7 +43,10 @@ export class Engine {
     this.clock = options.clock ?? (() => performance.now())
   }
 
-  async init() { this.ctx = rz.create(this.options.device ?? 0, this.K, this.options.sdef ? 1 : 0) }
+  async init() {
+    const o = this.options   // rz_config.flags: RZ_FLAG_SDEF 0x1, RZ_FLAG_OUTLINE 0x10, RZ_FLAG_INTERLEAVED 0x20
+    this.ctx = rz.create(o.device ?? 0, this.K, (o.sdef ? 0x1 : 0) | (o.outline ? 0x10 : 0) | (o.interleaved ? 0x20 : 0))
+  }
 
   async loadModel(path: string) {
     const model = await PmxLoader.load(path)
@@ -50,6 +55,20 @@ export class Engine {
     const sk = model.getSkinning()
     rz.loadMesh(this.ctx, model.getVertices(), sk.joints, sk.weights, model.getBoneInverseBindMatrices())
     this.world = new Float32Array(this.K * model.getBoneInverseBindMatrices().length)
+    if (this.options.outline) rz.loadEdgeSize(this.ctx, Engine.vertexEdgeSizes(model))
+  }
+
+  // Material.edgeSize per vertex: material m outlines its slice of the index buffer when (edgeFlag & 0x10) && edgeSize > 0
+  // (engine.ts:2016-2046); tested restatement: reze-engine_b200/engine.py Engine.vertexEdgeSizes
+  static vertexEdgeSizes(model: Model): Float32Array {
+    const idx = model.getIndices(), edge = new Float32Array(model.getVertexCount())
+    let start = 0
+    for (const m of model.getMaterials()) {
+      if ((m.edgeFlag & 0x10) !== 0 && m.edgeSize > 0)
+        for (let i = start; i < start + m.vertexCount; i++) edge[idx[i]] = Math.max(edge[idx[i]], m.edgeSize)
+      start += m.vertexCount
+    }
+    return edge
   }
 
   async loadAnimation(url: string) { this.animationFrames = await VMDLoader.load(url) }
@@ -82,6 +101,9 @@ export class Engine {
   stopRenderLoop() { this.running = false }
   getStats(): EngineStats { return rz.getStats(this.ctx) }
   readSkinned(instance: number, pos: Float32Array, nrm: Float32Array | null) { rz.readInstance(this.ctx, instance, pos, nrm) }
+  readOutline(instance: number, hull: Float32Array) { rz.readOutline(this.ctx, instance, hull) }
+  readInterleaved(instance: number, vtx8: Float32Array) { rz.readInterleaved(this.ctx, instance, vtx8) }
+  getOutputLayout() { return rz.getOutputLayout(this.ctx) }
   dispose() { this.stopRenderLoop(); this.ctx = null }
   // playAnimation / stopAnimation / breathing: identical scheduling to engine.ts:1425-1662 on top of this.setTimeout;
   // see reze-engine_b200/engine.py (playAnimation, _startBreathing) for the tested restatement.
