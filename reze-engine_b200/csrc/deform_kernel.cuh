@@ -276,8 +276,12 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
   constexpr uint32_t kPlaneB = 32 * kVtxB;             // bytes of one warp-private staging plane (32 vertices)
   constexpr uint32_t kNrmO = ILV ? 12u : kPlaneB;      // normal of a vertex relative to its position
   constexpr uint32_t kHullO = 2 * kPlaneB;             // outline hull position relative to its position (HULL)
-  constexpr uint32_t kInstB = PLANES * kPlaneB;        // one instance of one warp
-  constexpr uint32_t kBufB = I * kInstB;               // one staging buffer of one warp
+  // SDEF: the dense phase addresses I consecutive lanes to the SAME row / slot of I different instances, so every per-instance
+  // region (palette, quaternions, staging) is skewed by one 16-byte bank group per instance: otherwise those lanes collide
+  // I-fold in one bank group (ncu on config 3: 39 % of the shared-memory wavefronts were bank conflicts)
+  constexpr uint32_t kSkew = SDEF ? 16u : 0u;
+  constexpr uint32_t kInstB = PLANES * kPlaneB + kSkew; // one instance of one warp
+  constexpr uint32_t kBufB = I * kInstB - kSkew;       // one staging buffer of one warp (no skew after the last instance)
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const uint32_t sbase = smem_u32(smem_raw);
@@ -286,15 +290,17 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
   const uint32_t B = prm.B;
   const uint32_t sPal = sbase + kCtrlBytes;
   const uint32_t palBytes = GPAL ? 0u : B * 48u;
-  const uint32_t sMw = sPal + (uint32_t)I * palBytes;
+  const uint32_t palStride = GPAL ? 0u : palBytes + kSkew;
+  const uint32_t sMw = sPal + (uint32_t)I * palStride - (GPAL ? 0u : kSkew);
   const uint32_t mwBytes = MORPH ? prm.Mpad * 4u : 0u;
   const uint32_t sQuat = sMw + (uint32_t)I * mwBytes;               // [I][B] float4 quaternions (SDEF, palette in smem)
   const uint32_t quatBytes = (SDEF && !GPAL) ? B * 16u : 0u;
+  const uint32_t quatStride = (SDEF && !GPAL) ? quatBytes + kSkew : 0u;
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform by construction: TMA operands stay in uniform registers
   // warp-private staging: [kStageBufs][I][PLANES][32*3 floats], laid out exactly like 32 vertices of the output planes
-  const uint32_t sStageW = sQuat + (uint32_t)I * quatBytes + (uint32_t)warp * (kStageBufs * kBufB);
+  const uint32_t sStageW = sQuat + (uint32_t)I * quatStride - ((SDEF && !GPAL) ? kSkew : 0u) + (uint32_t)warp * (kStageBufs * kBufB);
 
   if (tid == 0) {
     mbar_init(palBar, 1);
@@ -333,9 +339,9 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
         mbar_expect_tx(palBar, (uint32_t)I * (palBytes + mwBytes + quatBytes));
 #pragma unroll
         for (int i = 0; i < I; ++i) {
-          if (!GPAL) bulk_g2s(sPal + (uint32_t)i * palBytes, gpal[i], palBytes, palBar, polLast);
+          if (!GPAL) bulk_g2s(sPal + (uint32_t)i * palStride, gpal[i], palBytes, palBar, polLast);
           if (SDEF && !GPAL)   // same palette index as gpal[i]: (gpal[i] - skin) / 12 floats = palette * B rows
-            bulk_g2s(sQuat + (uint32_t)i * quatBytes, prm.quat + (size_t)(gpal[i] - prm.skin) / 12, quatBytes, palBar, polLast);
+            bulk_g2s(sQuat + (uint32_t)i * quatStride, prm.quat + (size_t)(gpal[i] - prm.skin) / 12, quatBytes, palBar, polLast);
           if (MORPH) {
             const uint32_t k = kBase + min((uint32_t)i, nInst - 1);
             bulk_g2s(sMw + (uint32_t)i * mwBytes, prm.mweights + (size_t)k * prm.Mpad, mwBytes, palBar, polLast);
@@ -501,7 +507,7 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
             a0[ii] = pal[j0 / 16]; a1[ii] = pal[(j0 + rS) / 16]; a2[ii] = pal[(j0 + rS2) / 16];
             if (NMAX > 1) { b0[ii] = pal[j1 / 16]; b1[ii] = pal[(j1 + rS) / 16]; b2[ii] = pal[(j1 + rS2) / 16]; }
           } else {
-            const uint32_t pb = sPal + (uint32_t)i * palBytes;
+            const uint32_t pb = sPal + (uint32_t)i * palStride;
             a0[ii] = lds128(pb + j0); a1[ii] = lds128(pb + j0 + rS); a2[ii] = lds128(pb + j0 + rS2);
             if (NMAX > 1) { b0[ii] = lds128(pb + j1); b1[ii] = lds128(pb + j1 + rS); b2[ii] = lds128(pb + j1 + rS2); }
           }
@@ -521,13 +527,13 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
             if (NMAX > 2) {
               float4 c0, c1, c2;
               if (GPAL) { const float4* pal = reinterpret_cast<const float4*>(gpal[i]); c0 = pal[j2 / 16]; c1 = pal[(j2 + rS) / 16]; c2 = pal[(j2 + rS2) / 16]; }
-              else { const uint32_t pb = sPal + (uint32_t)i * palBytes; c0 = lds128(pb + j2); c1 = lds128(pb + j2 + rS); c2 = lds128(pb + j2 + rS2); }
+              else { const uint32_t pb = sPal + (uint32_t)i * palStride; c0 = lds128(pb + j2); c1 = lds128(pb + j2 + rS); c2 = lds128(pb + j2 + rS2); }
               mA = f4_fma(c0, w2_2, mA); mB = f4_fma(c1, w2_2, mB); mC = f4_fma(c2, w2_2, mC);
             }
             if (NMAX > 3) {
               float4 c0, c1, c2;
               if (GPAL) { const float4* pal = reinterpret_cast<const float4*>(gpal[i]); c0 = pal[j3 / 16]; c1 = pal[(j3 + rS) / 16]; c2 = pal[(j3 + rS2) / 16]; }
-              else { const uint32_t pb = sPal + (uint32_t)i * palBytes; c0 = lds128(pb + j3); c1 = lds128(pb + j3 + rS); c2 = lds128(pb + j3 + rS2); }
+              else { const uint32_t pb = sPal + (uint32_t)i * palStride; c0 = lds128(pb + j3); c1 = lds128(pb + j3 + rS); c2 = lds128(pb + j3 + rS2); }
               mA = f4_fma(c0, w3_2, mA); mB = f4_fma(c1, w3_2, mB); mC = f4_fma(c2, w3_2, mC);
             }
             // (ox,oy) = (m00,m10)*qx + (m01,m11)*qy + (m02,m12)*qz + (m03,m13);  oz = row 2 . (q,1)
@@ -619,7 +625,7 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
                 b0 = pal[(r1p * pS) / 16]; b1 = pal[(r1p * pS + rS) / 16]; b2 = pal[(r1p * pS + rS2) / 16];
                 qa = __ldg(prm.quat + (size_t)pidx * B + r0p); qb = __ldg(prm.quat + (size_t)pidx * B + r1p);
               } else {
-                const uint32_t pb = sPal + i * palBytes, qbase = sQuat + i * quatBytes;
+                const uint32_t pb = sPal + i * palStride, qbase = sQuat + i * quatStride;
                 a0 = lds128(pb + r0p * pS); a1 = lds128(pb + r0p * pS + rS); a2 = lds128(pb + r0p * pS + rS2);
                 b0 = lds128(pb + r1p * pS); b1 = lds128(pb + r1p * pS + rS); b2 = lds128(pb + r1p * pS + rS2);
                 qa = lds128(qbase + r0p * 16u); qb = lds128(qbase + r1p * 16u);

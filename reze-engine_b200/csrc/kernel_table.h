@@ -12,7 +12,7 @@ struct KernelEntry {
 #define RZ_SHAPES_FULL(X) \
   X(1, 256, 4, 1, 2) X(2, 256, 3, 2, 2) X(2, 256, 2, 2, 2) X(3, 256, 2, 3, 2) X(4, 256, 1, 4, 2) X(6, 256, 1, 3, 2) \
   X(1, 512, 2, 1, 2) X(2, 512, 2, 2, 2) X(2, 512, 1, 2, 2) X(3, 512, 1, 3, 2) X(4, 512, 1, 4, 2) X(6, 512, 1, 3, 1) \
-  X(2, 768, 1, 2, 2) X(3, 768, 1, 3, 2) X(2, 1024, 1, 2, 2) X(3, 1024, 1, 3, 2)
+  X(2, 768, 1, 2, 2) X(3, 768, 1, 3, 2) X(4, 768, 1, 2, 1) X(2, 1024, 1, 2, 2) X(3, 1024, 1, 3, 2)
 #define RZ_SHAPES_LITE(X) X(1, 256, 2, 1, 2) X(2, 256, 2, 2, 2) X(2, 512, 1, 2, 2) X(4, 512, 1, 4, 2)
 // feature sets compiled (bit meaning: deform_kernel.cuh FEAT_*); keep in sync with build.py
 // 32 / 39: outline hull plane (plain, + morph + SDEF + bounds); 64 / 71: interleaved 32-byte stream (same two)

@@ -215,6 +215,8 @@ size_t smem_needed(int I, int NT, int feat, uint32_t B, uint32_t Mpad, int nbuf 
   if (!(feat & FEAT_GPAL)) s += (size_t)I * B * 48;
   if (feat & FEAT_MORPH) s += (size_t)I * Mpad * 4;
   if ((feat & FEAT_SDEF) && !(feat & FEAT_GPAL)) s += (size_t)I * B * 16;   // per-bone quaternions
+  // SDEF skews every per-instance region by 16 bytes (deform_kernel.cuh kSkew): palette, quaternions, staging
+  if (feat & FEAT_SDEF) s += (size_t)(I - 1) * 16 * ((feat & FEAT_GPAL) ? 0 : 2) + (size_t)nbuf * (I - 1) * 16 * (NT / 32);
   const size_t vtxBytes = (feat & FEAT_ILV) ? 32 : (((feat & FEAT_NONRM) ? 1 : 2) + ((feat & FEAT_HULL) ? 1 : 0)) * 12;
   s += (size_t)nbuf * I * NT * vtxBytes;                                // warp-private staging, laid out like the output
   return s;

@@ -40,7 +40,7 @@ def wl_small():
 
 
 SHAPES = [(1, 256, 4), (2, 256, 3), (2, 256, 2), (3, 256, 2), (4, 256, 1), (1, 512, 2), (2, 512, 2), (2, 512, 1), (3, 512, 1),
-          (4, 512, 1), (2, 768, 1), (3, 768, 1), (2, 1024, 1), (3, 1024, 1), (6, 256, 1), (6, 512, 1)]     # csrc/kernel_table.h RZ_SHAPES_FULL
+          (4, 512, 1), (2, 768, 1), (3, 768, 1), (4, 768, 1), (2, 1024, 1), (3, 1024, 1), (6, 256, 1), (6, 512, 1)]     # csrc/kernel_table.h RZ_SHAPES_FULL
 
 
 @pytest.mark.parametrize("I,nt,mb", SHAPES)
