@@ -296,10 +296,8 @@ int rebuild_tables(rz_ctx_impl* c) {
       }
   }
   c->morphNnz = nnz;
-  c->tileMorphMax.assign(nTiles, 0);
-  for (uint32_t v = 0; v < V; ++v) c->tileMorphMax[v / kTile] = std::max(c->tileMorphMax[v / kTile], mcount[v]);
+  c->tileMorphMax.assign(nTiles, 0);       // filled with the row depth per warp once the lane plan is known (`mell` below)
   c->chunkKey = {};
-  // (the per-vertex lists above are re-laid out per warp once the lane plan is known, see `mell` below)
 
   // SDEF (only when enabled): which vertices take the spherical path.  The table itself needs the palette rows and is
   // built further down, after the bank-aware permutation.
@@ -507,21 +505,63 @@ int rebuild_tables(rz_ctx_impl* c) {
     metaArr[p] = meta;
   }
 
-  // ---- morph entries, lane-interleaved per warp (ELL): entry u of lane l sits at first + u*32 + l, padded with
-  // (delta 0, morph 0) up to the deepest vertex of the warp.  One LDG.128 per depth step is then a single coalesced
-  // 512-byte request for the warp instead of 32 scattered 16-byte ones (the L1 tag stage serialises those: measured
-  // +0.16 ms on config 3), and the loop bound is warp-uniform.  Within a lane the entries keep PMX morph order.
+  // ---- morph entries, lane-interleaved per warp (ELL): entry u of lane l sits at first + u*32 + l.  One LDG.128 per depth
+  // step is then a single coalesced 512-byte request for the warp instead of 32 scattered 16-byte ones (the L1 tag stage
+  // serialises those: measured +0.16 ms on config 3), and the loop bound is warp-uniform.  Within a lane the entries keep
+  // PMX morph order.  Two row formats, chosen per warp, identical to the kernel:
+  //   MORPH-MAJOR (default): row u = one morph for the whole warp, delta 0 on lanes that morph does not touch.  PMX morphs
+  //     are spatially coherent (the 32 vertices of a warp see the same morphs), so this costs no extra rows, and every lane
+  //     of a row looks up the SAME weight: a shared-memory broadcast instead of a 3-4-way bank conflict per lookup
+  //     (ncu on config 3: 39 % of the shared-memory wavefronts were conflicts).  fma(w, 0, p) == p: results unchanged.
+  //   COMPACT (fallback when the union of morphs is > 1.5x the deepest vertex): entry u = the lane's own u-th morph,
+  //     padded with (delta 0, morph 0).
   for (uint32_t w0 = 0; w0 < Vp; w0 += 32) {
     uint32_t deep = 0;
-    for (uint32_t l = 0; l < 32; ++l) { const uint32_t v = procVertex[w0 + l]; if (v != ~0u) deep = std::max(deep, mcount[v]); }
-    const uint32_t first = (uint32_t)mell.size();
-    mrange[w0 / 32] = make_uint2(first, deep);
-    if (!deep) continue;
-    mell.resize((size_t)first + (size_t)deep * 32, make_float4(0.f, 0.f, 0.f, 0.f));
+    bool dup = false;
+    std::vector<uint32_t> ids;
     for (uint32_t l = 0; l < 32; ++l) {
       const uint32_t v = procVertex[w0 + l];
       if (v == ~0u) continue;
-      for (uint32_t u = 0; u < mcount[v]; ++u) mell[(size_t)first + (size_t)u * 32 + l] = ments[mstart[v] + u];
+      deep = std::max(deep, mcount[v]);
+      for (uint32_t u = 0; u < mcount[v]; ++u) {
+        uint32_t m;
+        memcpy(&m, &ments[mstart[v] + u].w, 4);
+        if (u && m == ids.back()) dup = true;      // one morph lists this vertex twice: keep both entries (compact rows)
+        ids.push_back(m);
+      }
+    }
+    const uint32_t first = (uint32_t)mell.size();
+    if (!deep) { mrange[w0 / 32] = make_uint2(first, 0u); continue; }
+    std::sort(ids.begin(), ids.end());
+    ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+    const bool morphMajor = !dup && ids.size() <= (size_t)deep + deep / 2 + 1;
+    const uint32_t rows = morphMajor ? (uint32_t)ids.size() : deep;
+    mrange[w0 / 32] = make_uint2(first, rows);
+    c->tileMorphMax[w0 / kTile] = std::max(c->tileMorphMax[w0 / kTile], rows);
+    mell.resize((size_t)first + (size_t)rows * 32, make_float4(0.f, 0.f, 0.f, 0.f));
+    if (morphMajor)
+      for (uint32_t r = 0; r < rows; ++r) {
+        float idBits;
+        memcpy(&idBits, &ids[r], 4);
+        for (uint32_t l = 0; l < 32; ++l) mell[(size_t)first + (size_t)r * 32 + l].w = idBits;
+      }
+    for (uint32_t l = 0; l < 32; ++l) {
+      const uint32_t v = procVertex[w0 + l];
+      if (v == ~0u) continue;
+      uint32_t r = 0;
+      for (uint32_t u = 0; u < mcount[v]; ++u) {
+        const float4 e = ments[mstart[v] + u];
+        if (morphMajor) {
+          uint32_t m;
+          memcpy(&m, &e.w, 4);
+          while (ids[r] != m) ++r;                                  // both ascending
+          mell[(size_t)first + (size_t)r * 32 + l].x = e.x;
+          mell[(size_t)first + (size_t)r * 32 + l].y = e.y;
+          mell[(size_t)first + (size_t)r * 32 + l].z = e.z;
+        } else {
+          mell[(size_t)first + (size_t)u * 32 + l] = e;
+        }
+      }
     }
   }
   if (mell.empty()) mell.push_back(make_float4(0.f, 0.f, 0.f, 0.f));

@@ -123,6 +123,45 @@ def test_morphs(rzlib, orc, wl_small):
             check_all(orc, ctx, wl, world, None, K)
 
 
+def test_morph_row_formats(rzlib, orc):
+    """The per-warp morph rows come in two formats chosen at load time (morph-major when the warp's vertices share their
+    morphs, compact otherwise); both must equal the oracle, including a morph that lists one vertex twice and morphs
+    scattered over random vertices."""
+    rng = np.random.default_rng(90)
+    wl = synth.make_workload(3000, 40, seed=90)
+    V, M = wl.V, 48
+    offs, vidx, deltas = [0], [], []
+    for m in range(M):
+        if m % 3 == 0:                              # coherent block (morph-major rows)
+            a = int(rng.integers(0, V - 400))
+            v = np.arange(a, a + int(rng.integers(50, 400)))
+        else:                                       # scattered (compact rows in most warps)
+            v = np.sort(rng.choice(V, int(rng.integers(5, 200)), replace=False))
+        if m == 7:
+            v = np.concatenate([v, v[:3]])          # this morph lists three vertices twice
+        vidx.append(v.astype(np.uint32))
+        deltas.append(rng.normal(0, 0.05, (v.size, 3)).astype(np.float32))
+        offs.append(offs[-1] + v.size)
+    offs = np.array(offs, np.uint32)
+    vidx = np.concatenate(vidx)
+    deltas = np.concatenate(deltas)
+    K = 5
+    world = synth.make_palettes(wl.bones, K, rng)
+    w = rng.uniform(-0.5, 1.0, (K, M)).astype(np.float32)
+    for I, nt in ((0, 0), (1, 256), (2, 256), (4, 512)):
+        with capi.DeformContext(max_instances=K, instances_per_group=I, threads=nt) as ctx:
+            ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
+            ctx.load_morphs(offs, vidx, deltas)
+            ctx.set_palettes(world)
+            ctx.set_morph_weights(w, np.arange(M), K=K)
+            ctx.deform()
+            assert ctx.stats()["morphNnz"] == vidx.size
+            for k in range(K):
+                rp, rn = orc.deform(wl.vtx8, wl.joints, wl.weights, orc.skin_matrices(world[k], wl.invBind), morph=(offs, vidx, deltas), morphW=w[k])
+                gp, gn = ctx.read_instance(k)
+                assert rel_err(gp, rp) <= TOL and rel_err(gn, rn) <= TOL, (I, k, rel_err(gp, rp))
+
+
 def test_sdef_on_and_compat_off(rzlib, orc, wl_small):
     wl = wl_small
     K = 5
