@@ -1,4 +1,4 @@
-// deform_kernel.cuh — the fused morph + BDEF1/2/4/SDEF skinning kernel for sm_100a (v2).
+// deform_kernel.cuh — the fused morph + BDEF1/2/4/SDEF skinning kernel for sm_100a.
 //
 // Replaces the per-vertex blend the reference runs inside three WGSL vertex shaders
 // (engine.ts:245-276 main, 431-463 outline, 692-715 depth-only) and materialises the
@@ -6,19 +6,21 @@
 //
 // Work decomposition (B200: 148 SMs, 227 KB smem/SM, HBM-bound on the 24 B/vertex write):
 //   work item = (group of I instances) x (chunk of vertex tiles); persistent CTAs pull items from
-//   an atomic counter.  Per item the I bone palettes (B x 48 B each, 3x4 row-major skin matrices)
+//   an atomic counter.  Per item the I bone palettes (B x 48 B each, 3x4 skin matrices in "pair layout")
 //   are staged into shared memory with one cp.async.bulk (TMA bulk copy, mbarrier complete_tx) per
-//   instance.  NT compute threads each keep ONE vertex (pos, normal, 4 joints, 4 pre-normalised
-//   weights: 52 B, float4-vectorised, L2-resident, prefetched one pass ahead) in registers and
-//   evaluate it for the I instances, so the static mesh is read once per I outputs.
-//   Results go to a double-buffered shared-memory staging area laid out exactly like the output
-//   planes; a dedicated STORE WARP drains each buffer with cp.async.bulk shared->global (TMA bulk
-//   store, L2 evict-first).  Compute warps and the store warp are coupled only through full/empty
-//   mbarriers (no CTA-wide barrier inside an item), so warps of different cost (1..4 influences)
-//   run up to two steps apart.  The palette gather is the SM-side bottleneck (48 B per influence
-//   through the 128 B/clk shared-memory pipe), so the influence loop is specialised per warp on the
-//   warp-maximum influence count (warps are class-sorted at load time) and never branches per lane.
-//   No tensor cores: the work is a gather of 3x4 mat-vecs.
+//   instance.  Every thread keeps ONE vertex (pos, normal, 4 joints, 4 pre-normalised weights: 52 B,
+//   float4-vectorised, L2-resident, prefetched one pass ahead) in registers and evaluates it for the
+//   I instances, so the static mesh is read once per I outputs.
+//   Results go to a WARP-PRIVATE, double-buffered shared-memory staging area laid out exactly like 32
+//   vertices of the output planes and leave with cp.async.bulk shared->global (TMA bulk store, L2
+//   evict-first) issued by one elected lane: no CTA-wide barrier and no cross-warp dependency inside an
+//   item.  The palette gather is the SM-side bottleneck (48 B per influence through the 128 B/clk
+//   shared-memory pipe), so the influence loop is specialised per warp on the warp-maximum influence
+//   count, lanes and influence slots are arranged at load time so that aligned lane pairs read the same
+//   rows (lane_plan.h), and nothing branches per lane.
+//   Morphs: lane-interleaved rows per warp, accumulated before the blend.  SDEF: a dense second phase
+//   over (vertex, instance) pairs.  Fused consumers: AABB, outline hull plane, interleaved stream.
+//   No tensor cores: the work is a gather of 3x4 mat-vecs.  DESIGN.md section 4 has the details.
 #pragma once
 #include <cuda_runtime.h>
 #include <stddef.h>
