@@ -16,7 +16,7 @@ struct KernelEntry {
 #define RZ_SHAPES_LITE(X) X(1, 256, 2, 1, 2) X(2, 256, 2, 2, 2) X(2, 512, 1, 2, 2) X(4, 512, 1, 4, 2)
 // feature sets compiled (bit meaning: deform_kernel.cuh FEAT_*); keep in sync with build.py
 // 32 / 39: outline hull plane (plain, + morph + SDEF + bounds); 64 / 71: interleaved 32-byte stream (same two)
-#define RZ_FEAT_LIST(X) X(0) X(1) X(3) X(4) X(7) X(16) X(19) X(8) X(11) X(15) X(24) X(27) X(32) X(39) X(64) X(71)
+#define RZ_FEAT_LIST(X) X(0) X(1) X(3) X(4) X(7) X(16) X(19) X(20) X(8) X(11) X(15) X(24) X(27) X(32) X(39) X(64) X(71)
 #define RZ_DECL(f) KernelEntry lookup_feat_##f(int I, int NT, int MINB);
 RZ_FEAT_LIST(RZ_DECL)
 #undef RZ_DECL

@@ -319,7 +319,7 @@ int rebuild_tables(rz_ctx_impl* c) {
   std::vector<float2> uvArr((c->flags & RZ_FLAG_INTERLEAVED) ? Vp : 0, make_float2(0.f, 0.f));
   std::vector<uint2> mrange(Vp / 32);     // per warp: (first entry, depth) of its lane-interleaved morph entries
   std::vector<float4> mell;
-  std::vector<uint32_t> sdefIdx(Vp, 0);
+  std::vector<uint32_t> sdefIdx(Vp, ~0u);   // "no SDEF vertex": a feature kernel compiled with SDEF may run without the flag
   c->procToVertex.assign(Vp, ~0u);
 
   const bool packMeta = B <= 4096;  // palette rows fit 12 bits: meta rides in the joint words (deform_kernel.cuh)
@@ -459,7 +459,6 @@ int rebuild_tables(rz_ctx_impl* c) {
       c->sdefActive++;
     }
     if (sdefTab.size() / 3 >= (1u << 24)) return fail(c, RZ_ERR_INVALID_ARG, "rz_load_sdef: more than 2^24 SDEF vertices");
-    std::fill(sdefIdx.begin(), sdefIdx.end(), ~0u);
     for (uint32_t w0 = 0; w0 < Vp; w0 += 32) {
       uint32_t n = 0;
       for (uint32_t l = 0; l < 32; ++l) {
@@ -1300,6 +1299,12 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
   if (feat & FEAT_SDEF) {
     if ((rc = dev_reserve(c, c->d_quat, (size_t)c->P * c->B * 16))) return rc;
     prm.quat = reinterpret_cast<const float4*>(c->d_quat.p);
+  }
+  if ((feat & FEAT_BOUNDS) && !c->d_bounds.p) {
+    // the smallest compiled superset of the requested features may carry the AABB reduction although RZ_FLAG_BOUNDS
+    // is off: give it somewhere to write (rz_read_bounds still requires the flag)
+    if ((rc = dev_reserve(c, c->d_bounds, (size_t)c->maxK * 24))) return rc;
+    prm.bounds = reinterpret_cast<float*>(c->d_bounds.p);
   }
   CU_TRY(c, cudaEventRecord(c->evStart, c->stream));
   CU_TRY(c, cudaMemsetAsync(c->d_counter.p, 0, 4, c->stream));

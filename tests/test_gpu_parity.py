@@ -360,6 +360,41 @@ def test_interleaved_vertex_stream(rzlib, orc, wl_small, full):
             assert np.array_equal(outs[0][k][1], outs[capi.RZ_FLAG_INTERLEAVED][k][1])
 
 
+@pytest.mark.parametrize("flags,morph,sdef", [
+    (capi.RZ_FLAG_BOUNDS, True, False),                              # runs the morph+SDEF+bounds kernel without SDEF tables
+    (capi.RZ_FLAG_OUTLINE, True, False),                             # ... the outline superset without RZ_FLAG_BOUNDS
+    (capi.RZ_FLAG_INTERLEAVED | capi.RZ_FLAG_SDEF, True, True),      # ... the interleaved superset without RZ_FLAG_BOUNDS
+    (capi.RZ_FLAG_SDEF, False, True),                                # SDEF without morphs
+    (capi.RZ_FLAG_NO_NORMALS | capi.RZ_FLAG_BOUNDS, False, False),
+])
+def test_feature_supersets_run_clean(rzlib, orc, wl_small, flags, morph, sdef):
+    """rz_deform launches the smallest COMPILED feature set that covers the request; the extra features of that kernel
+    (SDEF phase without SDEF records, AABB reduction without RZ_FLAG_BOUNDS, ...) must be inert."""
+    wl = wl_small
+    K = 6
+    rng = np.random.default_rng(int(flags) + 100)
+    world = synth.make_palettes(wl.bones, K, rng)
+    dense = rng.uniform(0, 1, (K, wl.morphs.count)).astype(np.float32) if morph else None
+    for I, nt in ((0, 0), (2, 256), (4, 512)):
+        with capi.DeformContext(max_instances=K, flags=flags, instances_per_group=I, threads=nt) as ctx:
+            ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
+            if morph:
+                ctx.load_morphs(wl.morphs.offsets, wl.morphs.vertexIndex, wl.morphs.delta)
+            if sdef:
+                ctx.load_sdef(wl.sdef.vertexIndex, wl.sdef.c_r0_r1)
+            ctx.set_palettes(world)
+            if morph:
+                ctx.set_morph_weights(dense, np.arange(wl.morphs.count), K=K)
+            ctx.deform()
+            ctx.sync()
+            for k in range(K):
+                rp, rn = oracle_instance(orc, wl, world[k], None if dense is None else dense[k], sdef=sdef)
+                gp, gn = ctx.read_instance(k, normals=not (flags & capi.RZ_FLAG_NO_NORMALS))
+                assert rel_err(gp, rp) <= TOL, (I, k, rel_err(gp, rp))
+                if gn is not None:
+                    assert rel_err(gn, rn) <= TOL
+
+
 def test_bounds_and_positions_only(rzlib, orc, wl_small):
     wl = wl_small
     K = 9

@@ -13,12 +13,17 @@ rng = np.random.default_rng(1)
 K = 7
 world = synth.make_palettes(wl.bones, K, rng)
 mw = rng.uniform(0, 1, (K, 6)).astype(np.float32)
-for flags, I, nt in ((0, 2, 256), (capi.RZ_FLAG_SDEF | capi.RZ_FLAG_BOUNDS, 4, 512), (capi.RZ_FLAG_NO_NORMALS, 1, 256), (0, 2, 512)):
+edge = rng.uniform(0, 2, wl.V).astype(np.float32)
+for flags, I, nt in ((0, 2, 256), (capi.RZ_FLAG_SDEF | capi.RZ_FLAG_BOUNDS, 4, 512), (capi.RZ_FLAG_NO_NORMALS, 1, 256), (0, 2, 512),
+                     (capi.RZ_FLAG_SDEF, 2, 256), (capi.RZ_FLAG_SDEF | capi.RZ_FLAG_BOUNDS | capi.RZ_FLAG_OUTLINE, 2, 256),
+                     (capi.RZ_FLAG_SDEF | capi.RZ_FLAG_INTERLEAVED, 4, 512), (capi.RZ_FLAG_OUTLINE, 1, 256), (capi.RZ_FLAG_INTERLEAVED, 2, 512)):
     with capi.DeformContext(max_instances=K, flags=flags, instances_per_group=I, threads=nt) as ctx:
         ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
         ctx.load_morphs(wl.morphs.offsets, wl.morphs.vertexIndex, wl.morphs.delta)
         ctx.load_sdef(wl.sdef.vertexIndex, wl.sdef.c_r0_r1)
         ctx.load_skeleton(wl.bones)
+        if flags & capi.RZ_FLAG_OUTLINE:
+            ctx.load_edge_size(edge)
         ctx.set_palettes(world)
         ctx.set_morph_weights(mw, np.arange(6), K=K)
         ctx.deform()
