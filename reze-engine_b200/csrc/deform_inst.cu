@@ -25,6 +25,8 @@ KernelEntry RZ_CAT(lookup_feat_, RZ_FEAT)(int I, int NT, int MINB) {
 #define RZ_TRY(i, nt, mb, sb, nb) if (I == i && NT == nt && (MINB <= 0 || MINB == mb)) return entry<i, nt, mb, sb, nb>();
 #if RZ_FEAT == 0
   RZ_SHAPES_FULL(RZ_TRY)
+#elif RZ_FEAT_IS_MID(RZ_FEAT)
+  RZ_SHAPES_MID(RZ_TRY)
 #else
   RZ_SHAPES_LITE(RZ_TRY)
 #endif

@@ -14,6 +14,10 @@ struct KernelEntry {
   X(1, 512, 2, 1, 2) X(2, 512, 2, 2, 2) X(2, 512, 1, 2, 2) X(3, 512, 1, 3, 2) X(4, 512, 1, 4, 2) X(6, 512, 1, 3, 1) \
   X(2, 768, 1, 2, 2) X(3, 768, 1, 3, 2) X(4, 768, 1, 2, 1) X(2, 1024, 1, 2, 2) X(3, 1024, 1, 3, 2)
 #define RZ_SHAPES_LITE(X) X(1, 256, 2, 1, 2) X(2, 256, 2, 2, 2) X(2, 512, 1, 2, 2) X(4, 512, 1, 4, 2)
+// MID: feature sets without morph / SDEF / global palette (bounds, positions only, outline, interleaved): LITE + the two
+// wide single-buffered shapes the plain path prefers
+#define RZ_SHAPES_MID(X) RZ_SHAPES_LITE(X) X(6, 512, 1, 3, 1) X(4, 768, 1, 2, 1)
+#define RZ_FEAT_IS_MID(f) ((f) != 0 && ((f) & (1 | 2 | 8)) == 0)
 // feature sets compiled (bit meaning: deform_kernel.cuh FEAT_*); keep in sync with build.py
 // 32 / 39: outline hull plane (plain, + morph + SDEF + bounds); 64 / 71: interleaved 32-byte stream (same two)
 #define RZ_FEAT_LIST(X) X(0) X(1) X(3) X(4) X(7) X(16) X(19) X(20) X(8) X(11) X(15) X(24) X(27) X(32) X(39) X(64) X(71)

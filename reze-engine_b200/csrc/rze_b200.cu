@@ -1197,13 +1197,23 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
     // preference order (measured on B200, profiles/): most resident warps first, then wider instance groups
     static const int pref[][3] = {{6, 512, 1}, {4, 512, 1}, {3, 256, 2}, {2, 512, 2}, {2, 256, 3}, {3, 512, 1}, {2, 256, 2}, {2, 512, 1}, {4, 256, 1},
                                   {1, 256, 4}, {1, 256, 2}, {1, 512, 2}};
-    // feature kernels (morph / SDEF / bounds / ...) are compiled for fewer shapes
-    // (measured on config 3, profiles/r01_config3_split_*.jsonl: the wide group wins despite a few spilled registers --
-    // more (vertex, instance) pairs per SDEF dense pass, morph entries fetched once per 4 instances)
-    static const int prefLite[][3] = {{4, 512, 1}, {2, 256, 2}, {2, 512, 1}, {1, 256, 2}};
+    // feature kernels are compiled for fewer shapes; preference per feature set, measured on B200
+    // (profiles/r01_config3_split_*.jsonl, profiles/r01_fused_consumers_K2048.jsonl):
+    //   morph / SDEF: the wide group wins despite a few spilled registers (more (vertex, instance) pairs per SDEF dense
+    //     pass, morph rows fetched once per 4 instances);
+    //   AABB: 6 registers per instance for the bounds, I=6 spills -> I=4; outline hull: 36 B of staging per thread, the
+    //     double-buffered I=2 x 2 CTAs shape beats the wide single-buffered ones; interleaved: I=4 x 768; positions only: I=6
+    static const int prefWide4[][3] = {{4, 512, 1}, {4, 768, 1}, {2, 256, 2}, {2, 512, 1}, {1, 256, 2}};
+    static const int prefHull[][3] = {{2, 256, 2}, {4, 768, 1}, {2, 512, 1}, {4, 512, 1}, {1, 256, 2}};
+    static const int prefIlv[][3] = {{4, 768, 1}, {4, 512, 1}, {2, 256, 2}, {2, 512, 1}, {1, 256, 2}};
+    static const int prefWide6[][3] = {{6, 512, 1}, {4, 768, 1}, {4, 512, 1}, {2, 256, 2}, {2, 512, 1}};
+    const int (*prefLite)[3] = prefWide4;
+    if (feat & FEAT_HULL) prefLite = prefHull;
+    else if (feat & FEAT_ILV) prefLite = prefIlv;
+    else if (feat == FEAT_NONRM) prefLite = prefWide6;
     bool ok = false;
     if (feat != 0) {
-      for (const auto& p : prefLite) if (try_shape(p[0], p[1], p[2])) { ok = true; break; }
+      for (int q = 0; q < 5 && !ok; ++q) ok = try_shape(prefLite[q][0], prefLite[q][1], prefLite[q][2]);
     }
     if (!ok) {
       for (const auto& p : pref) {
