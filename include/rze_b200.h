@@ -200,6 +200,18 @@ int32_t rz_get_vertex_order(rz_ctx* ctx, uint32_t* order /* V */);
  * of packed warps by [slot count N][mixed slots m].  Any output may be NULL. */
 int32_t rz_plan_lanes(const uint16_t* joints, const uint8_t* weights, uint32_t V, uint32_t B, uint32_t mode,
                       uint32_t* laneVertex, uint16_t* laneJoints, float* laneWeights, uint64_t* stats);
+/* The per-warp morph rows rz_load_morphs builds for a given lane plan, device-free like rz_plan_lanes:
+ * warp w owns rows rowFirst[w] .. +rowDepth[w]-1, entry u of lane l at rows[(rowFirst[w] + 32*u + l)*4 .. +3] =
+ * (dx, dy, dz, morph id bits); morphMajor[w] = 1 when a row holds ONE morph for the whole warp.  laneVertex as returned by
+ * rz_plan_lanes.  rows may be NULL (size query: *rowsNeeded entries of 4 floats). */
+int32_t rz_plan_morph_rows(const uint32_t* laneVertex /* Vp */, uint32_t Vp, uint32_t V, const uint32_t* morphOffsets /* M+1 */,
+                           const uint32_t* vertIdx, const float* delta3, uint32_t M, uint32_t* rowFirst /* Vp/32 */,
+                           uint32_t* rowDepth /* Vp/32 */, uint8_t* morphMajor /* Vp/32 */, float* rows, uint64_t rowsCapacity,
+                           uint64_t* rowsNeeded);
+/* The cost-balanced chunk boundaries rz_deform uses when morphs are active: tileDepth[t] = deepest row list among the
+ * warps of 256-vertex tile t; tab receives nChunks+1 tile indices (room for nChunksTarget+1). */
+int32_t rz_plan_chunks(const uint32_t* tileDepth, uint32_t nTiles, uint32_t tilesPerPass, uint32_t nChunksTarget,
+                       uint32_t* tab, uint32_t* nChunks);
 int32_t rz_read_bounds(rz_ctx* ctx, uint32_t firstInstance, uint32_t count, float* minmax6 /* 6*count */);
 /* bit-exact integer view of the tables the kernel consumes, mapped back to caller order (parity tests) */
 int32_t rz_read_skinning(rz_ctx* ctx, uint16_t* joints /* 4V */, uint8_t* weights /* 4V */);

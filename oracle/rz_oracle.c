@@ -8,7 +8,7 @@
  * Pinning status:
  *   - loader integers (joints/weights quantisation, clamp + renormalise to 255, inverse
  *     bind): PINNED bit-exactly by the reference's own dump web/app/tutorial/model.json
- *     of 塞尔凯特.pmx (tests/test_loader_golden.py, run where /root/reference exists;
+ *     of 塞尔凯特.pmx (tests/test_loader.py, run where /root/reference exists;
  *     digests committed under tests/golden/).
  *   - float blend (engine.ts:253-272): the reference stores no golden skinned output and
  *     cannot be executed here (TypeScript + WGSL, no JS runtime / WebGPU in the image), so

@@ -32,6 +32,7 @@ EXPORTS = [
     "rz_sync", "rz_output_device_ptr", "rz_read_instance", "rz_get_vertex_order", "rz_plan_lanes", "rz_read_bounds", "rz_read_skinning",
     "rz_read_skin_matrices", "rz_get_stats", "rz_last_error",
     "rz_load_edge_size", "rz_get_output_layout", "rz_read_outline", "rz_read_interleaved",
+    "rz_plan_morph_rows", "rz_plan_chunks",
 ]
 
 
@@ -109,6 +110,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.rz_read_interleaved.argtypes = [vp, u32, vp]
     lib.rz_get_vertex_order.argtypes = [vp, vp]
     lib.rz_plan_lanes.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp, vp]
+    lib.rz_plan_morph_rows.argtypes = [vp, u32, u32, vp, vp, vp, u32, vp, vp, vp, vp, C.c_uint64, P(C.c_uint64)]
+    lib.rz_plan_chunks.argtypes = [vp, u32, u32, u32, vp, P(u32)]
     lib.rz_read_bounds.argtypes = [vp, u32, u32, vp]
     lib.rz_read_skinning.argtypes = [vp, vp, vp]
     lib.rz_read_skin_matrices.argtypes = [vp, u32, vp]
@@ -147,6 +150,40 @@ def plan_lanes(joints, weights, B: int, mode: int = 2, lib: Optional[C.CDLL] = N
         raise RzError(st, lib.rz_last_error(None).decode("utf-8", "replace"))
     return {"laneVertex": lane_vertex, "laneJoints": lane_joints, "laneWeights": lane_weights, "fast": int(stats[0]), "total": int(stats[1]),
             "hist": stats[2:].reshape(5, 5).astype(np.int64)}
+
+
+def plan_morph_rows(lane_vertex, V: int, offsets, vert_idx, delta3, lib: Optional[C.CDLL] = None) -> dict:
+    """Device-free: the per-warp morph rows rz_load_morphs builds for the lane plan `lane_vertex` (rz_plan_morph_rows)."""
+    lib = lib or load_library()
+    lv = _arr(lane_vertex, np.uint32).reshape(-1)
+    off = _arr(offsets, np.uint32).reshape(-1)
+    vi = _arr(vert_idx, np.uint32).reshape(-1)
+    d3 = _arr(delta3, np.float32).reshape(-1)
+    Vp, M = lv.size, max(off.size - 1, 0)
+    first = np.zeros(Vp // 32, np.uint32)
+    depth = np.zeros(Vp // 32, np.uint32)
+    mm = np.zeros(Vp // 32, np.uint8)
+    need = C.c_uint64(0)
+    st = lib.rz_plan_morph_rows(_ptr(lv), Vp, V, _ptr(off), _ptr(vi), _ptr(d3), M, _ptr(first), _ptr(depth), _ptr(mm), None, 0, C.byref(need))
+    if st != 0:
+        raise RzError(st, (lib.rz_last_error(None) or b"").decode())
+    rows = np.zeros((need.value, 4), np.float32)
+    st = lib.rz_plan_morph_rows(_ptr(lv), Vp, V, _ptr(off), _ptr(vi), _ptr(d3), M, None, None, None, _ptr(rows), need.value, None)
+    if st != 0:
+        raise RzError(st, (lib.rz_last_error(None) or b"").decode())
+    return dict(first=first, depth=depth, morphMajor=mm, rows=rows)
+
+
+def plan_chunks(tile_depth, tiles_per_pass: int, n_chunks_target: int, lib: Optional[C.CDLL] = None) -> np.ndarray:
+    """Device-free: cost-balanced chunk boundaries (rz_plan_chunks), in tiles."""
+    lib = lib or load_library()
+    td = _arr(tile_depth, np.uint32).reshape(-1)
+    tab = np.zeros(max(n_chunks_target, 1) + 1, np.uint32)
+    n = C.c_uint32(0)
+    st = lib.rz_plan_chunks(_ptr(td), td.size, tiles_per_pass, n_chunks_target, _ptr(tab), C.byref(n))
+    if st != 0:
+        raise RzError(st, (lib.rz_last_error(None) or b"").decode())
+    return tab[:n.value + 1].copy()
 
 
 class DeformContext:

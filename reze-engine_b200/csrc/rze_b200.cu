@@ -10,6 +10,7 @@
 #include "aux_kernels.cuh"
 #include "kernel_table.h"
 #include "lane_plan.h"
+#include "mesh_tables.h"
 
 #include <algorithm>
 #include <chrono>
@@ -278,23 +279,11 @@ int rebuild_tables(rz_ctx_impl* c) {
     VT = vt_s.data(); JT = jt_s.data(); WT = wt_s.data();
   }
 
-  // vertex-major morph CSR (caller vertex order)
-  std::vector<uint32_t> mcount(V, 0), mstart(V + 1, 0);
+  // vertex-major view of the morph table in stored vertex order (mesh_tables.h)
+  std::vector<uint32_t> mcount, mstart;
+  std::vector<F4> ments;
   const uint32_t nnz = c->M ? c->h_moff[c->M] : 0;
-  for (uint32_t e = 0; e < nnz; ++e) mcount[c->vinv[c->h_mvert[e]]]++;
-  for (uint32_t v = 0; v < V; ++v) mstart[v + 1] = mstart[v] + mcount[v];
-  std::vector<float4> ments(std::max<uint32_t>(nnz, 1));
-  {
-    std::vector<uint32_t> fill(mstart.begin(), mstart.end() - 1);
-    for (uint32_t m = 0; m < c->M; ++m)
-      for (uint32_t e = c->h_moff[m]; e < c->h_moff[m + 1]; ++e) {
-        const uint32_t v = c->vinv[c->h_mvert[e]];
-        float4 r;
-        r.x = c->h_mdelta[(size_t)e * 3]; r.y = c->h_mdelta[(size_t)e * 3 + 1]; r.z = c->h_mdelta[(size_t)e * 3 + 2];
-        memcpy(&r.w, &m, 4);
-        ments[fill[v]++] = r;
-      }
-  }
+  morphs_by_vertex(V, c->M, c->h_moff.data(), c->h_mvert.data(), c->h_mdelta.data(), c->vinv.data(), mcount, mstart, ments);
   c->morphNnz = nnz;
   c->tileMorphMax.assign(nTiles, 0);       // filled with the row depth per warp once the lane plan is known (`mell` below)
   c->chunkKey = {};
@@ -318,7 +307,6 @@ int rebuild_tables(rz_ctx_impl* c) {
   std::vector<float> edgeArr((c->flags & RZ_FLAG_OUTLINE) ? Vp : 0, 0.f);
   std::vector<float2> uvArr((c->flags & RZ_FLAG_INTERLEAVED) ? Vp : 0, make_float2(0.f, 0.f));
   std::vector<uint2> mrange(Vp / 32);     // per warp: (first entry, depth) of its lane-interleaved morph entries
-  std::vector<float4> mell;
   std::vector<uint32_t> sdefIdx(Vp, ~0u);   // "no SDEF vertex": a feature kernel compiled with SDEF may run without the flag
   c->procToVertex.assign(Vp, ~0u);
 
@@ -341,90 +329,8 @@ int rebuild_tables(rz_ctx_impl* c) {
   c->packFastSlots = plan.fastSlots;
   c->packTotalSlots = plan.totalSlots;
 
-  // ---- bank-aware palette permutation -------------------------------------------------------------------------
-  // A warp-wide LDS.128 costs max(2, distinct chunks / 4, 2 x chunks per 16-byte bank group) cycles on sm_100
-  // (profiles/r01_ubench_lds128.txt).  Rows are 48 B, so the bank group of row r of bone b is (3*pos(b)+r) mod 8:
-  // bones gathered by the same warp instruction should sit at positions that differ mod 8.  Greedy colouring of the
-  // bone co-occurrence graph into 8 classes, then class c occupies palette rows c, c+8, c+16, ...
-  c->bonePos.resize(B);
-  for (uint32_t b = 0; b < B; ++b) c->bonePos[b] = b;
-  if (c->colorMode && B >= 16) {
-    std::unordered_map<uint64_t, uint32_t> pairW;
-    std::vector<uint32_t> seen;
-    for (uint32_t w0 = 0; w0 < Vp; w0 += 32) {
-      for (uint32_t k = 0; k < 4; ++k) {
-        seen.clear();
-        for (uint32_t l = 0; l < 32; ++l) {
-          const uint32_t b = gatherJ[(size_t)(w0 + l) * 4 + k];
-          if (std::find(seen.begin(), seen.end(), b) == seen.end()) seen.push_back(b);
-        }
-        for (size_t a = 0; a < seen.size(); ++a)
-          for (size_t b2 = a + 1; b2 < seen.size(); ++b2) {
-            const uint32_t lo = std::min(seen[a], seen[b2]), hi = std::max(seen[a], seen[b2]);
-            pairW[((uint64_t)lo << 32) | hi] += 1;
-          }
-      }
-    }
-    std::vector<std::vector<std::pair<uint32_t, uint32_t>>> adj(B);
-    std::vector<uint64_t> tot(B, 0);
-    for (const auto& kv : pairW) {
-      const uint32_t lo = (uint32_t)(kv.first >> 32), hi = (uint32_t)kv.first;
-      adj[lo].push_back({hi, kv.second});
-      adj[hi].push_back({lo, kv.second});
-      tot[lo] += kv.second;
-      tot[hi] += kv.second;
-    }
-    std::vector<uint32_t> order(B);
-    for (uint32_t b = 0; b < B; ++b) order[b] = b;
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return tot[a] > tot[b]; });
-    uint32_t cap[8], cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (uint32_t cl = 0; cl < 8; ++cl) cap[cl] = (B - cl + 7) / 8;
-    std::vector<int> cls(B, -1);
-    for (uint32_t b : order) {
-      uint64_t cost[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      for (const auto& e : adj[b]) if (cls[e.first] >= 0) cost[cls[e.first]] += e.second;
-      int best = -1;
-      for (int cl = 0; cl < 8; ++cl) {
-        if (cnt[cl] >= cap[cl]) continue;
-        if (best < 0 || cost[cl] < cost[best] || (cost[cl] == cost[best] && cnt[cl] < cnt[best])) best = cl;
-      }
-      cls[b] = best;
-      cnt[best]++;
-    }
-    uint32_t next[8];
-    for (uint32_t cl = 0; cl < 8; ++cl) next[cl] = cl;
-    for (uint32_t b = 0; b < B; ++b) { c->bonePos[b] = next[cls[b]]; next[cls[b]] += 8; }
-    if (c->layoutMode == 1) {
-      // [3][B] layout: 8 consecutive palette rows share one 128-byte line per chunk, so bones gathered together should be
-      // NEIGHBOURS: greedy chaining -- start a group of 8 with the heaviest unplaced bone, then keep appending the unplaced
-      // bone with the largest co-occurrence weight to the bones already in the group.
-      std::vector<char> placed(B, 0);
-      std::vector<uint64_t> gain(B, 0);
-      uint32_t pos = 0;
-      size_t oi = 0;
-      while (pos < B) {
-        while (oi < B && placed[order[oi]]) ++oi;
-        uint32_t seed = order[oi];
-        std::vector<uint32_t> touched;
-        uint32_t cur = seed;
-        for (uint32_t g = 0; g < 8 && pos < B; ++g) {
-          placed[cur] = 1;
-          c->bonePos[cur] = pos++;
-          for (const auto& e : adj[cur]) if (!placed[e.first]) { if (!gain[e.first]) touched.push_back(e.first); gain[e.first] += e.second; }
-          uint32_t best = ~0u;
-          for (uint32_t t : touched) if (!placed[t] && (best == ~0u || gain[t] > gain[best])) best = t;
-          if (best == ~0u) {               // nothing related left: take the next heaviest bone
-            size_t oj = oi;
-            while (oj < B && placed[order[oj]]) ++oj;
-            if (oj >= B) break;
-            best = order[oj];
-          }
-          cur = best;
-        }
-        for (uint32_t t : touched) gain[t] = 0;
-      }
-    }
-  }
+  // ---- bank-aware palette permutation (mesh_tables.h)
+  plan_palette_rows(gatherJ.data(), Vp, B, c->colorMode, c->layoutMode, c->bonePos);
   c->boneAt.assign(B, 0);
   for (uint32_t b = 0; b < B; ++b) c->boneAt[c->bonePos[b]] = b;
 
@@ -504,66 +410,14 @@ int rebuild_tables(rz_ctx_impl* c) {
     metaArr[p] = meta;
   }
 
-  // ---- morph entries, lane-interleaved per warp (ELL): entry u of lane l sits at first + u*32 + l.  One LDG.128 per depth
-  // step is then a single coalesced 512-byte request for the warp instead of 32 scattered 16-byte ones (the L1 tag stage
-  // serialises those: measured +0.16 ms on config 3), and the loop bound is warp-uniform.  Within a lane the entries keep
-  // PMX morph order.  Two row formats, chosen per warp, identical to the kernel:
-  //   MORPH-MAJOR (default): row u = one morph for the whole warp, delta 0 on lanes that morph does not touch.  PMX morphs
-  //     are spatially coherent (the 32 vertices of a warp see the same morphs), so this costs no extra rows, and every lane
-  //     of a row looks up the SAME weight: a shared-memory broadcast instead of a 3-4-way bank conflict per lookup
-  //     (ncu on config 3: 39 % of the shared-memory wavefronts were conflicts).  fma(w, 0, p) == p: results unchanged.
-  //   COMPACT (fallback when the union of morphs is > 1.5x the deepest vertex): entry u = the lane's own u-th morph,
-  //     padded with (delta 0, morph 0).
-  for (uint32_t w0 = 0; w0 < Vp; w0 += 32) {
-    uint32_t deep = 0;
-    bool dup = false;
-    std::vector<uint32_t> ids;
-    for (uint32_t l = 0; l < 32; ++l) {
-      const uint32_t v = procVertex[w0 + l];
-      if (v == ~0u) continue;
-      deep = std::max(deep, mcount[v]);
-      for (uint32_t u = 0; u < mcount[v]; ++u) {
-        uint32_t m;
-        memcpy(&m, &ments[mstart[v] + u].w, 4);
-        if (u && m == ids.back()) dup = true;      // one morph lists this vertex twice: keep both entries (compact rows)
-        ids.push_back(m);
-      }
-    }
-    const uint32_t first = (uint32_t)mell.size();
-    if (!deep) { mrange[w0 / 32] = make_uint2(first, 0u); continue; }
-    std::sort(ids.begin(), ids.end());
-    ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
-    const bool morphMajor = !dup && ids.size() <= (size_t)deep + deep / 2 + 1;
-    const uint32_t rows = morphMajor ? (uint32_t)ids.size() : deep;
-    mrange[w0 / 32] = make_uint2(first, rows);
-    c->tileMorphMax[w0 / kTile] = std::max(c->tileMorphMax[w0 / kTile], rows);
-    mell.resize((size_t)first + (size_t)rows * 32, make_float4(0.f, 0.f, 0.f, 0.f));
-    if (morphMajor)
-      for (uint32_t r = 0; r < rows; ++r) {
-        float idBits;
-        memcpy(&idBits, &ids[r], 4);
-        for (uint32_t l = 0; l < 32; ++l) mell[(size_t)first + (size_t)r * 32 + l].w = idBits;
-      }
-    for (uint32_t l = 0; l < 32; ++l) {
-      const uint32_t v = procVertex[w0 + l];
-      if (v == ~0u) continue;
-      uint32_t r = 0;
-      for (uint32_t u = 0; u < mcount[v]; ++u) {
-        const float4 e = ments[mstart[v] + u];
-        if (morphMajor) {
-          uint32_t m;
-          memcpy(&m, &e.w, 4);
-          while (ids[r] != m) ++r;                                  // both ascending
-          mell[(size_t)first + (size_t)r * 32 + l].x = e.x;
-          mell[(size_t)first + (size_t)r * 32 + l].y = e.y;
-          mell[(size_t)first + (size_t)r * 32 + l].z = e.z;
-        } else {
-          mell[(size_t)first + (size_t)u * 32 + l] = e;
-        }
-      }
-    }
+  // ---- morph rows, lane-interleaved per warp (mesh_tables.h)
+  MorphRows mrows;
+  build_morph_rows(procVertex.data(), Vp, mcount, mstart, ments, mrows);
+  for (uint32_t w = 0; w < Vp / 32; ++w) {
+    mrange[w] = make_uint2(mrows.first[w], mrows.depth[w]);
+    c->tileMorphMax[w * 32 / kTile] = std::max(c->tileMorphMax[w * 32 / kTile], mrows.depth[w]);
   }
-  if (mell.empty()) mell.push_back(make_float4(0.f, 0.f, 0.f, 0.f));
+  const std::vector<F4>& mell = mrows.rows;
 
   int rc;
   if ((rc = dev_reserve(c, c->d_rec0, (size_t)Vp * 16))) return rc;
@@ -1272,24 +1126,9 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
     // leave a few very long items (measured: +70 % on config 3).  Chunk boundaries are placed so that every item carries
     // the same estimated time instead; the table only depends on the launch shape and is cached.
     if (c->chunkKey.tilesPerPass != tilesPerPass || c->chunkKey.target != nChunks || !c->d_chunkTab.p) {
-      std::vector<float> cost(nPasses);
-      double total = 0;
-      for (uint32_t p = 0; p < nPasses; ++p) {
-        uint32_t deep = 0;
-        for (uint32_t t = p * tilesPerPass; t < std::min(c->nTiles, (p + 1) * tilesPerPass); ++t) deep = std::max(deep, c->tileMorphMax[t]);
-        const uint32_t trips = deep > (uint32_t)kMorphPF ? (deep - kMorphPF + kMorphBatch - 1) / kMorphBatch : 0;
-        static const float tripCost = getenv("RZ_MORPH_TRIP_COST") ? (float)atof(getenv("RZ_MORPH_TRIP_COST")) : 0.5f;
-        cost[p] = 1.0f + (deep ? 0.25f : 0.f) + tripCost * (float)trips;   // in plain passes; an L2 round trip ~ half a pass
-        total += cost[p];
-      }
+      static const float tripCost = getenv("RZ_MORPH_TRIP_COST") ? (float)atof(getenv("RZ_MORPH_TRIP_COST")) : 0.5f;
       std::vector<uint32_t> tab;
-      tab.push_back(0);
-      double acc = 0;
-      for (uint32_t p = 0; p < nPasses; ++p) {
-        acc += cost[p];
-        if (acc >= total * (double)tab.size() / (double)nChunks && p + 1 < nPasses) tab.push_back((p + 1) * tilesPerPass);
-      }
-      tab.push_back(c->nTiles);
+      build_chunk_table(c->tileMorphMax.data(), c->nTiles, tilesPerPass, nChunks, tripCost, kMorphPF, kMorphBatch, tab);
       if ((rc = dev_reserve(c, c->d_chunkTab, tab.size() * 4))) return rc;
       CU_TRY(c, cudaMemcpyAsync(c->d_chunkTab.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, c->stream));
       CU_TRY(c, cudaStreamSynchronize(c->stream));                  // once per launch shape; `tab` goes out of scope
@@ -1492,6 +1331,43 @@ int32_t rz_plan_lanes(const uint16_t* joints, const uint8_t* weights, uint32_t V
     stats[0] = plan.fastSlots; stats[1] = plan.totalSlots;
     for (int n = 0; n < 5; ++n) for (int m = 0; m < 5; ++m) stats[2 + n * 5 + m] = plan.hist[n][m];
   }
+  return RZ_OK;
+}
+
+int32_t rz_plan_morph_rows(const uint32_t* laneVertex, uint32_t Vp, uint32_t V, const uint32_t* morphOffsets, const uint32_t* vertIdx,
+                           const float* delta3, uint32_t M, uint32_t* rowFirst, uint32_t* rowDepth, uint8_t* morphMajor, float* rows,
+                           uint64_t rowsCapacity, uint64_t* rowsNeeded) {
+  if (!laneVertex || Vp == 0 || Vp % 32 || V == 0) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_plan_morph_rows: bad lane table");
+  if (M && (!morphOffsets || morphOffsets[0] != 0)) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_plan_morph_rows: morphOffsets[0] must be 0");
+  const uint32_t nnz = M ? morphOffsets[M] : 0;
+  for (uint32_t e = 0; e < nnz; ++e)
+    if (vertIdx[e] >= V) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_plan_morph_rows: vertex index %u >= V=%u", vertIdx[e], V);
+  for (uint32_t p = 0; p < Vp; ++p)
+    if (laneVertex[p] != ~0u && laneVertex[p] >= V) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_plan_morph_rows: lane vertex out of range");
+  std::vector<uint32_t> mcount, mstart;
+  std::vector<F4> ments;
+  morphs_by_vertex(V, M, morphOffsets, vertIdx, delta3, nullptr, mcount, mstart, ments);
+  MorphRows mr;
+  build_morph_rows(laneVertex, Vp, mcount, mstart, ments, mr);
+  if (rowFirst) memcpy(rowFirst, mr.first.data(), (size_t)(Vp / 32) * 4);
+  if (rowDepth) memcpy(rowDepth, mr.depth.data(), (size_t)(Vp / 32) * 4);
+  if (morphMajor) memcpy(morphMajor, mr.morphMajor.data(), (size_t)(Vp / 32));
+  if (rowsNeeded) *rowsNeeded = mr.rows.size();
+  if (rows) {
+    if (rowsCapacity < mr.rows.size()) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_plan_morph_rows: rows buffer too small");
+    memcpy(rows, mr.rows.data(), mr.rows.size() * 16);
+  }
+  return RZ_OK;
+}
+
+int32_t rz_plan_chunks(const uint32_t* tileDepth, uint32_t nTiles, uint32_t tilesPerPass, uint32_t nChunksTarget, uint32_t* tab,
+                       uint32_t* nChunks) {
+  if (!tileDepth || nTiles == 0 || tilesPerPass == 0 || !tab || !nChunks)
+    return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_plan_chunks: bad argument");
+  std::vector<uint32_t> t;
+  build_chunk_table(tileDepth, nTiles, tilesPerPass, nChunksTarget, 0.5f, kMorphPF, kMorphBatch, t);
+  memcpy(tab, t.data(), t.size() * 4);
+  *nChunks = (uint32_t)t.size() - 1;
   return RZ_OK;
 }
 

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from helpers import numpy_blend_f64, random_pmx, rel_err, write_vmd
-from reze_engine_b200 import Engine, Model, PmxLoader, Quat, VMDLoader, crowd, synth
+from reze_engine_b200 import Engine, Model, PmxLoader, Quat, VMDLoader, capi, crowd, synth
 from reze_engine_b200.engine import ManualClock
 from reze_engine_b200.math3d import Mat4, easeInOut
 
@@ -240,6 +240,75 @@ def test_lane_plan_preserves_every_influence_and_packs_pairs(rzlib, mode):
         assert plan["hist"].sum() > 0
     else:
         assert plan["total"] == 0
+
+
+def test_morph_rows_hold_every_entry_once_in_pmx_order(rzlib):
+    """rz_plan_morph_rows (the table builder rz_load_morphs uses, device-free): every (vertex, morph, delta) of the caller's
+    table sits in exactly one row entry of the lane that evaluates the vertex, rows of a lane ascend in morph id, everything
+    else is an exact-zero delta; coherent warps get morph-major rows, scattered ones the compact format, and a morph that
+    lists a vertex twice keeps both entries."""
+    from reze_engine_b200 import synth
+    rng = np.random.default_rng(12)
+    wl = synth.make_workload(3000, 40, seed=12)
+    V, M = wl.V, 30
+    offs, vidx, deltas = [0], [], []
+    for m in range(M):
+        if m % 2 == 0:
+            a = int(rng.integers(0, V - 300))
+            v = np.arange(a, a + int(rng.integers(40, 300)))
+        else:
+            v = np.sort(rng.choice(V, int(rng.integers(5, 150)), replace=False))
+        if m == 4:
+            v = np.concatenate([v, v[:2]])
+        vidx.append(v.astype(np.uint32))
+        deltas.append(rng.normal(0, 0.05, (v.size, 3)).astype(np.float32))
+        offs.append(offs[-1] + v.size)
+    offs, vidx, deltas = np.array(offs, np.uint32), np.concatenate(vidx), np.concatenate(deltas)
+    mid = np.repeat(np.arange(M), np.diff(offs.astype(np.int64)))
+    plan = capi.plan_lanes(wl.joints, wl.weights, wl.B, 2, rzlib)
+    lv = np.asarray(plan["laneVertex"], np.uint32)
+    r = capi.plan_morph_rows(lv, V, offs, vidx, deltas, rzlib)
+    rows, first, depth, mm = r["rows"], r["first"], r["depth"], r["morphMajor"]
+    assert mm.any() and not mm[depth > 0].all()                    # both formats occur
+    want = {}
+    for e in range(vidx.size):
+        want.setdefault(int(vidx[e]), []).append((int(mid[e]), deltas[e].tobytes()))
+    seen = 0
+    for w in range(lv.size // 32):
+        block = rows[first[w]:first[w] + depth[w] * 32].reshape(depth[w], 32, 4)
+        ids = block[:, :, 3].copy().view(np.uint32)
+        if mm[w] and depth[w]:
+            assert (ids == ids[:, :1]).all() and (np.diff(ids[:, 0].astype(np.int64)) > 0).all()      # one morph per row, ascending
+        for l in range(32):
+            v = int(lv[w * 32 + l])
+            got = [(int(ids[u, l]), block[u, l, :3].tobytes()) for u in range(depth[w]) if block[u, l, :3].any()]
+            if v == 0xFFFFFFFF:
+                assert not got
+                continue
+            exp = [x for x in want.get(v, []) if np.frombuffer(x[1], np.float32).any()]
+            assert got == exp, (w, l, v)
+            seen += len(exp)
+    assert seen == sum(1 for e in range(vidx.size) if deltas[e].any())
+    with pytest.raises(capi.RzError):
+        capi.plan_morph_rows(lv, V, offs, vidx + V, deltas, rzlib)
+
+
+def test_chunk_table_balances_morph_cost(rzlib):
+    """rz_plan_chunks: boundaries are monotone multiples of the pass width that cover every tile, no chunk is empty, and chunks
+    over the deep (face) tiles are shorter than chunks over plain tiles."""
+    depth = np.zeros(782, np.uint32)
+    depth[40:130] = 20
+    for tpp in (1, 2, 3):
+        tab = capi.plan_chunks(depth, tpp, 19, rzlib)
+        assert tab[0] == 0 and tab[-1] == depth.size and (np.diff(tab.astype(np.int64)) > 0).all() and tab.size - 1 <= 19
+        assert (tab[:-1] % tpp == 0).all()
+        sizes = np.diff(tab.astype(np.int64))
+        deep = [s for a, s in zip(tab[:-1], sizes) if 40 <= a and a + s <= 130]
+        plain = [s for a, s in zip(tab[:-1], sizes) if a >= 130]
+        assert deep and plain and max(deep) < min(plain[:-1])
+    flat = capi.plan_chunks(np.zeros(100, np.uint32), 2, 10, rzlib)
+    assert (np.diff(flat.astype(np.int64)) == 10).all()
+    assert capi.plan_chunks(np.zeros(5, np.uint32), 2, 50, rzlib).tolist() == [0, 2, 4, 5]
 
 
 def test_lane_plan_rejects_bad_tables(rzlib):
