@@ -125,6 +125,9 @@ int32_t rz_load_edge_size(rz_ctx* ctx, const float* edgeSize /* V or NULL */);
  * instToPalette : K entries < P, or NULL for identity (then P must be >= K).
  * skin = world * invBind is evaluated on the device. */
 int32_t rz_set_palettes(rz_ctx* ctx, const float* world, uint32_t P, const uint32_t* instToPalette, uint32_t K);
+/* (Large identity-mapped uploads are pipelined: the matrices travel in ~16 MB blocks on an internal copy stream and
+ * rz_deform consumes them block by block — wait, skin matrices, deform that block's instances — so the PCIe transfer
+ * overlaps the deform.  Results are bit-identical; environment RZ_NO_PIPELINE=1 disables it.) */
 /* same, `world` / `instToPalette` are device pointers on this context's device (zero-copy producers) */
 int32_t rz_set_palettes_device(rz_ctx* ctx, const float* d_world, uint32_t P, const uint32_t* d_instToPalette, uint32_t K);
 /* pinned host staging the caller may fill directly and pass to rz_set_palettes (saves one host copy);

@@ -105,6 +105,16 @@ struct rz_ctx_impl {
   size_t h_smallBytes = 0;
   size_t instStrideF = 0, nrmOffF = 0;
 
+  // pipelined palette upload (rz_set_palettes with host matrices): blocks of palettes travel on a copy stream while the
+  // blocks before them are already being deformed; a block's skin-matrix pass is issued by rz_deform right before the
+  // deform launch of that block's instances
+  cudaStream_t copyStream = nullptr;
+  cudaEvent_t evWorldFree = nullptr;     // main stream: the last skin-matrix pass that reads d_world has been issued
+  bool worldFreeValid = false;
+  struct PendBlock { uint32_t pal0, n; cudaEvent_t ev; };
+  std::vector<PendBlock> pend;           // uploaded (or in flight) palettes whose skin matrices are not computed yet
+  std::vector<cudaEvent_t> evPool;
+
   // stats
   cudaEvent_t evStart = nullptr, evStop = nullptr;
   bool evPending = false;
@@ -481,6 +491,29 @@ int ensure_dense_weights(rz_ctx_impl* c) {
   return RZ_OK;
 }
 
+void launch_skin_block(rz_ctx_impl* c, const float* d_world, uint32_t pal0, uint32_t n) {
+  const uint32_t threads = n * c->B;
+  const size_t w4 = (size_t)pal0 * c->B * 4, s4 = (size_t)pal0 * c->B * 3;        // float4 offsets of the block
+  skin_matrices_kernel<<<(threads + 127) / 128, 128, 0, c->stream>>>(reinterpret_cast<const float4*>(d_world) + w4,
+                                                                    reinterpret_cast<const float4*>(c->d_invBind.p),
+                                                                    reinterpret_cast<float4*>(c->d_skin.p) + s4,
+                                                                    reinterpret_cast<const uint32_t*>(c->d_bonePos.p), n, c->B, (uint32_t)c->layoutMode);
+  c->launches++;
+}
+
+// skin-matrix passes of every uploaded block that has none yet (each waits for its block's copy)
+int flush_pending(rz_ctx_impl* c) {
+  if (c->pend.empty()) return RZ_OK;
+  for (const auto& b : c->pend) {
+    CU_TRY(c, cudaStreamWaitEvent(c->stream, b.ev, 0));
+    launch_skin_block(c, reinterpret_cast<const float*>(c->d_world.p), b.pal0, b.n);
+  }
+  c->pend.clear();
+  CU_TRY(c, cudaEventRecord(c->evWorldFree, c->stream));
+  c->worldFreeValid = true;
+  return RZ_OK;
+}
+
 }  // namespace
 
 struct rz_ctx : rz_ctx_impl {};
@@ -545,6 +578,8 @@ int32_t rz_create(const rz_config* cfg, rz_ctx** out) {
   if (const char* e3 = getenv("RZ_LAYOUT")) c->layoutMode = atoi(e3);
   cudaEventCreate(&c->evStart);
   cudaEventCreate(&c->evStop);
+  cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&c->evWorldFree, cudaEventDisableTiming);
   *out = c;
   return RZ_OK;
 }
@@ -552,7 +587,11 @@ int32_t rz_create(const rz_config* cfg, rz_ctx** out) {
 int32_t rz_destroy(rz_ctx* c) {
   if (!c) return RZ_OK;
   cudaSetDevice(c->device);
+  if (c->copyStream) cudaStreamSynchronize(c->copyStream);
   cudaStreamSynchronize(c->stream);
+  for (cudaEvent_t e : c->evPool) cudaEventDestroy(e);
+  if (c->evWorldFree) cudaEventDestroy(c->evWorldFree);
+  if (c->copyStream) cudaStreamDestroy(c->copyStream);
   DevBuf* bufs[] = {&c->d_rec0, &c->d_rec1, &c->d_rec2, &c->d_meta, &c->d_wbits, &c->d_mrange, &c->d_ments, &c->d_sdefIdx, &c->d_sdefTab,
                     &c->d_invBind, &c->d_bonePos, &c->d_world, &c->d_skin, &c->d_inst2pal, &c->d_mwIn, &c->d_mwIds, &c->d_mwDense,
                     &c->d_out, &c->d_bounds, &c->d_counter, &c->d_skParent, &c->d_skBindT, &c->d_skAppendParent, &c->d_skAppendRatio,
@@ -634,12 +673,10 @@ int32_t rz_load_sdef(rz_ctx* c, const uint32_t* vertIdx, const float* vec9, uint
 static int set_palettes_common(rz_ctx* c, const float* d_world, uint32_t P, uint32_t K) {
   int rc;
   if ((rc = dev_reserve(c, c->d_skin, (size_t)P * c->B * 48))) return rc;
-  const uint32_t n = P * c->B;
-  skin_matrices_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(reinterpret_cast<const float4*>(d_world),
-                                                              reinterpret_cast<const float4*>(c->d_invBind.p),
-                                                              reinterpret_cast<float4*>(c->d_skin.p), reinterpret_cast<const uint32_t*>(c->d_bonePos.p), P, c->B, (uint32_t)c->layoutMode);
+  c->pend.clear();                                           // superseded
+  launch_skin_block(c, d_world, 0, P);
   CU_TRY(c, cudaGetLastError());
-  c->launches++;
+  if (d_world == c->d_world.p) { CU_TRY(c, cudaEventRecord(c->evWorldFree, c->stream)); c->worldFreeValid = true; }
   c->P = P;
   c->K = K;
   c->palettesSet = true;
@@ -650,6 +687,7 @@ int32_t rz_palette_staging(rz_ctx* c, size_t bytes, void** host_ptr) {
   if (!c || !host_ptr) return fail(c, RZ_ERR_INVALID_ARG, "rz_palette_staging: null argument");
   CU_TRY(c, cudaSetDevice(c->device));
   if (bytes > c->h_stageBytes) CU_TRY(c, cudaStreamSynchronize(c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->copyStream));           // the caller is about to overwrite the staging buffer
   int rc = pinned_reserve(c, c->h_stage, c->h_stageBytes, bytes);
   if (rc) return rc;
   *host_ptr = c->h_stage;
@@ -674,10 +712,43 @@ int32_t rz_set_palettes(rz_ctx* c, const float* world, uint32_t P, const uint32_
   if (!inStage) {
     // the staging buffer may still be the source of the previous frame's copy
     CU_TRY(c, cudaStreamSynchronize(c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->copyStream));
     if ((rc = pinned_reserve(c, c->h_stage, c->h_stageBytes, bytes))) return rc;
     memcpy(c->h_stage, world, bytes);
     src = reinterpret_cast<const char*>(c->h_stage);
   }
+  // Large identity-mapped uploads (a crowd with one palette per instance, as the reference's per-model upload scales) are
+  // PIPELINED: blocks of ~16 MB go out on the copy stream, each followed by an event; rz_deform then alternates
+  // "wait for block b, skin matrices of block b, deform the instances of block b", so the PCIe transfer of block b+1
+  // overlaps the deform of block b instead of preceding the whole frame (measured: 4.6 -> 2.9 ms at K=4096, B=512).
+  static const bool noPipe = getenv("RZ_NO_PIPELINE") != nullptr;
+  const size_t palBytes = (size_t)c->B * 64;
+  uint32_t blk = (uint32_t)std::max<size_t>(64, ((size_t)16 << 20) / palBytes);
+  if (const char* eb = getenv("RZ_PIPELINE_BLOCK")) blk = (uint32_t)std::max(1, atoi(eb));   // palettes per block (tests)
+  if (!inst2pal && !noPipe && P >= 2 * blk) {
+    if ((rc = dev_reserve(c, c->d_skin, (size_t)P * c->B * 48))) return rc;
+    if (c->worldFreeValid) CU_TRY(c, cudaStreamWaitEvent(c->copyStream, c->evWorldFree, 0));   // d_world is no longer being read
+    c->pend.clear();
+    const uint32_t nb = (P + blk - 1) / blk;
+    while (c->evPool.size() < nb) {
+      cudaEvent_t e;
+      CU_TRY(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      c->evPool.push_back(e);
+    }
+    for (uint32_t b = 0; b < nb; ++b) {
+      const uint32_t pal0 = b * blk, n = std::min(blk, P - pal0);
+      CU_TRY(c, cudaMemcpyAsync(reinterpret_cast<char*>(c->d_world.p) + (size_t)pal0 * palBytes, src + (size_t)pal0 * palBytes,
+                                (size_t)n * palBytes, cudaMemcpyHostToDevice, c->copyStream));
+      CU_TRY(c, cudaEventRecord(c->evPool[b], c->copyStream));
+      c->pend.push_back({pal0, n, c->evPool[b]});
+    }
+    c->haveInst2pal = false;
+    c->P = P;
+    c->K = K;
+    c->palettesSet = true;
+    return RZ_OK;
+  }
+  if (!c->pend.empty()) CU_TRY(c, cudaStreamWaitEvent(c->stream, c->pend.back().ev, 0));    // an unconsumed pipelined upload still targets d_world
   CU_TRY(c, cudaMemcpyAsync(c->d_world.p, src, bytes, cudaMemcpyHostToDevice, c->stream));
   if (inst2pal) {
     if ((rc = dev_reserve(c, c->d_inst2pal, (size_t)c->maxK * 4))) return rc;
@@ -790,6 +861,7 @@ int32_t rz_load_skeleton(rz_ctx* c, const int32_t* parent, const float* bindT, c
 extern "C++" {
 template <int MODE>
 static int launch_pose(rz_ctx* c, uint32_t P) {
+  c->pend.clear();   // the palettes are about to be produced on the device: an unconsumed host upload is superseded
   const size_t smem = (size_t)c->B * 64;
   if (smem > (size_t)c->maxSmemOptin)
     return fail(c, RZ_ERR_INVALID_ARG, "GPU pose evaluation supports up to %d bones (B=%u): use rz_set_palettes", c->maxSmemOptin / 64, c->B);
@@ -1021,6 +1093,10 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
   if (feat < 0)
     return fail(c, RZ_ERR_INVALID_ARG, "rz_deform: feature combination 0x%x is not built%s", need,
                 (need & FEAT_GPAL) && (need & (FEAT_HULL | FEAT_ILV)) ? " (outline / interleaved output need the palette in shared memory: B too large)" : "");
+  // a pipelined upload (rz_set_palettes) is consumed block by block below; feature sets with per-launch side kernels or
+  // count-dependent tables take the whole upload first
+  const bool pipelined = !c->pend.empty() && !(feat & (FEAT_MORPH | FEAT_SDEF | FEAT_BOUNDS | FEAT_GPAL));
+  if (!pipelined && (rc = flush_pending(c))) return rc;
   KernelEntry ke{nullptr, 0, 0, 0, 0, 0, feat};
   size_t smem = 0;
   int occ = 0;
@@ -1110,8 +1186,16 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
   prm.bounds = reinterpret_cast<float*>(c->d_bounds.p);
   prm.instStrideF = c->instStrideF;
   prm.nrmOffF = c->nrmOffF;
-  prm.V = c->V; prm.B = c->B; prm.nTiles = c->nTiles; prm.K0 = first; prm.Kcount = count; prm.Mpad = Mpad;
-  prm.nGroups = (count + ke.I - 1) / ke.I;
+  prm.V = c->V; prm.B = c->B; prm.nTiles = c->nTiles; prm.Mpad = Mpad;
+  prm.counter = reinterpret_cast<uint32_t*>(c->d_counter.p);
+  prm.packedMeta = c->packedMeta ? 1u : 0u;
+  prm.posStride = c->layoutMode ? 16u : 48u;
+  prm.rowStride = c->layoutMode ? c->B * 16u : 16u;
+  uint32_t gridUsed = 0;
+  // one launch over the instance range [f, f+n)
+  auto launch_range = [&](uint32_t f, uint32_t n) -> int {
+  prm.K0 = f; prm.Kcount = n;
+  prm.nGroups = (n + ke.I - 1) / ke.I;
   const uint32_t tilesPerPass = ke.NT / kTile;
   const uint32_t nPasses = (c->nTiles + tilesPerPass - 1) / tilesPerPass;
   uint32_t grid = (uint32_t)(c->numSM * occ);
@@ -1138,12 +1222,15 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
     prm.chunkTab = reinterpret_cast<const uint32_t*>(c->d_chunkTab.p);
     prm.nChunks = c->chunkCount;
   }
-  prm.counter = reinterpret_cast<uint32_t*>(c->d_counter.p);
-  prm.packedMeta = c->packedMeta ? 1u : 0u;
-  prm.posStride = c->layoutMode ? 16u : 48u;
-  prm.rowStride = c->layoutMode ? c->B * 16u : 16u;
   const uint32_t nItems = prm.nGroups * prm.nChunks;
   grid = std::min(grid, nItems);
+  gridUsed = std::max(gridUsed, grid);
+  CU_TRY(c, cudaMemsetAsync(c->d_counter.p, 0, 4, c->stream));
+  void* args[] = {&prm};
+  CU_TRY(c, cudaLaunchKernel(ke.fn, dim3(grid), dim3(ke.NT), args, smem, c->stream));
+  c->launches++;
+  return RZ_OK;
+  };
 
   if (feat & FEAT_SDEF) {
     if ((rc = dev_reserve(c, c->d_quat, (size_t)c->P * c->B * 16))) return rc;
@@ -1156,7 +1243,6 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
     prm.bounds = reinterpret_cast<float*>(c->d_bounds.p);
   }
   CU_TRY(c, cudaEventRecord(c->evStart, c->stream));
-  CU_TRY(c, cudaMemsetAsync(c->d_counter.p, 0, 4, c->stream));
   if (feat & FEAT_SDEF) {
     // rotation of every skin matrix as a quaternion, once per (palette, bone) instead of once per SDEF vertex-instance
     const uint32_t n = c->P * c->B;
@@ -1168,13 +1254,32 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
     bounds_reset_kernel<<<(count * 6 + 127) / 128, 128, 0, c->stream>>>(reinterpret_cast<int*>(c->d_bounds.p) + (size_t)first * 6, count * 6);
     c->launches++;
   }
-  void* args[] = {&prm};
-  CU_TRY(c, cudaLaunchKernel(ke.fn, dim3(grid), dim3(ke.NT), args, smem, c->stream));
+  if (pipelined) {
+    // identity mapping: instance k reads palette k.  Blocks that do not touch [first, first+count) stay pending; parts of
+    // the range whose blocks were consumed by an earlier call are launched as they are.
+    std::vector<rz_ctx_impl::PendBlock> keep;
+    uint32_t cursor = first;
+    const uint32_t end = first + count;
+    for (const auto& b : c->pend) {                                 // ascending pal0
+      const uint32_t lo = std::max(first, b.pal0), hi = std::min(end, b.pal0 + b.n);
+      if (lo >= hi) { keep.push_back(b); continue; }
+      if (lo > cursor && (rc = launch_range(cursor, lo - cursor))) return rc;
+      CU_TRY(c, cudaStreamWaitEvent(c->stream, b.ev, 0));
+      launch_skin_block(c, reinterpret_cast<const float*>(c->d_world.p), b.pal0, b.n);
+      CU_TRY(c, cudaEventRecord(c->evWorldFree, c->stream));
+      c->worldFreeValid = true;
+      if ((rc = launch_range(lo, hi - lo))) return rc;
+      cursor = hi;
+    }
+    if (cursor < end && (rc = launch_range(cursor, end - cursor))) return rc;
+    c->pend.swap(keep);
+  } else {
+    if ((rc = launch_range(first, count))) return rc;
+  }
   CU_TRY(c, cudaEventRecord(c->evStop, c->stream));
-  c->launches++;
   c->evPending = true;
   c->frames++;
-  c->usedI = ke.I; c->usedStore = 2; c->usedCtas = grid; c->usedThreads = ke.NT; c->usedSmem = (uint32_t)smem;
+  c->usedI = ke.I; c->usedStore = 2; c->usedCtas = gridUsed; c->usedThreads = ke.NT; c->usedSmem = (uint32_t)smem;
   c->lastVerts = (uint64_t)count * c->V;
   // compulsory DRAM bytes: outputs + mesh + palettes + invBind + morph entries/weights + sdef records
   // (fused consumers add their own compulsory bytes: +12 B per vertex-instance for the hull plane, 32 B instead of 24 B
@@ -1436,6 +1541,10 @@ int32_t rz_read_skin_matrices(rz_ctx* c, uint32_t palette, float* skin3x4) {
   if (!c->palettesSet) return fail(c, RZ_ERR_STATE, "rz_read_skin_matrices before rz_set_palettes");
   if (palette >= c->P) return fail(c, RZ_ERR_INVALID_ARG, "rz_read_skin_matrices: palette %u >= P=%u", palette, c->P);
   CU_TRY(c, cudaSetDevice(c->device));
+  {
+    int rcf;
+    if ((rcf = flush_pending(c))) return rcf;                 // a pipelined upload computes its skin matrices lazily
+  }
   std::vector<float> tmp((size_t)c->B * 12);
   CU_TRY(c, cudaMemcpyAsync(tmp.data(), reinterpret_cast<const float*>(c->d_skin.p) + (size_t)palette * c->B * 12, (size_t)c->B * 48,
                             cudaMemcpyDeviceToHost, c->stream));

@@ -449,6 +449,37 @@ def test_reordered_vertex_storage_is_transparent_to_host_readers(rzlib, orc, wl_
         assert np.array_equal(plane, gp[order])
 
 
+def test_reordered_storage_with_fused_consumers(rzlib, orc, wl_small):
+    """RZ_FLAG_REORDER_VERTICES together with the outline plane / the interleaved stream: edge sizes and texture coordinates
+    follow their vertices, host readers stay in caller order."""
+    wl = wl_small
+    K = 3
+    rng = np.random.default_rng(15)
+    world = synth.make_palettes(wl.bones, K, rng)
+    edge = rng.uniform(0.0, 2.0, wl.V).astype(np.float32)
+    with capi.DeformContext(max_instances=K, flags=capi.RZ_FLAG_REORDER_VERTICES | capi.RZ_FLAG_OUTLINE) as ctx:
+        ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
+        ctx.load_edge_size(edge)
+        ctx.set_palettes(world)
+        ctx.deform()
+        for k in range(K):
+            rp, rn = oracle_instance(orc, wl, world[k])
+            gp, gn = ctx.read_instance(k)
+            assert rel_err(gp, rp) <= TOL and rel_err(gn, rn) <= TOL
+            assert rel_err(ctx.read_outline(k), orc.outline_hull(rp, rn, edge)) <= TOL
+    with capi.DeformContext(max_instances=K, flags=capi.RZ_FLAG_REORDER_VERTICES | capi.RZ_FLAG_INTERLEAVED) as ctx:
+        ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
+        ctx.set_palettes(world)
+        ctx.deform()
+        for k in range(K):
+            rp, rn = oracle_instance(orc, wl, world[k])
+            st = ctx.read_interleaved(k)
+            ref = orc.interleaved(rp, rn, wl.vtx8)
+            assert rel_err(st[:, :6], ref[:, :6]) <= TOL and np.array_equal(st[:, 6:], ref[:, 6:])
+            gp, gn = ctx.read_instance(k)
+            assert np.array_equal(gp, st[:, :3]) and np.array_equal(gn, st[:, 3:6])
+
+
 def test_sub_range_deform_and_device_palettes(rzlib, orc, wl_small):
     import torch
     wl = wl_small
@@ -465,6 +496,57 @@ def test_sub_range_deform_and_device_palettes(rzlib, orc, wl_small):
         check_all(orc, ctx, wl, world, None, K, instances=[2, 3, 4])
         base, stride, noff = ctx.output_device_ptr()
         assert stride % 16 == 0 and noff % 16 == 0 and noff >= wl.V * 12
+
+
+def test_pipelined_palette_upload(rzlib, orc, wl_small, monkeypatch):
+    """rz_set_palettes with host matrices and one palette per instance uploads in blocks on a copy stream; rz_deform consumes
+    them block by block (wait, skin matrices, deform).  Same bits as the unpipelined path, for whole-range and partial-range
+    deforms in any order, repeated uploads, readers that need the skin matrices early, and feature sets that cannot pipeline."""
+    wl = wl_small
+    K = 37                                          # 8 + 8 + 8 + 8 + 5
+    rng = np.random.default_rng(33)
+    world = synth.make_palettes(wl.bones, K, rng)
+    world2 = synth.make_palettes(wl.bones, K, rng)
+
+    def run(pipelined: bool, flags=0):
+        if pipelined:
+            monkeypatch.setenv("RZ_PIPELINE_BLOCK", "8")
+            monkeypatch.delenv("RZ_NO_PIPELINE", raising=False)
+        else:
+            monkeypatch.setenv("RZ_NO_PIPELINE", "1")
+        outs = []
+        with capi.DeformContext(max_instances=K, flags=flags) as ctx:
+            ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
+            if flags & capi.RZ_FLAG_SDEF:
+                ctx.load_sdef(wl.sdef.vertexIndex, wl.sdef.c_r0_r1)
+            ctx.set_palettes(world)
+            ctx.deform()
+            outs.append([ctx.read_instance(k) for k in range(K)])
+            ctx.set_palettes(world2)                # partial ranges, out of order, with a hole consumed earlier
+            ctx.deform(10, 9)
+            ctx.deform(0, 30)
+            ctx.deform(28, 9)
+            outs.append([ctx.read_instance(k) for k in range(K)])
+            ctx.set_palettes(world2)                # superseded before it is consumed
+            ctx.set_palettes(world)
+            sm = ctx.read_skin_matrices(K - 1)      # needs the skin matrices before any deform
+            ctx.deform()
+            outs.append([ctx.read_instance(k) for k in range(K)])
+            outs.append(sm)
+        return outs
+
+    for flags in (0, capi.RZ_FLAG_INTERLEAVED, capi.RZ_FLAG_SDEF):
+        a, b = run(True, flags), run(False, flags)
+        for fa, fb in zip(a[:3], b[:3]):
+            for (pa, na), (pb, nb) in zip(fa, fb):
+                assert np.array_equal(pa, pb) and np.array_equal(na, nb)
+        assert np.array_equal(a[3], b[3])
+        if flags == 0:
+            for k in (0, 7, 8, 31, 36):
+                rp, rn = oracle_instance(orc, wl, world[k])
+                assert rel_err(a[0][k][0], rp) <= TOL and rel_err(a[0][k][1], rn) <= TOL
+                rp, rn = oracle_instance(orc, wl, world2[k])
+                assert rel_err(a[1][k][0], rp) <= TOL and rel_err(a[1][k][1], rn) <= TOL
 
 
 def test_huge_bone_count_uses_global_palette_path(rzlib, orc):
