@@ -18,7 +18,7 @@ LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(LIBDIR, "obj")
 LIB = os.path.join(LIBDIR, "librze_b200.so")
 # keep in sync with csrc/kernel_table.h RZ_FEAT_LIST
-FEATS = [0, 1, 3, 4, 7, 16, 19, 20, 8, 11, 15, 24, 27, 32, 39, 64, 71]
+FEATS = [0, 1, 3, 4, 7, 16, 19, 20, 23, 8, 11, 15, 24, 31, 32, 39, 40, 47, 64, 71, 72, 79]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 

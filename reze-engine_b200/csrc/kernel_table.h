@@ -19,8 +19,11 @@ struct KernelEntry {
 #define RZ_SHAPES_MID(X) RZ_SHAPES_LITE(X) X(6, 512, 1, 3, 1) X(4, 768, 1, 2, 1)
 #define RZ_FEAT_IS_MID(f) ((f) != 0 && ((f) & (1 | 2 | 8)) == 0)
 // feature sets compiled (bit meaning: deform_kernel.cuh FEAT_*); keep in sync with build.py
-// 32 / 39: outline hull plane (plain, + morph + SDEF + bounds); 64 / 71: interleaved 32-byte stream (same two)
-#define RZ_FEAT_LIST(X) X(0) X(1) X(3) X(4) X(7) X(16) X(19) X(20) X(8) X(11) X(15) X(24) X(27) X(32) X(39) X(64) X(71)
+// Every combination of the public flags resolves to one of these (rze_b200.cu resolve_feat picks the smallest superset;
+// extras of a superset are inert): per output layout {planar, positions only 16, outline 32, interleaved 64} x palette
+// {shared, global 8} there is the bare set and the "everything" set (morph 1 + SDEF 2 + bounds 4), plus the common ones.
+#define RZ_FEAT_LIST(X) X(0) X(1) X(3) X(4) X(7) X(16) X(19) X(20) X(23) X(8) X(11) X(15) X(24) X(31) X(32) X(39) X(40) X(47) \
+  X(64) X(71) X(72) X(79)
 #define RZ_DECL(f) KernelEntry lookup_feat_##f(int I, int NT, int MINB);
 RZ_FEAT_LIST(RZ_DECL)
 #undef RZ_DECL

@@ -1090,9 +1090,7 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
   const size_t smemMax = (size_t)c->maxSmemOptin;
   if (smem_needed(1, 256, need, c->B, Mpad) > smemMax) need |= FEAT_GPAL;   // palette does not fit: gather from global
   const int feat = resolve_feat(need);
-  if (feat < 0)
-    return fail(c, RZ_ERR_INVALID_ARG, "rz_deform: feature combination 0x%x is not built%s", need,
-                (need & FEAT_GPAL) && (need & (FEAT_HULL | FEAT_ILV)) ? " (outline / interleaved output need the palette in shared memory: B too large)" : "");
+  if (feat < 0) return fail(c, RZ_ERR_INVALID_ARG, "rz_deform: feature combination 0x%x is not built", need);
   // a pipelined upload (rz_set_palettes) is consumed block by block below; feature sets with per-launch side kernels or
   // count-dependent tables take the whole upload first
   const bool pipelined = !c->pend.empty() && !(feat & (FEAT_MORPH | FEAT_SDEF | FEAT_BOUNDS | FEAT_GPAL));

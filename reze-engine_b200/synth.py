@@ -95,7 +95,7 @@ def make_mesh(V: int, bones: List[Bone], rng, mix=(0.277, 0.529, 0.127, 0.067), 
                     frontier.append(nbr)
                     if len(S) >= size:
                         break
-        while len(S) < 4:
+        while len(S) < min(4, B):                     # (skeletons with fewer than 4 bones: fewer influences per vertex)
             x = int(rng.integers(0, B))
             if x not in S:
                 S.append(x)
@@ -104,7 +104,7 @@ def make_mesh(V: int, bones: List[Bone], rng, mix=(0.277, 0.529, 0.127, 0.067), 
         for i in range(v, v + run):
             redraw = js is None
             if js is None or rng.random() > p_keep_count:
-                k = int(rng.choice(4, p=mixp)) + 1
+                k = min(int(rng.choice(4, p=mixp)) + 1, len(S))
                 redraw = True
             if redraw or rng.random() > p_keep_bones:
                 js = [S[t] for t in rng.permutation(len(S))[:k]]
@@ -146,7 +146,7 @@ def make_crowd_tween(B: int, P: int, rng, stagger: bool = True, first: int = 0):
 
 def make_morphs(V: int, M: int, rng, face_frac: float = 0.12, touch_frac: float = 0.03) -> VertexMorphs:
     face0 = int(V * 0.05)
-    faceN = max(int(V * face_frac), 8)
+    faceN = min(max(int(V * face_frac), 8), V - face0)      # (tiny meshes: the face region is the mesh)
     offs = [0]
     vis, dls = [], []
     for m in range(M):

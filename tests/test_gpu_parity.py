@@ -395,6 +395,45 @@ def test_feature_supersets_run_clean(rzlib, orc, wl_small, flags, morph, sdef):
                     assert rel_err(gn, rn) <= TOL
 
 
+@pytest.mark.parametrize("B", [48, 5000])            # palette in shared memory / too large for it (gathered from global)
+def test_every_flag_combination_runs_and_matches(rzlib, orc, B):
+    """Every combination of the public flags (output layout x bounds x SDEF, with and without active morphs) resolves to a
+    compiled kernel and equals the oracle, for a palette that fits shared memory and for one that does not."""
+    wl = synth.make_workload(700, B, M=5, sdef=True, seed=B)
+    K = 3
+    rng = np.random.default_rng(B)
+    world = synth.make_palettes(wl.bones, K, rng)
+    dense = rng.uniform(0, 1, (K, wl.morphs.count)).astype(np.float32)
+    edge = rng.uniform(0, 2, wl.V).astype(np.float32)
+    for layout in (0, capi.RZ_FLAG_NO_NORMALS, capi.RZ_FLAG_OUTLINE, capi.RZ_FLAG_INTERLEAVED):
+        for bounds in (0, capi.RZ_FLAG_BOUNDS):
+            for sd in (0, capi.RZ_FLAG_SDEF):
+                for morph in (False, True):
+                    flags = layout | bounds | sd
+                    with capi.DeformContext(max_instances=K, flags=flags) as ctx:
+                        ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
+                        ctx.load_sdef(wl.sdef.vertexIndex, wl.sdef.c_r0_r1)
+                        if morph:
+                            ctx.load_morphs(wl.morphs.offsets, wl.morphs.vertexIndex, wl.morphs.delta)
+                        if layout == capi.RZ_FLAG_OUTLINE:
+                            ctx.load_edge_size(edge)
+                        ctx.set_palettes(world)
+                        if morph:
+                            ctx.set_morph_weights(dense, np.arange(wl.morphs.count), K=K)
+                        ctx.deform()
+                        for k in range(K):
+                            rp, rn = oracle_instance(orc, wl, world[k], dense[k] if morph else None, sdef=bool(sd))
+                            gp, gn = ctx.read_instance(k, normals=layout != capi.RZ_FLAG_NO_NORMALS)
+                            assert rel_err(gp, rp) <= TOL, (flags, morph, k, rel_err(gp, rp))
+                            if gn is not None:
+                                assert rel_err(gn, rn) <= TOL, (flags, morph, k)
+                            if layout == capi.RZ_FLAG_OUTLINE:
+                                assert rel_err(ctx.read_outline(k), orc.outline_hull(rp, rn, edge)) <= TOL
+                            if bounds:
+                                bb = ctx.read_bounds(k, 1)[0]
+                                assert np.array_equal(bb[:3], gp.min(axis=0)) and np.array_equal(bb[3:], gp.max(axis=0))
+
+
 def test_bounds_and_positions_only(rzlib, orc, wl_small):
     wl = wl_small
     K = 9
