@@ -176,6 +176,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-reorder", action="store_true")
+    ap.add_argument("--single-buffer", action="store_true", help="one result buffer and blocking read-backs in the e2e legs")
     ap.add_argument("--ipg", type=int, default=0)
     ap.add_argument("--store", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
@@ -209,8 +210,10 @@ def main():
     # a real (non-default) stream: the library launches on it and torch.cuda.Event times it
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
+    # two result buffers (RZ_FLAG_DOUBLE_BUFFER): the e2e legs read frame n back while frame n+1 is being deformed
     ctx = capi.DeformContext(max_instances=K, device=local_rank, stream=stream.cuda_stream, instances_per_group=args.ipg,
-                             store_mode=args.store, threads=args.threads, chunks=args.chunks, ctas_per_sm=args.ctas)
+                             store_mode=args.store, threads=args.threads, chunks=args.chunks, ctas_per_sm=args.ctas,
+                             flags=0 if args.single_buffer else capi.RZ_FLAG_DOUBLE_BUFFER)
     ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
     d_world = torch.from_numpy(world).cuda()
     d_i2p = torch.from_numpy(i2p.astype(np.int64)).to(torch.int32).cuda() if i2p is not None else None
@@ -256,6 +259,18 @@ def main():
     # pinned destination of the per-step result read-back
     h_pos = torch.empty((V, 3), dtype=torch.float32, pin_memory=True).numpy()
     h_nrm = torch.empty((V, 3), dtype=torch.float32, pin_memory=True).numpy()
+    h_pos2 = torch.empty((V, 3), dtype=torch.float32, pin_memory=True).numpy()
+    h_nrm2 = torch.empty((V, 3), dtype=torch.float32, pin_memory=True).numpy()
+
+    def read_back(s):
+        """Every step's result comes back to the host inside the timed region.  With two result buffers the copy of step s
+        is queued behind step s's deform and collected one step later (the next frame is written to the other buffer
+        meanwhile) -- what a renderer consuming the stream does; --single-buffer blocks on it at once."""
+        if args.single_buffer:
+            ctx.read_instance(s % K, out_pos=h_pos, out_nrm=h_nrm)
+        else:
+            ctx.read_wait()                                     # step s-1 has landed
+            ctx.read_instance_async(s % K, h_pos2 if s & 1 else h_pos, h_nrm2 if s & 1 else h_nrm)
 
     # ---- e2e: host palettes -> H2D -> deform -> one instance back to the host, per step -------------------------
     for _ in range(2):
@@ -270,7 +285,8 @@ def main():
     for s in range(esteps):
         ctx.set_palettes(stage, i2p, K=K)
         ctx.deform()
-        ctx.read_instance(s % K, out_pos=h_pos, out_nrm=h_nrm)
+        read_back(s)
+    ctx.read_wait()
     e1.record()
     barrier()
     e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - wall0) * 1e3) / esteps
@@ -296,7 +312,8 @@ def main():
     for s in range(esteps):
         ctx.set_instance_clocks(clock_ms, i2p, K=K)
         ctx.deform()
-        ctx.read_instance(s % K, out_pos=h_pos, out_nrm=h_nrm)
+        read_back(s)
+    ctx.read_wait()
     g1.record()
     barrier()
     pose_ms = sharding.max_over_ranks(max(g0.elapsed_time(g1), (time.perf_counter() - wall0) * 1e3) / esteps)
@@ -344,6 +361,8 @@ def main():
                     traffic = tj.get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
+        readback_path = ("rz_read_instance (blocking)" if args.single_buffer else
+                         "rz_read_instance_async of every step, collected one step later (RZ_FLAG_DOUBLE_BUFFER)")
         out = {
             "metric": "skinned_vertices_per_sec", "value": value, "unit": "verts/s", "n_gpus": world_size, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -356,9 +375,9 @@ def main():
                                   "ctas": st["ctas"], "smem_bytes": st["smemBytes"]}},
             "clocks": clocks,
             "e2e": {"value": pose_value, "unit": "verts/s", "ms_per_step": pose_ms, "h2d_bytes_per_step": pose_h2d, "d2h_bytes_per_step": d2h,
-                    "path": "rz_set_instance_clocks(host clocks; tween + bone hierarchy + skin matrices on the device) + rz_deform + rz_read_instance"},
+                    "path": "rz_set_instance_clocks(host clocks; tween + bone hierarchy + skin matrices on the device) + rz_deform + " + readback_path},
             "e2e_world_upload": {"value": e2e_value, "unit": "verts/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                                 "path": "rz_set_palettes(pinned host world matrices, as the reference uploads them) + rz_deform + rz_read_instance"},
+                                 "path": "rz_set_palettes(pinned host world matrices, as the reference uploads them; pipelined in blocks) + rz_deform + " + readback_path},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "kernel": "rz::deform_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg},

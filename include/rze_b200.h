@@ -57,6 +57,11 @@ typedef enum rz_status {
                                      draw instance k with an identity palette.  uv is passed through from rz_load_mesh.
                                      Not combinable with RZ_FLAG_NO_NORMALS / RZ_FLAG_OUTLINE */
 
+#define RZ_FLAG_DOUBLE_BUFFER 0x40u /* two result buffers: every palette update (rz_set_palettes*, rz_set_local_rotations,
+                                     rz_set_instance_clocks = a new frame) flips to the other one, so a consumer keeps
+                                     reading frame n (rz_read_instance_async, or a renderer holding the pointer of
+                                     rz_get_output_layout) while frame n+1 is written.  Doubles the result memory */
+
 typedef struct rz_config {
   uint32_t struct_size;    /* sizeof(rz_config), for forward compatibility */
   int32_t  device;         /* CUDA device ordinal this context owns (one process per GPU) */
@@ -188,6 +193,12 @@ typedef struct rz_output_layout {
 } rz_output_layout;
 int32_t rz_get_output_layout(rz_ctx* ctx, rz_output_layout* out);
 int32_t rz_read_instance(rz_ctx* ctx, uint32_t inst, float* pos3 /* 3V or NULL */, float* nrm3 /* 3V or NULL */);
+/* Asynchronous variant: the copies are queued behind the work issued so far on an internal read stream and the call
+ * returns at once; rz_read_wait blocks until they have landed.  pos3 / nrm3 should be page-locked.  A later rz_deform that
+ * would overwrite the buffer being read waits for the copy on the device (never with RZ_FLAG_DOUBLE_BUFFER, where the
+ * next frame goes to the other buffer).  Planar layout in caller order only. */
+int32_t rz_read_instance_async(rz_ctx* ctx, uint32_t inst, float* pos3 /* 3V or NULL */, float* nrm3 /* 3V or NULL */);
+int32_t rz_read_wait(rz_ctx* ctx);
 /* outline hull positions of one instance (RZ_FLAG_OUTLINE), caller vertex order */
 int32_t rz_read_outline(rz_ctx* ctx, uint32_t inst, float* hull3 /* 3V */);
 /* the interleaved stream of one instance (RZ_FLAG_INTERLEAVED), caller vertex order: 8 f32 per vertex */

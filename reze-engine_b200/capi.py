@@ -23,6 +23,7 @@ RZ_FLAG_BOUNDS = 0x4
 RZ_FLAG_REORDER_VERTICES = 0x8
 RZ_FLAG_OUTLINE = 0x10
 RZ_FLAG_INTERLEAVED = 0x20
+RZ_FLAG_DOUBLE_BUFFER = 0x40
 RZ_NO_ATTRIBUTE = (1 << (8 * C.sizeof(C.c_size_t))) - 1
 
 EXPORTS = [
@@ -32,7 +33,7 @@ EXPORTS = [
     "rz_sync", "rz_output_device_ptr", "rz_read_instance", "rz_get_vertex_order", "rz_plan_lanes", "rz_read_bounds", "rz_read_skinning",
     "rz_read_skin_matrices", "rz_get_stats", "rz_last_error",
     "rz_load_edge_size", "rz_get_output_layout", "rz_read_outline", "rz_read_interleaved",
-    "rz_plan_morph_rows", "rz_plan_chunks",
+    "rz_plan_morph_rows", "rz_plan_chunks", "rz_read_instance_async", "rz_read_wait",
 ]
 
 
@@ -104,6 +105,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.rz_sync.argtypes = [vp]
     lib.rz_output_device_ptr.argtypes = [vp, P(vp), P(sz), P(sz)]
     lib.rz_read_instance.argtypes = [vp, u32, vp, vp]
+    lib.rz_read_instance_async.argtypes = [vp, u32, vp, vp]
+    lib.rz_read_wait.argtypes = [vp]
     lib.rz_load_edge_size.argtypes = [vp, vp]
     lib.rz_get_output_layout.argtypes = [vp, P(RzOutputLayout)]
     lib.rz_read_outline.argtypes = [vp, u32, vp]
@@ -362,6 +365,14 @@ class DeformContext:
             nrm = out_nrm if out_nrm is not None else np.empty((self.V, 3), dtype=np.float32)
         self._check(self.lib.rz_read_instance(self.h, inst, _ptr(pos), _ptr(nrm)))
         return pos, nrm
+
+    def read_instance_async(self, inst: int, out_pos: np.ndarray, out_nrm: Optional[np.ndarray] = None):
+        """Queue the read-back of one instance behind the work issued so far and return at once; the (preferably pinned)
+        arrays are valid after read_wait()."""
+        self._check(self.lib.rz_read_instance_async(self.h, inst, _ptr(out_pos), _ptr(out_nrm)))
+
+    def read_wait(self):
+        self._check(self.lib.rz_read_wait(self.h))
 
     def load_edge_size(self, edge_size):
         """Per-vertex Material.edgeSize (0 = no outline) for RZ_FLAG_OUTLINE; None resets to zero."""

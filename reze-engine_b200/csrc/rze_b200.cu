@@ -97,6 +97,14 @@ struct rz_ctx_impl {
   uint32_t P = 0, K = 0;
   DevBuf d_quat;
   DevBuf d_world, d_skin, d_inst2pal, d_mwIn, d_mwIds, d_mwDense, d_out, d_bounds, d_counter;
+  // RZ_FLAG_DOUBLE_BUFFER: a second result buffer; every palette update (= a new frame) flips `cur`, so a consumer --
+  // rz_read_instance_async on the read stream, or a renderer holding rz_get_output_layout's pointer -- keeps reading
+  // frame n while frame n+1 is being written
+  DevBuf d_out2;
+  uint32_t cur = 0;
+  cudaStream_t readStream = nullptr;
+  cudaEvent_t evReadReady = nullptr, evReadDone[2] = {nullptr, nullptr};   // per result buffer
+  bool readPending[2] = {false, false};
   bool haveInst2pal = false, palettesSet = false;
   uint32_t Mact = 0, Mpad = 4;
   void* h_stage = nullptr;
@@ -471,6 +479,7 @@ int rebuild_tables(rz_ctx_impl* c) {
   if (c->flags & RZ_FLAG_OUTLINE) { c->hullOffF = 2 * c->nrmOffF; c->instStrideF = 3 * c->nrmOffF; }
   if (c->flags & RZ_FLAG_INTERLEAVED) { c->nrmOffF = 3; c->instStrideF = (size_t)V * 8; }   // one stream of 8 f32 per vertex
   if ((rc = dev_reserve(c, c->d_out, (size_t)c->maxK * c->instStrideF * 4))) return rc;
+  if ((c->flags & RZ_FLAG_DOUBLE_BUFFER) && (rc = dev_reserve(c, c->d_out2, (size_t)c->maxK * c->instStrideF * 4))) return rc;
   if (c->flags & RZ_FLAG_BOUNDS)
     if ((rc = dev_reserve(c, c->d_bounds, (size_t)c->maxK * 24))) return rc;
   if ((rc = dev_reserve(c, c->d_counter, 16))) return rc;
@@ -489,6 +498,13 @@ int ensure_dense_weights(rz_ctx_impl* c) {
     c->Mact = 0;
   }
   return RZ_OK;
+}
+
+inline float* out_base(rz_ctx_impl* c) { return reinterpret_cast<float*>((c->cur && c->d_out2.p) ? c->d_out2.p : c->d_out.p); }
+
+// a palette update starts a new frame
+inline void begin_frame(rz_ctx_impl* c) {
+  if (c->flags & RZ_FLAG_DOUBLE_BUFFER) c->cur ^= 1u;
 }
 
 void launch_skin_block(rz_ctx_impl* c, const float* d_world, uint32_t pal0, uint32_t n) {
@@ -579,6 +595,10 @@ int32_t rz_create(const rz_config* cfg, rz_ctx** out) {
   cudaEventCreate(&c->evStart);
   cudaEventCreate(&c->evStop);
   cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&c->readStream, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&c->evReadReady, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&c->evReadDone[0], cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&c->evReadDone[1], cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->evWorldFree, cudaEventDisableTiming);
   *out = c;
   return RZ_OK;
@@ -588,13 +608,16 @@ int32_t rz_destroy(rz_ctx* c) {
   if (!c) return RZ_OK;
   cudaSetDevice(c->device);
   if (c->copyStream) cudaStreamSynchronize(c->copyStream);
+  if (c->readStream) { cudaStreamSynchronize(c->readStream); cudaStreamDestroy(c->readStream); }
+  if (c->evReadReady) cudaEventDestroy(c->evReadReady);
+  for (cudaEvent_t e : c->evReadDone) if (e) cudaEventDestroy(e);
   cudaStreamSynchronize(c->stream);
   for (cudaEvent_t e : c->evPool) cudaEventDestroy(e);
   if (c->evWorldFree) cudaEventDestroy(c->evWorldFree);
   if (c->copyStream) cudaStreamDestroy(c->copyStream);
   DevBuf* bufs[] = {&c->d_rec0, &c->d_rec1, &c->d_rec2, &c->d_meta, &c->d_wbits, &c->d_mrange, &c->d_ments, &c->d_sdefIdx, &c->d_sdefTab,
                     &c->d_invBind, &c->d_bonePos, &c->d_world, &c->d_skin, &c->d_inst2pal, &c->d_mwIn, &c->d_mwIds, &c->d_mwDense,
-                    &c->d_out, &c->d_bounds, &c->d_counter, &c->d_skParent, &c->d_skBindT, &c->d_skAppendParent, &c->d_skAppendRatio,
+                    &c->d_out, &c->d_out2, &c->d_bounds, &c->d_counter, &c->d_skParent, &c->d_skBindT, &c->d_skAppendParent, &c->d_skAppendRatio,
                     &c->d_skLevelBones, &c->d_skLevelStart, &c->d_skChainStart, &c->d_skChainBones, &c->d_twStart, &c->d_twTarget, &c->d_twRest, &c->d_twStartMs, &c->d_twDurMs,
                     &c->d_twActive, &c->d_localRot, &c->d_nowMs, &c->d_trStart, &c->d_trMs, &c->d_trQ, &c->d_quat, &c->d_chunkTab, &c->d_edge, &c->d_uv};
   for (DevBuf* b : bufs) dev_free(c, *b);
@@ -674,6 +697,7 @@ static int set_palettes_common(rz_ctx* c, const float* d_world, uint32_t P, uint
   int rc;
   if ((rc = dev_reserve(c, c->d_skin, (size_t)P * c->B * 48))) return rc;
   c->pend.clear();                                           // superseded
+  begin_frame(c);
   launch_skin_block(c, d_world, 0, P);
   CU_TRY(c, cudaGetLastError());
   if (d_world == c->d_world.p) { CU_TRY(c, cudaEventRecord(c->evWorldFree, c->stream)); c->worldFreeValid = true; }
@@ -746,6 +770,7 @@ int32_t rz_set_palettes(rz_ctx* c, const float* world, uint32_t P, const uint32_
     c->P = P;
     c->K = K;
     c->palettesSet = true;
+    begin_frame(c);
     return RZ_OK;
   }
   if (!c->pend.empty()) CU_TRY(c, cudaStreamWaitEvent(c->stream, c->pend.back().ev, 0));    // an unconsumed pipelined upload still targets d_world
@@ -861,6 +886,7 @@ int32_t rz_load_skeleton(rz_ctx* c, const int32_t* parent, const float* bindT, c
 extern "C++" {
 template <int MODE>
 static int launch_pose(rz_ctx* c, uint32_t P) {
+  begin_frame(c);
   c->pend.clear();   // the palettes are about to be produced on the device: an unconsumed host upload is superseded
   const size_t smem = (size_t)c->B * 64;
   if (smem > (size_t)c->maxSmemOptin)
@@ -1180,7 +1206,7 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
   prm.edge = reinterpret_cast<const float*>(c->d_edge.p);
   prm.uv = reinterpret_cast<const float2*>(c->d_uv.p);
   prm.hullOffF = c->hullOffF;
-  prm.out = reinterpret_cast<float*>(c->d_out.p);
+  prm.out = out_base(c);
   prm.bounds = reinterpret_cast<float*>(c->d_bounds.p);
   prm.instStrideF = c->instStrideF;
   prm.nrmOffF = c->nrmOffF;
@@ -1240,6 +1266,8 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
     if ((rc = dev_reserve(c, c->d_bounds, (size_t)c->maxK * 24))) return rc;
     prm.bounds = reinterpret_cast<float*>(c->d_bounds.p);
   }
+  // an asynchronous read-back still copying from the buffer this frame writes (with two buffers: the read of two frames ago)
+  if (c->readPending[c->cur]) CU_TRY(c, cudaStreamWaitEvent(c->stream, c->evReadDone[c->cur], 0));
   CU_TRY(c, cudaEventRecord(c->evStart, c->stream));
   if (feat & FEAT_SDEF) {
     // rotation of every skin matrix as a quaternion, once per (palette, bone) instead of once per SDEF vertex-instance
@@ -1302,7 +1330,7 @@ int32_t rz_sync(rz_ctx* c) {
 int32_t rz_output_device_ptr(rz_ctx* c, void** base, size_t* stride, size_t* nrmOff) {
   if (!c || !base) return fail(c, RZ_ERR_INVALID_ARG, "rz_output_device_ptr: null argument");
   if (c->V == 0) return fail(c, RZ_ERR_STATE, "rz_output_device_ptr before rz_load_mesh");
-  *base = c->d_out.p;
+  *base = out_base(c);
   if (stride) *stride = c->instStrideF * 4;
   if (nrmOff) *nrmOff = (c->flags & RZ_FLAG_NO_NORMALS) ? 0 : c->nrmOffF * 4;   // (interleaved: 12, see rz_get_output_layout)
   return RZ_OK;
@@ -1311,7 +1339,7 @@ int32_t rz_output_device_ptr(rz_ctx* c, void** base, size_t* stride, size_t* nrm
 // one interleaved instance (RZ_FLAG_INTERLEAVED) to the host in CALLER vertex order, 8 floats per vertex
 static int fetch_interleaved(rz_ctx* c, uint32_t inst, std::vector<float>& tmp) {
   tmp.resize((size_t)c->V * 8);
-  const float* src = reinterpret_cast<const float*>(c->d_out.p) + (size_t)inst * c->instStrideF;
+  const float* src = out_base(c) + (size_t)inst * c->instStrideF;
   CU_TRY(c, cudaMemcpyAsync(tmp.data(), src, (size_t)c->V * 32, cudaMemcpyDeviceToHost, c->stream));
   CU_TRY(c, cudaStreamSynchronize(c->stream));
   if (c->flags & RZ_FLAG_REORDER_VERTICES) {
@@ -1341,7 +1369,7 @@ int32_t rz_read_outline(rz_ctx* c, uint32_t inst, float* hull3) {
   if (!(c->flags & RZ_FLAG_OUTLINE)) return fail(c, RZ_ERR_STATE, "rz_read_outline: context was created without RZ_FLAG_OUTLINE");
   if (inst >= c->maxK) return fail(c, RZ_ERR_INVALID_ARG, "rz_read_outline: instance %u >= max_instances %u", inst, c->maxK);
   CU_TRY(c, cudaSetDevice(c->device));
-  const float* src = reinterpret_cast<const float*>(c->d_out.p) + (size_t)inst * c->instStrideF + c->hullOffF;
+  const float* src = out_base(c) + (size_t)inst * c->instStrideF + c->hullOffF;
   if (c->flags & RZ_FLAG_REORDER_VERTICES) {
     std::vector<float> tmp((size_t)c->V * 3);
     CU_TRY(c, cudaMemcpyAsync(tmp.data(), src, (size_t)c->V * 12, cudaMemcpyDeviceToHost, c->stream));
@@ -1358,7 +1386,7 @@ int32_t rz_get_output_layout(rz_ctx* c, rz_output_layout* out) {
   if (!c || !out) return fail(c, RZ_ERR_INVALID_ARG, "rz_get_output_layout: null argument");
   if (c->V == 0) return fail(c, RZ_ERR_STATE, "rz_get_output_layout before rz_load_mesh");
   const bool ilv = (c->flags & RZ_FLAG_INTERLEAVED) != 0;
-  out->base = c->d_out.p;
+  out->base = out_base(c);
   out->instanceStride = c->instStrideF * 4;
   out->vertexStride = ilv ? 32 : 12;
   out->positionOffset = 0;
@@ -1394,7 +1422,7 @@ int32_t rz_read_instance(rz_ctx* c, uint32_t inst, float* pos3, float* nrm3) {
     }
     return RZ_OK;
   }
-  const float* src = reinterpret_cast<const float*>(c->d_out.p) + (size_t)inst * c->instStrideF;
+  const float* src = out_base(c) + (size_t)inst * c->instStrideF;
   if (c->flags & RZ_FLAG_REORDER_VERTICES) {
     // device planes are in the library's stored order: hand them back in the caller's vertex order
     std::vector<float> tmp((size_t)c->V * 3);
@@ -1410,6 +1438,34 @@ int32_t rz_read_instance(rz_ctx* c, uint32_t inst, float* pos3, float* nrm3) {
   if (pos3) CU_TRY(c, cudaMemcpyAsync(pos3, src, (size_t)c->V * 12, cudaMemcpyDeviceToHost, c->stream));
   if (nrm3) CU_TRY(c, cudaMemcpyAsync(nrm3, src + c->nrmOffF, (size_t)c->V * 12, cudaMemcpyDeviceToHost, c->stream));
   CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return RZ_OK;
+}
+
+int32_t rz_read_instance_async(rz_ctx* c, uint32_t inst, float* pos3, float* nrm3) {
+  if (!c) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_read_instance_async: null ctx");
+  if (c->V == 0) return fail(c, RZ_ERR_STATE, "rz_read_instance_async before rz_load_mesh");
+  if (inst >= c->maxK) return fail(c, RZ_ERR_INVALID_ARG, "rz_read_instance_async: instance %u >= max_instances %u", inst, c->maxK);
+  if (c->flags & (RZ_FLAG_REORDER_VERTICES | RZ_FLAG_INTERLEAVED))
+    return fail(c, RZ_ERR_STATE, "rz_read_instance_async: needs the planar layout in caller order (use rz_read_instance / rz_read_interleaved)");
+  if (nrm3 && (c->flags & RZ_FLAG_NO_NORMALS)) return fail(c, RZ_ERR_STATE, "rz_read_instance_async: context was created with RZ_FLAG_NO_NORMALS");
+  CU_TRY(c, cudaSetDevice(c->device));
+  const float* src = out_base(c) + (size_t)inst * c->instStrideF;
+  CU_TRY(c, cudaEventRecord(c->evReadReady, c->stream));                 // everything issued so far (the frame's deform) ...
+  CU_TRY(c, cudaStreamWaitEvent(c->readStream, c->evReadReady, 0));      // ... precedes the copies on the read stream
+  if (pos3) CU_TRY(c, cudaMemcpyAsync(pos3, src, (size_t)c->V * 12, cudaMemcpyDeviceToHost, c->readStream));
+  if (nrm3) CU_TRY(c, cudaMemcpyAsync(nrm3, src + c->nrmOffF, (size_t)c->V * 12, cudaMemcpyDeviceToHost, c->readStream));
+  CU_TRY(c, cudaEventRecord(c->evReadDone[c->cur], c->readStream));
+  c->readPending[c->cur] = true;
+  return RZ_OK;
+}
+
+int32_t rz_read_wait(rz_ctx* c) {
+  if (!c) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_read_wait: null ctx");
+  CU_TRY(c, cudaSetDevice(c->device));
+  for (int b = 0; b < 2; ++b) {
+    if (c->readPending[b]) CU_TRY(c, cudaEventSynchronize(c->evReadDone[b]));
+    c->readPending[b] = false;
+  }
   return RZ_OK;
 }
 

@@ -588,6 +588,45 @@ def test_pipelined_palette_upload(rzlib, orc, wl_small, monkeypatch):
                 assert rel_err(a[1][k][0], rp) <= TOL and rel_err(a[1][k][1], rn) <= TOL
 
 
+@pytest.mark.parametrize("double", [False, True])
+def test_async_read_back_keeps_the_frame_it_was_issued_for(rzlib, orc, wl_small, double):
+    """rz_read_instance_async returns at once; the frame it was issued for arrives even when the next frame is uploaded and
+    deformed before rz_read_wait -- into the other result buffer with RZ_FLAG_DOUBLE_BUFFER, after the copy otherwise."""
+    import torch
+    wl = wl_small
+    K = 6
+    rng = np.random.default_rng(44)
+    frames = [synth.make_palettes(wl.bones, K, rng) for _ in range(4)]
+    pin = lambda: torch.empty((wl.V, 3), dtype=torch.float32, pin_memory=True).numpy()
+    bufs = [(pin(), pin()) for _ in range(2)]
+    with capi.DeformContext(max_instances=K, flags=capi.RZ_FLAG_DOUBLE_BUFFER if double else 0) as ctx:
+        ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
+        bases = []
+        got = []
+        for f, world in enumerate(frames):
+            ctx.set_palettes(world)
+            ctx.deform()
+            bases.append(ctx.output_device_ptr()[0])
+            ctx.read_wait()                                   # frame f-1 has landed in bufs[(f-1) & 1]
+            if f:
+                got.append((bufs[(f - 1) & 1][0].copy(), bufs[(f - 1) & 1][1].copy()))
+            ctx.read_instance_async(f % K, *bufs[f & 1])
+        ctx.read_wait()
+        got.append((bufs[(len(frames) - 1) & 1][0].copy(), bufs[(len(frames) - 1) & 1][1].copy()))
+        assert (len(set(bases)) == 2 and bases[0] == bases[2] and bases[1] == bases[3]) if double else len(set(bases)) == 1
+        for f, world in enumerate(frames):
+            rp, rn = oracle_instance(orc, wl, world[f % K])
+            assert rel_err(got[f][0], rp) <= TOL and rel_err(got[f][1], rn) <= TOL, f
+        # the synchronous reader sees the current frame
+        gp, gn = ctx.read_instance(2)
+        rp, rn = oracle_instance(orc, wl, frames[-1][2])
+        assert rel_err(gp, rp) <= TOL and rel_err(gn, rn) <= TOL
+    with capi.DeformContext(max_instances=1, flags=capi.RZ_FLAG_INTERLEAVED) as ctx:
+        ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
+        with pytest.raises(capi.RzError):
+            ctx.read_instance_async(0, bufs[0][0], bufs[0][1])
+
+
 def test_huge_bone_count_uses_global_palette_path(rzlib, orc):
     wl = synth.make_workload(3000, 6000, seed=77)
     world = synth.make_palettes(wl.bones, 2, np.random.default_rng(9))
