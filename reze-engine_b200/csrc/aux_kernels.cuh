@@ -306,6 +306,189 @@ __global__ void pose_chain_kernel(PoseSkeleton sk, PoseTweens tw, PoseTracks tr,
   }
 }
 
+// Same evaluation by POINTER JUMPING: the chain walk above multiplies depth x 36 FMA per bone (a 23-level average on the
+// benchmark skeleton makes the kernel instruction-bound: 0.17 ms for 4096 poses x 512 bones); here every bone holds the
+// product of its local transforms over a window of ancestors that doubles each round,
+//     W[b] <- W[anc(b)] * W[b],  anc(b) <- anc(anc(b)),
+// so ceil(log2(depth)) rounds of one 3x4 product + one barrier finish the whole skeleton (6 rounds for depth 44).  The
+// products associate differently from the reference's recursion (model.ts:405-411), a <= 1e-6 relative difference of the
+// matrices, inside the 1e-5 tolerance of the path.  MODE 1 (shared tween table) also takes the per-bone slerp constants
+// (angle, 1/sin, hemisphere sign: functions of the two keys only) from `twAux`, computed once in rz_set_tweens, so a
+// (pose, bone) rotation costs two polynomial sines instead of acos + three sines.
+// Shared memory: two ping-pong copies of W ([B][3] float4 each), two of anc ([B] int), the local rotations alias the
+// second W copy until the rounds start.
+template <int MODE>
+__global__ void pose_jump_kernel(PoseSkeleton sk, PoseTweens tw, PoseTracks tr, const float4* __restrict__ twAux,
+                                 const float4* __restrict__ localRot, const float* __restrict__ nowMs, const float4* __restrict__ invBind,
+                                 const float4* __restrict__ invBindSoA /* [4][B]: column c of bone b at c*B + b (coalesced) */,
+                                 const uint32_t* __restrict__ bonePos, float4* __restrict__ skin, uint32_t rounds, uint32_t soa) {
+  extern __shared__ float4 s_w[];                      // [2][B][3]
+  const uint32_t p = blockIdx.x, B = sk.B;
+  float4* wA = s_w;
+  float4* wB = s_w + (size_t)B * 3;
+  int32_t* ancA = reinterpret_cast<int32_t*>(s_w + (size_t)B * 6);
+  int32_t* ancB = ancA + B;
+  float4* s_q = wB;                                    // alias: dead before the first round writes wB
+  for (uint32_t b = threadIdx.x; b < B; b += blockDim.x) {
+    float4 q;
+    if (MODE == 1) {
+      if (!tw.active[b]) {
+        q = tw.rest[b];
+      } else {
+        const float dur = fmaxf(1.0f, tw.durMs[b]);
+        const float t = fminf(1.0f, fmaxf(0.0f, (nowMs[p] - tw.startMs[b]) / dur));
+        const float e = ease_in_out(t);
+        const float4 a = tw.start[b], ax = twAux[b];   // ax = (theta0, 1/sin(theta0), lerp branch flag, hemisphere sign)
+        float4 bq = tw.target[b];
+        bq.x *= ax.w; bq.y *= ax.w; bq.z *= ax.w; bq.w *= ax.w;
+        if (ax.z != 0.f) {                             // cos > 0.9995: lerp + normalise (math.ts:166-175)
+          const float x = a.x + e * (bq.x - a.x), y = a.y + e * (bq.y - a.y), z = a.z + e * (bq.z - a.z), w = a.w + e * (bq.w - a.w);
+          const float inv = rsqrtf(x * x + y * y + z * z + w * w);
+          q = make_float4(x * inv, y * inv, z * inv, w * inv);
+        } else {
+          const float th = ax.x * e;
+          const float s0 = sin_0_halfpi(ax.x - th) * ax.y, s1 = sin_0_halfpi(th) * ax.y;
+          q = make_float4(s0 * a.x + s1 * bq.x, s0 * a.y + s1 * bq.y, s0 * a.z + s1 * bq.z, s0 * a.w + s1 * bq.w);
+        }
+      }
+    } else {
+      q = eval_rotation<MODE>(b, p, B, tw, tr, localRot, nowMs);
+    }
+    s_q[b] = q;
+  }
+  __syncthreads();
+  // local transforms T(bind) * R (R = append * local, model.ts:356-386) into registers, then into wA (s_q stays intact: it
+  // lives in wB)
+  for (uint32_t b = threadIdx.x; b < B; b += blockDim.x) {
+    float R[3][3];
+    q_to_rows(s_q[b], R);
+    const int32_t ap = sk.appendParent[b];
+    const float ratio = sk.appendRatio[b];
+    if (ap >= 0 && fabsf(ratio) > 1e-6f) {
+      float4 a = s_q[ap];
+      if (ratio < 0.f) { a.x = -a.x; a.y = -a.y; a.z = -a.z; }
+      const float4 aq = q_slerp(make_float4(0.f, 0.f, 0.f, 1.f), a, fabsf(ratio));
+      float A[3][3], T[3][3];
+      q_to_rows(aq, A);
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) T[r][c] = A[r][0] * R[0][c] + A[r][1] * R[1][c] + A[r][2] * R[2][c];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) R[r][c] = T[r][c];
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) wA[(size_t)b * 3 + r] = make_float4(R[r][0], R[r][1], R[r][2], sk.bindT[(size_t)b * 3 + r]);
+    ancA[b] = sk.parent[b];
+  }
+  __syncthreads();
+  if (B <= blockDim.x) {
+    // one bone per thread: the own window stays in registers, a round reads the ancestor's window (48 B) and, after a
+    // barrier, publishes the product in place (48 B); bones whose window has reached the root drop out of both
+    const uint32_t b = threadIdx.x;
+    const bool mine = b < B;
+    float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0, w2 = w0;
+    int32_t a = -1;
+    if (mine) { w0 = wA[(size_t)b * 3]; w1 = wA[(size_t)b * 3 + 1]; w2 = wA[(size_t)b * 3 + 2]; a = ancA[b]; }
+    for (uint32_t r = 0; r < rounds; ++r) {
+      const bool act = a >= 0;
+      int32_t na = -1;
+      if (act) {
+        const float4 u0 = wA[(size_t)a * 3], u1 = wA[(size_t)a * 3 + 1], u2 = wA[(size_t)a * 3 + 2];
+        na = ancA[a];
+        const float4 n0 = make_float4(u0.x * w0.x + u0.y * w1.x + u0.z * w2.x, u0.x * w0.y + u0.y * w1.y + u0.z * w2.y,
+                                      u0.x * w0.z + u0.y * w1.z + u0.z * w2.z, u0.x * w0.w + u0.y * w1.w + u0.z * w2.w + u0.w);
+        const float4 n1 = make_float4(u1.x * w0.x + u1.y * w1.x + u1.z * w2.x, u1.x * w0.y + u1.y * w1.y + u1.z * w2.y,
+                                      u1.x * w0.z + u1.y * w1.z + u1.z * w2.z, u1.x * w0.w + u1.y * w1.w + u1.z * w2.w + u1.w);
+        const float4 n2 = make_float4(u2.x * w0.x + u2.y * w1.x + u2.z * w2.x, u2.x * w0.y + u2.y * w1.y + u2.z * w2.y,
+                                      u2.x * w0.z + u2.y * w1.z + u2.z * w2.z, u2.x * w0.w + u2.y * w1.w + u2.z * w2.w + u2.w);
+        w0 = n0; w1 = n1; w2 = n2;
+      }
+      if (!__syncthreads_or(act)) break;                 // (uniform) every window has reached its root
+      if (act) {
+        wA[(size_t)b * 3] = w0; wA[(size_t)b * 3 + 1] = w1; wA[(size_t)b * 3 + 2] = w2;
+        ancA[b] = na;
+        a = na;
+      }
+      __syncthreads();
+    }
+    // skin = W * invBind, assembled in shared memory in palette order (wB is free) and written out as one contiguous
+    // B x 48-byte block: 3 fully coalesced 16-byte stores per thread instead of 3 scattered ones (32 lines each)
+    if (mine) {
+      const float W[3][4] = {{w0.x, w0.y, w0.z, w0.w}, {w1.x, w1.y, w1.z, w1.w}, {w2.x, w2.y, w2.z, w2.w}};
+      float S[3][4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 ib = __ldg(invBindSoA + (size_t)c * B + b);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) S[r][c] = W[r][0] * ib.x + W[r][1] * ib.y + W[r][2] * ib.z + W[r][3] * ib.w;
+      }
+      const float4 cA = make_float4(S[0][0], S[1][0], S[0][1], S[1][1]);
+      const float4 cB = make_float4(S[0][2], S[1][2], S[0][3], S[1][3]);
+      const float4 cC = make_float4(S[2][0], S[2][1], S[2][2], S[2][3]);
+      const uint32_t pos = __ldg(bonePos + b);
+      if (soa) { wB[pos] = cA; wB[B + pos] = cB; wB[2 * (size_t)B + pos] = cC; }
+      else { wB[(size_t)pos * 3] = cA; wB[(size_t)pos * 3 + 1] = cB; wB[(size_t)pos * 3 + 2] = cC; }
+    }
+    __syncthreads();
+    float4* dst = skin + (size_t)p * B * 3;
+    for (uint32_t i = threadIdx.x; i < B * 3; i += blockDim.x) dst[i] = wB[i];
+    return;
+  }
+  float4* wc = wA;
+  float4* wn = wB;
+  int32_t* ac = ancA;
+  int32_t* an = ancB;
+  for (uint32_t r = 0; r < rounds; ++r) {
+    for (uint32_t b = threadIdx.x; b < B; b += blockDim.x) {
+      const int32_t a = ac[b];
+      float4 w0 = wc[(size_t)b * 3], w1 = wc[(size_t)b * 3 + 1], w2 = wc[(size_t)b * 3 + 2];
+      int32_t na = -1;
+      if (a >= 0) {
+        // W <- W[a] * W[b] (affine 3x4): rows of the ancestor window times the own window
+        const float4 u0 = wc[(size_t)a * 3], u1 = wc[(size_t)a * 3 + 1], u2 = wc[(size_t)a * 3 + 2];
+        const float4 n0 = make_float4(u0.x * w0.x + u0.y * w1.x + u0.z * w2.x, u0.x * w0.y + u0.y * w1.y + u0.z * w2.y,
+                                      u0.x * w0.z + u0.y * w1.z + u0.z * w2.z, u0.x * w0.w + u0.y * w1.w + u0.z * w2.w + u0.w);
+        const float4 n1 = make_float4(u1.x * w0.x + u1.y * w1.x + u1.z * w2.x, u1.x * w0.y + u1.y * w1.y + u1.z * w2.y,
+                                      u1.x * w0.z + u1.y * w1.z + u1.z * w2.z, u1.x * w0.w + u1.y * w1.w + u1.z * w2.w + u1.w);
+        const float4 n2 = make_float4(u2.x * w0.x + u2.y * w1.x + u2.z * w2.x, u2.x * w0.y + u2.y * w1.y + u2.z * w2.y,
+                                      u2.x * w0.z + u2.y * w1.z + u2.z * w2.z, u2.x * w0.w + u2.y * w1.w + u2.z * w2.w + u2.w);
+        w0 = n0; w1 = n1; w2 = n2;
+        na = ac[a];
+      }
+      wn[(size_t)b * 3] = w0; wn[(size_t)b * 3 + 1] = w1; wn[(size_t)b * 3 + 2] = w2;
+      an[b] = na;
+    }
+    __syncthreads();
+    float4* tw_ = wc; wc = wn; wn = tw_;
+    int32_t* ta = ac; ac = an; an = ta;
+  }
+  for (uint32_t b = threadIdx.x; b < B; b += blockDim.x) {
+    const float4 w0 = wc[(size_t)b * 3], w1 = wc[(size_t)b * 3 + 1], w2 = wc[(size_t)b * 3 + 2];
+    const float W[3][4] = {{w0.x, w0.y, w0.z, w0.w}, {w1.x, w1.y, w1.z, w1.w}, {w2.x, w2.y, w2.z, w2.w}};
+    float S[3][4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float4 ib = __ldg(invBind + (size_t)b * 4 + c);
+#pragma unroll
+      for (int r = 0; r < 3; ++r) S[r][c] = W[r][0] * ib.x + W[r][1] * ib.y + W[r][2] * ib.z + W[r][3] * ib.w;
+    }
+    const float4 cA = make_float4(S[0][0], S[1][0], S[0][1], S[1][1]);
+    const float4 cB = make_float4(S[0][2], S[1][2], S[0][3], S[1][3]);
+    const float4 cC = make_float4(S[2][0], S[2][1], S[2][2], S[2][3]);
+    const size_t pos = __ldg(bonePos + b);
+    if (soa) {
+      const size_t pb = (size_t)p * B * 3;
+      skin[pb + pos] = cA; skin[pb + B + pos] = cB; skin[pb + 2 * (size_t)B + pos] = cC;
+    } else {
+      const size_t row = (size_t)p * B + pos;
+      skin[row * 3] = cA; skin[row * 3 + 1] = cB; skin[row * 3 + 2] = cC;
+    }
+  }
+}
+
 __global__ void bounds_reset_kernel(int* b, uint32_t n6) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n6) b[i] = (i % 6) < 3 ? 0x7F7FFFFF : (int)(0x7F7FFFFF ^ 0x7FFFFFFF) | (int)0x80000000;

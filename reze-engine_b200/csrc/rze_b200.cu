@@ -91,7 +91,7 @@ struct rz_ctx_impl {
   DevBuf d_skParent, d_skBindT, d_skAppendParent, d_skAppendRatio, d_skLevelBones, d_skLevelStart, d_skChainStart, d_skChainBones;
   bool useChains = false;
   bool packedMeta = false;
-  DevBuf d_twStart, d_twTarget, d_twRest, d_twStartMs, d_twDurMs, d_twActive, d_localRot, d_nowMs;
+  DevBuf d_twStart, d_twTarget, d_twRest, d_twStartMs, d_twDurMs, d_twActive, d_localRot, d_nowMs, d_twAux, d_invBindSoA;
 
   // per-frame
   uint32_t P = 0, K = 0;
@@ -460,6 +460,11 @@ int rebuild_tables(rz_ctx_impl* c) {
   if (!sdefTab.empty())
     CU_TRY(c, cudaMemcpyAsync(c->d_sdefTab.p, sdefTab.data(), sdefTab.size() * 16, cudaMemcpyHostToDevice, c->stream));
   CU_TRY(c, cudaMemcpyAsync(c->d_invBind.p, c->h_invBind.data(), (size_t)B * 64, cudaMemcpyHostToDevice, c->stream));
+  std::vector<float> ibSoA((size_t)B * 16);                     // [4][B] float4: column c of bone b at c*B + b (pose kernels)
+  for (uint32_t b = 0; b < B; ++b)
+    for (uint32_t col = 0; col < 4; ++col) memcpy(&ibSoA[((size_t)col * B + b) * 4], &c->h_invBind[(size_t)b * 16 + col * 4], 16);
+  if ((rc = dev_reserve(c, c->d_invBindSoA, (size_t)B * 64))) return rc;
+  CU_TRY(c, cudaMemcpyAsync(c->d_invBindSoA.p, ibSoA.data(), (size_t)B * 64, cudaMemcpyHostToDevice, c->stream));
   CU_TRY(c, cudaMemcpyAsync(c->d_bonePos.p, c->bonePos.data(), (size_t)B * 4, cudaMemcpyHostToDevice, c->stream));
   if (!edgeArr.empty()) {
     if ((rc = dev_reserve(c, c->d_edge, (size_t)Vp * 4))) return rc;
@@ -619,7 +624,7 @@ int32_t rz_destroy(rz_ctx* c) {
                     &c->d_invBind, &c->d_bonePos, &c->d_world, &c->d_skin, &c->d_inst2pal, &c->d_mwIn, &c->d_mwIds, &c->d_mwDense,
                     &c->d_out, &c->d_out2, &c->d_bounds, &c->d_counter, &c->d_skParent, &c->d_skBindT, &c->d_skAppendParent, &c->d_skAppendRatio,
                     &c->d_skLevelBones, &c->d_skLevelStart, &c->d_skChainStart, &c->d_skChainBones, &c->d_twStart, &c->d_twTarget, &c->d_twRest, &c->d_twStartMs, &c->d_twDurMs,
-                    &c->d_twActive, &c->d_localRot, &c->d_nowMs, &c->d_trStart, &c->d_trMs, &c->d_trQ, &c->d_quat, &c->d_chunkTab, &c->d_edge, &c->d_uv};
+                    &c->d_twActive, &c->d_localRot, &c->d_nowMs, &c->d_twAux, &c->d_invBindSoA, &c->d_trStart, &c->d_trMs, &c->d_trQ, &c->d_quat, &c->d_chunkTab, &c->d_edge, &c->d_uv};
   for (DevBuf* b : bufs) dev_free(c, *b);
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->h_small) cudaFreeHost(c->h_small);
@@ -914,7 +919,26 @@ static int launch_pose(rz_ctx* c, uint32_t P) {
   tr.keyStart = reinterpret_cast<const uint32_t*>(c->d_trStart.p);
   tr.keyMs = reinterpret_cast<const float*>(c->d_trMs.p);
   tr.keyQ = reinterpret_cast<const float4*>(c->d_trQ.p);
-  if (c->useChains) {
+  // pointer jumping: ceil(log2(depth)) rounds of one product per bone instead of depth products (aux_kernels.cuh)
+  static const int poseAlgo = getenv("RZ_POSE") ? atoi(getenv("RZ_POSE")) : 2;          // 0 levels, 1 chains, 2 jumping
+  const size_t smemJump = (size_t)c->B * (96 + 8);
+  if (poseAlgo >= 2 && c->nLevels > 4 && smemJump <= (size_t)c->maxSmemOptin && (MODE != 1 || c->d_twAux.p)) {
+    uint32_t rounds = 0;
+    while ((1u << rounds) < c->nLevels) ++rounds;
+    CU_TRY(c, cudaFuncSetAttribute(pose_jump_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemJump));
+    const int threads = c->B <= 1024 ? (int)std::max<uint32_t>(64u, (c->B + 31u) / 32u * 32u) : 512;   // one bone per thread when possible
+    pose_jump_kernel<MODE><<<P, threads, smemJump, c->stream>>>(sk, tw, tr, reinterpret_cast<const float4*>(c->d_twAux.p),
+                                                                reinterpret_cast<const float4*>(c->d_localRot.p),
+                                                                reinterpret_cast<const float*>(c->d_nowMs.p),
+                                                                reinterpret_cast<const float4*>(c->d_invBind.p),
+                                                                reinterpret_cast<const float4*>(c->d_invBindSoA.p),
+                                                                reinterpret_cast<const uint32_t*>(c->d_bonePos.p),
+                                                                reinterpret_cast<float4*>(c->d_skin.p), rounds, (uint32_t)c->layoutMode);
+    CU_TRY(c, cudaGetLastError());
+    c->launches++;
+    return RZ_OK;
+  }
+  if (c->useChains && poseAlgo >= 1) {
     CU_TRY(c, cudaFuncSetAttribute(pose_chain_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     pose_chain_kernel<MODE><<<P, 256, smem, c->stream>>>(sk, tw, tr, reinterpret_cast<const uint32_t*>(c->d_skChainStart.p),
                                                          reinterpret_cast<const uint32_t*>(c->d_skChainBones.p),
@@ -993,6 +1017,20 @@ int32_t rz_set_tweens(rz_ctx* c, const float* startQ, const float* targetQ, cons
   if ((rc = upload(c, c->d_twStartMs, startMs, B * 4))) return rc;
   if ((rc = upload(c, c->d_twDurMs, durMs, B * 4))) return rc;
   if ((rc = upload(c, c->d_twActive, active, B))) return rc;
+  // per-bone slerp constants (functions of the two keys only, math.ts:156-189): angle, 1/sin(angle), lerp-branch flag,
+  // hemisphere sign -- every pose of the crowd reuses them (aux_kernels.cuh pose_jump_kernel)
+  std::vector<float> aux(B * 4);
+  for (size_t b = 0; b < B; ++b) {
+    const float* a = startQ + b * 4;
+    const float* t = targetQ + b * 4;
+    float cs = a[0] * t[0] + a[1] * t[1] + a[2] * t[2] + a[3] * t[3];
+    float sign = 1.f;
+    if (cs < 0.f) { cs = -cs; sign = -1.f; }
+    const bool lerp = cs > 0.9995f;
+    const float th0 = lerp ? 0.f : acosf(std::min(cs, 1.0f));
+    aux[b * 4] = th0; aux[b * 4 + 1] = lerp ? 0.f : 1.0f / sinf(th0); aux[b * 4 + 2] = lerp ? 1.f : 0.f; aux[b * 4 + 3] = sign;
+  }
+  if ((rc = upload(c, c->d_twAux, aux.data(), B * 16))) return rc;
   CU_TRY(c, cudaStreamSynchronize(c->stream));    // pageable sources
   c->haveTweens = true;
   return RZ_OK;
