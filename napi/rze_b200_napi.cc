@@ -251,6 +251,32 @@ napi_value GetOutputLayout(napi_env env, napi_callback_info info) {
   return o;
 }
 
+// readInstanceAsync(ctx, inst, Float32Array pos, Float32Array|null nrm): queued behind the frame's deform, returns at once;
+// readWait(ctx) blocks until the arrays are filled.  With RZ_FLAG_DOUBLE_BUFFER (0x40) the next frame is deformed meanwhile.
+// (The arrays must stay alive until readWait; a Promise-returning wrapper belongs in ts/engine.ts.)
+napi_value ReadInstanceAsync(napi_env env, napi_callback_info info) {
+  size_t argc = 4;
+  napi_value a[4];
+  NAPI_OK(env, napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+  rz_ctx* c = unwrap(env, a[0]);
+  size_t np = 0, nn = 0;
+  float* pos = typed<float>(env, a[2], &np, napi_float32_array);
+  napi_valuetype vt;
+  napi_typeof(env, a[3], &vt);
+  float* nrm = (vt == napi_null || vt == napi_undefined) ? nullptr : typed<float>(env, a[3], &nn, napi_float32_array);
+  if (c) check(env, c, rz_read_instance_async(c, u32(env, a[1]), pos, nrm));
+  return nullptr;
+}
+
+napi_value ReadWait(napi_env env, napi_callback_info info) {
+  size_t argc = 1;
+  napi_value a[1];
+  NAPI_OK(env, napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+  rz_ctx* c = unwrap(env, a[0]);
+  if (c) check(env, c, rz_read_wait(c));
+  return nullptr;
+}
+
 // getStats(ctx) -> {fps, frameTime, gpuMemory, vertsPerSec, achievedGBs}  (EngineStats, engine.ts:16-20 + additions)
 napi_value GetStats(napi_env env, napi_callback_info info) {
   size_t argc = 1;
@@ -287,6 +313,8 @@ napi_value Init(napi_env env, napi_value exports) {
       {"readOutline", nullptr, ReadOutline, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"readInterleaved", nullptr, ReadInterleaved, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"getOutputLayout", nullptr, GetOutputLayout, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"readInstanceAsync", nullptr, ReadInstanceAsync, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"readWait", nullptr, ReadWait, nullptr, nullptr, nullptr, napi_default, nullptr},
   };
   napi_define_properties(env, exports, sizeof d / sizeof d[0], d);
   return exports;

@@ -23,6 +23,7 @@ export type EngineOptions = {
   sdef?: boolean            // new: evaluate SDEF spherically instead of as BDEF2
   outline?: boolean         // new: also produce the outline pass' hull positions (engine.ts:458-461) as a third plane
   interleaved?: boolean     // new: result in the reference's own 32-byte vertex layout [pos, nrm, uv] (engine.ts:340-347)
+  doubleBuffer?: boolean    // new: two result buffers, frame n is read / drawn while frame n+1 is deformed
   clock?: () => number      // new: replaces performance.now() (model.ts:160,249) for reproducible playback
 }
 export interface EngineStats { fps: number; frameTime: number; gpuMemory: number; vertsPerSec?: number; achievedGBs?: number }
@@ -45,7 +46,7 @@ export class Engine {
 
   async init() {
     const o = this.options   // rz_config.flags: RZ_FLAG_SDEF 0x1, RZ_FLAG_OUTLINE 0x10, RZ_FLAG_INTERLEAVED 0x20
-    this.ctx = rz.create(o.device ?? 0, this.K, (o.sdef ? 0x1 : 0) | (o.outline ? 0x10 : 0) | (o.interleaved ? 0x20 : 0))
+    this.ctx = rz.create(o.device ?? 0, this.K, (o.sdef ? 0x1 : 0) | (o.outline ? 0x10 : 0) | (o.interleaved ? 0x20 : 0) | (o.doubleBuffer ? 0x40 : 0))
   }
 
   async loadModel(path: string) {
@@ -101,6 +102,9 @@ export class Engine {
   stopRenderLoop() { this.running = false }
   getStats(): EngineStats { return rz.getStats(this.ctx) }
   readSkinned(instance: number, pos: Float32Array, nrm: Float32Array | null) { rz.readInstance(this.ctx, instance, pos, nrm) }
+  // frame n comes back while frame n+1 is being deformed: resolve after the NEXT render() (or call readWait yourself)
+  readSkinnedAsync(instance: number, pos: Float32Array, nrm: Float32Array | null) { rz.readInstanceAsync(this.ctx, instance, pos, nrm) }
+  readWait() { rz.readWait(this.ctx) }
   readOutline(instance: number, hull: Float32Array) { rz.readOutline(this.ctx, instance, hull) }
   readInterleaved(instance: number, vtx8: Float32Array) { rz.readInterleaved(this.ctx, instance, vtx8) }
   getOutputLayout() { return rz.getOutputLayout(this.ctx) }
