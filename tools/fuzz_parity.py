@@ -57,21 +57,27 @@ def main():
             flags |= capi.RZ_FLAG_SDEF
         if rng.integers(0, 4) == 0:
             flags |= capi.RZ_FLAG_REORDER_VERTICES
-        plain = M == 0 and not sdef and not (flags & ~capi.RZ_FLAG_REORDER_VERTICES)
+        if rng.integers(0, 3) == 0:
+            flags |= capi.RZ_FLAG_DOUBLE_BUFFER
+        # host uploads with one palette per instance are pipelined in blocks of this many palettes (rze_b200.cu)
+        os.environ["RZ_PIPELINE_BLOCK"] = str(int(rng.choice([1, 2, 3, 64])))
+        plain = M == 0 and not sdef and not (flags & ~(capi.RZ_FLAG_REORDER_VERTICES | capi.RZ_FLAG_DOUBLE_BUFFER))
         I, nt = (FULL if plain else LITE)[int(rng.integers(0, len(FULL if plain else LITE)))]
-        if I > K:
+        first = int(rng.integers(0, K))
+        count = int(rng.integers(1, K - first + 1))
+        if I > count:                                        # a tuned group wider than the instance range is refused
             I, nt = 0, 0
         wl = synth.make_workload(V, B, M=M, sdef=sdef, seed=int(rng.integers(1, 1 << 30)))
-        P = int(rng.integers(1, K + 1))
+        P = K if rng.integers(0, 3) == 0 else int(rng.integers(1, K + 1))     # one palette per instance a third of the time
+        world0 = synth.make_palettes(wl.bones, P, rng)          # a first frame that must leave no trace
         world = synth.make_palettes(wl.bones, P, rng)
-        i2p = None if P == K and rng.integers(0, 2) else rng.integers(0, P, K).astype(np.uint32)
+        i2p = None if P == K and rng.integers(0, 4) else rng.integers(0, P, K).astype(np.uint32)
         if i2p is None and P < K:
             i2p = rng.integers(0, P, K).astype(np.uint32)
         mw = rng.uniform(-0.3, 1.0, (K, max(M, 1))).astype(np.float32)
         edge = rng.uniform(0, 2, V).astype(np.float32)
-        first = int(rng.integers(0, K))
-        count = int(rng.integers(1, K - first + 1))
-        row = dict(case=case, V=V, B=B, K=K, P=P, M=M, sdef=sdef, flags=flags, I=I, nt=nt, first=first, count=count)
+        row = dict(case=case, V=V, B=B, K=K, P=P, M=M, sdef=sdef, flags=flags, I=I, nt=nt, first=first, count=count,
+                   pipe_block=os.environ["RZ_PIPELINE_BLOCK"], identity=i2p is None)
         try:
             with capi.DeformContext(max_instances=K, flags=flags, instances_per_group=I, threads=nt) as ctx:
                 ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
@@ -81,10 +87,12 @@ def main():
                     ctx.load_sdef(wl.sdef.vertexIndex, wl.sdef.c_r0_r1)
                 if flags & capi.RZ_FLAG_OUTLINE:
                     ctx.load_edge_size(edge)
-                ctx.set_palettes(world, i2p, K=K)
-                if M:
-                    ctx.set_morph_weights(mw, np.arange(M), K=K)
                 try:
+                    ctx.set_palettes(world0, i2p, K=K)
+                    if M:
+                        ctx.set_morph_weights(mw, np.arange(M), K=K)
+                    ctx.deform()
+                    ctx.set_palettes(world, i2p, K=K)
                     ctx.deform(first, count)
                 except capi.RzError as e:
                     if "not built" in str(e) or "does not fit" in str(e):
