@@ -281,7 +281,7 @@ def main():
     wall0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    esteps = max(3, min(args.steps, 10))
+    esteps = max(3, min(args.steps, 20))
     for s in range(esteps):
         ctx.set_palettes(stage, i2p, K=K)
         ctx.deform()

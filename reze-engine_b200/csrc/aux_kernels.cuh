@@ -36,6 +36,9 @@ __global__ void skin_matrices_kernel(const float4* __restrict__ world, const flo
   }
 }
 
+// (A one-CTA-per-palette variant with coalesced loads and stores through shared memory runs 52.7 -> 38.9 us on its own but
+//  makes the frame SLOWER, 1.870 -> 1.894 ms: its 64 KB of shared memory per CTA cannot share an SM with the deform kernel's
+//  221 KB, so the tails of the two kernels stop overlapping.  This shared-memory-free kernel stays.)
 // quat[p][row] = rotation part of skin[p][row] as a quaternion (math.ts:406-448 Mat4.toQuatFromArray, via
 // deform_kernel.cuh quat_from_rows).  Feeds the SDEF dense phase: the deform kernel slerps these instead of converting
 // two matrices per SDEF vertex-instance.  One thread per (palette, palette row).
@@ -315,20 +318,22 @@ __global__ void pose_chain_kernel(PoseSkeleton sk, PoseTweens tw, PoseTracks tr,
 // matrices, inside the 1e-5 tolerance of the path.  MODE 1 (shared tween table) also takes the per-bone slerp constants
 // (angle, 1/sin, hemisphere sign: functions of the two keys only) from `twAux`, computed once in rz_set_tweens, so a
 // (pose, bone) rotation costs two polynomial sines instead of acos + three sines.
-// Shared memory: two ping-pong copies of W ([B][3] float4 each), two of anc ([B] int), the local rotations alias the
-// second W copy until the rounds start.
+// Shared memory, one bone per thread (B <= blockDim.x): W [B][3] float4, the local rotations [B] float4, anc [B] int =
+// 68 B per bone (34 KB at B = 512: under the 48 KB that needs no opt-in); more bones than threads: two ping-pong copies of W
+// and of anc, the rotations alias the second W copy (104 B per bone).
 template <int MODE>
 __global__ void pose_jump_kernel(PoseSkeleton sk, PoseTweens tw, PoseTracks tr, const float4* __restrict__ twAux,
                                  const float4* __restrict__ localRot, const float* __restrict__ nowMs, const float4* __restrict__ invBind,
                                  const float4* __restrict__ invBindSoA /* [4][B]: column c of bone b at c*B + b (coalesced) */,
                                  const uint32_t* __restrict__ bonePos, float4* __restrict__ skin, uint32_t rounds, uint32_t soa) {
-  extern __shared__ float4 s_w[];                      // [2][B][3]
+  extern __shared__ float4 s_w[];
   const uint32_t p = blockIdx.x, B = sk.B;
+  const bool onePerThread = B <= blockDim.x;
   float4* wA = s_w;
-  float4* wB = s_w + (size_t)B * 3;
-  int32_t* ancA = reinterpret_cast<int32_t*>(s_w + (size_t)B * 6);
+  float4* wB = s_w + (size_t)B * 3;                    // (ping-pong copy: only when a thread owns several bones)
+  float4* s_q = wB;                                    // [B]; aliases wB, dead before the first round writes it
+  int32_t* ancA = reinterpret_cast<int32_t*>(s_w + (size_t)B * (onePerThread ? 4 : 6));
   int32_t* ancB = ancA + B;
-  float4* s_q = wB;                                    // alias: dead before the first round writes wB
   for (uint32_t b = threadIdx.x; b < B; b += blockDim.x) {
     float4 q;
     if (MODE == 1) {
@@ -384,7 +389,7 @@ __global__ void pose_jump_kernel(PoseSkeleton sk, PoseTweens tw, PoseTracks tr, 
     ancA[b] = sk.parent[b];
   }
   __syncthreads();
-  if (B <= blockDim.x) {
+  if (onePerThread) {
     // one bone per thread: the own window stays in registers, a round reads the ancestor's window (48 B) and, after a
     // barrier, publishes the product in place (48 B); bones whose window has reached the root drop out of both
     const uint32_t b = threadIdx.x;
@@ -414,8 +419,8 @@ __global__ void pose_jump_kernel(PoseSkeleton sk, PoseTweens tw, PoseTracks tr, 
       }
       __syncthreads();
     }
-    // skin = W * invBind, assembled in shared memory in palette order (wB is free) and written out as one contiguous
-    // B x 48-byte block: 3 fully coalesced 16-byte stores per thread instead of 3 scattered ones (32 lines each)
+    // skin = W * invBind, assembled in shared memory in palette order (over W: nobody reads the windows any more, the
+    // loop ended on a barrier) and written out as one contiguous B x 48-byte block: 3 fully coalesced 16-byte stores per thread instead of 3 scattered ones (32 lines each)
     if (mine) {
       const float W[3][4] = {{w0.x, w0.y, w0.z, w0.w}, {w1.x, w1.y, w1.z, w1.w}, {w2.x, w2.y, w2.z, w2.w}};
       float S[3][4];
@@ -429,12 +434,12 @@ __global__ void pose_jump_kernel(PoseSkeleton sk, PoseTweens tw, PoseTracks tr, 
       const float4 cB = make_float4(S[0][2], S[1][2], S[0][3], S[1][3]);
       const float4 cC = make_float4(S[2][0], S[2][1], S[2][2], S[2][3]);
       const uint32_t pos = __ldg(bonePos + b);
-      if (soa) { wB[pos] = cA; wB[B + pos] = cB; wB[2 * (size_t)B + pos] = cC; }
-      else { wB[(size_t)pos * 3] = cA; wB[(size_t)pos * 3 + 1] = cB; wB[(size_t)pos * 3 + 2] = cC; }
+      if (soa) { wA[pos] = cA; wA[B + pos] = cB; wA[2 * (size_t)B + pos] = cC; }
+      else { wA[(size_t)pos * 3] = cA; wA[(size_t)pos * 3 + 1] = cB; wA[(size_t)pos * 3 + 2] = cC; }
     }
     __syncthreads();
     float4* dst = skin + (size_t)p * B * 3;
-    for (uint32_t i = threadIdx.x; i < B * 3; i += blockDim.x) dst[i] = wB[i];
+    for (uint32_t i = threadIdx.x; i < B * 3; i += blockDim.x) dst[i] = wA[i];
     return;
   }
   float4* wc = wA;

@@ -921,11 +921,11 @@ static int launch_pose(rz_ctx* c, uint32_t P) {
   tr.keyQ = reinterpret_cast<const float4*>(c->d_trQ.p);
   // pointer jumping: ceil(log2(depth)) rounds of one product per bone instead of depth products (aux_kernels.cuh)
   static const int poseAlgo = getenv("RZ_POSE") ? atoi(getenv("RZ_POSE")) : 2;          // 0 levels, 1 chains, 2 jumping
-  const size_t smemJump = (size_t)c->B * (96 + 8);
+  const size_t smemJump = (size_t)c->B * (c->B <= 1024 ? 68 : 104);
   if (poseAlgo >= 2 && c->nLevels > 4 && smemJump <= (size_t)c->maxSmemOptin && (MODE != 1 || c->d_twAux.p)) {
     uint32_t rounds = 0;
     while ((1u << rounds) < c->nLevels) ++rounds;
-    CU_TRY(c, cudaFuncSetAttribute(pose_jump_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemJump));
+    if (smemJump > 48 * 1024) CU_TRY(c, cudaFuncSetAttribute(pose_jump_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemJump));
     const int threads = c->B <= 1024 ? (int)std::max<uint32_t>(64u, (c->B + 31u) / 32u * 32u) : 512;   // one bone per thread when possible
     pose_jump_kernel<MODE><<<P, threads, smemJump, c->stream>>>(sk, tw, tr, reinterpret_cast<const float4*>(c->d_twAux.p),
                                                                 reinterpret_cast<const float4*>(c->d_localRot.p),
