@@ -65,7 +65,7 @@ class Engine:
     def __init__(self, canvas=None, options: Optional[dict] = None, *, instances: int = 1, device: int = 0,
                  clock: Optional[Callable[[], float]] = None, sdef: bool = False, bounds: bool = False, stream: int = 0,
                  gpu_pose: bool = False, crowd: bool = False, reorder_vertices: bool = False, outline: bool = False,
-                 interleaved: bool = False):
+                 interleaved: bool = False, double_buffer: bool = False):
         o = options or {}
         # EngineOptions (engine.ts:8-14): kept so existing call sites construct unchanged; they only
         # parameterise passes this repo does not replace.
@@ -82,7 +82,9 @@ class Engine:
                        | (capi.RZ_FLAG_REORDER_VERTICES if reorder_vertices else 0)
                        # fused consumers of the skinned stream: the outline pass' hull positions
                        # (engine.ts:431-463) as a third plane / the result in the reference's 32-byte vertex layout
-                       | (capi.RZ_FLAG_OUTLINE if outline else 0) | (capi.RZ_FLAG_INTERLEAVED if interleaved else 0))
+                       | (capi.RZ_FLAG_OUTLINE if outline else 0) | (capi.RZ_FLAG_INTERLEAVED if interleaved else 0)
+                       # two result buffers: frame n stays readable (readSkinnedAsync) while render() produces frame n+1
+                       | (capi.RZ_FLAG_DOUBLE_BUFFER if double_buffer else 0))
         self._stream = stream
         self.gpu_pose = gpu_pose or crowd   # walk the bone hierarchy on the GPU (rz_set_local_rotations) instead of in Model
         # crowd mode: ONE shared skeleton runtime + animation clip, every instance plays it at its own clock offset; tweens /
@@ -443,6 +445,13 @@ class Engine:
     def readInterleaved(self, instance: int = 0) -> np.ndarray:
         """One instance in the reference's vertex-buffer layout [x,y,z,nx,ny,nz,u,v] (Engine(interleaved=True))."""
         return self.ctx.read_interleaved(instance)
+
+    def readSkinnedAsync(self, instance: int, out_pos: np.ndarray, out_nrm: Optional[np.ndarray] = None):
+        """Queue the read-back of the frame just rendered and return at once; the arrays are valid after readWait()."""
+        self.ctx.read_instance_async(instance, out_pos, out_nrm)
+
+    def readWait(self):
+        self.ctx.read_wait()
 
     def readSkinned(self, instance: int = 0):
         """Skinned positions and normals of one instance, [V,3] float32 each."""
