@@ -164,6 +164,19 @@ int32_t rz_set_instance_clocks(rz_ctx* ctx, const float* nowMs /* P */, uint32_t
 int32_t rz_load_animation(rz_ctx* ctx, const uint32_t* keyOffsets /* B+1 */, const float* keyTimesMs, const float* keyQuats /* 4*nKeys */,
                           const float* restQuat /* 4B or NULL */);
 
+/* ---- physics -> bone feedback, the matrix plumbing of Physics.step (physics.ts:534-569, 714-751); the solver itself
+ * (Bullet / Ammo wasm) stays with the caller ----
+ * rz_load_rigid_bodies: per body the bone it is attached to (RigidBody.boneIndex; < 0 or >= B: none), whether it is
+ *   RigidbodyType.Dynamic (only those drive bones), and bodyOffsetMatrixInverse (physics.ts:560-585, column-major).
+ * rz_apply_body_transforms: after this frame's palette update and before rz_deform; posQuat = per palette, per body the
+ *   solver's world transform (origin x,y,z + rotation x,y,z,w).  Every bone driven by dynamic bodies gets
+ *   boneWorld = fromPositionRotation(pos, rot) x bodyOffsetMatrixInverse, bodies in index order, NaN / >= 1e6 results skipped
+ *   (physics.ts:744-748); other bones — including the children of driven bones — keep the matrices of the pose evaluation,
+ *   exactly like the reference's in-place edit. */
+int32_t rz_load_rigid_bodies(rz_ctx* ctx, const int32_t* boneIndex /* n */, const uint8_t* dynamic /* n */,
+                             const float* bodyOffsetInverse /* 16*n */, uint32_t n);
+int32_t rz_apply_body_transforms(rz_ctx* ctx, const float* posQuat /* P*n*7 */, uint32_t P);
+
 /* Per-instance weights of the active morphs: w[k*M_active + a] scales morph activeIds[a] for instance k.
  * K must match the instance count in use; M_active = 0 disables morphing. */
 int32_t rz_set_morph_weights(rz_ctx* ctx, const float* w, const uint32_t* activeIds, uint32_t M_active, uint32_t K);

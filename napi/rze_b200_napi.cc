@@ -277,6 +277,32 @@ napi_value ReadWait(napi_env env, napi_callback_info info) {
   return nullptr;
 }
 
+// loadRigidBodies(ctx, Int32Array boneIndex, Uint8Array dynamic, Float32Array bodyOffsetMatrixInverse /*16 per body*/)
+//   and applyBodyTransforms(ctx, Float32Array posQuat /*P*n*7*/, P): physics.ts:714-751 on the device, the solver stays in JS
+napi_value LoadRigidBodies(napi_env env, napi_callback_info info) {
+  size_t argc = 4;
+  napi_value a[4];
+  NAPI_OK(env, napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+  rz_ctx* c = unwrap(env, a[0]);
+  size_t nb = 0, nd = 0, no = 0;
+  const int32_t* bi = typed<int32_t>(env, a[1], &nb, napi_int32_array);
+  const uint8_t* dy = typed<uint8_t>(env, a[2], &nd, napi_uint8_array);
+  const float* oi = typed<float>(env, a[3], &no, napi_float32_array);
+  if (c && bi && dy && oi) check(env, c, rz_load_rigid_bodies(c, bi, dy, oi, (uint32_t)nb));
+  return nullptr;
+}
+
+napi_value ApplyBodyTransforms(napi_env env, napi_callback_info info) {
+  size_t argc = 3;
+  napi_value a[3];
+  NAPI_OK(env, napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+  rz_ctx* c = unwrap(env, a[0]);
+  size_t n = 0;
+  const float* pq = typed<float>(env, a[1], &n, napi_float32_array);
+  if (c && pq) check(env, c, rz_apply_body_transforms(c, pq, u32(env, a[2])));
+  return nullptr;
+}
+
 // getStats(ctx) -> {fps, frameTime, gpuMemory, vertsPerSec, achievedGBs}  (EngineStats, engine.ts:16-20 + additions)
 napi_value GetStats(napi_env env, napi_callback_info info) {
   size_t argc = 1;
@@ -314,6 +340,8 @@ napi_value Init(napi_env env, napi_value exports) {
       {"readInterleaved", nullptr, ReadInterleaved, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"getOutputLayout", nullptr, GetOutputLayout, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"readInstanceAsync", nullptr, ReadInstanceAsync, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"loadRigidBodies", nullptr, LoadRigidBodies, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"applyBodyTransforms", nullptr, ApplyBodyTransforms, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"readWait", nullptr, ReadWait, nullptr, nullptr, nullptr, napi_default, nullptr},
   };
   napi_define_properties(env, exports, sizeof d / sizeof d[0], d);

@@ -34,6 +34,7 @@ EXPORTS = [
     "rz_read_skin_matrices", "rz_get_stats", "rz_last_error",
     "rz_load_edge_size", "rz_get_output_layout", "rz_read_outline", "rz_read_interleaved",
     "rz_plan_morph_rows", "rz_plan_chunks", "rz_read_instance_async", "rz_read_wait",
+    "rz_load_rigid_bodies", "rz_apply_body_transforms",
 ]
 
 
@@ -105,6 +106,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.rz_sync.argtypes = [vp]
     lib.rz_output_device_ptr.argtypes = [vp, P(vp), P(sz), P(sz)]
     lib.rz_read_instance.argtypes = [vp, u32, vp, vp]
+    lib.rz_load_rigid_bodies.argtypes = [vp, vp, vp, vp, u32]
+    lib.rz_apply_body_transforms.argtypes = [vp, vp, u32]
     lib.rz_read_instance_async.argtypes = [vp, u32, vp, vp]
     lib.rz_read_wait.argtypes = [vp]
     lib.rz_load_edge_size.argtypes = [vp, vp]
@@ -335,6 +338,23 @@ class DeformContext:
             K = t.size if i2p is None else i2p.size
         self._check(self.lib.rz_set_instance_clocks(self.h, _ptr(t), t.size, _ptr(i2p), K))
         self.K = K
+
+    def load_rigid_bodies(self, bone_index, dynamic, offset_inverse):
+        """Rigid bodies that may drive bones (physics.ts:560-585 gives offset_inverse, see physics_bridge.compute_body_offsets)."""
+        bi = _arr(bone_index, np.int32).reshape(-1)
+        dy = _arr(dynamic, np.uint8).reshape(-1)
+        oi = _arr(offset_inverse, np.float32).reshape(-1)
+        if dy.size != bi.size or oi.size != bi.size * 16:
+            raise ValueError("dynamic / offset_inverse must match bone_index")
+        self._n_bodies = bi.size
+        self._check(self.lib.rz_load_rigid_bodies(self.h, _ptr(bi), _ptr(dy), _ptr(oi), bi.size))
+
+    def apply_body_transforms(self, pos_quat):
+        """Solver output [P, nBodies, 7] (x,y,z, qx,qy,qz,qw) over this frame's palettes (physics.ts:714-751 on the device)."""
+        pq = _arr(pos_quat, np.float32)
+        n = getattr(self, "_n_bodies", 0)
+        P = pq.size // (7 * n) if n else 0
+        self._check(self.lib.rz_apply_body_transforms(self.h, _ptr(pq.reshape(-1)), P))
 
     def set_morph_weights(self, w, active_ids, K: Optional[int] = None):
         ids = _arr(active_ids, np.uint32).reshape(-1)

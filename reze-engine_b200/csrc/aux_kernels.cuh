@@ -494,6 +494,65 @@ __global__ void pose_jump_kernel(PoseSkeleton sk, PoseTweens tw, PoseTracks tr, 
   }
 }
 
+// Physics -> bone feedback (physics.ts:714-751): for every bone driven by dynamic rigid bodies,
+//   boneWorld = fromPositionRotation(bodyPos, bodyRot) x bodyOffsetMatrixInverse,      skin = boneWorld x invBind,
+// written over the palette row that the pose evaluation produced (children are NOT re-evaluated, exactly like the
+// reference's in-place edit).  Bodies of one bone are applied in index order and a result whose [0] or [15] is NaN or
+// >= 1e6 in magnitude is skipped, so the last VALID body wins.  One thread per (palette, driven bone).
+//   boneList [nBones] driven bones; bodyStart [nBones+1] into bodyIds (ascending body index); offInv [nBodies][16] col-major;
+//   posQuat [P][nBodies][7] = x,y,z, qx,qy,qz,qw.
+__global__ void apply_bodies_kernel(const uint32_t* __restrict__ boneList, const uint32_t* __restrict__ bodyStart,
+                                    const uint32_t* __restrict__ bodyIds, const float* __restrict__ offInv, const float* __restrict__ posQuat,
+                                    const float4* __restrict__ invBind, const uint32_t* __restrict__ bonePos, float4* __restrict__ skin,
+                                    uint32_t nBones, uint32_t nBodies, uint32_t P, uint32_t B, uint32_t soa) {
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P * nBones) return;
+  const uint32_t p = idx / nBones, li = idx - p * nBones, bone = boneList[li];
+  float W[4][4];                                        // W[r][c]
+  bool have = false;
+  for (uint32_t k = bodyStart[li]; k < bodyStart[li + 1]; ++k) {
+    const uint32_t body = bodyIds[k];
+    const float* pq = posQuat + ((size_t)p * nBodies + body) * 7;
+    float R[3][3];
+    q_to_rows(make_float4(pq[3], pq[4], pq[5], pq[6]), R);           // math.ts:352-384 via fromPositionRotation (387-393)
+    const float* o = offInv + (size_t)body * 16;                        // column-major: o[c*4 + r]
+    float N[4][4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) N[r][c] = R[r][0] * o[c * 4] + R[r][1] * o[c * 4 + 1] + R[r][2] * o[c * 4 + 2] + pq[r] * o[c * 4 + 3];
+      N[3][c] = o[c * 4 + 3];                                           // bottom row of the node matrix is (0,0,0,1)
+    }
+    const bool ok = !isnan(N[0][0]) && !isnan(N[3][3]) && fabsf(N[0][0]) < 1e6f && fabsf(N[3][3]) < 1e6f;
+    if (ok) {
+      have = true;
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) W[r][c] = N[r][c];
+    }
+  }
+  if (!have) return;
+  float S[3][4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float4 ib = __ldg(invBind + (size_t)bone * 4 + c);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) S[r][c] = W[r][0] * ib.x + W[r][1] * ib.y + W[r][2] * ib.z + W[r][3] * ib.w;
+  }
+  const float4 cA = make_float4(S[0][0], S[1][0], S[0][1], S[1][1]);
+  const float4 cB = make_float4(S[0][2], S[1][2], S[0][3], S[1][3]);
+  const float4 cC = make_float4(S[2][0], S[2][1], S[2][2], S[2][3]);
+  const size_t pos = __ldg(bonePos + bone);
+  if (soa) {
+    const size_t pb = (size_t)p * B * 3;
+    skin[pb + pos] = cA; skin[pb + B + pos] = cB; skin[pb + 2 * (size_t)B + pos] = cC;
+  } else {
+    const size_t row = (size_t)p * B + pos;
+    skin[row * 3] = cA; skin[row * 3 + 1] = cB; skin[row * 3 + 2] = cC;
+  }
+}
+
 __global__ void bounds_reset_kernel(int* b, uint32_t n6) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n6) b[i] = (i % 6) < 3 ? 0x7F7FFFFF : (int)(0x7F7FFFFF ^ 0x7FFFFFFF) | (int)0x80000000;

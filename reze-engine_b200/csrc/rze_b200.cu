@@ -91,6 +91,9 @@ struct rz_ctx_impl {
   DevBuf d_skParent, d_skBindT, d_skAppendParent, d_skAppendRatio, d_skLevelBones, d_skLevelStart, d_skChainStart, d_skChainBones;
   bool useChains = false;
   bool packedMeta = false;
+  // physics -> bone feedback (rz_load_rigid_bodies / rz_apply_body_transforms)
+  DevBuf d_rbBones, d_rbStart, d_rbIds, d_rbOffInv, d_rbPosQuat;
+  uint32_t rbBones = 0, rbBodies = 0;
   DevBuf d_twStart, d_twTarget, d_twRest, d_twStartMs, d_twDurMs, d_twActive, d_localRot, d_nowMs, d_twAux, d_invBindSoA;
 
   // per-frame
@@ -624,7 +627,7 @@ int32_t rz_destroy(rz_ctx* c) {
                     &c->d_invBind, &c->d_bonePos, &c->d_world, &c->d_skin, &c->d_inst2pal, &c->d_mwIn, &c->d_mwIds, &c->d_mwDense,
                     &c->d_out, &c->d_out2, &c->d_bounds, &c->d_counter, &c->d_skParent, &c->d_skBindT, &c->d_skAppendParent, &c->d_skAppendRatio,
                     &c->d_skLevelBones, &c->d_skLevelStart, &c->d_skChainStart, &c->d_skChainBones, &c->d_twStart, &c->d_twTarget, &c->d_twRest, &c->d_twStartMs, &c->d_twDurMs,
-                    &c->d_twActive, &c->d_localRot, &c->d_nowMs, &c->d_twAux, &c->d_invBindSoA, &c->d_trStart, &c->d_trMs, &c->d_trQ, &c->d_quat, &c->d_chunkTab, &c->d_edge, &c->d_uv};
+                    &c->d_twActive, &c->d_localRot, &c->d_nowMs, &c->d_twAux, &c->d_invBindSoA, &c->d_rbBones, &c->d_rbStart, &c->d_rbIds, &c->d_rbOffInv, &c->d_rbPosQuat, &c->d_trStart, &c->d_trMs, &c->d_trQ, &c->d_quat, &c->d_chunkTab, &c->d_edge, &c->d_uv};
   for (DevBuf* b : bufs) dev_free(c, *b);
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->h_small) cudaFreeHost(c->h_small);
@@ -654,6 +657,7 @@ int32_t rz_load_mesh(rz_ctx* c, const float* vtx8, const uint16_t* joints, const
   c->h_moff.clear(); c->h_mvert.clear(); c->h_mdelta.clear();
   c->h_sdefVert.clear(); c->h_sdefVec.clear();
   c->h_edgeSize.clear();
+  c->rbBones = c->rbBodies = 0;
   c->palettesSet = false;
   c->haveSkeleton = false;
   c->haveTweens = false;
@@ -1000,6 +1004,62 @@ int32_t rz_set_local_rotations(rz_ctx* c, const float* quats, uint32_t P, const 
   CU_TRY(c, cudaMemcpyAsync(c->d_localRot.p, src, bytes, cudaMemcpyHostToDevice, c->stream));
   if ((rc = launch_pose<0>(c, P))) return rc;
   c->P = P; c->K = K; c->palettesSet = true;
+  return RZ_OK;
+}
+
+int32_t rz_load_rigid_bodies(rz_ctx* c, const int32_t* boneIndex, const uint8_t* dynamic, const float* offsetInverse, uint32_t n) {
+  if (!c) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_load_rigid_bodies: null ctx");
+  if (c->V == 0) return fail(c, RZ_ERR_STATE, "rz_load_rigid_bodies before rz_load_mesh");
+  if (n && (!boneIndex || !dynamic || !offsetInverse)) return fail(c, RZ_ERR_INVALID_ARG, "rz_load_rigid_bodies: null table");
+  CU_TRY(c, cudaSetDevice(c->device));
+  // bone -> its dynamic bodies in index order (the reference applies them sequentially, the last valid one wins)
+  std::vector<std::vector<uint32_t>> per(c->B);
+  for (uint32_t i = 0; i < n; ++i)
+    if (dynamic[i] && boneIndex[i] >= 0 && (uint32_t)boneIndex[i] < c->B) per[(uint32_t)boneIndex[i]].push_back(i);
+  std::vector<uint32_t> bones, start(1, 0), ids;
+  for (uint32_t b = 0; b < c->B; ++b)
+    if (!per[b].empty()) {
+      bones.push_back(b);
+      ids.insert(ids.end(), per[b].begin(), per[b].end());
+      start.push_back((uint32_t)ids.size());
+    }
+  c->rbBones = (uint32_t)bones.size();
+  c->rbBodies = n;
+  int rc;
+  if (c->rbBones) {
+    if ((rc = upload(c, c->d_rbBones, bones.data(), bones.size() * 4))) return rc;
+    if ((rc = upload(c, c->d_rbStart, start.data(), start.size() * 4))) return rc;
+    if ((rc = upload(c, c->d_rbIds, ids.data(), ids.size() * 4))) return rc;
+    if ((rc = upload(c, c->d_rbOffInv, offsetInverse, (size_t)n * 64))) return rc;
+    CU_TRY(c, cudaStreamSynchronize(c->stream));    // pageable sources
+  }
+  return RZ_OK;
+}
+
+int32_t rz_apply_body_transforms(rz_ctx* c, const float* posQuat, uint32_t P) {
+  if (!c) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_apply_body_transforms: null ctx");
+  if (!c->palettesSet) return fail(c, RZ_ERR_STATE, "rz_apply_body_transforms before this frame's palettes were set");
+  if (P != c->P) return fail(c, RZ_ERR_INVALID_ARG, "rz_apply_body_transforms: P=%u but the frame has %u palettes", P, c->P);
+  if (c->rbBones == 0) return RZ_OK;                  // nothing drives a bone
+  if (!posQuat) return fail(c, RZ_ERR_INVALID_ARG, "rz_apply_body_transforms: null transforms");
+  CU_TRY(c, cudaSetDevice(c->device));
+  int rc;
+  if ((rc = flush_pending(c))) return rc;            // a pipelined upload computes its skin matrices lazily: do it now
+  const size_t bytes = (size_t)P * c->rbBodies * 28;
+  if ((rc = dev_reserve(c, c->d_rbPosQuat, bytes))) return rc;
+  if ((rc = pinned_reserve(c, c->h_small, c->h_smallBytes, std::max(bytes, (size_t)c->maxK * 4)))) return rc;
+  CU_TRY(c, cudaStreamSynchronize(c->stream));        // h_small may still feed an earlier copy
+  memcpy(c->h_small, posQuat, bytes);
+  CU_TRY(c, cudaMemcpyAsync(c->d_rbPosQuat.p, c->h_small, bytes, cudaMemcpyHostToDevice, c->stream));
+  const uint32_t n = P * c->rbBones;
+  apply_bodies_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(
+      reinterpret_cast<const uint32_t*>(c->d_rbBones.p), reinterpret_cast<const uint32_t*>(c->d_rbStart.p),
+      reinterpret_cast<const uint32_t*>(c->d_rbIds.p), reinterpret_cast<const float*>(c->d_rbOffInv.p),
+      reinterpret_cast<const float*>(c->d_rbPosQuat.p), reinterpret_cast<const float4*>(c->d_invBind.p),
+      reinterpret_cast<const uint32_t*>(c->d_bonePos.p), reinterpret_cast<float4*>(c->d_skin.p), c->rbBones, c->rbBodies, P, c->B,
+      (uint32_t)c->layoutMode);
+  CU_TRY(c, cudaGetLastError());
+  c->launches++;
   return RZ_OK;
 }
 

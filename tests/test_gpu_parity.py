@@ -627,6 +627,77 @@ def test_async_read_back_keeps_the_frame_it_was_issued_for(rzlib, orc, wl_small,
             ctx.read_instance_async(0, bufs[0][0], bufs[0][1])
 
 
+def test_physics_feedback_patches_the_palette_like_the_reference(rzlib, orc):
+    """rz_load_rigid_bodies + rz_apply_body_transforms (physics.ts:714-751 on the device) against the host restatement:
+    skin matrices of the driven bones, untouched bones bit-identical, and the deformed mesh through the oracle -- with host
+    palettes (plain and pipelined upload) and with GPU pose evaluation."""
+    from reze_engine_b200 import physics_bridge as pb
+    rng = np.random.default_rng(77)
+    wl = synth.make_workload(3000, 40, seed=77)
+    ib = np.asarray(wl.invBind, np.float32).reshape(-1, 16)
+    n, P = 14, 6
+    bone_index = rng.integers(-1, wl.B, n).astype(np.int32)
+    bone_index[1] = bone_index[0] = max(int(bone_index[0]), 0)
+    dynamic = (rng.random(n) < 0.6).astype(np.uint8)
+    dynamic[0] = dynamic[1] = 1
+    off, inv = pb.compute_body_offsets(ib, bone_index, rng.normal(0, 3, (n, 3)), rng.uniform(-1.5, 1.5, (n, 3)))
+    world = synth.make_palettes(wl.bones, P, rng)
+    pos = rng.normal(0, 5, (P, n, 3))
+    quat = rng.normal(size=(P, n, 4))
+    quat /= np.linalg.norm(quat, axis=2, keepdims=True)
+    pos[2, 1] = np.nan                                    # one invalid transform: the earlier body of that bone stays
+    pq = np.concatenate([pos, quat], axis=2).astype(np.float32)
+    want = world.copy()
+    for p in range(P):
+        pb.apply_bodies_to_bones(want[p], bone_index, dynamic, inv, pos[p], quat[p])
+    driven = sorted({int(b) for b, d in zip(bone_index, dynamic) if d and b >= 0})
+    for block in ("", "2"):
+        if block:
+            os.environ["RZ_PIPELINE_BLOCK"] = block
+        try:
+            with capi.DeformContext(max_instances=P) as ctx:
+                ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
+                ctx.load_rigid_bodies(bone_index, dynamic, inv)
+                ctx.set_palettes(world)
+                plain = [ctx.read_skin_matrices(p) for p in range(P)]
+                ctx.set_palettes(world)
+                ctx.apply_body_transforms(pq)
+                ctx.deform()
+                for p in range(P):
+                    sm = ctx.read_skin_matrices(p)
+                    ref = orc.skin_matrices(want[p], wl.invBind).reshape(-1, 4, 4).transpose(0, 2, 1)[:, :3, :].reshape(-1, 12)
+                    scale = max(np.abs(ref).max(), 1.0)
+                    assert np.abs(sm - ref).max() / scale <= 2e-6, (p, np.abs(sm - ref).max())
+                    others = [b for b in range(wl.B) if b not in driven]
+                    assert np.array_equal(sm[others], plain[p][others])
+                    rp, rn = orc.deform(wl.vtx8, wl.joints, wl.weights, orc.skin_matrices(want[p], wl.invBind))
+                    gp, gn = ctx.read_instance(p)
+                    assert rel_err(gp, rp) <= TOL and rel_err(gn, rn) <= TOL, (p, rel_err(gp, rp))
+        finally:
+            os.environ.pop("RZ_PIPELINE_BLOCK", None)
+    # with GPU pose evaluation: the driven bones are patched after the hierarchy walk, their children keep the posed matrices
+    lr = np.tile(np.array([0, 0, 0, 1], np.float32), (P, wl.B, 1))
+    lr[:, :, :3] = rng.normal(0, 0.2, (P, wl.B, 3))
+    lr /= np.linalg.norm(lr, axis=2, keepdims=True)
+    posed = crowd.world_matrices_batch(wl.bones, lr.astype(np.float64))
+    want = posed.copy()
+    for p in range(P):
+        pb.apply_bodies_to_bones(want[p], bone_index, dynamic, inv, pos[p], quat[p])
+    with capi.DeformContext(max_instances=P) as ctx:
+        ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
+        ctx.load_skeleton(wl.bones)
+        ctx.load_rigid_bodies(bone_index, dynamic, inv)
+        ctx.set_local_rotations(lr)
+        ctx.apply_body_transforms(pq)
+        ctx.deform()
+        for p in range(P):
+            rp, rn = orc.deform(wl.vtx8, wl.joints, wl.weights, orc.skin_matrices(want[p], wl.invBind))
+            gp, gn = ctx.read_instance(p)
+            assert rel_err(gp, rp) <= TOL and rel_err(gn, rn) <= TOL, (p, rel_err(gp, rp))
+        with pytest.raises(capi.RzError):
+            ctx.apply_body_transforms(pq[:2])            # P must match the frame
+
+
 def test_huge_bone_count_uses_global_palette_path(rzlib, orc):
     wl = synth.make_workload(3000, 6000, seed=77)
     world = synth.make_palettes(wl.bones, 2, np.random.default_rng(9))

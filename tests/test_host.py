@@ -10,7 +10,7 @@ import pytest
 from helpers import numpy_blend_f64, random_pmx, rel_err, write_vmd
 from reze_engine_b200 import Engine, Model, PmxLoader, Quat, VMDLoader, capi, crowd, synth
 from reze_engine_b200.engine import ManualClock
-from reze_engine_b200.math3d import Mat4, easeInOut
+from reze_engine_b200.math3d import Mat4, Vec3, easeInOut
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -181,6 +181,58 @@ def test_vertex_edge_sizes_follow_the_outline_draw_rule(orc):
     assert np.allclose(hull[0] - pos[0], [0, 0.009, 0.012], atol=1e-6)
     st = orc.interleaved(pos, nrm, vtx)
     assert st.shape == (V, 8) and np.array_equal(st[:, :3], pos) and np.array_equal(st[:, 6:], vtx[:, 6:])
+
+
+def _random_bodies(rng, bones, inv_bind, n):
+    from reze_engine_b200 import physics_bridge as pb
+    B = len(bones)
+    bone_index = rng.integers(-1, B, n).astype(np.int32)
+    bone_index[1] = bone_index[0] = max(int(bone_index[0]), 0)          # two bodies on one bone
+    dynamic = (rng.random(n) < 0.6).astype(np.uint8)
+    dynamic[0] = dynamic[1] = 1
+    shape_pos = rng.normal(0, 3, (n, 3))
+    shape_rot = rng.uniform(-1.5, 1.5, (n, 3))
+    off, inv = pb.compute_body_offsets(inv_bind, bone_index, shape_pos, shape_rot)
+    return bone_index, dynamic, off, inv
+
+
+def test_physics_bridge_follows_the_reference_feedback_rule():
+    """physics.ts:560-585 / 714-751 restated on the host: offsets invert cleanly, only DYNAMIC bodies with a valid bone write,
+    bodies apply in index order (the last valid one wins), NaN / huge matrices are skipped, children are left alone."""
+    from reze_engine_b200 import physics_bridge as pb
+    rng = np.random.default_rng(21)
+    wl = synth.make_workload(64, 24, seed=21)
+    ib = np.asarray(wl.invBind, np.float32).reshape(-1, 16)
+    n = 10
+    bone_index, dynamic, off, inv = _random_bodies(rng, wl.bones, ib, n)
+    for i in range(n):
+        prod = Mat4(off[i]).multiply(Mat4(inv[i])).values.reshape(4, 4)
+        assert np.abs(prod - np.eye(4)).max() < 2e-5
+    world = synth.make_palettes(wl.bones, 1, rng)[0].copy()
+    before = world.copy()
+    pos = rng.normal(0, 5, (n, 3))
+    quat = rng.normal(size=(n, 4))
+    quat /= np.linalg.norm(quat, axis=1, keepdims=True)
+    pos[1] = np.nan                                                     # the second body of bone b0 is invalid -> body 0 stays
+    wrote = pb.apply_bodies_to_bones(world, bone_index, dynamic, inv, pos, quat)
+    driven = {int(b) for b, d in zip(bone_index, dynamic) if d and b >= 0}
+    assert wrote >= len(driven)
+    for b in range(len(wl.bones)):
+        if b not in driven:
+            assert np.array_equal(world[b], before[b])                  # static / kinematic bodies and children: untouched
+    b0 = int(bone_index[0])
+    last = max(i for i in range(n) if dynamic[i] and bone_index[i] == b0 and i != 1)
+    want = Mat4.fromPositionRotation(Vec3(*pos[last]), Quat(*quat[last])).multiply(Mat4(inv[last])).values
+    assert np.array_equal(world[b0], want)
+    # a body sitting exactly where the bone's bind shape is reproduces the bone's own world matrix
+    one = np.array([b0], np.int32)
+    sp, sr = rng.normal(0, 2, (1, 3)), rng.uniform(-1, 1, (1, 3))
+    o1, i1 = pb.compute_body_offsets(ib, one, sp, sr)
+    node = Mat4(before[b0]).multiply(Mat4(o1[0]))                       # nodeWorld = boneWorld x bodyOffset (physics.ts:600-603)
+    w2 = before.copy()
+    pb.apply_bodies_to_bones(w2, one, np.ones(1, np.uint8), i1, [list(node.getPosition().__dict__.values())] if hasattr(node.getPosition(), "__dict__") else [[node.values[12], node.values[13], node.values[14]]],
+                             [node.toQuat().toArray()])
+    assert np.abs(w2[b0] - before[b0]).max() < 5e-5
 
 
 def test_capi_exports_every_declared_symbol(rzlib):
