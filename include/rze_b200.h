@@ -235,6 +235,13 @@ int32_t rz_plan_morph_rows(const uint32_t* laneVertex /* Vp */, uint32_t Vp, uin
                            const uint32_t* vertIdx, const float* delta3, uint32_t M, uint32_t* rowFirst /* Vp/32 */,
                            uint32_t* rowDepth /* Vp/32 */, uint8_t* morphMajor /* Vp/32 */, float* rows, uint64_t rowsCapacity,
                            uint64_t* rowsNeeded);
+/* The SDEF records and per-warp descriptor lists rz_load_sdef builds, device-free: records receives 12
+ * floats per evaluated SDEF vertex (C, c0, c1, w0, w1, then the two bone ids as one u32: j0 | j1 << 16 — palette rows once a
+ * mesh is loaded), desc [Vp] the descriptor word of every lane (table index | output slot << 24, 0xFFFFFFFF = none),
+ * nActive the number of records (vertices with a third or fourth influence are not SDEF and are dropped). */
+int32_t rz_plan_sdef(const uint32_t* laneVertex /* Vp */, uint32_t Vp, const uint16_t* joints, const uint8_t* weights, uint32_t V,
+                     uint32_t B, const uint32_t* sdefVertIdx /* n */, const float* c_r0_r1 /* 9*n */, uint32_t n,
+                     float* records /* 12*n or NULL */, uint32_t* desc /* Vp or NULL */, uint32_t* nActive);
 /* The cost-balanced chunk boundaries rz_deform uses when morphs are active: tileDepth[t] = deepest row list among the
  * warps of 256-vertex tile t; tab receives nChunks+1 tile indices (room for nChunksTarget+1). */
 int32_t rz_plan_chunks(const uint32_t* tileDepth, uint32_t nTiles, uint32_t tilesPerPass, uint32_t nChunksTarget,

@@ -34,7 +34,7 @@ EXPORTS = [
     "rz_read_skin_matrices", "rz_get_stats", "rz_last_error",
     "rz_load_edge_size", "rz_get_output_layout", "rz_read_outline", "rz_read_interleaved",
     "rz_plan_morph_rows", "rz_plan_chunks", "rz_read_instance_async", "rz_read_wait",
-    "rz_load_rigid_bodies", "rz_apply_body_transforms",
+    "rz_load_rigid_bodies", "rz_apply_body_transforms", "rz_plan_sdef",
 ]
 
 
@@ -118,6 +118,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.rz_plan_lanes.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp, vp]
     lib.rz_plan_morph_rows.argtypes = [vp, u32, u32, vp, vp, vp, u32, vp, vp, vp, vp, C.c_uint64, P(C.c_uint64)]
     lib.rz_plan_chunks.argtypes = [vp, u32, u32, u32, vp, P(u32)]
+    lib.rz_plan_sdef.argtypes = [vp, u32, vp, vp, u32, u32, vp, vp, u32, vp, vp, P(u32)]
     lib.rz_read_bounds.argtypes = [vp, u32, u32, vp]
     lib.rz_read_skinning.argtypes = [vp, vp, vp]
     lib.rz_read_skin_matrices.argtypes = [vp, u32, vp]
@@ -178,6 +179,22 @@ def plan_morph_rows(lane_vertex, V: int, offsets, vert_idx, delta3, lib: Optiona
     if st != 0:
         raise RzError(st, (lib.rz_last_error(None) or b"").decode())
     return dict(first=first, depth=depth, morphMajor=mm, rows=rows)
+
+
+def plan_sdef(lane_vertex, joints, weights, B: int, sdef_vert_idx, c_r0_r1, lib: Optional[C.CDLL] = None) -> dict:
+    """Device-free: SDEF records [n,12] and per-lane descriptor words for the lane plan `lane_vertex` (rz_plan_sdef)."""
+    lib = lib or load_library()
+    lv = _arr(lane_vertex, np.uint32).reshape(-1)
+    j, w = _arr(joints, np.uint16).reshape(-1), _arr(weights, np.uint8).reshape(-1)
+    vi = _arr(sdef_vert_idx, np.uint32).reshape(-1)
+    vec = _arr(c_r0_r1, np.float32).reshape(-1)
+    rec = np.zeros((max(vi.size, 1), 12), np.float32)
+    desc = np.zeros(lv.size, np.uint32)
+    n = C.c_uint32(0)
+    st = lib.rz_plan_sdef(_ptr(lv), lv.size, _ptr(j), _ptr(w), j.size // 4, B, _ptr(vi), _ptr(vec), vi.size, _ptr(rec), _ptr(desc), C.byref(n))
+    if st != 0:
+        raise RzError(st, (lib.rz_last_error(None) or b"").decode())
+    return dict(records=rec[:n.value], desc=desc, active=n.value)
 
 
 def plan_chunks(tile_depth, tiles_per_pass: int, n_chunks_target: int, lib: Optional[C.CDLL] = None) -> np.ndarray:

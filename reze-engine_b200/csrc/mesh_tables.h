@@ -194,6 +194,61 @@ inline void build_morph_rows(const uint32_t* procVertex, uint32_t Vp, const std:
   if (mell.empty()) mell.push_back(F4{0.f, 0.f, 0.f, 0.f});
 }
 
+// ---- SDEF tables ----------------------------------------------------------------------------------------------------
+// One 48-byte record per SDEF vertex and, per warp, the descriptor list the kernel's dense phase walks (deform_kernel.cuh):
+//   record  = (C.xyz, c0.x) (c0.yz, c1.xy) (c1.z, w0, w1, palette rows j0 | j1 << 16)
+//             rw = w0*R0 + w1*R1, r0 = C + R0 - rw, r1 = C + R1 - rw, c0 = (C + r0)/2, c1 = (C + r1)/2      
+//             w0, w1 = the reference's shader-time normalisation of the two unorm8 weights (engine.ts:255-258), f32
+//   desc[w*32 + l] = table index | output slot << 24 of the l-th SDEF vertex among warp w's 32 outputs, ~0u beyond.
+// sdefOf [V]: index into vec9 (the caller's C, R0, R1) of stored vertex v or -1; JT / WT: joints and unorm8 weights in stored
+// vertex order; bonePos: palette row of every bone.  Returns false when there are more than 2^24 SDEF vertices.
+struct SdefTables {
+  std::vector<F4> tab;              // 3 per SDEF vertex
+  std::vector<uint32_t> desc;       // [Vp]
+  uint32_t active = 0;
+};
+inline bool build_sdef_tables(const int32_t* sdefOf, const float* vec9, const uint16_t* JT, const uint8_t* WT, const uint32_t* bonePos,
+                              const uint32_t* procVertex, const uint32_t* procSlot, uint32_t V, uint32_t Vp, SdefTables& out) {
+  out.tab.clear();
+  out.desc.assign(Vp, ~0u);
+  out.active = 0;
+  std::vector<int32_t> recOf(V, -1);
+  for (uint32_t v = 0; v < V; ++v) {
+    if (sdefOf[v] < 0) continue;
+    const uint8_t* w = &WT[(size_t)v * 4];
+    const float* s = &vec9[(size_t)sdefOf[v] * 9];
+    float w0 = (float)w[0] / 255.0f, w1 = (float)w[1] / 255.0f;        // weights exactly as the kernel derives them
+    const float ws = w0 + w1 + 0.f + 0.f;
+    if (ws > 0.0001f) { const float inv = 1.0f / ws; w0 *= inv; w1 *= inv; } else { w0 = 1.f; w1 = 0.f; }
+    float C[3] = {s[0], s[1], s[2]}, c0[3], c1[3];
+    for (int k = 0; k < 3; ++k) {
+      const float R0 = s[3 + k], R1 = s[6 + k];
+      const float rw = w0 * R0 + w1 * R1;
+      const float r0 = C[k] + R0 - rw, r1 = C[k] + R1 - rw;
+      c0[k] = (C[k] + r0) * 0.5f;
+      c1[k] = (C[k] + r1) * 0.5f;
+    }
+    const uint32_t rows = bonePos[JT[(size_t)v * 4]] | (bonePos[JT[(size_t)v * 4 + 1]] << 16);
+    float rowsF;
+    memcpy(&rowsF, &rows, 4);
+    recOf[v] = (int32_t)(out.tab.size() / 3);
+    out.tab.push_back(F4{C[0], C[1], C[2], c0[0]});
+    out.tab.push_back(F4{c0[1], c0[2], c1[0], c1[1]});
+    out.tab.push_back(F4{c1[2], w0, w1, rowsF});
+    out.active++;
+  }
+  if (out.tab.size() / 3 >= (1u << 24)) return false;
+  for (uint32_t w0 = 0; w0 < Vp; w0 += 32) {
+    uint32_t n = 0;
+    for (uint32_t l = 0; l < 32; ++l) {
+      const uint32_t v = procVertex[w0 + l];
+      if (v == ~0u || recOf[v] < 0) continue;
+      out.desc[w0 + n++] = (uint32_t)recOf[v] | (procSlot[w0 + l] << 24);
+    }
+  }
+  return true;
+}
+
 // ---- cost-balanced chunks -------------------------------------------------------------------------------------------
 // Morph passes are latency chains (record -> rows -> weights: one L2 round trip per `batch` rows beyond the `prefetch`ed
 // ones), several times longer than a plain pass, and PMX morphs cluster on the face: uniform chunks would leave a few very

@@ -312,7 +312,6 @@ int rebuild_tables(rz_ctx_impl* c) {
   // SDEF (only when enabled): which vertices take the spherical path.  The table itself needs the palette rows and is
   // built further down, after the bank-aware permutation.
   std::vector<int32_t> sdefOf(V, -1);     // stored vertex -> record n of the caller's rz_load_sdef arrays
-  std::vector<float4> sdefTab;
   c->sdefActive = 0;
   if (c->flags & RZ_FLAG_SDEF) {
     for (size_t n = 0; n < c->h_sdefVert.size(); ++n) {
@@ -355,46 +354,15 @@ int rebuild_tables(rz_ctx_impl* c) {
   c->boneAt.assign(B, 0);
   for (uint32_t b = 0; b < B; ++b) c->boneAt[c->bonePos[b]] = b;
 
-  // ---- SDEF table (36 B of vectors + weights + palette rows per vertex) and the per-warp descriptor list: word l of a
-  // warp describes the l-th SDEF vertex among the warp's 32 outputs (table index | output slot << 24), ~0u beyond
+  // ---- SDEF records + per-warp descriptor lists (mesh_tables.h)
+  SdefTables sdt;
   if (c->flags & RZ_FLAG_SDEF) {
-    std::vector<int32_t> recOf(V, -1);
-    for (uint32_t v = 0; v < V; ++v) {
-      if (sdefOf[v] < 0) continue;
-      const size_t n = (size_t)sdefOf[v];
-      const uint8_t* w = &WT[(size_t)v * 4];
-      const float* s = &c->h_sdefVec[n * 9];
-      // weights exactly as the kernel derives them
-      float w0 = (float)w[0] / 255.0f, w1 = (float)w[1] / 255.0f;
-      const float ws = w0 + w1 + 0.f + 0.f;
-      if (ws > 0.0001f) { const float inv = 1.0f / ws; w0 *= inv; w1 *= inv; } else { w0 = 1.f; w1 = 0.f; }
-      float C[3] = {s[0], s[1], s[2]}, c0[3], c1[3];
-      for (int k = 0; k < 3; ++k) {
-        const float R0 = s[3 + k], R1 = s[6 + k];
-        const float rw = w0 * R0 + w1 * R1;
-        const float r0 = C[k] + R0 - rw, r1 = C[k] + R1 - rw;
-        c0[k] = (C[k] + r0) * 0.5f;
-        c1[k] = (C[k] + r1) * 0.5f;
-      }
-      const uint32_t rows = c->bonePos[JT[(size_t)v * 4]] | (c->bonePos[JT[(size_t)v * 4 + 1]] << 16);
-      float rowsF;
-      memcpy(&rowsF, &rows, 4);
-      recOf[v] = (int32_t)(sdefTab.size() / 3);
-      sdefTab.push_back(make_float4(C[0], C[1], C[2], c0[0]));
-      sdefTab.push_back(make_float4(c0[1], c0[2], c1[0], c1[1]));
-      sdefTab.push_back(make_float4(c1[2], w0, w1, rowsF));
-      c->sdefActive++;
-    }
-    if (sdefTab.size() / 3 >= (1u << 24)) return fail(c, RZ_ERR_INVALID_ARG, "rz_load_sdef: more than 2^24 SDEF vertices");
-    for (uint32_t w0 = 0; w0 < Vp; w0 += 32) {
-      uint32_t n = 0;
-      for (uint32_t l = 0; l < 32; ++l) {
-        const uint32_t v = procVertex[w0 + l];
-        if (v == ~0u || recOf[v] < 0) continue;
-        sdefIdx[w0 + n++] = (uint32_t)recOf[v] | (procSlot[w0 + l] << 24);
-      }
-    }
+    if (!build_sdef_tables(sdefOf.data(), c->h_sdefVec.data(), JT, WT, c->bonePos.data(), procVertex.data(), procSlot.data(), V, Vp, sdt))
+      return fail(c, RZ_ERR_INVALID_ARG, "rz_load_sdef: more than 2^24 SDEF vertices");
+    c->sdefActive = sdt.active;
+    sdefIdx = sdt.desc;
   }
+  const std::vector<F4>& sdefTab = sdt.tab;
 
   for (uint32_t p = 0; p < Vp; ++p) {
     const uint32_t v = procVertex[p], slot = procSlot[p], ni = devN[p];
@@ -1614,6 +1582,35 @@ int32_t rz_plan_morph_rows(const uint32_t* laneVertex, uint32_t Vp, uint32_t V, 
     if (rowsCapacity < mr.rows.size()) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_plan_morph_rows: rows buffer too small");
     memcpy(rows, mr.rows.data(), mr.rows.size() * 16);
   }
+  return RZ_OK;
+}
+
+int32_t rz_plan_sdef(const uint32_t* laneVertex, uint32_t Vp, const uint16_t* joints, const uint8_t* weights, uint32_t V,
+                     uint32_t B, const uint32_t* sdefVertIdx, const float* c_r0_r1, uint32_t n, float* records, uint32_t* desc, uint32_t* nActive) {
+  if (!laneVertex || Vp == 0 || Vp % 32 || !joints || !weights || V == 0 || B == 0)
+    return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_plan_sdef: bad lane / skinning tables");
+  if (n && (!sdefVertIdx || !c_r0_r1)) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_plan_sdef: null SDEF arrays");
+  std::vector<int32_t> sdefOf(V, -1);
+  for (uint32_t i = 0; i < n; ++i) {
+    if (sdefVertIdx[i] >= V) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_plan_sdef: vertex index %u >= V=%u", sdefVertIdx[i], V);
+    const uint8_t* w = &weights[(size_t)sdefVertIdx[i] * 4];
+    if (w[2] != 0 || w[3] != 0) continue;                 // not a two-influence vertex: stays linear (as rz_load_sdef)
+    sdefOf[sdefVertIdx[i]] = (int32_t)i;
+  }
+  std::vector<uint32_t> ident(B);
+  for (uint32_t b = 0; b < B; ++b) ident[b] = b;         // records carry bone ids here (no palette permutation without a mesh)
+  std::vector<uint32_t> laneSlotV(Vp, 0);               // a warp owns 32 consecutive vertices: output slot = vertex mod 32
+  for (uint32_t p = 0; p < Vp; ++p) {
+    if (laneVertex[p] != ~0u && laneVertex[p] >= V) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_plan_sdef: lane vertex out of range");
+    laneSlotV[p] = laneVertex[p] == ~0u ? 0u : (laneVertex[p] & 31u);
+  }
+  const uint32_t* laneSlot = laneSlotV.data();
+  SdefTables t;
+  if (!build_sdef_tables(sdefOf.data(), c_r0_r1, joints, weights, ident.data(), laneVertex, laneSlot, V, Vp, t))
+    return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_plan_sdef: more than 2^24 SDEF vertices");
+  if (records) memcpy(records, t.tab.data(), t.tab.size() * 16);
+  if (desc) memcpy(desc, t.desc.data(), (size_t)Vp * 4);
+  if (nActive) *nActive = t.active;
   return RZ_OK;
 }
 

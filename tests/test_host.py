@@ -345,6 +345,46 @@ def test_morph_rows_hold_every_entry_once_in_pmx_order(rzlib):
         capi.plan_morph_rows(lv, V, offs, vidx + V, deltas, rzlib)
 
 
+def test_sdef_tables_and_descriptors(rzlib):
+    """rz_plan_sdef (the table builder of rz_load_sdef, device-free): one record per two-influence SDEF vertex with the
+    load-time constants of SURVEY 8c, weights normalised like the reference's shader, and per warp a dense descriptor list
+    (the l-th word names the l-th SDEF vertex of the warp and its output slot)."""
+    rng = np.random.default_rng(31)
+    wl = synth.make_workload(2000, 30, sdef=True, seed=31)
+    J, W = wl.joints.reshape(-1, 4), wl.weights.reshape(-1, 4)
+    vi = np.concatenate([wl.sdef.vertexIndex, np.nonzero(W[:, 2] > 0)[0][:5].astype(np.uint32)])     # + 5 that must be dropped
+    vec = np.concatenate([wl.sdef.c_r0_r1.reshape(-1, 9), rng.normal(size=(5, 9)).astype(np.float32)])
+    plan = capi.plan_lanes(J, W, wl.B, 2, rzlib)
+    lv = np.asarray(plan["laneVertex"], np.uint32)
+    r = capi.plan_sdef(lv, J, W, wl.B, vi, vec, rzlib)
+    rec, desc = r["records"], r["desc"]
+    assert r["active"] == wl.sdef.vertexIndex.size
+    seen = set()
+    for w0 in range(0, lv.size, 32):
+        d = desc[w0:w0 + 32]
+        k = int((d != 0xFFFFFFFF).sum())
+        assert (d[:k] != 0xFFFFFFFF).all() and (d[k:] == 0xFFFFFFFF).all()                       # dense prefix
+        want = sorted(int(v) for v in lv[w0:w0 + 32] if v != 0xFFFFFFFF and int(v) in set(wl.sdef.vertexIndex.tolist()))
+        got = []
+        for word in d[:k]:
+            idx, slot = int(word) & 0xFFFFFF, int(word) >> 24
+            v = w0 + slot                                                                        # output slot -> vertex of this warp
+            got.append(v)
+            i = int(np.nonzero(vi == v)[0][0])
+            C_, R0, R1 = vec[i, :3], vec[i, 3:6], vec[i, 6:9]
+            w0f, w1f = np.float32(W[v, 0]) / np.float32(255), np.float32(W[v, 1]) / np.float32(255)
+            inv = np.float32(1) / (w0f + w1f)
+            w0f, w1f = w0f * inv, w1f * inv
+            rw = w0f * R0 + w1f * R1
+            c0, c1 = (C_ + (C_ + R0 - rw)) * np.float32(0.5), (C_ + (C_ + R1 - rw)) * np.float32(0.5)
+            assert np.allclose(rec[idx, :3], C_, atol=0) and np.allclose(rec[idx, 3:6], c0, atol=1e-6) and np.allclose(rec[idx, 6:9], c1, atol=1e-6)
+            assert rec[idx, 9] == w0f and rec[idx, 10] == w1f
+            assert int(rec[idx, 11:12].view(np.uint32)[0]) == int(J[v, 0]) | (int(J[v, 1]) << 16)
+            seen.add(idx)
+        assert sorted(got) == want
+    assert seen == set(range(r["active"]))
+
+
 def test_chunk_table_balances_morph_cost(rzlib):
     """rz_plan_chunks: boundaries are monotone multiples of the pass width that cover every tile, no chunk is empty, and chunks
     over the deep (face) tiles are shorter than chunks over plain tiles."""
