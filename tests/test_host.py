@@ -235,6 +235,24 @@ def test_physics_bridge_follows_the_reference_feedback_rule():
     assert np.abs(w2[b0] - before[b0]).max() < 5e-5
 
 
+def test_bench_reference_arm_prints_one_contract_line(orc):
+    """`bench.py --impl reference` (the CPU port of the reference arithmetic, the arm the driver times next to the GPU
+    path): exactly one JSON line on stdout with the contract's keys, no GPU needed."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                          "--verts", "3000", "--instances", "16", "--bones", "32", "--cpu-seconds", "0.3"],
+                         capture_output=True, text=True, timeout=300, check=True).stdout.strip().splitlines()
+    assert len(out) == 1
+    r = json.loads(out[0])
+    assert r["impl"] == "reference" and r["metric"] == "skinned_vertices_per_sec" and r["unit"] == "verts/s" and r["higher_is_better"] is True
+    assert r["n_gpus"] == 1 and r["steps"] == 2 and r["warmup"] == 1 and r["value"] > 0 and r["vs_baseline"] is None
+    assert r["cpu_baseline"]["kind"] == "port" and r["cpu_baseline"]["cores"] >= 1 and r["cpu_baseline"]["value"] == r["value"]
+    assert r["e2e"] == {"value": r["value"], "unit": "verts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert r["config"]["V"] == 3000 and r["config"]["K_per_gpu"] == 16 and "workload" in r["config"]
+
+
 def test_capi_exports_every_declared_symbol(rzlib):
     from reze_engine_b200 import capi
     hdr = open(os.path.join(ROOT, "include", "rze_b200.h")).read()
