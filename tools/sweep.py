@@ -24,11 +24,17 @@ def main():
     ap.add_argument("--chunks", default="0")
     ap.add_argument("--pair-coherent", type=int, default=0, help="experiment: make groups of N consecutive vertices share joints (upper bound of lane packing)")
     ap.add_argument("--flags", type=lambda x: int(x, 0), default=0, help="rz_config.flags, e.g. 0x8 = RZ_FLAG_REORDER_VERTICES")
+    ap.add_argument("--npz", default="", help="real model dumped by tests/golden/make_fixtures.py (e.g. tests/golden/_local/serqet2.npz) instead of the synthetic mesh")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.jsonl"))
     a = ap.parse_args()
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     V, B, K = a.verts, a.bones, a.instances
     wl = synth.make_workload(V, B)
+    if a.npz:
+        z = np.load(a.npz)
+        wl.vtx8, wl.joints, wl.weights, wl.invBind = z["vtx8"], z["joints"], z["weights"], z["invBind"]
+        V, B = wl.vtx8.size // 8, wl.invBind.size // 16
+        wl.bones = synth.make_workload(64, B).bones          # poses only need a skeleton with B bones
     if a.pair_coherent > 1:
         g = a.pair_coherent
         n = (V // g) * g
