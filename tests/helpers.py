@@ -236,3 +236,77 @@ def numpy_blend_f64(vtx8, joints, weights, skin16):
     ln = np.linalg.norm(nrm, axis=1, keepdims=True)
     nrm = np.where(ln > 0, nrm / np.where(ln > 0, ln, 1), 0)
     return pos, nrm
+
+
+def numpy_morph_sdef_f64(vtx8, joints, weights, skin16, morph=None, morphW=None, sdef=None):
+    """Independent f64 restatement of the two extensions the reference does not have, vertex by vertex in plain
+    numpy -- a second implementation next to oracle/rz_oracle_body.inc so that the unpinned features are at least pinned to
+    each other.  Morph: p~ = p + sum_m w_m * delta_m[v] in PMX morph order, before skinning.  SDEF (two-influence vertices
+    only): q = slerp(quat(M0), quat(M1), w1) with the reference's own toQuatFromArray / slerp / fromQuat (math.ts:406-448,
+    156-189, 352-384), pos' = R(q)(p~ - C) + w0 M0 c0 + w1 M1 c1, n' = normalize(R(q) n); the load-time constants c0, c1 are
+    float32 like in the product (rze_b200.cu / mesh_tables.h)."""
+    vtx8 = np.asarray(vtx8, np.float64).reshape(-1, 8)
+    V = vtx8.shape[0]
+    J = np.asarray(joints).reshape(V, 4)
+    W8 = np.asarray(weights).reshape(V, 4)
+    M = np.asarray(skin16, np.float64).reshape(-1, 4, 4).transpose(0, 2, 1)     # [B,row,col]
+    P = vtx8[:, :3].copy()
+    if morph is not None and morphW is not None:
+        off, vi, d3 = np.asarray(morph[0], np.int64), np.asarray(morph[1], np.int64), np.asarray(morph[2], np.float64).reshape(-1, 3)
+        for m in range(len(off) - 1):                                            # PMX order; a vertex listed twice adds twice
+            for e in range(off[m], off[m + 1]):
+                P[vi[e]] = P[vi[e]] + np.float64(np.float32(morphW[m])) * d3[e]
+    pos, nrm = numpy_blend_f64(np.concatenate([P, vtx8[:, 3:]], axis=1), joints, weights, skin16)
+
+    def quat_of(m):
+        m00, m01, m02, m10, m11, m12, m20, m21, m22 = m[0, 0], m[0, 1], m[0, 2], m[1, 0], m[1, 1], m[1, 2], m[2, 0], m[2, 1], m[2, 2]
+        tr = m00 + m11 + m22
+        if tr > 0:
+            s_ = np.sqrt(tr + 1.0) * 2
+            q = np.array([(m21 - m12) / s_, (m02 - m20) / s_, (m10 - m01) / s_, 0.25 * s_])
+        elif m00 > m11 and m00 > m22:
+            s_ = np.sqrt(1.0 + m00 - m11 - m22) * 2
+            q = np.array([0.25 * s_, (m01 + m10) / s_, (m02 + m20) / s_, (m21 - m12) / s_])
+        elif m11 > m22:
+            s_ = np.sqrt(1.0 + m11 - m00 - m22) * 2
+            q = np.array([(m01 + m10) / s_, 0.25 * s_, (m12 + m21) / s_, (m02 - m20) / s_])
+        else:
+            s_ = np.sqrt(1.0 + m22 - m00 - m11) * 2
+            q = np.array([(m02 + m20) / s_, (m12 + m21) / s_, 0.25 * s_, (m10 - m01) / s_])
+        return q / np.linalg.norm(q)
+
+    def slerp(a, b, t):
+        c = float(a @ b)
+        if c < 0:
+            c, b = -c, -b
+        if c > 0.9995:
+            v = a + t * (b - a)
+            return v / np.linalg.norm(v)
+        th0 = np.arccos(c)
+        return (np.sin(th0 - th0 * t) * a + np.sin(th0 * t) * b) / np.sin(th0)
+
+    def rot_of(q):
+        x, y, z, w = q
+        return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                         [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                         [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+    if sdef is not None:
+        sv, vec = np.asarray(sdef[0], np.int64), np.asarray(sdef[1], np.float32).reshape(-1, 9)
+        for i, v in enumerate(sv):
+            if W8[v, 2] != 0 or W8[v, 3] != 0:
+                continue
+            w = W8[v].astype(np.float64) / 255.0
+            w = w / w.sum() if w.sum() > 1e-4 else np.array([1.0, 0, 0, 0])
+            w0f, w1f = np.float32(w[0]), np.float32(w[1])
+            C, R0, R1 = vec[i, :3], vec[i, 3:6], vec[i, 6:9]
+            rw = w0f * R0 + w1f * R1                                             # float32 arithmetic, like the table builder
+            c0 = ((C + (C + R0 - rw)) * np.float32(0.5)).astype(np.float64)
+            c1 = ((C + (C + R1 - rw)) * np.float32(0.5)).astype(np.float64)
+            M0, M1 = M[J[v, 0]], M[J[v, 1]]
+            R = rot_of(slerp(quat_of(M0), quat_of(M1), w[1]))
+            pos[v] = R @ (P[v] - C.astype(np.float64)) + w[0] * (M0[:3, :3] @ c0 + M0[:3, 3]) + w[1] * (M1[:3, :3] @ c1 + M1[:3, 3])
+            n = R @ vtx8[v, 3:6]
+            ln = np.linalg.norm(n)
+            nrm[v] = n / ln if ln > 0 else 0
+    return pos, nrm

@@ -140,6 +140,24 @@ def test_oracle_against_independent_numpy_restatement(orc):
     assert rel_err(p32, p64) < 2e-6 and rel_err(n32, n64) < 2e-6        # f32 oracle vs f64 oracle (reported in DESIGN.md)
 
 
+def test_oracle_morph_and_sdef_against_independent_numpy_restatement(orc):
+    """The two features the reference cannot pin (vertex morphs, SDEF) are at least pinned by two independent
+    restatements of SURVEY 8c agreeing: the C oracle (f64 variant) and a vertex-by-vertex numpy one."""
+    from helpers import numpy_morph_sdef_f64
+    wl = synth.make_workload(1500, 32, M=6, sdef=True, seed=9)
+    rng = np.random.default_rng(9)
+    world = synth.make_palettes(wl.bones, 2, rng)[1]
+    mw = rng.uniform(-0.5, 1.0, wl.morphs.count).astype(np.float32)
+    skin64 = orc.skin_matrices(world, wl.invBind, np.float64)
+    morph = (wl.morphs.offsets, wl.morphs.vertexIndex, wl.morphs.delta)
+    sd = (wl.sdef.vertexIndex, wl.sdef.c_r0_r1)
+    for m, s_ in ((morph, None), (None, sd), (morph, sd)):
+        po, no = orc.deform(wl.vtx8, wl.joints, wl.weights, skin64, morph=m, morphW=mw if m else None, sdef=s_, dtype=np.float64)
+        pn, nn = numpy_morph_sdef_f64(wl.vtx8, wl.joints, wl.weights, skin64, morph=m, morphW=mw if m else None, sdef=s_)
+        assert rel_err(po, pn) < 1e-9 and rel_err(no, nn) < 1e-9, (m is not None, s_ is not None, rel_err(po, pn), rel_err(no, nn))
+    assert wl.sdef.vertexIndex.size > 50 and wl.morphs.vertexIndex.size > 50
+
+
 def test_oracle_morph_and_sdef_reduce_to_pinned_path(orc):
     wl = synth.make_workload(2000, 32, M=6, sdef=True)
     world = synth.make_palettes(wl.bones, 1, np.random.default_rng(9))[0]
