@@ -801,6 +801,11 @@ def test_gpu_pose_evaluation_local_rotations(rzlib, orc):
         b.parentIndex = i - 1
     inv2 = compute_inverse_bind(wl2.bones)
     cases.append((wl2.bones, wl2.vtx8, wl2.joints, wl2.weights, inv2))
+    # more bones than threads: the ping-pong path of the pointer-jumping kernel (1500) and, beyond its shared-memory budget,
+    # the chain-walk fallback (2600)
+    for nb in (1500, 2600):
+        wl3 = synth.make_workload(800, nb, seed=nb)
+        cases.append((wl3.bones, wl3.vtx8, wl3.joints, wl3.weights, wl3.invBind))
     for bones, vtx, J, W, inv in cases:
         B, P = len(bones), 5
         qa, qb, _ = synth.make_crowd_tween(B, P, rng)
