@@ -235,6 +235,10 @@ int32_t rz_plan_morph_rows(const uint32_t* laneVertex /* Vp */, uint32_t Vp, uin
                            const uint32_t* vertIdx, const float* delta3, uint32_t M, uint32_t* rowFirst /* Vp/32 */,
                            uint32_t* rowDepth /* Vp/32 */, uint8_t* morphMajor /* Vp/32 */, float* rows, uint64_t rowsCapacity,
                            uint64_t* rowsNeeded);
+/* The bank-aware palette permutation rz_load_mesh applies: bonePos[b] = palette row of bone b, chosen so
+ * that bones gathered by the same warp instruction sit in different 16-byte bank groups.  laneJoints as returned by
+ * rz_plan_lanes. */
+int32_t rz_plan_palette_rows(const uint16_t* laneJoints /* Vp*4 */, uint32_t Vp, uint32_t B, uint32_t* bonePos /* B */);
 /* The SDEF records and per-warp descriptor lists rz_load_sdef builds, device-free: records receives 12
  * floats per evaluated SDEF vertex (C, c0, c1, w0, w1, then the two bone ids as one u32: j0 | j1 << 16 — palette rows once a
  * mesh is loaded), desc [Vp] the descriptor word of every lane (table index | output slot << 24, 0xFFFFFFFF = none),

@@ -34,7 +34,7 @@ EXPORTS = [
     "rz_read_skin_matrices", "rz_get_stats", "rz_last_error",
     "rz_load_edge_size", "rz_get_output_layout", "rz_read_outline", "rz_read_interleaved",
     "rz_plan_morph_rows", "rz_plan_chunks", "rz_read_instance_async", "rz_read_wait",
-    "rz_load_rigid_bodies", "rz_apply_body_transforms", "rz_plan_sdef",
+    "rz_load_rigid_bodies", "rz_apply_body_transforms", "rz_plan_sdef", "rz_plan_palette_rows",
 ]
 
 
@@ -118,6 +118,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.rz_plan_lanes.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp, vp]
     lib.rz_plan_morph_rows.argtypes = [vp, u32, u32, vp, vp, vp, u32, vp, vp, vp, vp, C.c_uint64, P(C.c_uint64)]
     lib.rz_plan_chunks.argtypes = [vp, u32, u32, u32, vp, P(u32)]
+    lib.rz_plan_palette_rows.argtypes = [vp, u32, u32, vp]
     lib.rz_plan_sdef.argtypes = [vp, u32, vp, vp, u32, u32, vp, vp, u32, vp, vp, P(u32)]
     lib.rz_read_bounds.argtypes = [vp, u32, u32, vp]
     lib.rz_read_skinning.argtypes = [vp, vp, vp]
@@ -179,6 +180,17 @@ def plan_morph_rows(lane_vertex, V: int, offsets, vert_idx, delta3, lib: Optiona
     if st != 0:
         raise RzError(st, (lib.rz_last_error(None) or b"").decode())
     return dict(first=first, depth=depth, morphMajor=mm, rows=rows)
+
+
+def plan_palette_rows(lane_joints, B: int, lib: Optional[C.CDLL] = None) -> np.ndarray:
+    """Device-free: the bank-aware palette permutation for the gather table `lane_joints` [Vp,4] (rz_plan_palette_rows)."""
+    lib = lib or load_library()
+    lj = _arr(lane_joints, np.uint16).reshape(-1)
+    pos = np.zeros(B, np.uint32)
+    st = lib.rz_plan_palette_rows(_ptr(lj), lj.size // 4, B, _ptr(pos))
+    if st != 0:
+        raise RzError(st, (lib.rz_last_error(None) or b"").decode())
+    return pos
 
 
 def plan_sdef(lane_vertex, joints, weights, B: int, sdef_vert_idx, c_r0_r1, lib: Optional[C.CDLL] = None) -> dict:

@@ -1585,6 +1585,16 @@ int32_t rz_plan_morph_rows(const uint32_t* laneVertex, uint32_t Vp, uint32_t V, 
   return RZ_OK;
 }
 
+int32_t rz_plan_palette_rows(const uint16_t* laneJoints, uint32_t Vp, uint32_t B, uint32_t* bonePos) {
+  if (!laneJoints || Vp == 0 || Vp % 32 || B == 0 || !bonePos) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_plan_palette_rows: bad argument");
+  for (size_t i = 0; i < (size_t)Vp * 4; ++i)
+    if (laneJoints[i] >= B) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_plan_palette_rows: joint %u >= B=%u", (unsigned)laneJoints[i], B);
+  std::vector<uint32_t> pos;
+  plan_palette_rows(laneJoints, Vp, B, 1, 0, pos);
+  memcpy(bonePos, pos.data(), (size_t)B * 4);
+  return RZ_OK;
+}
+
 int32_t rz_plan_sdef(const uint32_t* laneVertex, uint32_t Vp, const uint16_t* joints, const uint8_t* weights, uint32_t V,
                      uint32_t B, const uint32_t* sdefVertIdx, const float* c_r0_r1, uint32_t n, float* records, uint32_t* desc, uint32_t* nActive) {
   if (!laneVertex || Vp == 0 || Vp % 32 || !joints || !weights || V == 0 || B == 0)

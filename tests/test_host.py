@@ -381,6 +381,30 @@ def test_morph_rows_hold_every_entry_once_in_pmx_order(rzlib):
         capi.plan_morph_rows(lv, V, offs, vidx + V, deltas, rzlib)
 
 
+def test_palette_permutation_spreads_co_gathered_bones_over_bank_groups(rzlib):
+    """rz_plan_palette_rows: a permutation of the bones under which the rows one warp instruction gathers collide less in the
+    eight 16-byte bank groups (row r of palette position q lives in group (3q + r) mod 8) than under the identity."""
+    wl = synth.make_workload(20000, 256, seed=5)
+    plan = capi.plan_lanes(wl.joints, wl.weights, wl.B, 2, rzlib)
+    lj = np.asarray(plan["laneJoints"], np.int64).reshape(-1, 32, 4)
+    pos = capi.plan_palette_rows(plan["laneJoints"], wl.B, rzlib).astype(np.int64)
+    assert sorted(pos.tolist()) == list(range(wl.B))
+
+    def collisions(perm):
+        total = 0
+        for k in range(4):
+            rows = perm[lj[:, :, k]]                                   # [warps, 32] palette positions gathered by slot k
+            for w in range(rows.shape[0]):
+                u = np.unique(rows[w])
+                total += int((np.bincount((3 * u) % 8, minlength=8) - 1).clip(min=0).sum())
+        return total
+    ident = np.arange(wl.B)
+    c_id, c_perm = collisions(ident), collisions(pos)
+    assert c_perm < 0.8 * c_id, (c_id, c_perm)
+    with pytest.raises(capi.RzError):
+        capi.plan_palette_rows(np.full((256, 4), wl.B, np.uint16), wl.B, rzlib)
+
+
 def test_sdef_tables_and_descriptors(rzlib):
     """rz_plan_sdef (the table builder of rz_load_sdef, device-free): one record per two-influence SDEF vertex with the
     load-time constants of SURVEY 8c, weights normalised like the reference's shader, and per warp a dense descriptor list
