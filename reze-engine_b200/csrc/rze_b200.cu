@@ -722,7 +722,7 @@ int32_t rz_set_palettes(rz_ctx* c, const float* world, uint32_t P, const uint32_
   // PIPELINED: blocks of ~16 MB go out on the copy stream, each followed by an event; rz_deform then alternates
   // "wait for block b, skin matrices of block b, deform the instances of block b", so the PCIe transfer of block b+1
   // overlaps the deform of block b instead of preceding the whole frame (measured: 4.6 -> 2.9 ms at K=4096, B=512).
-  static const bool noPipe = getenv("RZ_NO_PIPELINE") != nullptr;
+  const bool noPipe = getenv("RZ_NO_PIPELINE") != nullptr;        // (per call: the tests flip it inside one process)
   const size_t palBytes = (size_t)c->B * 64;
   uint32_t blk = (uint32_t)std::max<size_t>(64, ((size_t)16 << 20) / palBytes);
   if (const char* eb = getenv("RZ_PIPELINE_BLOCK")) blk = (uint32_t)std::max(1, atoi(eb));   // palettes per block (tests)
