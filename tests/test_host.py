@@ -271,6 +271,38 @@ def test_bench_reference_arm_prints_one_contract_line(orc):
     assert r["config"]["V"] == 3000 and r["config"]["K_per_gpu"] == 16 and "workload" in r["config"]
 
 
+def test_header_is_plain_c_and_matches_the_ctypes_mirrors(tmp_path):
+    """include/rze_b200.h is the drop-in boundary: it must compile as plain C99 (what cgo / N-API / ctypes generators consume),
+    and the struct layouts the Python mirror declares must be the compiler's."""
+    import ctypes as C
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text('''
+#include <stdio.h>
+#include <stddef.h>
+#include "rze_b200.h"
+int main(void) {
+  printf("%zu %zu %zu ", sizeof(rz_config), sizeof(rz_stats), sizeof(rz_output_layout));
+  printf("%zu %zu %zu %zu ", offsetof(rz_config, stream), offsetof(rz_config, tune_ctas_per_sm), offsetof(rz_stats, frames), offsetof(rz_stats, fastGatherPermille));
+  printf("%zu %zu %zu\\n", offsetof(rz_output_layout, vertexStride), offsetof(rz_output_layout, hullOffset), offsetof(rz_output_layout, uvOffset));
+  printf("%u %u %u %u %u %u %u %d\\n", RZ_FLAG_SDEF, RZ_FLAG_NO_NORMALS, RZ_FLAG_BOUNDS, RZ_FLAG_REORDER_VERTICES, RZ_FLAG_OUTLINE,
+         RZ_FLAG_INTERLEAVED, RZ_FLAG_DOUBLE_BUFFER, RZE_B200_ABI_VERSION);
+  return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    nums = [int(x) for x in out]
+    assert nums[:3] == [C.sizeof(capi.RzConfig), C.sizeof(capi.RzStats), C.sizeof(capi.RzOutputLayout)]
+    assert nums[3:7] == [capi.RzConfig.stream.offset, capi.RzConfig.tune_ctas_per_sm.offset, capi.RzStats.frames.offset,
+                         capi.RzStats.fastGatherPermille.offset]
+    assert nums[7:10] == [capi.RzOutputLayout.vertexStride.offset, capi.RzOutputLayout.hullOffset.offset, capi.RzOutputLayout.uvOffset.offset]
+    assert nums[10:17] == [capi.RZ_FLAG_SDEF, capi.RZ_FLAG_NO_NORMALS, capi.RZ_FLAG_BOUNDS, capi.RZ_FLAG_REORDER_VERTICES, capi.RZ_FLAG_OUTLINE,
+                           capi.RZ_FLAG_INTERLEAVED, capi.RZ_FLAG_DOUBLE_BUFFER]
+    assert nums[17] == 2
+
+
 def test_capi_exports_every_declared_symbol(rzlib):
     from reze_engine_b200 import capi
     hdr = open(os.path.join(ROOT, "include", "rze_b200.h")).read()
