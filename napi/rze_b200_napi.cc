@@ -6,8 +6,8 @@
 //
 // NOT BUILT IN THIS IMAGE: no Node.js / node_api.h exists here or on the GPU box, so this file is
 // compiled only where <node_api.h> is available:
-//     g++ -O2 -fPIC -shared -I$(node -p "require('node-addon-api').include_dir") -Iinclude napi/rze_b200_napi.cc \
-//         -Lreze-engine_b200/lib -lrze_b200 -o rze_b200.node
+//     g++ -O2 -fPIC -shared -I$(node -p "require('node-addon-api').include_dir") -Iinclude napi/rze_b200_napi.cc
+//         -Lreze-engine_b200/lib -lrze_b200 -o rze_b200.node          (one command line)
 // The tested boundary is the C ABI itself (tests/ drive it through ctypes with the same argument marshalling).
 #if __has_include(<node_api.h>)
 #include <node_api.h>

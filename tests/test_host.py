@@ -303,6 +303,21 @@ int main(void) {
     assert nums[17] == 2
 
 
+def test_napi_shim_type_checks_against_the_c_abi(rzlib, tmp_path):
+    """napi/rze_b200_napi.cc cannot be linked or run here (no Node.js), but it must at least COMPILE: against a minimal
+    stand-in for <node_api.h> (tests/mock_node_api, public N-API signatures) and the real include/rze_b200.h, warnings as
+    errors; and every rz_* symbol it references must be exported by the library."""
+    import subprocess
+    obj = tmp_path / "shim.o"
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-fPIC", "-c", "-I", os.path.join(ROOT, "tests", "mock_node_api"),
+                    "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "napi", "rze_b200_napi.cc"), "-o", str(obj)], check=True)
+    syms = subprocess.run(["nm", "-u", str(obj)], capture_output=True, text=True, check=True).stdout.split()
+    used = sorted({x for x in syms if x.startswith("rz_")})
+    assert len(used) >= 18 and set(used) <= set(capi.EXPORTS), set(used) - set(capi.EXPORTS)
+    defined = subprocess.run(["nm", "--defined-only", str(obj)], capture_output=True, text=True, check=True).stdout
+    assert "napi_register_module_v1" in defined
+
+
 def test_capi_exports_every_declared_symbol(rzlib):
     from reze_engine_b200 import capi
     hdr = open(os.path.join(ROOT, "include", "rze_b200.h")).read()
