@@ -63,3 +63,16 @@ def apply_bodies_to_bones(world, bone_index, dynamic, offset_inverse, body_posit
             w[b] = v
             written += 1
     return written
+
+
+def bodies_from_model(model):
+    """The arrays rz_load_rigid_bodies wants, from a loaded Model (Model.getRigidbodies(), pmx-loader.ts:603-690):
+    (bone_index int32[n], dynamic uint8[n] = RigidbodyType.Dynamic, body_offset float32[n,16], body_offset_inverse float32[n,16])."""
+    rbs = model.getRigidbodies()
+    n = len(rbs)
+    bone_index = np.array([int(r["boneIndex"]) for r in rbs], np.int32).reshape(n)
+    dynamic = np.array([1 if int(r["type"]) == 1 else 0 for r in rbs], np.uint8).reshape(n)
+    pos = np.array([r["shapePosition"] for r in rbs], np.float64).reshape(n, 3)
+    rot = np.array([r["shapeRotation"] for r in rbs], np.float64).reshape(n, 3)
+    off, inv = compute_body_offsets(model.getBoneInverseBindMatrices(), bone_index, pos, rot)
+    return bone_index, dynamic, off, inv

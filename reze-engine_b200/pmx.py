@@ -16,8 +16,10 @@ over them) and vertex/group morphs (pmx-loader.ts:450-553 walks and discards
 them).  Morph strides follow the PMX 2.0 spec (bone morph 7 floats, UV morph 4
 floats) so files containing those types stay in sync.
 
-Sections after the morphs (display frames, rigid bodies, joints) belong to
-physics/UI and are not read: out of scope.
+Sections after the morphs: display frames are stepped over, rigid bodies and
+joints are kept as the reference's records (pmx-loader.ts:555-789) -- the solver
+that consumes them is out of scope, but the rigid bodies feed the
+physics -> bone feedback plumbing (physics_bridge.py, rz_load_rigid_bodies).
 """
 from __future__ import annotations
 
@@ -99,11 +101,21 @@ class PmxLoader:
         materials = self.parseMaterials()
         bones = self.parseBones()
         morphs = self.parseMorphs(vtx.shape[0])
+        # display frames are stepped over, rigid bodies and joints kept (pmx-loader.ts:42-48, 555-789): they feed the
+        # physics -> bone feedback (physics_bridge.py); soft failures leave the lists empty like the reference's try/catch
+        rigidbodies, pjoints = [], []
+        try:
+            if self.skipDisplayFrames():
+                rigidbodies = self.parseRigidbodies()
+                pjoints = self.parseJoints()
+        except (PmxFormatError, struct.error, IndexError, ValueError):
+            pass
         invBind = compute_inverse_bind(bones)
         finalize_skinning(joints, weights, len(bones))
         skeleton = Skeleton(bones=bones, inverseBindMatrices=invBind)
         return Model(vtx.reshape(-1), indices, textures, materials, skeleton,
-                     Skinning(joints=joints, weights=weights), morphs=morphs, sdef=sdef, clock=clock)
+                     Skinning(joints=joints, weights=weights), rigidbodies=rigidbodies, joints=pjoints, morphs=morphs, sdef=sdef,
+                     clock=clock)
 
     # ---- primitive readers (pmx-loader.ts:965-1053) ------------------------------------
     def _need(self, n: int):
@@ -335,6 +347,74 @@ class PmxLoader:
             bones.append(Bone(name=name, parentIndex=parent, bindTranslation=bt, appendParentIndex=ap,
                               appendRatio=ar, appendRotate=arot, appendMove=amov))
         return bones
+
+    def skipDisplayFrames(self) -> bool:
+        """pmx-loader.ts:555-601: name, english name, flag, then n x (u8 kind + bone | morph index)."""
+        if self.offset + 4 > len(self.buf):
+            return False
+        count = self.i32()
+        if count < 0 or count > 100000:
+            self.offset -= 4
+            return False
+        for _ in range(count):
+            self.text()
+            self.text()
+            self.u8()
+            n = self.i32()
+            for _j in range(n):
+                kind = self.u8()
+                if kind == 0:
+                    self.index(self.boneIndexSize)
+                elif kind == 1:
+                    self.index(self.morphIndexSize)
+        return True
+
+    def parseRigidbodies(self) -> list:
+        """pmx-loader.ts:603-690: the reference's Rigidbody records (model.ts:52-70 field names).  type 0 static, 1 dynamic
+        (the only ones that drive bones, physics.ts:729), 2 kinematic; rotations are ZXY Euler angles in radians."""
+        if self.offset + 4 > len(self.buf):
+            return []
+        count = self.i32()
+        if count < 0 or count > 10000:
+            return []
+        out = []
+        for _ in range(count):
+            if self.offset >= len(self.buf):
+                break
+            name = self.text()
+            englishName = self.text()
+            boneIndex = self.index(self.boneIndexSize)
+            group = self.u8()
+            collisionMask = self.u16()
+            shape = self.u8()
+            f = [self.f32() for _k in range(14)]
+            rtype = self.u8()
+            out.append(dict(name=name, englishName=englishName, boneIndex=boneIndex, group=group, collisionMask=collisionMask, shape=shape,
+                            size=f[0:3], shapePosition=f[3:6], shapeRotation=f[6:9], mass=f[9], linearDamping=f[10],
+                            angularDamping=f[11], restitution=f[12], friction=f[13], type=rtype))
+        return out
+
+    def parseJoints(self) -> list:
+        """pmx-loader.ts:692-789: 6-DoF spring joints between two rigid bodies (indices use rigidBodyIndexSize)."""
+        if self.offset + 4 > len(self.buf):
+            return []
+        count = self.i32()
+        if count < 0 or count > 10000:
+            return []
+        out = []
+        for _ in range(count):
+            if self.offset >= len(self.buf):
+                break
+            name = self.text()
+            englishName = self.text()
+            jtype = self.u8()
+            a = self.index(self.rigidBodyIndexSize)
+            b = self.index(self.rigidBodyIndexSize)
+            f = [self.f32() for _k in range(24)]
+            out.append(dict(name=name, englishName=englishName, type=jtype, rigidbodyIndexA=a, rigidbodyIndexB=b, position=f[0:3],
+                            rotation=f[3:6], positionMin=f[6:9], positionMax=f[9:12], rotationMin=f[12:15], rotationMax=f[15:18],
+                            springPosition=f[18:21], springRotation=f[21:24]))
+        return out
 
     def parseMorphs(self, vertexCount: int) -> VertexMorphs:
         """Vertex (type 1) and group (type 0) morphs; layout as documented by the

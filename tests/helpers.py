@@ -139,8 +139,36 @@ class PmxWriter:
                     self.idx(it[0], self.vs, signed=False)
                     self.b += struct.pack("<4f", *([0.0] * 4))
 
-    def tail(self):
-        self.b += struct.pack("<iii", 0, 0, 0)  # display frames, rigid bodies, joints
+    def tail(self, display=(), bodies=(), joints=()):
+        """Display frames (name, flag, elements (kind 0 bone | 1 morph, index)), rigid bodies and joints: the sections after the
+        morphs as pmx-loader.ts:555-789 reads them.  rbs = rigid-body index size."""
+        rbs = getattr(self, "rbs", 1)
+        self.b += struct.pack("<i", len(display))
+        for name, elems in display:
+            self.text(name)
+            self.text("")
+            self.b += bytes([0]) + struct.pack("<i", len(elems))
+            for kind, index in elems:
+                self.b += bytes([kind])
+                self.idx(index, self.bs if kind == 0 else self.ms)
+        self.b += struct.pack("<i", len(bodies))
+        for rb in bodies:
+            self.text(rb["name"])
+            self.text("")
+            self.idx(rb["boneIndex"], self.bs)
+            self.b += bytes([rb["group"]]) + struct.pack("<H", rb["collisionMask"]) + bytes([rb["shape"]])
+            self.b += struct.pack("<14f", *rb["size"], *rb["shapePosition"], *rb["shapeRotation"], rb["mass"], rb["linearDamping"],
+                                  rb["angularDamping"], rb["restitution"], rb["friction"])
+            self.b += bytes([rb["type"]])
+        self.b += struct.pack("<i", len(joints))
+        for jt in joints:
+            self.text(jt["name"])
+            self.text("")
+            self.b += bytes([jt["type"]])
+            self.idx(jt["rigidbodyIndexA"], rbs)
+            self.idx(jt["rigidbodyIndexB"], rbs)
+            self.b += struct.pack("<24f", *jt["position"], *jt["rotation"], *jt["positionMin"], *jt["positionMax"], *jt["rotationMin"],
+                                  *jt["rotationMax"], *jt["springPosition"], *jt["springRotation"])
 
     def bytes(self) -> bytes:
         return bytes(self.b)
@@ -213,7 +241,15 @@ def random_pmx(rng, V=300, B=12, n_morph=3, with_sdef=True, **kw):
         morphs.append(dict(name="bonem", type=2, items=[(0, None)]))
         morphs.append(dict(name="uvm", type=3, items=[(0, None), (1, None)]))
     w.morphs(morphs)
-    w.tail()
+    f3 = lambda: [float(np.float32(x)) for x in rng.normal(size=3)]
+    bodies = [dict(name=f"rb{i}", boneIndex=int(rng.integers(-1, B)), group=int(rng.integers(0, 16)), collisionMask=int(rng.integers(0, 65536)),
+                   shape=int(rng.integers(0, 3)), size=f3(), shapePosition=f3(), shapeRotation=f3(), mass=float(np.float32(rng.uniform(0, 2))),
+                   linearDamping=0.5, angularDamping=0.25, restitution=0.0, friction=0.5, type=int(rng.integers(0, 3))) for i in range(5)]
+    pjoints = [dict(name=f"j{i}", type=0, rigidbodyIndexA=int(rng.integers(-1, 5)), rigidbodyIndexB=int(rng.integers(0, 5)), position=f3(), rotation=f3(),
+                    positionMin=f3(), positionMax=f3(), rotationMin=f3(), rotationMax=f3(), springPosition=f3(), springRotation=f3()) for i in range(3)]
+    w.tail(display=[("Root", [(0, 0)]), ("表情", [(1, 0), (1, 1), (0, 2)])], bodies=bodies, joints=pjoints)
+    w.rigid = (bodies, pjoints)
+    random_pmx.last_rigid = (bodies, pjoints)
     return w.bytes(), verts, bones, morphs
 
 

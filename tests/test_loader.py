@@ -106,6 +106,76 @@ def test_finalize_skinning_matches_oracle(orc):
     assert (s == 255).mean() > 0.99          # the reference's own fix-ups leave rare non-255 rows; we match them
 
 
+def test_rigid_bodies_and_joints_roundtrip():
+    """The sections after the morphs (pmx-loader.ts:555-789): display frames are stepped over, rigid bodies and joints come back
+    field for field, and the reader ends exactly at the end of the file."""
+    from reze_engine_b200.pmx import PmxLoader as L
+    rng = np.random.default_rng(8)
+    for kw in (dict(), dict(encoding=1, bone_index_size=1), dict(bone_index_size=4, morph_index_size=2)):
+        data, *_ = random_pmx(rng, V=120, B=9, **kw)
+        bodies, joints = random_pmx.last_rigid
+        ld = L(data)
+        m = ld.parse()
+        assert ld.offset == len(data)
+        got = m.getRigidbodies()
+        assert len(got) == len(bodies) and len(m.getJoints()) == len(joints)
+        for g, w in zip(got, bodies):
+            for k in ("name", "boneIndex", "group", "collisionMask", "shape", "type"):
+                assert g[k] == w[k], k
+            for k in ("size", "shapePosition", "shapeRotation"):
+                assert np.allclose(g[k], w[k], rtol=0, atol=0)
+            assert g["mass"] == w["mass"] and g["friction"] == w["friction"]
+        for g, w in zip(m.getJoints(), joints):
+            assert (g["rigidbodyIndexA"], g["rigidbodyIndexB"], g["type"]) == (w["rigidbodyIndexA"], w["rigidbodyIndexB"], w["type"])
+            assert np.allclose(g["springRotation"], w["springRotation"], rtol=0, atol=0) and np.allclose(g["position"], w["position"], rtol=0, atol=0)
+    # a file cut inside the rigid-body table still loads (the reference catches and keeps what it has: pmx-loader.ts:676-684)
+    m = L(data[:-200]).parse()
+    assert m.getVertexCount() == 120
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_ROOT), reason="reference assets not mounted")
+def test_shipped_models_rigid_body_tables():
+    """塞尔凯特.pmx / 塞尔凯特2.pmx / 武器.pmx: 349 / 257 / 0 rigid bodies (SURVEY appendix A probe), all attached to existing bones,
+    joints between existing bodies, and the parser consumes the file to its last byte."""
+    import glob
+    from reze_engine_b200.pmx import PmxLoader as L
+    want = {28789: (349, 553), 28842: (257, 406), 2095: (0, 0)}
+    seen = 0
+    for f in glob.glob(os.path.join(REF_ROOT, "web", "public", "models", "*", "*.pmx")):
+        with open(f, "rb") as fh:
+            data = fh.read()
+        ld = L(data)
+        m = ld.parse()
+        rb, jt = m.getRigidbodies(), m.getJoints()
+        assert (len(rb), len(jt)) == want[m.getVertexCount()]
+        assert ld.offset == len(data)
+        B = len(m.getSkeleton().bones)
+        assert all(-1 <= r["boneIndex"] < B and r["type"] in (0, 1, 2) and r["shape"] in (0, 1, 2) for r in rb)
+        assert all(-1 <= j["rigidbodyIndexA"] < len(rb) and -1 <= j["rigidbodyIndexB"] < len(rb) for j in jt)
+        seen += 1
+    assert seen == 3
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_ROOT), reason="reference assets not mounted")
+def test_shipped_model_bodies_at_rest_reproduce_the_bind_pose():
+    """physics.ts:560-585 + 714-751 on the real rig: a dynamic body that sits exactly where its bind shape is
+    (shapePosition / shapeRotation) must hand its bone the bone's own bind-pose world matrix back."""
+    from reze_engine_b200 import physics_bridge as pb
+    from reze_engine_b200.math3d import Mat4, Quat, Vec3
+    m = PmxLoader.load(os.path.join(REF_ROOT, "web/public/models/塞尔凯特2/塞尔凯特2.pmx"))
+    bone_index, dynamic, off, inv = pb.bodies_from_model(m)
+    assert dynamic.sum() == 236 and bone_index.size == 257
+    m.evaluatePose()                                               # T-pose
+    world = np.asarray(m.getBoneWorldMatrices(), np.float32).reshape(-1, 16).copy()
+    before = world.copy()
+    rbs = m.getRigidbodies()
+    pos = np.array([r["shapePosition"] for r in rbs], np.float64)
+    quat = np.array([Quat.fromEuler(*r["shapeRotation"]).toArray() for r in rbs], np.float64)
+    wrote = pb.apply_bodies_to_bones(world, bone_index, dynamic, inv, pos, quat)
+    assert wrote == int(((dynamic == 1) & (bone_index >= 0)).sum()) and wrote >= 200      # a few dynamic bodies hang on no bone
+    assert np.abs(world - before).max() < 2e-4                     # f32 products of translations up to ~20 units
+
+
 def test_synthetic_pmx_roundtrip_all_weight_types(orc):
     rng = np.random.default_rng(3)
     for kw in (dict(), dict(encoding=1, vertex_index_size=1, bone_index_size=1), dict(vertex_index_size=4, bone_index_size=4, extra_vec4=2)):
