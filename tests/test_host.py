@@ -377,6 +377,60 @@ def test_lane_plan_preserves_every_influence_and_packs_pairs(rzlib, mode):
         assert plan["total"] == 0
 
 
+def test_lane_plan_properties_on_adversarial_tables(rzlib):
+    """hypothesis: arbitrary tiny skinning tables (one bone, duplicate bones, all-zero weights, sums != 255, ragged vertex
+    counts) through rz_plan_lanes + rz_plan_palette_rows + rz_plan_morph_rows: never crash, every vertex evaluated exactly
+    once by a lane of its own 32-vertex warp, its non-zero shader-normalised influences preserved, palette rows a permutation,
+    every morph entry present once."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 130), st.integers(1, 9), st.integers(0, 2 ** 32 - 1), st.integers(0, 2))
+    def run(V, B, seed, mode):
+        rng = np.random.default_rng(seed)
+        J = rng.integers(0, B, (V, 4)).astype(np.uint16)
+        W = rng.integers(0, 256, (V, 4)).astype(np.uint8)
+        W[rng.random((V, 4)) < 0.45] = 0                          # many zero weights, some all-zero rows
+        plan = capi.plan_lanes(J, W, B, mode, rzlib)
+        lv, lj, lw = plan["laneVertex"], plan["laneJoints"], plan["laneWeights"]
+        real = lv != 0xFFFFFFFF
+        assert np.array_equal(np.sort(lv[real]), np.arange(V)) and lj.max() < B
+        wf = W.astype(np.float32) / np.float32(255.0)
+        ssum = (wf[:, 0] + wf[:, 1]) + wf[:, 2] + wf[:, 3]
+        for p in np.nonzero(real)[0]:
+            v = int(lv[p])
+            assert v // 32 == p // 32
+            if ssum[v] > 1e-4:
+                inv = np.float32(1.0) / ssum[v]
+                want = {}
+                for k in range(4):
+                    if wf[v, k] != 0:
+                        want.setdefault(int(J[v, k]), []).append(float(wf[v, k] * inv))
+            else:
+                want = {int(J[v, 0]): [1.0]}
+            got = {}
+            for s_ in range(4):
+                if lw[p, s_] != 0:
+                    got.setdefault(int(lj[p, s_]), []).append(float(lw[p, s_]))
+            assert {k: sorted(x) for k, x in want.items()} == {k: sorted(x) for k, x in got.items()}, (v, want, got)
+        pos = capi.plan_palette_rows(lj, B, rzlib)
+        assert sorted(pos.tolist()) == list(range(B))
+        M = int(rng.integers(0, 5))
+        offs, vi, dl = [0], [], []
+        for _m in range(M):
+            n = int(rng.integers(0, V + 1))
+            vi.append(rng.integers(0, V, n).astype(np.uint32))    # duplicates allowed
+            dl.append(rng.normal(0, 1, (n, 3)).astype(np.float32) + 3.0)      # (never exactly zero)
+            offs.append(offs[-1] + n)
+        vi = np.concatenate(vi) if vi else np.zeros(0, np.uint32)
+        dl = np.concatenate(dl) if dl else np.zeros((0, 3), np.float32)
+        r = capi.plan_morph_rows(lv, V, np.array(offs, np.uint32), vi, dl, rzlib)
+        rows = r["rows"]
+        assert int((np.abs(rows[:, :3]).sum(axis=1) > 0).sum()) == vi.size
+        assert abs(float(rows[:, :3].sum()) - float(dl.sum())) <= 1e-3 * max(1.0, float(np.abs(dl).sum()))
+    run()
+
+
 def test_morph_rows_hold_every_entry_once_in_pmx_order(rzlib):
     """rz_plan_morph_rows (the table builder rz_load_morphs uses, device-free): every (vertex, morph, delta) of the caller's
     table sits in exactly one row entry of the lane that evaluates the vertex, rows of a lane ascend in morph id, everything
