@@ -564,6 +564,20 @@ def test_chunk_table_balances_morph_cost(rzlib):
     assert capi.plan_chunks(np.zeros(5, np.uint32), 2, 50, rzlib).tolist() == [0, 2, 4, 5]
 
 
+def test_chunk_table_properties(rzlib):
+    """hypothesis: any depth profile, pass width and chunk target give a strictly increasing table from 0 to nTiles whose inner
+    boundaries are multiples of the pass width and that never has more chunks than asked for."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.lists(st.integers(0, 40), min_size=1, max_size=300), st.integers(1, 4), st.integers(1, 400))
+    def run(depth, tpp, target):
+        tab = capi.plan_chunks(np.array(depth, np.uint32), tpp, target, rzlib).astype(np.int64)
+        assert tab[0] == 0 and tab[-1] == len(depth) and (np.diff(tab) > 0).all()
+        assert (tab[:-1] % tpp == 0).all() and tab.size - 1 <= max(1, min(target, (len(depth) + tpp - 1) // tpp))
+    run()
+
+
 def test_lane_plan_rejects_bad_tables(rzlib):
     from reze_engine_b200 import capi
     with pytest.raises(capi.RzError):
