@@ -21,6 +21,64 @@ struct LanePlan {
   uint32_t hist[5][5] = {};           // packed warps by [slot count N][mixed slots m*]
 };
 
+// Maximum matching in a general graph on at most MAXN nodes (Edmonds' blossom algorithm, O(n^3)): the lane planners ask
+// "is there a PERFECT matching whose every pair satisfies a threshold?" for increasing thresholds (bottleneck matching).
+template <int MAXN>
+struct BlossomMatcher {
+  int n = MAXN;
+  bool adj[MAXN][MAXN];
+  int match[MAXN], par[MAXN], base[MAXN], q[2 * MAXN];
+  bool used[MAXN], blossom[MAXN];
+  int lca(int a, int b2) {
+    bool seen[MAXN] = {false};
+    for (;;) { a = base[a]; seen[a] = true; if (match[a] < 0) break; a = par[match[a]]; }
+    for (;;) { b2 = base[b2]; if (seen[b2]) return b2; b2 = par[match[b2]]; }
+  }
+  void mark_path(int v, int bb, int child) {
+    while (base[v] != bb) {
+      blossom[base[v]] = blossom[base[match[v]]] = true;
+      par[v] = child; child = match[v]; v = par[match[v]];
+    }
+  }
+  int find_path(int root) {
+    for (int i = 0; i < n; ++i) { used[i] = false; par[i] = -1; base[i] = i; }
+    int qh = 0, qt = 0;
+    used[root] = true; q[qt++] = root;
+    while (qh < qt) {
+      const int v = q[qh++];
+      for (int to = 0; to < n; ++to) {
+        if (!adj[v][to] || base[v] == base[to] || match[v] == to) continue;
+        if (to == root || (match[to] >= 0 && par[match[to]] >= 0)) {
+          const int cb = lca(v, to);
+          for (int i = 0; i < n; ++i) blossom[i] = false;
+          mark_path(v, cb, to); mark_path(to, cb, v);
+          for (int i = 0; i < n; ++i)
+            if (blossom[base[i]]) { base[i] = cb; if (!used[i]) { used[i] = true; q[qt++] = i; } }
+        } else if (par[to] < 0) {
+          par[to] = v;
+          if (match[to] < 0) return to;
+          used[match[to]] = true; q[qt++] = match[to];
+        }
+      }
+    }
+    return -1;
+  }
+  // maximum matching; returns the number of matched pairs
+  int solve() {
+    for (int i = 0; i < n; ++i) match[i] = -1;
+    for (int i = 0; i < n; ++i)                       // greedy start: nearest unmatched neighbour in key order
+      if (match[i] < 0) for (int j = i + 1; j < n; ++j) if (match[j] < 0 && adj[i][j]) { match[i] = j; match[j] = i; break; }
+    for (int i = 0; i < n; ++i)
+      if (match[i] < 0) {
+        int v = find_path(i);
+        while (v >= 0) { const int pv = par[v], ppv = match[pv]; match[v] = pv; match[pv] = v; v = ppv; }
+      }
+    int m = 0;
+    for (int i = 0; i < n; ++i) if (match[i] >= 0) ++m;
+    return m / 2;
+  }
+};
+
 // JT [V][4] joints, WT [V][4] unorm8 weights, isSdef [V] or nullptr, kTileVerts = tile granularity the vertex count is
 // padded to.  permMode: 0 natural lane order, 1 lanes sorted by (influence count, bones), 2 pair packing.
 inline void plan_lanes(const uint16_t* JT, const uint8_t* WT, const uint8_t* isSdef, uint32_t V, uint32_t B, uint32_t tileVerts,
@@ -115,60 +173,7 @@ inline void plan_lanes(const uint16_t* JT, const uint8_t* WT, const uint8_t* isS
   // one slot list, each with weight 0 where the bone is not its own).  The warp needs a perfect matching of its 32 lanes
   // minimising the largest m (bottleneck matching: thresholds 0..N, Edmonds' blossom algorithm for each); the mixed slots
   // of all pairs are then parked in the LAST m* slots, so N - m* gather instructions of the warp run at the fast rate.
-  struct PairMatcher {
-    int n = 32;
-    bool adj[32][32];
-    int match[32], par[32], base[32], q[64];
-    bool used[32], blossom[32];
-    int lca(int a, int b2) {
-      bool seen[32] = {false};
-      for (;;) { a = base[a]; seen[a] = true; if (match[a] < 0) break; a = par[match[a]]; }
-      for (;;) { b2 = base[b2]; if (seen[b2]) return b2; b2 = par[match[b2]]; }
-    }
-    void mark_path(int v, int bb, int child) {
-      while (base[v] != bb) {
-        blossom[base[v]] = blossom[base[match[v]]] = true;
-        par[v] = child; child = match[v]; v = par[match[v]];
-      }
-    }
-    int find_path(int root) {
-      for (int i = 0; i < n; ++i) { used[i] = false; par[i] = -1; base[i] = i; }
-      int qh = 0, qt = 0;
-      used[root] = true; q[qt++] = root;
-      while (qh < qt) {
-        const int v = q[qh++];
-        for (int to = 0; to < n; ++to) {
-          if (!adj[v][to] || base[v] == base[to] || match[v] == to) continue;
-          if (to == root || (match[to] >= 0 && par[match[to]] >= 0)) {
-            const int cb = lca(v, to);
-            for (int i = 0; i < n; ++i) blossom[i] = false;
-            mark_path(v, cb, to); mark_path(to, cb, v);
-            for (int i = 0; i < n; ++i)
-              if (blossom[base[i]]) { base[i] = cb; if (!used[i]) { used[i] = true; q[qt++] = i; } }
-          } else if (par[to] < 0) {
-            par[to] = v;
-            if (match[to] < 0) return to;
-            used[match[to]] = true; q[qt++] = match[to];
-          }
-        }
-      }
-      return -1;
-    }
-    // maximum matching; returns the number of matched pairs
-    int solve() {
-      for (int i = 0; i < n; ++i) match[i] = -1;
-      for (int i = 0; i < n; ++i)                       // greedy start: nearest unmatched neighbour in key order
-        if (match[i] < 0) for (int j = i + 1; j < n; ++j) if (match[j] < 0 && adj[i][j]) { match[i] = j; match[j] = i; break; }
-      for (int i = 0; i < n; ++i)
-        if (match[i] < 0) {
-          int v = find_path(i);
-          while (v >= 0) { const int pv = par[v], ppv = match[pv]; match[v] = pv; match[pv] = v; v = ppv; }
-        }
-      int m = 0;
-      for (int i = 0; i < n; ++i) if (match[i] >= 0) ++m;
-      return m / 2;
-    }
-  };
+  using PairMatcher = BlossomMatcher<32>;
   struct LaneSet { uint32_t v; int n; uint16_t b[4]; float w[4]; uint8_t src[4]; uint64_t key; };
   uint64_t packStat[5] = {0, 0, 0, 0, 0};   // warp-slots: total, fast
   auto fill_packed = [&](uint32_t w0) -> bool {
