@@ -235,6 +235,15 @@ int32_t rz_plan_morph_rows(const uint32_t* laneVertex /* Vp */, uint32_t Vp, uin
                            const uint32_t* vertIdx, const float* delta3, uint32_t M, uint32_t* rowFirst /* Vp/32 */,
                            uint32_t* rowDepth /* Vp/32 */, uint8_t* morphMajor /* Vp/32 */, float* rows, uint64_t rowsCapacity,
                            uint64_t* rowsNeeded);
+/* GROUNDWORK, not used by this round's kernel: the lane plan for TWO vertices per lane.  Windows of 64
+ * consecutive vertices become one group of 32 lanes x 2 vertices sharing one list of <= 4 palette rows per lane (groupPaired = 1)
+ * or, where no such pairing exists, two ordinary groups of 32 lanes x 1 vertex.  Per group: first output vertex, vertex count;
+ * per lane (group*32 + lane): the two vertices (0xFFFFFFFF = none), the four rows it gathers, the shader-normalised weight of
+ * every row for vertex A and for vertex B (0 where the row is not that vertex' bone).  stats[4]: gather instructions on the
+ * fast path, all gather instructions, paired windows, fallback windows.  Call with every output NULL to learn *nGroups. */
+int32_t rz_plan_lanes2(const uint16_t* joints, const uint8_t* weights, uint32_t V, uint32_t B, uint32_t groupCapacity,
+                       uint32_t* groupFirst, uint32_t* groupCount, uint8_t* groupPaired, uint32_t* laneVertA, uint32_t* laneVertB,
+                       uint16_t* laneJoints, float* laneWeightsA, float* laneWeightsB, uint64_t* stats, uint32_t* nGroups);
 /* The bank-aware palette permutation rz_load_mesh applies: bonePos[b] = palette row of bone b, chosen so
  * that bones gathered by the same warp instruction sit in different 16-byte bank groups.  laneJoints as returned by
  * rz_plan_lanes. */

@@ -49,7 +49,7 @@ def _run(cmd, log):
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJDIR, exist_ok=True)
     nvcc = _nvcc()
-    hdrs = [os.path.join(CSRC, h) for h in ("deform_kernel.cuh", "kernel_table.h", "aux_kernels.cuh", "lane_plan.h", "mesh_tables.h")]
+    hdrs = [os.path.join(CSRC, h) for h in ("deform_kernel.cuh", "kernel_table.h", "aux_kernels.cuh", "lane_plan.h", "lane_plan2.h", "mesh_tables.h")]
     hdrs.append(os.path.join(os.path.dirname(HERE), "include", "rze_b200.h"))
     jobs = []
     objs = []

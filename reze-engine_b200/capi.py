@@ -34,7 +34,7 @@ EXPORTS = [
     "rz_read_skin_matrices", "rz_get_stats", "rz_last_error",
     "rz_load_edge_size", "rz_get_output_layout", "rz_read_outline", "rz_read_interleaved",
     "rz_plan_morph_rows", "rz_plan_chunks", "rz_read_instance_async", "rz_read_wait",
-    "rz_load_rigid_bodies", "rz_apply_body_transforms", "rz_plan_sdef", "rz_plan_palette_rows",
+    "rz_load_rigid_bodies", "rz_apply_body_transforms", "rz_plan_sdef", "rz_plan_palette_rows", "rz_plan_lanes2",
 ]
 
 
@@ -119,6 +119,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.rz_plan_morph_rows.argtypes = [vp, u32, u32, vp, vp, vp, u32, vp, vp, vp, vp, C.c_uint64, P(C.c_uint64)]
     lib.rz_plan_chunks.argtypes = [vp, u32, u32, u32, vp, P(u32)]
     lib.rz_plan_palette_rows.argtypes = [vp, u32, u32, vp]
+    lib.rz_plan_lanes2.argtypes = [vp, vp, u32, u32, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, P(u32)]
     lib.rz_plan_sdef.argtypes = [vp, u32, vp, vp, u32, u32, vp, vp, u32, vp, vp, P(u32)]
     lib.rz_read_bounds.argtypes = [vp, u32, u32, vp]
     lib.rz_read_skinning.argtypes = [vp, vp, vp]
@@ -180,6 +181,29 @@ def plan_morph_rows(lane_vertex, V: int, offsets, vert_idx, delta3, lib: Optiona
     if st != 0:
         raise RzError(st, (lib.rz_last_error(None) or b"").decode())
     return dict(first=first, depth=depth, morphMajor=mm, rows=rows)
+
+
+def plan_lanes2(joints, weights, B: int, lib: Optional[C.CDLL] = None) -> dict:
+    """rz_plan_lanes2 (groundwork for two vertices per lane, device-free): groups of 32 lanes covering up to 64 vertices."""
+    lib = lib or load_library()
+    j, w = _arr(joints, np.uint16).reshape(-1, 4), _arr(weights, np.uint8).reshape(-1, 4)
+    V = j.shape[0]
+    n = C.c_uint32(0)
+    stats = np.zeros(4, np.uint64)
+    st = lib.rz_plan_lanes2(_ptr(j), _ptr(w), V, B, 0, None, None, None, None, None, None, None, None, _ptr(stats), C.byref(n))
+    if st != 0:
+        raise RzError(st, (lib.rz_last_error(None) or b"").decode())
+    G = n.value
+    out = dict(groupFirst=np.zeros(G, np.uint32), groupCount=np.zeros(G, np.uint32), groupPaired=np.zeros(G, np.uint8),
+               vertA=np.zeros(G * 32, np.uint32), vertB=np.zeros(G * 32, np.uint32), laneJoints=np.zeros((G * 32, 4), np.uint16),
+               wA=np.zeros((G * 32, 4), np.float32), wB=np.zeros((G * 32, 4), np.float32))
+    st = lib.rz_plan_lanes2(_ptr(j), _ptr(w), V, B, G, _ptr(out["groupFirst"]), _ptr(out["groupCount"]), _ptr(out["groupPaired"]),
+                            _ptr(out["vertA"]), _ptr(out["vertB"]), _ptr(out["laneJoints"]), _ptr(out["wA"]), _ptr(out["wB"]), _ptr(stats),
+                            C.byref(n))
+    if st != 0:
+        raise RzError(st, (lib.rz_last_error(None) or b"").decode())
+    out.update(fast=int(stats[0]), total=int(stats[1]), pairedWindows=int(stats[2]), fallbackWindows=int(stats[3]))
+    return out
 
 
 def plan_palette_rows(lane_joints, B: int, lib: Optional[C.CDLL] = None) -> np.ndarray:

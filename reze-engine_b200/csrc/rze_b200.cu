@@ -10,6 +10,7 @@
 #include "aux_kernels.cuh"
 #include "kernel_table.h"
 #include "lane_plan.h"
+#include "lane_plan2.h"
 #include "mesh_tables.h"
 
 #include <algorithm>
@@ -1582,6 +1583,30 @@ int32_t rz_plan_morph_rows(const uint32_t* laneVertex, uint32_t Vp, uint32_t V, 
     if (rowsCapacity < mr.rows.size()) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_plan_morph_rows: rows buffer too small");
     memcpy(rows, mr.rows.data(), mr.rows.size() * 16);
   }
+  return RZ_OK;
+}
+
+int32_t rz_plan_lanes2(const uint16_t* joints, const uint8_t* weights, uint32_t V, uint32_t B, uint32_t groupCapacity, uint32_t* groupFirst,
+                       uint32_t* groupCount, uint8_t* groupPaired, uint32_t* laneVertA, uint32_t* laneVertB, uint16_t* laneJoints,
+                       float* laneWeightsA, float* laneWeightsB, uint64_t* stats, uint32_t* nGroups) {
+  if (!joints || !weights || V == 0 || B == 0 || !nGroups) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_plan_lanes2: null or empty tables");
+  for (size_t i = 0; i < (size_t)V * 4; ++i)
+    if (joints[i] >= B) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_plan_lanes2: joint %u >= B=%u", (unsigned)joints[i], B);
+  LanePlan2 plan;
+  plan_lanes2(joints, weights, V, B, plan);
+  *nGroups = plan.nGroups;
+  if (stats) { stats[0] = plan.fastSlots; stats[1] = plan.slots; stats[2] = plan.pairedWindows; stats[3] = plan.fallbackWindows; }
+  if (!groupFirst && !laneVertA) return RZ_OK;              // size query
+  if (groupCapacity < plan.nGroups) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_plan_lanes2: room for %u groups, need %u", groupCapacity, plan.nGroups);
+  const size_t L = (size_t)plan.nGroups * 32;
+  if (groupFirst) memcpy(groupFirst, plan.groupFirst.data(), (size_t)plan.nGroups * 4);
+  if (groupCount) memcpy(groupCount, plan.groupCount.data(), (size_t)plan.nGroups * 4);
+  if (groupPaired) memcpy(groupPaired, plan.groupPaired.data(), plan.nGroups);
+  if (laneVertA) memcpy(laneVertA, plan.vertA.data(), L * 4);
+  if (laneVertB) memcpy(laneVertB, plan.vertB.data(), L * 4);
+  if (laneJoints) memcpy(laneJoints, plan.gatherJ.data(), L * 8);
+  if (laneWeightsA) memcpy(laneWeightsA, plan.wA.data(), L * 16);
+  if (laneWeightsB) memcpy(laneWeightsB, plan.wB.data(), L * 16);
   return RZ_OK;
 }
 

@@ -377,6 +377,76 @@ def test_lane_plan_preserves_every_influence_and_packs_pairs(rzlib, mode):
         assert plan["total"] == 0
 
 
+def _check_plan2(J, W, B, r):
+    V = J.shape[0]
+    gf, gc, gp = r["groupFirst"].astype(np.int64), r["groupCount"].astype(np.int64), r["groupPaired"]
+    assert gf[0] == 0 and np.array_equal(gf[1:], (gf + gc)[:-1]) and gf[-1] + gc[-1] == V          # groups tile the vertex range
+    assert (gc[gp == 1] <= 64).all() and (gc[gp == 0] <= 32).all() and (gc > 0).all()
+    wf = W.astype(np.float32) / np.float32(255.0)
+    ssum = (wf[:, 0] + wf[:, 1]) + wf[:, 2] + wf[:, 3]
+    seen = np.zeros(V, np.int64)
+    lj = r["laneJoints"]
+    assert lj.max() < B
+    for side, wkey in (("vertA", "wA"), ("vertB", "wB")):
+        vv, ww = r[side], r[wkey]
+        for p in np.nonzero(vv != 0xFFFFFFFF)[0]:
+            v, g = int(vv[p]), p // 32
+            assert gf[g] <= v < gf[g] + gc[g]                                                        # outputs of a group are contiguous
+            assert side == "vertA" or gp[g] == 1
+            seen[v] += 1
+            if ssum[v] > 1e-4:
+                inv = np.float32(1.0) / ssum[v]
+                want = sorted((int(J[v, k]), float(wf[v, k] * inv)) for k in range(4) if wf[v, k] != 0)
+            else:
+                want = [(int(J[v, 0]), 1.0)]
+            got = sorted((int(lj[p, k]), float(ww[p, k])) for k in range(4) if ww[p, k] != 0)
+            assert want == got, (v, want, got)
+    assert (seen == 1).all()
+    none = (r["vertA"] == 0xFFFFFFFF)
+    assert (r["vertB"][none] == 0xFFFFFFFF).all() and not r["wA"][none].any() and not r["wB"][none].any()
+
+
+def test_two_vertices_per_lane_plan(rzlib):
+    """rz_plan_lanes2 (groundwork for the next kernel generation): every vertex evaluated exactly once, by a lane of the group
+    that owns its 64-vertex window; both vertices of a lane find all their (bone, weight) pairs among the lane's four rows;
+    and on the benchmark mesh the plan needs a third fewer gather instructions than today's, most of them on the fast path."""
+    wl = synth.make_workload(20_000, 256, seed=6)
+    J, W = wl.joints.reshape(-1, 4).copy(), wl.weights.reshape(-1, 4).copy()
+    W[7] = 0                                            # weight sum 0
+    J[200], W[200] = (3, 3, 9, 0), (100, 55, 100, 0)    # a bone listed twice: its window falls back to one vertex per lane
+    r = capi.plan_lanes2(J, W, wl.B, rzlib)
+    _check_plan2(J, W, wl.B, r)
+    g200 = int(np.searchsorted(r["groupFirst"], 200, side="right") - 1)
+    assert r["groupPaired"][g200] == 0
+    one = capi.plan_lanes(J, W, wl.B, 2, rzlib)
+    assert r["pairedWindows"] > 8 * r["fallbackWindows"]
+    assert r["total"] < 0.75 * one["total"] and r["fast"] > 0.85 * r["total"]
+    # fast-path accounting: aligned lane pairs of a packed group really gather the same row in that many slots
+    lj = r["laneJoints"].reshape(-1, 32, 4)
+    used = ((r["wA"] != 0) | (r["wB"] != 0)).reshape(-1, 32, 4)
+    coherent = 0
+    for g in range(lj.shape[0]):
+        n = int(max(1, used[g].any(axis=0).nonzero()[0].max(initial=0) + 1))
+        for s_ in range(n):
+            coherent += bool(np.all(lj[g, 0::2, s_] == lj[g, 1::2, s_]))
+    assert coherent >= r["fast"]
+
+
+def test_two_vertices_per_lane_plan_properties(rzlib):
+    """hypothesis: adversarial tiny tables through rz_plan_lanes2."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 200), st.integers(1, 9), st.integers(0, 2 ** 32 - 1))
+    def run(V, B, seed):
+        rng = np.random.default_rng(seed)
+        J = rng.integers(0, B, (V, 4)).astype(np.uint16)
+        W = rng.integers(0, 256, (V, 4)).astype(np.uint8)
+        W[rng.random((V, 4)) < 0.5] = 0
+        _check_plan2(J, W, B, capi.plan_lanes2(J, W, B, rzlib))
+    run()
+
+
 def test_lane_plan_properties_on_adversarial_tables(rzlib):
     """hypothesis: arbitrary tiny skinning tables (one bone, duplicate bones, all-zero weights, sums != 255, ragged vertex
     counts) through rz_plan_lanes + rz_plan_palette_rows + rz_plan_morph_rows: never crash, every vertex evaluated exactly

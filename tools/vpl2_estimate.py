@@ -119,6 +119,12 @@ def analyse(name, J, W, B):
                staging_cycles_per_64=24.0)
     t1, t2 = c1 / n64 + 24.0, c2 / n64 + 24.0
     row["lsu_cycles_per_64"] = dict(today=t1, two_per_lane=t2, saving=1 - t2 / t1)
+    # the real planner (csrc/lane_plan2.h: bottleneck blossom matching instead of the greedy pairing above)
+    r = capi.plan_lanes2(J, W, B)
+    c3 = r["fast"] * FAST + (r["total"] - r["fast"]) * SLOW
+    row["rz_plan_lanes2"] = dict(slot_gathers_per_64=r["total"] / n64, fast_share=r["fast"] / max(r["total"], 1), gather_cycles_per_64=c3 / n64,
+                                 paired_windows=r["pairedWindows"], fallback_windows=r["fallbackWindows"],
+                                 lsu_saving=1 - (c3 / n64 + 24.0) / t1)
     print(json.dumps(row))
     return row
 
