@@ -432,6 +432,42 @@ def test_two_vertices_per_lane_plan(rzlib):
     assert coherent >= r["fast"]
 
 
+def _emulate_lanes(vtx8, skin16, lane_vertex, lane_joints, lane_weights):
+    """What the deform kernel computes from a lane plan, in numpy f64: M = sum_s w_s * skin[row_s], pos = M [p,1], n = norm(M3 n)."""
+    M = np.asarray(skin16, np.float64).reshape(-1, 4, 4).transpose(0, 2, 1)[:, :3, :]           # [B,3,4]
+    vt = np.asarray(vtx8, np.float64).reshape(-1, 8)
+    V = vt.shape[0]
+    pos, nrm = np.full((V, 3), np.nan), np.full((V, 3), np.nan)
+    real = np.nonzero(lane_vertex != 0xFFFFFFFF)[0]
+    v = lane_vertex[real].astype(np.int64)
+    Mb = np.einsum("ls,lsrc->lrc", lane_weights[real].astype(np.float64), M[lane_joints[real].astype(np.int64)])
+    pos[v] = np.einsum("lrc,lc->lr", Mb[:, :, :3], vt[v, :3]) + Mb[:, :, 3]
+    n = np.einsum("lrc,lc->lr", Mb[:, :, :3], vt[v, 3:6])
+    ln = np.linalg.norm(n, axis=1, keepdims=True)
+    nrm[v] = np.where(ln > 0, n / np.where(ln > 0, ln, 1), 0)
+    return pos, nrm
+
+
+def test_lane_plans_reproduce_the_blend_when_emulated(rzlib, orc):
+    """End-to-end check of the load-time plans without a GPU: the arithmetic the kernel performs on a plan (blend the gathered
+    rows with the lane's weights, transform) equals the oracle's blend -- for today's plan (all three modes) and for the
+    two-vertices-per-lane groundwork plan."""
+    wl = synth.make_workload(6000, 64, seed=12)
+    J, W = wl.joints.reshape(-1, 4), wl.weights.reshape(-1, 4)
+    world = synth.make_palettes(wl.bones, 1, np.random.default_rng(12))[0]
+    skin = orc.skin_matrices(world, wl.invBind, np.float64)
+    rp, rn = orc.deform(wl.vtx8, wl.joints, wl.weights, skin, dtype=np.float64)
+    for mode in (0, 1, 2):
+        pl = capi.plan_lanes(J, W, wl.B, mode, rzlib)
+        gp, gn = _emulate_lanes(wl.vtx8, skin, pl["laneVertex"], pl["laneJoints"], pl["laneWeights"])
+        assert rel_err(gp, rp) < 2e-6 and rel_err(gn, rn) < 2e-6, mode        # (the lane weights are f32)
+    p2 = capi.plan_lanes2(J, W, wl.B, rzlib)
+    pa, na = _emulate_lanes(wl.vtx8, skin, p2["vertA"], p2["laneJoints"], p2["wA"])
+    pb, nb = _emulate_lanes(wl.vtx8, skin, p2["vertB"], p2["laneJoints"], p2["wB"])
+    gp, gn = np.where(np.isnan(pa), pb, pa), np.where(np.isnan(na), nb, na)
+    assert not np.isnan(gp).any() and rel_err(gp, rp) < 2e-6 and rel_err(gn, rn) < 2e-6
+
+
 def test_two_vertices_per_lane_plan_properties(rzlib):
     """hypothesis: adversarial tiny tables through rz_plan_lanes2."""
     from hypothesis import given, settings, strategies as st
