@@ -468,6 +468,41 @@ def test_lane_plans_reproduce_the_blend_when_emulated(rzlib, orc):
     assert not np.isnan(gp).any() and rel_err(gp, rp) < 2e-6 and rel_err(gn, rn) < 2e-6
 
 
+def test_morph_rows_reproduce_the_morphed_positions_when_emulated(rzlib, orc):
+    """The per-warp morph rows, applied the way the kernel applies them (row by row: p += w[morph] * delta in f32, PMX morph
+    order, padding rows adding exact zeros), give the oracle's morphed positions to the last ulp or two (the kernel fuses the
+    multiply-add, the f32 oracle rounds twice)."""
+    wl = synth.make_workload(4000, 32, M=12, seed=14)
+    rng = np.random.default_rng(14)
+    mw = rng.uniform(-0.5, 1.0, wl.morphs.count).astype(np.float32)
+    J, W = wl.joints.reshape(-1, 4), wl.weights.reshape(-1, 4)
+    lv = capi.plan_lanes(J, W, wl.B, 2, rzlib)["laneVertex"]
+    r = capi.plan_morph_rows(lv, wl.V, wl.morphs.offsets, wl.morphs.vertexIndex, wl.morphs.delta, rzlib)
+    P = wl.vtx8.reshape(-1, 8)[:, :3].astype(np.float32).copy()
+    for w in range(lv.size // 32):
+        d = int(r["depth"][w])
+        if not d:
+            continue
+        block = r["rows"][r["first"][w]:r["first"][w] + d * 32].reshape(d, 32, 4)
+        ids = block[:, :, 3].copy().view(np.uint32)
+        for l in range(32):
+            v = int(lv[w * 32 + l])
+            if v == 0xFFFFFFFF:
+                continue
+            p = P[v].copy()
+            for u in range(d):
+                p = (mw[ids[u, l]] * block[u, l, :3] + p).astype(np.float32)
+            P[v] = p
+    # oracle with an identity palette: positions = morphed positions (f32 oracle: p = p + w * d, two roundings; fma has one:
+    # compare within 1 ulp of the position magnitude)
+    ident = np.tile(np.eye(4, dtype=np.float32).T.reshape(1, 16), (wl.B, 1))
+    rp, _ = orc.deform(wl.vtx8, wl.joints, wl.weights, ident, morph=(wl.morphs.offsets, wl.morphs.vertexIndex, wl.morphs.delta), morphW=mw)
+    touched = np.unique(wl.morphs.vertexIndex)
+    assert np.abs(P[touched] - rp[touched]).max() <= 4e-6 and touched.size > 100
+    untouched = np.setdiff1d(np.arange(wl.V), touched)
+    assert np.array_equal(P[untouched], wl.vtx8.reshape(-1, 8)[untouched, :3])
+
+
 def test_two_vertices_per_lane_plan_properties(rzlib):
     """hypothesis: adversarial tiny tables through rz_plan_lanes2."""
     from hypothesis import given, settings, strategies as st
