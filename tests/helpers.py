@@ -346,3 +346,48 @@ def numpy_morph_sdef_f64(vtx8, joints, weights, skin16, morph=None, morphW=None,
             ln = np.linalg.norm(n)
             nrm[v] = n / ln if ln > 0 else 0
     return pos, nrm
+
+
+def sdef_from_record(rec, M, p, n):
+    """Evaluate ONE SDEF vertex from its 12-float device record (C, c0, c1, w0, w1, rows j0 | j1 << 16) the way the kernel's dense
+    phase does, in f64: q = slerp(quat(M0), quat(M1), w1), pos = R(q)(p - C) + w0 M0 c0 + w1 M1 c1, n = normalize(R(q) n).
+    M: [B,4,4] row-major skin matrices."""
+    C, c0, c1 = rec[0:3].astype(np.float64), rec[3:6].astype(np.float64), rec[6:9].astype(np.float64)
+    w0, w1 = float(rec[9]), float(rec[10])
+    rows = int(rec[11:12].view(np.uint32)[0])
+    M0, M1 = M[rows & 0xFFFF], M[rows >> 16]
+
+    def quat_of(m):
+        m00, m01, m02, m10, m11, m12, m20, m21, m22 = m[0, 0], m[0, 1], m[0, 2], m[1, 0], m[1, 1], m[1, 2], m[2, 0], m[2, 1], m[2, 2]
+        tr = m00 + m11 + m22
+        if tr > 0:
+            s_ = np.sqrt(tr + 1.0) * 2
+            q = np.array([(m21 - m12) / s_, (m02 - m20) / s_, (m10 - m01) / s_, 0.25 * s_])
+        elif m00 > m11 and m00 > m22:
+            s_ = np.sqrt(1.0 + m00 - m11 - m22) * 2
+            q = np.array([0.25 * s_, (m01 + m10) / s_, (m02 + m20) / s_, (m21 - m12) / s_])
+        elif m11 > m22:
+            s_ = np.sqrt(1.0 + m11 - m00 - m22) * 2
+            q = np.array([(m01 + m10) / s_, 0.25 * s_, (m12 + m21) / s_, (m02 - m20) / s_])
+        else:
+            s_ = np.sqrt(1.0 + m22 - m00 - m11) * 2
+            q = np.array([(m02 + m20) / s_, (m12 + m21) / s_, 0.25 * s_, (m10 - m01) / s_])
+        return q / np.linalg.norm(q)
+    a, b = quat_of(M0), quat_of(M1)
+    c = float(a @ b)
+    if c < 0:
+        c, b = -c, -b
+    if c > 0.9995:
+        q = a + w1 * (b - a)
+        q /= np.linalg.norm(q)
+    else:
+        th0 = np.arccos(c)
+        q = (np.sin(th0 - th0 * w1) * a + np.sin(th0 * w1) * b) / np.sin(th0)
+    x, y, z, w = q
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                  [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                  [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+    pos = R @ (p - C) + w0 * (M0[:3, :3] @ c0 + M0[:3, 3]) + w1 * (M1[:3, :3] @ c1 + M1[:3, 3])
+    nn = R @ n
+    ln = np.linalg.norm(nn)
+    return pos, (nn / ln if ln > 0 else nn * 0)

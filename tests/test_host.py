@@ -503,6 +503,31 @@ def test_morph_rows_reproduce_the_morphed_positions_when_emulated(rzlib, orc):
     assert np.array_equal(P[untouched], wl.vtx8.reshape(-1, 8)[untouched, :3])
 
 
+def test_sdef_records_reproduce_the_spherical_blend_when_emulated(rzlib, orc):
+    """The 48-byte SDEF records + per-warp descriptors, evaluated the way the kernel's dense phase does, give the oracle's SDEF
+    result for exactly the vertices the descriptors name (every SDEF vertex once)."""
+    from helpers import sdef_from_record
+    wl = synth.make_workload(3000, 40, sdef=True, seed=15)
+    J, W = wl.joints.reshape(-1, 4), wl.weights.reshape(-1, 4)
+    world = synth.make_palettes(wl.bones, 1, np.random.default_rng(15))[0]
+    skin = orc.skin_matrices(world, wl.invBind, np.float64)
+    M = skin.reshape(-1, 4, 4).transpose(0, 2, 1)
+    rp, rn = orc.deform(wl.vtx8, wl.joints, wl.weights, skin, sdef=(wl.sdef.vertexIndex, wl.sdef.c_r0_r1), dtype=np.float64)
+    lv = capi.plan_lanes(J, W, wl.B, 2, rzlib)["laneVertex"]
+    r = capi.plan_sdef(lv, J, W, wl.B, wl.sdef.vertexIndex, wl.sdef.c_r0_r1, rzlib)
+    vt = wl.vtx8.reshape(-1, 8).astype(np.float64)
+    done = []
+    for w0 in range(0, lv.size, 32):
+        for word in r["desc"][w0:w0 + 32]:
+            if word == 0xFFFFFFFF:
+                break
+            idx, v = int(word) & 0xFFFFFF, w0 + (int(word) >> 24)
+            pos, nrm = sdef_from_record(r["records"][idx], M, vt[v, :3], vt[v, 3:6])
+            assert np.abs(pos - rp[v]).max() <= 1e-5 and np.abs(nrm - rn[v]).max() <= 1e-6, (v, np.abs(pos - rp[v]).max())
+            done.append(v)
+    assert sorted(done) == sorted(wl.sdef.vertexIndex.tolist()) and len(done) > 100
+
+
 def test_two_vertices_per_lane_plan_properties(rzlib):
     """hypothesis: adversarial tiny tables through rz_plan_lanes2."""
     from hypothesis import given, settings, strategies as st
