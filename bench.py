@@ -22,7 +22,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -47,57 +46,89 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+_SAMPLER_SRC = r"""
+import sys, time
+idx, out = int(sys.argv[1]), sys.argv[2]
+import pynvml as nv
+nv.nvmlInit()
+h = nv.nvmlDeviceGetHandleByIndex(idx)
+mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+with open(out, "w", buffering=1) as f:
+    f.write("ready %f\n" % time.time())
+    while True:
+        sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        try:
+            pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+        except Exception:
+            pw = float("nan")
+        f.write("%f %d %d %f %d\n" % (time.time(), sm, mx, pw, int(get_reasons(h))))
+        time.sleep(0.003)
+"""
+
+
 class ClockSampler:
     """SM clock / throttle-reason sampling DURING the timed region (B200_PROFILING.md clocks line).
-    NVML polled every ~2 ms from a thread (the timed region is tens of ms: `nvidia-smi -lms` is too coarse)."""
+
+    NVML is polled every ~3 ms by a SEPARATE PROCESS started at the very beginning of the bench (nvmlInit alone takes
+    longer than the whole 37 ms timed region, and a poller thread inside this process competes with the launch loop for
+    the GIL); every sample carries a wall-clock stamp and the parent keeps those that fall inside [mark_begin, mark_end]."""
 
     def __init__(self, index: int):
-        self.index = index
-        self.samples = []
-        self.stop_flag = False
-        self.thread = None
-        self.err = None
-
-    def _loop(self):
+        import tempfile
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[index]) if vis and index < len(vis.split(",")) and vis.split(",")[index].isdigit() else index
+        self.path = os.path.join(tempfile.gettempdir(), f"rz_clocks_{os.getpid()}_{index}.txt")
+        self.t0 = self.t1 = None
         try:
-            import pynvml as nv
-            nv.nvmlInit()
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
-            h = nv.nvmlDeviceGetHandleByIndex(idx)
-            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
-            while not self.stop_flag:
-                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
-                try:
-                    pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
-                except Exception:
-                    pw = float("nan")
-                self.samples.append((sm, mx, pw, int(get_reasons(h))))
-                time.sleep(0.002)
+            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, str(idx), self.path], stdout=subprocess.DEVNULL,
+                                         stderr=subprocess.DEVNULL)
         except Exception as e:  # noqa: BLE001
+            self.proc = None
             self.err = repr(e)
 
-    def start(self):
-        self.thread = threading.Thread(target=self._loop, daemon=True)
-        self.thread.start()
-        time.sleep(0.01)
+    def wait_ready(self, timeout=20.0):
+        t = time.time()
+        while self.proc and self.proc.poll() is None and time.time() - t < timeout:
+            try:
+                if open(self.path).readline().startswith("ready"):
+                    return True
+            except OSError:
+                pass
+            time.sleep(0.01)
+        return False
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
-        self.stop_flag = True
-        if self.thread:
-            self.thread.join(timeout=2)
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"nvml unavailable: {self.err}"]}
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:  # noqa: BLE001
+                self.proc.kill()
+        rows = []
+        try:
+            for ln in open(self.path):
+                f = ln.split()
+                if len(f) == 5:
+                    rows.append((float(f[0]), int(f[1]), int(f[2]), float(f[3]), int(f[4])))
+            os.unlink(self.path)
+        except OSError:
+            pass
+        inside = [r for r in rows if self.t0 is not None and self.t0 <= r[0] <= self.t1]
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"nvml sampler: {len(rows)} samples, none inside the timed region"]}
         bits = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
-        reasons = set()
-        for s in self.samples:
-            for b, n in bits.items():
-                if s[3] & b:
-                    reasons.add(n)
-        sm = [s[0] for s in self.samples]
-        return {"sm_mhz": float(np.median(sm)), "sm_min_mhz": float(min(sm)), "sm_max_mhz": float(self.samples[0][1]),
-                "power_w_max": float(np.nanmax([s[2] for s in self.samples])), "samples": len(sm), "reasons": sorted(reasons)}
+        reasons = sorted({n for r in inside for b, n in bits.items() if r[4] & b})
+        sm = [r[1] for r in inside]
+        return {"sm_mhz": float(np.median(sm)), "sm_min_mhz": float(min(sm)), "sm_max_mhz": float(inside[0][2]),
+                "power_w_max": float(np.nanmax([r[3] for r in inside])), "samples": len(sm), "reasons": reasons,
+                "how": "NVML polled every ~3 ms by a helper process; samples stamped inside the timed region"}
 
 
 def make_inputs(V, B, K, P, seed=None, first=0):
@@ -139,7 +170,7 @@ def run_reference(args):
         return
     V, B, K = args.verts, args.bones, args.instances
     threads = os.cpu_count() or 1
-    Pc = min(K, max(threads * 4, 64))
+    Pc = args.palettes or K                                   # same palette set as the b200 arm (one palette per instance)
     wl, world = make_inputs(V, B, K, Pc)
     rates, samples = [], None
     for i in range(args.warmup + args.steps):
@@ -153,7 +184,9 @@ def run_reference(args):
         "impl": "reference", "metric": "skinned_vertices_per_sec", "value": val, "unit": "verts/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": samples[1] * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(V, B, K), "V": V, "B": B, "K_per_gpu": K, "M": 0},
+        "config": {"workload": workload_name(V, B, K), "V": V, "B": B, "K_per_gpu": K, "P_per_gpu": Pc, "M": 0,
+                   "note": "CPU port of the reference arithmetic on ONE host's cores (rank 0 only under torchrun: at N GPUs the "
+                           "b200 arm is N GPUs against this one host); each step is a bounded sample of the K instances"},
         "cpu_baseline": {"value": val, "unit": "verts/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "verts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
@@ -197,6 +230,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the deform path has no CPU fallback")
+    sampler = ClockSampler(local_rank)                          # helper process: has seconds to get through nvmlInit
+    # N > 1: host threads + pinned staging next to this rank's GPU (N = 1 keeps every core for the CPU baseline)
+    numa = sharding.bind_to_gpu_numa(local_rank) if world_size > 1 else {"bound": False}
     torch.cuda.set_device(local_rank)
     if world_size > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -217,8 +253,6 @@ def main():
     ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
     d_world = torch.from_numpy(world).cuda()
     d_i2p = torch.from_numpy(i2p.astype(np.int64)).to(torch.int32).cuda() if i2p is not None else None
-    stage = ctx.palette_staging(P)
-    stage[:] = world
     torch.cuda.synchronize()
 
     def step_resident():
@@ -231,30 +265,41 @@ def main():
         torch.cuda.synchronize()
 
     # ---- value: resident inputs, device-timed ---------------------------------------------------------------
+    # A step = rz_set_palettes_device (marks the skin-matrix pass pending) + rz_deform, which replays the frame's CUDA graph
+    # [skin-matrix pass, counter reset, deform kernel]: one driver call per step.
     for _ in range(args.warmup):
         step_resident()
+    sampler.wait_ready()
     barrier()
     launches0 = ctx.stats()["kernelLaunches"]
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark_begin()
     t0.record()
     for s in range(args.steps):
-        ctx.set_palettes_device(d_world.data_ptr(), P, d_i2p.data_ptr() if d_i2p is not None else 0, K)
-        ev[s][0].record()
-        ctx.deform()
-        ev[s][1].record()
+        step_resident()
     t1.record()
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop()
-    total_ms = t0.elapsed_time(t1)
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    my_total_ms = t0.elapsed_time(t1)
     st = ctx.stats()
     launches = int(st["kernelLaunches"] - launches0)
-    total_ms = sharding.max_over_ranks(total_ms)               # device time, max over ranks
+    total_ms = sharding.max_over_ranks(my_total_ms)            # device time, max over ranks
     ms_per_step = total_ms / args.steps
     value = world_size * K * V / (ms_per_step * 1e-3)
+
+    # ---- the deform kernel alone (roofline): `steps` back-to-back rz_deform launches without a palette update, i.e. the
+    # graph [counter reset (4-byte memset), deform kernel]; CUDA events on the launching stream
+    ctx.deform()
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for s in range(args.steps):
+        ctx.deform()
+    k1.record()
+    torch.cuda.synchronize()
+    kernel_ms = k0.elapsed_time(k1) / args.steps
+    alg_bytes = ctx.stats()["algorithmicBytes"]
 
     # pinned destination of the per-step result read-back
     h_pos = torch.empty((V, 3), dtype=torch.float32, pin_memory=True).numpy()
@@ -272,10 +317,25 @@ def main():
             ctx.read_wait()                                     # step s-1 has landed
             ctx.read_instance_async(s % K, h_pos2 if s & 1 else h_pos, h_nrm2 if s & 1 else h_nrm)
 
-    # ---- e2e: host palettes -> H2D -> deform -> one instance back to the host, per step -------------------------
+    # ---- e2e_world_upload: host world matrices -> H2D -> deform -> one instance back to the host, per step ------------
+    # The producer protocol of the ABI is followed every step: rz_palette_staging (waits until the upload that last read
+    # the returned buffer has completed; two buffers alternate) and a host write into it before rz_set_palettes.  Both
+    # staging buffers hold the crowd's matrices; per step the host rewrites one palette (a real producer would rewrite all
+    # of them -- its pose evaluation is its own cost, not part of this path).
+    stages = []
     for _ in range(2):
+        st_ = ctx.palette_staging(P)
+        st_[:] = world
+        stages.append(st_)
+
+    def step_upload(s):
+        stage = ctx.palette_staging(P)
+        stage[s % P] = world[s % P]
         ctx.set_palettes(stage, i2p, K=K)
         ctx.deform()
+
+    for s in range(2):
+        step_upload(s)
         ctx.read_instance(0, out_pos=h_pos, out_nrm=h_nrm)
     barrier()
     wall0 = time.perf_counter()
@@ -283,14 +343,13 @@ def main():
     e0.record()
     esteps = max(3, min(args.steps, 20))
     for s in range(esteps):
-        ctx.set_palettes(stage, i2p, K=K)
-        ctx.deform()
+        step_upload(s)
         read_back(s)
     ctx.read_wait()
     e1.record()
     barrier()
-    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - wall0) * 1e3) / esteps
-    e2e_ms = sharding.max_over_ranks(e2e_ms)
+    e2e_ms_rank = max(e0.elapsed_time(e1), (time.perf_counter() - wall0) * 1e3) / esteps
+    e2e_ms = sharding.max_over_ranks(e2e_ms_rank)
     e2e_value = world_size * K * V / (e2e_ms * 1e-3)
     h2d = P * B * 64 + (K * 4 if i2p is not None else 0)
     d2h = V * 24
@@ -316,9 +375,29 @@ def main():
     ctx.read_wait()
     g1.record()
     barrier()
-    pose_ms = sharding.max_over_ranks(max(g0.elapsed_time(g1), (time.perf_counter() - wall0) * 1e3) / esteps)
+    pose_ms_rank = max(g0.elapsed_time(g1), (time.perf_counter() - wall0) * 1e3) / esteps
+    pose_ms = sharding.max_over_ranks(pose_ms_rank)
     pose_value = world_size * K * V / (pose_ms * 1e-3)
     pose_h2d = P * 4 + (K * 4 if i2p is not None else 0)
+
+    # ---- one-off: the WHOLE result of a frame copied to the host (what a host-side consumer of every instance would pay;
+    # the per-step legs above read ONE instance back because the stream is meant to stay on the device, engine.ts:270-274)
+    full = None
+    if rank == 0:
+        ctx.set_instance_clocks(clock_ms, i2p, K=K)
+        ctx.read_wait()
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        ctx.deform()
+        for k in range(K):
+            ctx.read_instance_async(k, h_pos2 if k & 1 else h_pos, h_nrm2 if k & 1 else h_nrm)
+            if k & 1:
+                ctx.read_wait()
+        ctx.read_wait()
+        torch.cuda.synchronize()
+        fms = (time.perf_counter() - w0) * 1e3
+        full = {"value": K * V / (fms * 1e-3), "unit": "verts/s", "ms_per_step": fms, "d2h_bytes_per_step": K * V * 24,
+                "path": "one frame: rz_deform + rz_read_instance_async of ALL %d instances into pinned host memory (PCIe-bound), measured once" % K}
 
     # ---- informational: the opt-in vertex reordering (RZ_FLAG_REORDER_VERTICES), same workload, deform kernel only ----
     reord = None
@@ -343,14 +422,14 @@ def main():
 
     # trivial result gather (the only collective): one small record per GPU
     if world_size > 1:
-        per_gpu = sharding.gather_records([float(K * V), kernel_ms, float(launches), K * V / (kernel_ms * 1e-3)])
+        per_gpu = sharding.gather_records([float(K * V), kernel_ms, float(launches), K * V / (kernel_ms * 1e-3), my_total_ms, e2e_ms_rank, pose_ms_rank])
         launches = int(sum(r[2] for r in per_gpu))
     else:
         per_gpu = None
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        alg = st["algorithmicBytes"]
+        alg = alg_bytes
         achieved = alg / (kernel_ms * 1e-3) / 1e9
         traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of one launch of THIS workload (ncu --set full), if captured
         tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -361,32 +440,39 @@ def main():
                     traffic = tj.get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        readback_path = ("rz_read_instance (blocking)" if args.single_buffer else
-                         "rz_read_instance_async of every step, collected one step later (RZ_FLAG_DOUBLE_BUFFER)")
+        readback_path = (("rz_read_instance (blocking)" if args.single_buffer else
+                          "rz_read_instance_async, collected one step later (RZ_FLAG_DOUBLE_BUFFER)") +
+                         f" of ONE of the {K} instances per step (2.4 MB of the {K * V * 24 / 1e9:.2f} GB result; the stream stays on the device, "
+                         "see e2e_full_readback for the whole result on the host)")
         out = {
             "metric": "skinned_vertices_per_sec", "value": value, "unit": "verts/s", "n_gpus": world_size, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(V, B, K), "V": V, "B": B, "K_per_gpu": K, "P_per_gpu": P, "M": 0,
                        "parallelism": f"instances sharded over {world_size} GPU(s), no data-path collective",
+                       "host_affinity": numa,
+                       "step": "rz_set_palettes_device + rz_deform = one CUDA graph launch [skin-matrix pass, counter reset, deform kernel]",
                        "l2": "no flush needed: each step writes K*V*24 B = %.2f GB >> 126 MB L2" % (K * V * 24 / 1e9),
                        "kernel": {"instances_per_group": st["instancesPerGroup"], "threads": st["threads"],
                                   "store_mode": {1: "direct st.global.cs", 2: "smem-staged TMA bulk store"}.get(st["storeMode"]),
                                   "ctas": st["ctas"], "smem_bytes": st["smemBytes"]}},
             "clocks": clocks,
             "e2e": {"value": pose_value, "unit": "verts/s", "ms_per_step": pose_ms, "h2d_bytes_per_step": pose_h2d, "d2h_bytes_per_step": d2h,
-                    "path": "rz_set_instance_clocks(host clocks; tween + bone hierarchy + skin matrices on the device) + rz_deform + " + readback_path},
+                    "path": "rz_set_instance_clocks(one host clock value per instance, 16 KB; tween + bone hierarchy + skin matrices evaluated on the device) + rz_deform + " + readback_path},
             "e2e_world_upload": {"value": e2e_value, "unit": "verts/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                                 "path": "rz_set_palettes(pinned host world matrices, as the reference uploads them; pipelined in blocks) + rz_deform + " + readback_path},
+                                 "path": "rz_palette_staging + rz_set_palettes(pinned host world matrices exactly as getBoneWorldMatrices() returns them, the reference's feed; uploaded in blocks pipelined against the deform) + rz_deform + " + readback_path},
+            "e2e_full_readback": full,
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "kernel": "rz::deform_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg},
+                         "peak_source": peak_src, "kernel": "rz::deform_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg,
+                         "kernel_ms_how": "mean of `steps` back-to-back rz_deform launches (graph: 4-byte counter reset + deform kernel) right after the timed region, CUDA events on the launching stream"},
         }
         if reord:
             reord["frac_of_hbm_peak"] = reord["algorithmic_GBs"] / peak
             out["reordered_vertices"] = reord
         if per_gpu:
-            out["per_gpu"] = [{"verts_per_step": r[0], "deform_kernel_ms": r[1], "launches": r[2], "verts_per_s_kernel": r[3]} for r in per_gpu]
+            out["per_gpu"] = [{"verts_per_step": r[0], "deform_kernel_ms": r[1], "launches": r[2], "verts_per_s_kernel": r[3],
+                               "total_ms": r[4], "e2e_world_upload_ms_per_step": r[5], "e2e_ms_per_step": r[6]} for r in per_gpu]
         if not args.no_cpu and world_size == 1:
             threads = os.cpu_count() or 1
             rate, Ks, dt = cpu_reference_rate(wl, world, K, args.cpu_seconds, threads)

@@ -133,10 +133,18 @@ int32_t rz_set_palettes(rz_ctx* ctx, const float* world, uint32_t P, const uint3
 /* (Large identity-mapped uploads are pipelined: the matrices travel in ~16 MB blocks on an internal copy stream and
  * rz_deform consumes them block by block — wait, skin matrices, deform that block's instances — so the PCIe transfer
  * overlaps the deform.  Results are bit-identical; environment RZ_NO_PIPELINE=1 disables it.) */
-/* same, `world` / `instToPalette` are device pointers on this context's device (zero-copy producers) */
+/* same, `world` / `instToPalette` are device pointers on this context's device (zero-copy producers).
+ * The skin-matrix pass over `d_world` is issued by the next rz_deform as part of that frame's CUDA graph (or by whichever
+ * other entry point needs the matrices first: rz_sync, rz_read_skin_matrices, rz_apply_body_transforms): keep `d_world`
+ * unchanged until then. */
 int32_t rz_set_palettes_device(rz_ctx* ctx, const float* d_world, uint32_t P, const uint32_t* d_instToPalette, uint32_t K);
-/* pinned host staging the caller may fill directly and pass to rz_set_palettes (saves one host copy);
- * valid until the next call that asks for a larger size or rz_destroy */
+/* Pinned host staging the caller fills directly and passes to rz_set_palettes / rz_set_local_rotations /
+ * rz_set_instance_clocks (saves one host copy; uploads from it are asynchronous).  OWNERSHIP: the library keeps TWO staging
+ * buffers and hands them out alternately; the call blocks until the upload that last read the buffer it returns has
+ * completed, so the producer refills one buffer while the other is still in flight.  Call it before EVERY refill — a
+ * pointer obtained earlier must not be written again (its upload may still be running).  A returned pointer stays valid
+ * until the second-next call or rz_destroy.  Arguments that do not point into a staging buffer are copied through
+ * library-owned pinned memory (never through the caller's staging). */
 int32_t rz_palette_staging(rz_ctx* ctx, size_t bytes, void** host_ptr);
 
 /* ---- GPU pose evaluation (replaces Model.evaluatePose, model.ts:325-328, + the palette upload for crowds) ----
@@ -260,7 +268,12 @@ int32_t rz_plan_sdef(const uint32_t* laneVertex /* Vp */, uint32_t Vp, const uin
 int32_t rz_plan_chunks(const uint32_t* tileDepth, uint32_t nTiles, uint32_t tilesPerPass, uint32_t nChunksTarget,
                        uint32_t* tab, uint32_t* nChunks);
 int32_t rz_read_bounds(rz_ctx* ctx, uint32_t firstInstance, uint32_t count, float* minmax6 /* 6*count */);
-/* bit-exact integer view of the tables the kernel consumes, mapped back to caller order (parity tests) */
+/* Integer view of the tables the KERNEL consumes, read back from the device records and mapped to caller order (parity
+ * tests): joints = the palette rows the kernel gathers mapped back to bone ids, weights = the kernel's pre-normalised f32
+ * weights (engine.ts:255-258 applied at load) re-quantised round(w*255).  Bit-identical to the input of rz_load_mesh
+ * whenever the weights of a vertex sum to 255 — the loader's invariant (pmx-loader.ts:892-938); for other inputs the
+ * NORMALISED weights come back (what the shader rule makes of them; all-zero -> 255,0,0,0).  Slots whose weight is zero
+ * gather a borrowed row on the device (they cannot influence the result); the caller's own joint index is reported there. */
 int32_t rz_read_skinning(rz_ctx* ctx, uint16_t* joints /* 4V */, uint8_t* weights /* 4V */);
 /* device-computed skin matrices of palette p as 3x4 row-major (12 floats per bone) */
 int32_t rz_read_skin_matrices(rz_ctx* ctx, uint32_t palette, float* skin3x4 /* 12*B */);

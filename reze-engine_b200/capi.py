@@ -322,7 +322,8 @@ class DeformContext:
 
     # -- per frame
     def palette_staging(self, P: int) -> np.ndarray:
-        """Pinned host buffer shaped [P, B, 16] the caller may fill and hand to set_palettes."""
+        """Pinned host buffer shaped [P, B, 16] the caller fills and hands to set_palettes.  Call it before EVERY refill: the
+        library alternates between two buffers and blocks until the upload that last read the returned one has completed."""
         nbytes = P * self.B * 64
         p = C.c_void_p()
         self._check(self.lib.rz_palette_staging(self.h, nbytes, C.byref(p)))

@@ -743,7 +743,9 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
     __syncthreads();   // everyone is done with this item's palettes before they are overwritten
   }
 
-  if (lane == 0) bulk_wait0();                           // staging must outlive the TMA reads
+  // staging must outlive the TMA reads.  Bulk groups are tracked per THREAD and elect.sync only promises a deterministic
+  // leader, not lane 0: every lane waits (a lane that committed no group returns at once)
+  bulk_wait0();
 }
 
 }  // namespace rz

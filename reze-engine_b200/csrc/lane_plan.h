@@ -9,6 +9,8 @@
 
 namespace rz {
 
+constexpr uint8_t kNoSlot = 0xFF;    // LanePlan::slotMap: the caller's influence has zero weight and occupies no device slot
+
 struct LanePlan {
   uint32_t V = 0, Vp = 0;
   std::vector<uint32_t> procVertex;   // [Vp] vertex evaluated by processing index p = warp*32 + lane (~0u: padding)
@@ -16,7 +18,7 @@ struct LanePlan {
   std::vector<uint16_t> gatherJ;      // [Vp][4] bone whose palette row influence slot s gathers (never out of range)
   std::vector<float> devW;            // [Vp][4] weight of slot s (shader-normalised, engine.ts:255-258)
   std::vector<uint8_t> devN;          // [Vp] highest slot with a non-zero weight + 1
-  std::vector<uint8_t> slotMap;       // [Vp][4] device slot that holds the caller's influence k
+  std::vector<uint8_t> slotMap;       // [Vp][4] device slot that holds the caller's influence k (kNoSlot: zero weight, none)
   uint64_t fastSlots = 0, totalSlots = 0;   // packed warps: gather instructions on the broadcast fast path / all
   uint32_t hist[5][5] = {};           // packed warps by [slot count N][mixed slots m*]
 };
@@ -274,7 +276,7 @@ inline void plan_lanes(const uint16_t* JT, const uint8_t* WT, const uint8_t* isS
         uint16_t* dj = &devJ[(size_t)p * 4];
         float* dw = &devW[(size_t)p * 4];
         uint8_t* sm = &out.slotMap[(size_t)p * 4];
-        for (int k = 0; k < 4; ++k) { dj[k] = kBorrow; dw[k] = 0.f; sm[k] = (uint8_t)k; }
+        for (int k = 0; k < 4; ++k) { dj[k] = kBorrow; dw[k] = 0.f; sm[k] = kNoSlot; }
         if (S.v == ~0u) {
           while (padSlot < 32 && slotUsed[padSlot]) ++padSlot;
           procVertex[p] = ~0u; procSlot[p] = padSlot; slotUsed[padSlot] = true;

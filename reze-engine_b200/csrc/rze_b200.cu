@@ -20,6 +20,7 @@
 #include <cstring>
 #include <cmath>
 #include <cstdlib>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -78,7 +79,7 @@ struct rz_ctx_impl {
   //   colorMode  1: bank-aware palette permutation (8-colouring of the bone co-occurrence graph); 0: identity
   //   layoutMode 0: palette rows of 48 B ([B][3] float4); 1: [3][B] float4 + co-occurrence clustering (measured slower)
   int permMode = 2, colorMode = 1, layoutMode = 0;       // vertex ordering inside a tile / bank-aware palette permutation
-  DevBuf d_rec0, d_rec1, d_rec2, d_meta, d_wbits, d_mrange, d_ments, d_sdefIdx, d_sdefTab, d_invBind;
+  DevBuf d_rec0, d_rec1, d_rec2, d_meta, d_mrange, d_ments, d_sdefIdx, d_sdefTab, d_invBind;
   uint32_t morphNnz = 0, sdefActive = 0;
   std::vector<uint32_t> tileMorphMax;     // [nTiles] most morph entries on one vertex of the tile (chunk balancing)
   DevBuf d_chunkTab;
@@ -87,7 +88,7 @@ struct rz_ctx_impl {
 
   // skeleton for GPU pose evaluation
   bool haveSkeleton = false, haveTweens = false, haveAnimation = false;
-  DevBuf d_trStart, d_trMs, d_trQ;
+  DevBuf d_trStart, d_trMs, d_trQ, d_trRest;
   uint32_t nLevels = 0;
   DevBuf d_skParent, d_skBindT, d_skAppendParent, d_skAppendRatio, d_skLevelBones, d_skLevelStart, d_skChainStart, d_skChainBones;
   bool useChains = false;
@@ -111,10 +112,18 @@ struct rz_ctx_impl {
   bool readPending[2] = {false, false};
   bool haveInst2pal = false, palettesSet = false;
   uint32_t Mact = 0, Mpad = 4;
-  void* h_stage = nullptr;
-  size_t h_stageBytes = 0;
-  void* h_small = nullptr;      // pinned scratch for index / weight uploads
-  size_t h_smallBytes = 0;
+  // Pinned host memory.  Every buffer carries the event of the last asynchronous copy that reads it; nobody (library or
+  // caller) rewrites a buffer before that event has completed (pinned_acquire).
+  //   stage[2]   : caller-visible palette staging, handed out alternately by rz_palette_staging (the producer fills one
+  //                while the upload of the other is in flight)
+  //   big        : library-owned copy of a pageable `world` / `quats` argument (never the caller's staging)
+  //   scratch[4] : ring of small library-owned buffers for index / weight / clock uploads; a ring so that consecutive
+  //                calls of one frame do not wait for each other's copies (which sit behind the previous deform)
+  struct PinnedBuf { void* p = nullptr; size_t bytes = 0; cudaEvent_t done = nullptr; bool pending = false; };
+  PinnedBuf stage[2], big, scratch[4];
+  uint32_t stageCur = 0, scratchCur = 0;
+  bool noPipeline = false;            // RZ_NO_PIPELINE (read once at rz_create)
+  uint32_t pipelineBlock = 0;         // RZ_PIPELINE_BLOCK: palettes per upload block (0 = ~16 MB)
   size_t instStrideF = 0, nrmOffF = 0;
 
   // pipelined palette upload (rz_set_palettes with host matrices): blocks of palettes travel on a copy stream while the
@@ -123,9 +132,23 @@ struct rz_ctx_impl {
   cudaStream_t copyStream = nullptr;
   cudaEvent_t evWorldFree = nullptr;     // main stream: the last skin-matrix pass that reads d_world has been issued
   bool worldFreeValid = false;
-  struct PendBlock { uint32_t pal0, n; cudaEvent_t ev; };
-  std::vector<PendBlock> pend;           // uploaded (or in flight) palettes whose skin matrices are not computed yet
+  // palettes whose skin matrices are not computed yet: blocks of a pipelined upload (ev = completion of the block's copy on
+  // the copy stream) or a whole resident set (ev = nullptr: rz_set_palettes_device / unpipelined rz_set_palettes; the pass
+  // is issued by the next rz_deform, inside its CUDA graph, or by whichever other entry point needs the matrices first)
+  struct PendBlock { uint32_t pal0, n; cudaEvent_t ev; const float* src; };
+  std::vector<PendBlock> pend;
   std::vector<cudaEvent_t> evPool;
+
+  // CUDA graphs of recorded frames (rz_deform)
+  struct GraphKey {
+    const void* fn; uint32_t grid, nt; size_t smem; DeformParams prm; int feat; uint32_t first, count, P;
+    const void* invBind; const void* bonePos; int layoutMode;
+    uint32_t nPend; const void* pendSrc[4]; uint32_t pendPal0[4], pendN[4];
+  };
+  struct GraphEntry { GraphKey key; cudaGraphExec_t exec = nullptr; uint32_t nodes = 0; };
+  std::vector<GraphEntry> graphs;
+  bool useGraphs = true;               // RZ_NO_GRAPH=1: direct launches (debugging, profilers that dislike graphs)
+  uint64_t graphLaunches = 0;
 
   // stats
   cudaEvent_t evStart = nullptr, evStop = nullptr;
@@ -192,17 +215,72 @@ void dev_free(rz_ctx_impl* c, DevBuf& b) {
   b.bytes = 0;
 }
 
-int pinned_reserve(rz_ctx_impl* c, void*& p, size_t& have, size_t bytes) {
-  if (bytes <= have && p) return RZ_OK;
-  if (p) cudaFreeHost(p);
-  p = nullptr;
-  have = 0;
-  CU_TRY(c, cudaMallocHost(&p, std::max<size_t>(bytes, 4096)));
-  have = std::max<size_t>(bytes, 4096);
+// Wait until the last asynchronous copy sourced from `b` has completed, then make sure it holds `bytes`.
+int pinned_acquire(rz_ctx_impl* c, rz_ctx_impl::PinnedBuf& b, size_t bytes) {
+  if (b.pending) {
+    CU_TRY(c, cudaEventSynchronize(b.done));
+    b.pending = false;
+  }
+  if (!b.done) CU_TRY(c, cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
+  if (bytes <= b.bytes && b.p) return RZ_OK;
+  if (b.p) cudaFreeHost(b.p);
+  b.p = nullptr;
+  b.bytes = 0;
+  CU_TRY(c, cudaMallocHost(&b.p, std::max<size_t>(bytes, 4096)));
+  b.bytes = std::max<size_t>(bytes, 4096);
   return RZ_OK;
+}
+// The copies queued on `s` so far are the last readers of `b`.
+int pinned_release(rz_ctx_impl* c, rz_ctx_impl::PinnedBuf& b, cudaStream_t s) {
+  CU_TRY(c, cudaEventRecord(b.done, s));
+  b.pending = true;
+  return RZ_OK;
+}
+void pinned_free(rz_ctx_impl::PinnedBuf& b) {
+  if (b.pending) cudaEventSynchronize(b.done);
+  if (b.done) cudaEventDestroy(b.done);
+  if (b.p) cudaFreeHost(b.p);
+  b = rz_ctx_impl::PinnedBuf();
+}
+// the caller's staging buffer that holds [src, src+bytes), or nullptr
+rz_ctx_impl::PinnedBuf* staging_of(rz_ctx_impl* c, const void* src, size_t bytes) {
+  const char* s0 = reinterpret_cast<const char*>(src);
+  for (auto& b : c->stage)
+    if (b.p && s0 >= (char*)b.p && s0 + bytes <= (char*)b.p + b.bytes) return &b;
+  return nullptr;
+}
+// H2D copy of a small pageable array through the scratch ring (no stream synchronisation)
+int upload_small(rz_ctx_impl* c, void* dst, const void* src, size_t bytes, const void* src2 = nullptr, void* dst2 = nullptr, size_t bytes2 = 0) {
+  rz_ctx_impl::PinnedBuf& b = c->scratch[c->scratchCur];
+  c->scratchCur = (c->scratchCur + 1) % 4;
+  int rc;
+  if ((rc = pinned_acquire(c, b, bytes + bytes2))) return rc;
+  memcpy(b.p, src, bytes);
+  CU_TRY(c, cudaMemcpyAsync(dst, b.p, bytes, cudaMemcpyHostToDevice, c->stream));
+  if (bytes2) {
+    memcpy((char*)b.p + bytes, src2, bytes2);
+    CU_TRY(c, cudaMemcpyAsync(dst2, (char*)b.p + bytes, bytes2, cudaMemcpyHostToDevice, c->stream));
+  }
+  return pinned_release(c, b, c->stream);
 }
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of the FUNCTION on a device, shared by every context of the
+// process: it is only ever raised (a smaller request of another context must not undercut a launch already planned), and
+// the driver is only called when it actually rises -- not once per launch.
+cudaError_t raise_smem_limit(int device, const void* fn, size_t bytes) {
+  static std::mutex mu;
+  static std::unordered_map<uint64_t, size_t> cur;
+  const uint64_t key = (uint64_t)reinterpret_cast<uintptr_t>(fn) * 64u + (uint64_t)(device & 63);
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cur.find(key);
+  if (it != cur.end() && it->second >= bytes) return cudaSuccess;
+  if (bytes <= 48 * 1024 && it == cur.end()) { cur[key] = 48 * 1024; return cudaSuccess; }   // the default limit
+  const cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) cur[key] = bytes;
+  return e;
+}
 
 KernelEntry lookup_kernel(int feat, int I, int NT, int MINB) {
   switch (feat) {
@@ -324,7 +402,7 @@ int rebuild_tables(rz_ctx_impl* c) {
   }
 
   std::vector<float4> rec0(Vp), rec1(Vp), rec2(Vp);
-  std::vector<uint32_t> metaArr(Vp), wbits(Vp, 0);
+  std::vector<uint32_t> metaArr(Vp);
   std::vector<float> edgeArr((c->flags & RZ_FLAG_OUTLINE) ? Vp : 0, 0.f);
   std::vector<float2> uvArr((c->flags & RZ_FLAG_INTERLEAVED) ? Vp : 0, make_float2(0.f, 0.f));
   std::vector<uint2> mrange(Vp / 32);     // per warp: (first entry, depth) of its lane-interleaved morph entries
@@ -386,7 +464,6 @@ int rebuild_tables(rz_ctx_impl* c) {
       const float* x = &VT[(size_t)v * 8];
       rec0[p] = make_float4(x[0], x[1], x[2], w[0]);
       rec1[p] = make_float4(x[3], x[4], x[5], w[1]);
-      memcpy(&wbits[p], &WT[(size_t)v * 4], 4);
       // engine.ts:459-460: worldNormal * material.edgeSize * scaleFactor, scaleFactor = 0.01
       if (!edgeArr.empty() && !c->h_edgeSize.empty()) edgeArr[p] = c->h_edgeSize[c->vorder[v]] * 0.01f;
       if (!uvArr.empty()) uvArr[p] = make_float2(x[6], x[7]);
@@ -414,7 +491,6 @@ int rebuild_tables(rz_ctx_impl* c) {
   if ((rc = dev_reserve(c, c->d_rec1, (size_t)Vp * 16))) return rc;
   if ((rc = dev_reserve(c, c->d_rec2, (size_t)Vp * 16))) return rc;
   if ((rc = dev_reserve(c, c->d_meta, (size_t)Vp * 4))) return rc;
-  if ((rc = dev_reserve(c, c->d_wbits, (size_t)Vp * 4))) return rc;
   if ((rc = dev_reserve(c, c->d_mrange, (size_t)(Vp / 32) * 8))) return rc;
   if ((rc = dev_reserve(c, c->d_ments, mell.size() * 16))) return rc;
   if ((rc = dev_reserve(c, c->d_sdefIdx, (size_t)Vp * 4))) return rc;
@@ -425,7 +501,6 @@ int rebuild_tables(rz_ctx_impl* c) {
   CU_TRY(c, cudaMemcpyAsync(c->d_rec1.p, rec1.data(), (size_t)Vp * 16, cudaMemcpyHostToDevice, c->stream));
   CU_TRY(c, cudaMemcpyAsync(c->d_rec2.p, rec2.data(), (size_t)Vp * 16, cudaMemcpyHostToDevice, c->stream));
   CU_TRY(c, cudaMemcpyAsync(c->d_meta.p, metaArr.data(), (size_t)Vp * 4, cudaMemcpyHostToDevice, c->stream));
-  CU_TRY(c, cudaMemcpyAsync(c->d_wbits.p, wbits.data(), (size_t)Vp * 4, cudaMemcpyHostToDevice, c->stream));
   CU_TRY(c, cudaMemcpyAsync(c->d_mrange.p, mrange.data(), (size_t)(Vp / 32) * 8, cudaMemcpyHostToDevice, c->stream));
   CU_TRY(c, cudaMemcpyAsync(c->d_ments.p, mell.data(), mell.size() * 16, cudaMemcpyHostToDevice, c->stream));
   CU_TRY(c, cudaMemcpyAsync(c->d_sdefIdx.p, sdefIdx.data(), (size_t)Vp * 4, cudaMemcpyHostToDevice, c->stream));
@@ -497,13 +572,18 @@ void launch_skin_block(rz_ctx_impl* c, const float* d_world, uint32_t pal0, uint
 // skin-matrix passes of every uploaded block that has none yet (each waits for its block's copy)
 int flush_pending(rz_ctx_impl* c) {
   if (c->pend.empty()) return RZ_OK;
+  bool readsWorld = false;
   for (const auto& b : c->pend) {
-    CU_TRY(c, cudaStreamWaitEvent(c->stream, b.ev, 0));
-    launch_skin_block(c, reinterpret_cast<const float*>(c->d_world.p), b.pal0, b.n);
+    if (b.ev) CU_TRY(c, cudaStreamWaitEvent(c->stream, b.ev, 0));
+    launch_skin_block(c, b.src, b.pal0, b.n);
+    readsWorld |= b.src == c->d_world.p;
   }
   c->pend.clear();
-  CU_TRY(c, cudaEventRecord(c->evWorldFree, c->stream));
-  c->worldFreeValid = true;
+  CU_TRY(c, cudaGetLastError());
+  if (readsWorld) {
+    CU_TRY(c, cudaEventRecord(c->evWorldFree, c->stream));
+    c->worldFreeValid = true;
+  }
   return RZ_OK;
 }
 
@@ -569,14 +649,22 @@ int32_t rz_create(const rz_config* cfg, rz_ctx** out) {
   if (const char* e1 = getenv("RZ_PERM")) c->permMode = atoi(e1);        // experiment knobs (tuning)
   if (const char* e2 = getenv("RZ_COLOR")) c->colorMode = atoi(e2);
   if (const char* e3 = getenv("RZ_LAYOUT")) c->layoutMode = atoi(e3);
-  cudaEventCreate(&c->evStart);
-  cudaEventCreate(&c->evStop);
-  cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking);
-  cudaStreamCreateWithFlags(&c->readStream, cudaStreamNonBlocking);
-  cudaEventCreateWithFlags(&c->evReadReady, cudaEventDisableTiming);
-  cudaEventCreateWithFlags(&c->evReadDone[0], cudaEventDisableTiming);
-  cudaEventCreateWithFlags(&c->evReadDone[1], cudaEventDisableTiming);
-  cudaEventCreateWithFlags(&c->evWorldFree, cudaEventDisableTiming);
+  c->noPipeline = getenv("RZ_NO_PIPELINE") != nullptr;
+  c->useGraphs = getenv("RZ_NO_GRAPH") == nullptr;
+  if (const char* eb = getenv("RZ_PIPELINE_BLOCK")) c->pipelineBlock = (uint32_t)std::max(1, atoi(eb));
+  e = cudaEventCreate(&c->evStart);
+  if (e == cudaSuccess) e = cudaEventCreate(&c->evStop);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->readStream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->evReadReady, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->evReadDone[0], cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->evReadDone[1], cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->evWorldFree, cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    const int code = fail(nullptr, e == cudaErrorMemoryAllocation ? RZ_ERR_OOM : RZ_ERR_CUDA, "rz_create: stream / event creation failed: %s", cudaGetErrorString(e));
+    rz_destroy(c);
+    return code;
+  }
   *out = c;
   return RZ_OK;
 }
@@ -589,17 +677,19 @@ int32_t rz_destroy(rz_ctx* c) {
   if (c->evReadReady) cudaEventDestroy(c->evReadReady);
   for (cudaEvent_t e : c->evReadDone) if (e) cudaEventDestroy(e);
   cudaStreamSynchronize(c->stream);
+  for (auto& g : c->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   for (cudaEvent_t e : c->evPool) cudaEventDestroy(e);
   if (c->evWorldFree) cudaEventDestroy(c->evWorldFree);
   if (c->copyStream) cudaStreamDestroy(c->copyStream);
-  DevBuf* bufs[] = {&c->d_rec0, &c->d_rec1, &c->d_rec2, &c->d_meta, &c->d_wbits, &c->d_mrange, &c->d_ments, &c->d_sdefIdx, &c->d_sdefTab,
+  DevBuf* bufs[] = {&c->d_rec0, &c->d_rec1, &c->d_rec2, &c->d_meta, &c->d_mrange, &c->d_ments, &c->d_sdefIdx, &c->d_sdefTab,
                     &c->d_invBind, &c->d_bonePos, &c->d_world, &c->d_skin, &c->d_inst2pal, &c->d_mwIn, &c->d_mwIds, &c->d_mwDense,
                     &c->d_out, &c->d_out2, &c->d_bounds, &c->d_counter, &c->d_skParent, &c->d_skBindT, &c->d_skAppendParent, &c->d_skAppendRatio,
                     &c->d_skLevelBones, &c->d_skLevelStart, &c->d_skChainStart, &c->d_skChainBones, &c->d_twStart, &c->d_twTarget, &c->d_twRest, &c->d_twStartMs, &c->d_twDurMs,
-                    &c->d_twActive, &c->d_localRot, &c->d_nowMs, &c->d_twAux, &c->d_invBindSoA, &c->d_rbBones, &c->d_rbStart, &c->d_rbIds, &c->d_rbOffInv, &c->d_rbPosQuat, &c->d_trStart, &c->d_trMs, &c->d_trQ, &c->d_quat, &c->d_chunkTab, &c->d_edge, &c->d_uv};
+                    &c->d_twActive, &c->d_localRot, &c->d_nowMs, &c->d_twAux, &c->d_invBindSoA, &c->d_rbBones, &c->d_rbStart, &c->d_rbIds, &c->d_rbOffInv, &c->d_rbPosQuat, &c->d_trStart, &c->d_trMs, &c->d_trQ, &c->d_trRest, &c->d_quat, &c->d_chunkTab, &c->d_edge, &c->d_uv};
   for (DevBuf* b : bufs) dev_free(c, *b);
-  if (c->h_stage) cudaFreeHost(c->h_stage);
-  if (c->h_small) cudaFreeHost(c->h_small);
+  for (auto& b : c->stage) pinned_free(b);
+  for (auto& b : c->scratch) pinned_free(b);
+  pinned_free(c->big);
   if (c->evStart) cudaEventDestroy(c->evStart);
   if (c->evStop) cudaEventDestroy(c->evStop);
   if (c->ownStream) cudaStreamDestroy(c->stream);
@@ -612,7 +702,7 @@ int32_t rz_load_mesh(rz_ctx* c, const float* vtx8, const uint16_t* joints, const
   if (!c) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_load_mesh: null ctx");
   if (!vtx8 || !joints || !weights || !invBind) return fail(c, RZ_ERR_INVALID_ARG, "rz_load_mesh: null table");
   if (V == 0 || B == 0) return fail(c, RZ_ERR_INVALID_ARG, "rz_load_mesh: V and B must be > 0 (the reference throws 'Model has no bones')");
-  if (B > 65536) return fail(c, RZ_ERR_INVALID_ARG, "rz_load_mesh: B=%u exceeds the u16 joint range", B);
+  if (B > 65535) return fail(c, RZ_ERR_INVALID_ARG, "rz_load_mesh: B=%u exceeds the joint range (u16 ids 0..65534; 65535 is reserved)", B);
   for (size_t i = 0; i < (size_t)V * 4; ++i)
     if (joints[i] >= B) return fail(c, RZ_ERR_INVALID_ARG, "rz_load_mesh: joint %u of vertex %zu >= bone count %u", joints[i], i / 4, B);
   CU_TRY(c, cudaSetDevice(c->device));
@@ -676,9 +766,7 @@ static int set_palettes_common(rz_ctx* c, const float* d_world, uint32_t P, uint
   if ((rc = dev_reserve(c, c->d_skin, (size_t)P * c->B * 48))) return rc;
   c->pend.clear();                                           // superseded
   begin_frame(c);
-  launch_skin_block(c, d_world, 0, P);
-  CU_TRY(c, cudaGetLastError());
-  if (d_world == c->d_world.p) { CU_TRY(c, cudaEventRecord(c->evWorldFree, c->stream)); c->worldFreeValid = true; }
+  c->pend.push_back({0, P, nullptr, d_world});               // skin-matrix pass: issued lazily (flush_pending / rz_deform's graph)
   c->P = P;
   c->K = K;
   c->palettesSet = true;
@@ -688,11 +776,13 @@ static int set_palettes_common(rz_ctx* c, const float* d_world, uint32_t P, uint
 int32_t rz_palette_staging(rz_ctx* c, size_t bytes, void** host_ptr) {
   if (!c || !host_ptr) return fail(c, RZ_ERR_INVALID_ARG, "rz_palette_staging: null argument");
   CU_TRY(c, cudaSetDevice(c->device));
-  if (bytes > c->h_stageBytes) CU_TRY(c, cudaStreamSynchronize(c->stream));
-  CU_TRY(c, cudaStreamSynchronize(c->copyStream));           // the caller is about to overwrite the staging buffer
-  int rc = pinned_reserve(c, c->h_stage, c->h_stageBytes, bytes);
+  // two buffers, handed out alternately: the one returned now was last uploaded two calls ago; wait for THAT copy only,
+  // so the producer refills one buffer while the upload of the other is still in flight
+  c->stageCur ^= 1u;
+  rz_ctx_impl::PinnedBuf& b = c->stage[c->stageCur];
+  int rc = pinned_acquire(c, b, bytes);
   if (rc) return rc;
-  *host_ptr = c->h_stage;
+  *host_ptr = b.p;
   return RZ_OK;
 }
 
@@ -710,23 +800,22 @@ int32_t rz_set_palettes(rz_ctx* c, const float* world, uint32_t P, const uint32_
   int rc;
   if ((rc = dev_reserve(c, c->d_world, bytes))) return rc;
   const char* src = reinterpret_cast<const char*>(world);
-  const bool inStage = c->h_stage && src >= (char*)c->h_stage && src + bytes <= (char*)c->h_stage + c->h_stageBytes;
-  if (!inStage) {
-    // the staging buffer may still be the source of the previous frame's copy
-    CU_TRY(c, cudaStreamSynchronize(c->stream));
-    CU_TRY(c, cudaStreamSynchronize(c->copyStream));
-    if ((rc = pinned_reserve(c, c->h_stage, c->h_stageBytes, bytes))) return rc;
-    memcpy(c->h_stage, world, bytes);
-    src = reinterpret_cast<const char*>(c->h_stage);
+  rz_ctx_impl::PinnedBuf* srcBuf = staging_of(c, world, bytes);
+  if (!srcBuf) {
+    // pageable source: through the library's own pinned copy (waits for the upload that last read it)
+    if ((rc = pinned_acquire(c, c->big, bytes))) return rc;
+    memcpy(c->big.p, world, bytes);
+    src = reinterpret_cast<const char*>(c->big.p);
+    srcBuf = &c->big;
   }
   // Large identity-mapped uploads (a crowd with one palette per instance, as the reference's per-model upload scales) are
   // PIPELINED: blocks of ~16 MB go out on the copy stream, each followed by an event; rz_deform then alternates
   // "wait for block b, skin matrices of block b, deform the instances of block b", so the PCIe transfer of block b+1
   // overlaps the deform of block b instead of preceding the whole frame (measured: 4.6 -> 2.9 ms at K=4096, B=512).
-  const bool noPipe = getenv("RZ_NO_PIPELINE") != nullptr;        // (per call: the tests flip it inside one process)
+  const bool noPipe = c->noPipeline;
   const size_t palBytes = (size_t)c->B * 64;
   uint32_t blk = (uint32_t)std::max<size_t>(64, ((size_t)16 << 20) / palBytes);
-  if (const char* eb = getenv("RZ_PIPELINE_BLOCK")) blk = (uint32_t)std::max(1, atoi(eb));   // palettes per block (tests)
+  if (c->pipelineBlock) blk = c->pipelineBlock;                    // palettes per block (tests)
   if (!inst2pal && !noPipe && P >= 2 * blk) {
     if ((rc = dev_reserve(c, c->d_skin, (size_t)P * c->B * 48))) return rc;
     if (c->worldFreeValid) CU_TRY(c, cudaStreamWaitEvent(c->copyStream, c->evWorldFree, 0));   // d_world is no longer being read
@@ -742,8 +831,9 @@ int32_t rz_set_palettes(rz_ctx* c, const float* world, uint32_t P, const uint32_
       CU_TRY(c, cudaMemcpyAsync(reinterpret_cast<char*>(c->d_world.p) + (size_t)pal0 * palBytes, src + (size_t)pal0 * palBytes,
                                 (size_t)n * palBytes, cudaMemcpyHostToDevice, c->copyStream));
       CU_TRY(c, cudaEventRecord(c->evPool[b], c->copyStream));
-      c->pend.push_back({pal0, n, c->evPool[b]});
+      c->pend.push_back({pal0, n, c->evPool[b], reinterpret_cast<const float*>(c->d_world.p)});
     }
+    if ((rc = pinned_release(c, *srcBuf, c->copyStream))) return rc;
     c->haveInst2pal = false;
     c->P = P;
     c->K = K;
@@ -751,15 +841,12 @@ int32_t rz_set_palettes(rz_ctx* c, const float* world, uint32_t P, const uint32_
     begin_frame(c);
     return RZ_OK;
   }
-  if (!c->pend.empty()) CU_TRY(c, cudaStreamWaitEvent(c->stream, c->pend.back().ev, 0));    // an unconsumed pipelined upload still targets d_world
+  if (!c->pend.empty() && c->pend.back().ev) CU_TRY(c, cudaStreamWaitEvent(c->stream, c->pend.back().ev, 0));    // an unconsumed pipelined upload still targets d_world
   CU_TRY(c, cudaMemcpyAsync(c->d_world.p, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = pinned_release(c, *srcBuf, c->stream))) return rc;
   if (inst2pal) {
     if ((rc = dev_reserve(c, c->d_inst2pal, (size_t)c->maxK * 4))) return rc;
-    if (!inStage || true) {
-      if ((rc = pinned_reserve(c, c->h_small, c->h_smallBytes, (size_t)c->maxK * 4))) return rc;
-    }
-    memcpy(c->h_small, inst2pal, (size_t)K * 4);
-    CU_TRY(c, cudaMemcpyAsync(c->d_inst2pal.p, c->h_small, (size_t)K * 4, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = upload_small(c, c->d_inst2pal.p, inst2pal, (size_t)K * 4))) return rc;
   }
   c->haveInst2pal = inst2pal != nullptr;
   return set_palettes_common(c, reinterpret_cast<const float*>(c->d_world.p), P, K);
@@ -869,7 +956,6 @@ static int launch_pose(rz_ctx* c, uint32_t P) {
   const size_t smem = (size_t)c->B * 64;
   if (smem > (size_t)c->maxSmemOptin)
     return fail(c, RZ_ERR_INVALID_ARG, "GPU pose evaluation supports up to %d bones (B=%u): use rz_set_palettes", c->maxSmemOptin / 64, c->B);
-  CU_TRY(c, cudaFuncSetAttribute(pose_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int rc;
   if ((rc = dev_reserve(c, c->d_skin, (size_t)P * c->B * 48))) return rc;
   PoseSkeleton sk;
@@ -884,7 +970,7 @@ static int launch_pose(rz_ctx* c, uint32_t P) {
   PoseTweens tw;
   tw.start = reinterpret_cast<const float4*>(c->d_twStart.p);
   tw.target = reinterpret_cast<const float4*>(c->d_twTarget.p);
-  tw.rest = reinterpret_cast<const float4*>(c->d_twRest.p);
+  tw.rest = reinterpret_cast<const float4*>(MODE == 2 ? c->d_trRest.p : c->d_twRest.p);
   tw.startMs = reinterpret_cast<const float*>(c->d_twStartMs.p);
   tw.durMs = reinterpret_cast<const float*>(c->d_twDurMs.p);
   tw.active = reinterpret_cast<const uint8_t*>(c->d_twActive.p);
@@ -898,7 +984,7 @@ static int launch_pose(rz_ctx* c, uint32_t P) {
   if (poseAlgo >= 2 && c->nLevels > 4 && smemJump <= (size_t)c->maxSmemOptin && (MODE != 1 || c->d_twAux.p)) {
     uint32_t rounds = 0;
     while ((1u << rounds) < c->nLevels) ++rounds;
-    if (smemJump > 48 * 1024) CU_TRY(c, cudaFuncSetAttribute(pose_jump_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemJump));
+    CU_TRY(c, raise_smem_limit(c->device, reinterpret_cast<const void*>(&pose_jump_kernel<MODE>), smemJump));
     const int threads = c->B <= 1024 ? (int)std::max<uint32_t>(64u, (c->B + 31u) / 32u * 32u) : 512;   // one bone per thread when possible
     pose_jump_kernel<MODE><<<P, threads, smemJump, c->stream>>>(sk, tw, tr, reinterpret_cast<const float4*>(c->d_twAux.p),
                                                                 reinterpret_cast<const float4*>(c->d_localRot.p),
@@ -912,7 +998,7 @@ static int launch_pose(rz_ctx* c, uint32_t P) {
     return RZ_OK;
   }
   if (c->useChains && poseAlgo >= 1) {
-    CU_TRY(c, cudaFuncSetAttribute(pose_chain_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_TRY(c, raise_smem_limit(c->device, reinterpret_cast<const void*>(&pose_chain_kernel<MODE>), smem));
     pose_chain_kernel<MODE><<<P, 256, smem, c->stream>>>(sk, tw, tr, reinterpret_cast<const uint32_t*>(c->d_skChainStart.p),
                                                          reinterpret_cast<const uint32_t*>(c->d_skChainBones.p),
                                                          reinterpret_cast<const float4*>(c->d_localRot.p),
@@ -924,6 +1010,7 @@ static int launch_pose(rz_ctx* c, uint32_t P) {
     c->launches++;
     return RZ_OK;
   }
+  CU_TRY(c, raise_smem_limit(c->device, reinterpret_cast<const void*>(&pose_kernel<MODE>), smem));
   pose_kernel<MODE><<<P, 128, smem, c->stream>>>(sk, tw, tr, reinterpret_cast<const float4*>(c->d_localRot.p),
                                                  reinterpret_cast<const float*>(c->d_nowMs.p),
                                                  reinterpret_cast<const float4*>(c->d_invBind.p),
@@ -944,10 +1031,7 @@ static int set_mapping(rz_ctx* c, const uint32_t* inst2pal, uint32_t P, uint32_t
       if (inst2pal[k] >= P) return fail(c, RZ_ERR_INVALID_ARG, "%s: instToPalette[%u]=%u >= P=%u", who, k, inst2pal[k], P);
     int rc;
     if ((rc = dev_reserve(c, c->d_inst2pal, (size_t)c->maxK * 4))) return rc;
-    CU_TRY(c, cudaStreamSynchronize(c->stream));
-    if ((rc = pinned_reserve(c, c->h_small, c->h_smallBytes, (size_t)c->maxK * 4))) return rc;
-    memcpy(c->h_small, inst2pal, (size_t)K * 4);
-    CU_TRY(c, cudaMemcpyAsync(c->d_inst2pal.p, c->h_small, (size_t)K * 4, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = upload_small(c, c->d_inst2pal.p, inst2pal, (size_t)K * 4))) return rc;
   }
   c->haveInst2pal = inst2pal != nullptr;
   return RZ_OK;
@@ -963,14 +1047,15 @@ int32_t rz_set_local_rotations(rz_ctx* c, const float* quats, uint32_t P, const 
   const size_t bytes = (size_t)P * c->B * 16;
   if ((rc = dev_reserve(c, c->d_localRot, bytes))) return rc;
   const char* src = reinterpret_cast<const char*>(quats);
-  const bool inStage = c->h_stage && src >= (char*)c->h_stage && src + bytes <= (char*)c->h_stage + c->h_stageBytes;
-  if (!inStage) {
-    CU_TRY(c, cudaStreamSynchronize(c->stream));
-    if ((rc = pinned_reserve(c, c->h_stage, c->h_stageBytes, bytes))) return rc;
-    memcpy(c->h_stage, quats, bytes);
-    src = reinterpret_cast<const char*>(c->h_stage);
+  rz_ctx_impl::PinnedBuf* srcBuf = staging_of(c, quats, bytes);
+  if (!srcBuf) {
+    if ((rc = pinned_acquire(c, c->big, bytes))) return rc;
+    memcpy(c->big.p, quats, bytes);
+    src = reinterpret_cast<const char*>(c->big.p);
+    srcBuf = &c->big;
   }
   CU_TRY(c, cudaMemcpyAsync(c->d_localRot.p, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = pinned_release(c, *srcBuf, c->stream))) return rc;
   if ((rc = launch_pose<0>(c, P))) return rc;
   c->P = P; c->K = K; c->palettesSet = true;
   return RZ_OK;
@@ -1016,10 +1101,7 @@ int32_t rz_apply_body_transforms(rz_ctx* c, const float* posQuat, uint32_t P) {
   if ((rc = flush_pending(c))) return rc;            // a pipelined upload computes its skin matrices lazily: do it now
   const size_t bytes = (size_t)P * c->rbBodies * 28;
   if ((rc = dev_reserve(c, c->d_rbPosQuat, bytes))) return rc;
-  if ((rc = pinned_reserve(c, c->h_small, c->h_smallBytes, std::max(bytes, (size_t)c->maxK * 4)))) return rc;
-  CU_TRY(c, cudaStreamSynchronize(c->stream));        // h_small may still feed an earlier copy
-  memcpy(c->h_small, posQuat, bytes);
-  CU_TRY(c, cudaMemcpyAsync(c->d_rbPosQuat.p, c->h_small, bytes, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = upload_small(c, c->d_rbPosQuat.p, posQuat, bytes))) return rc;
   const uint32_t n = P * c->rbBones;
   apply_bodies_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(
       reinterpret_cast<const uint32_t*>(c->d_rbBones.p), reinterpret_cast<const uint32_t*>(c->d_rbStart.p),
@@ -1073,15 +1155,12 @@ int32_t rz_set_instance_clocks(rz_ctx* c, const float* nowMs, uint32_t P, const 
   int rc;
   if ((rc = set_mapping(c, inst2pal, P, K, "rz_set_instance_clocks"))) return rc;
   if ((rc = dev_reserve(c, c->d_nowMs, (size_t)P * 4))) return rc;
-  const char* src = reinterpret_cast<const char*>(nowMs);
-  const bool inStage = c->h_stage && src >= (char*)c->h_stage && src + (size_t)P * 4 <= (char*)c->h_stage + c->h_stageBytes;
-  if (!inStage) {
-    CU_TRY(c, cudaStreamSynchronize(c->stream));
-    if ((rc = pinned_reserve(c, c->h_stage, c->h_stageBytes, (size_t)P * 4))) return rc;
-    memcpy(c->h_stage, nowMs, (size_t)P * 4);
-    src = reinterpret_cast<const char*>(c->h_stage);
+  if (rz_ctx_impl::PinnedBuf* sb = staging_of(c, nowMs, (size_t)P * 4)) {
+    CU_TRY(c, cudaMemcpyAsync(c->d_nowMs.p, nowMs, (size_t)P * 4, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = pinned_release(c, *sb, c->stream))) return rc;
+  } else if ((rc = upload_small(c, c->d_nowMs.p, nowMs, (size_t)P * 4))) {
+    return rc;
   }
-  CU_TRY(c, cudaMemcpyAsync(c->d_nowMs.p, src, (size_t)P * 4, cudaMemcpyHostToDevice, c->stream));
   if ((rc = c->haveAnimation ? launch_pose<2>(c, P) : launch_pose<1>(c, P))) return rc;
   c->P = P; c->K = K; c->palettesSet = true;
   return RZ_OK;
@@ -1097,12 +1176,12 @@ int32_t rz_load_animation(rz_ctx* c, const uint32_t* keyOffsets, const float* ke
   }
   const uint32_t B = c->B, n = keyOffsets[B];
   if (keyOffsets[0] != 0) return fail(c, RZ_ERR_INVALID_ARG, "rz_load_animation: keyOffsets[0] must be 0");
+  if (n && (!keyTimesMs || !keyQuats)) return fail(c, RZ_ERR_INVALID_ARG, "rz_load_animation: null keys");
   for (uint32_t b = 0; b < B; ++b) {
     if (keyOffsets[b + 1] < keyOffsets[b]) return fail(c, RZ_ERR_INVALID_ARG, "rz_load_animation: offsets not monotone at bone %u", b);
     for (uint32_t k = keyOffsets[b] + 1; k < keyOffsets[b + 1]; ++k)
       if (keyTimesMs[k] < keyTimesMs[k - 1]) return fail(c, RZ_ERR_INVALID_ARG, "rz_load_animation: key times of bone %u not ascending", b);
   }
-  if (n && (!keyTimesMs || !keyQuats)) return fail(c, RZ_ERR_INVALID_ARG, "rz_load_animation: null keys");
   // normalise like Model.rotateBones does (model.ts:248; zero-length -> identity, math.ts:96-100)
   std::vector<float> q((size_t)std::max<uint32_t>(n, 1) * 4, 0.f);
   for (uint32_t k = 0; k < n; ++k) {
@@ -1120,7 +1199,7 @@ int32_t rz_load_animation(rz_ctx* c, const uint32_t* keyOffsets, const float* ke
   if ((rc = upload(c, c->d_trStart, keyOffsets, (size_t)(B + 1) * 4))) return rc;
   if ((rc = upload(c, c->d_trMs, n ? keyTimesMs : rest.data(), (size_t)std::max<uint32_t>(n, 1) * 4))) return rc;
   if ((rc = upload(c, c->d_trQ, q.data(), q.size() * 4))) return rc;
-  if ((rc = upload(c, c->d_twRest, rest.data(), (size_t)B * 16))) return rc;
+  if ((rc = upload(c, c->d_trRest, rest.data(), (size_t)B * 16))) return rc;   // the clip's own rest rotations (d_twRest belongs to rz_set_tweens)
   CU_TRY(c, cudaStreamSynchronize(c->stream));
   c->haveAnimation = true;
   return RZ_OK;
@@ -1144,12 +1223,7 @@ int32_t rz_set_morph_weights(rz_ctx* c, const float* w, const uint32_t* ids, uin
   const size_t wBytes = (size_t)K * Mact * 4, idBytes = (size_t)Mact * 4;
   if ((rc = dev_reserve(c, c->d_mwIn, wBytes))) return rc;
   if ((rc = dev_reserve(c, c->d_mwIds, idBytes))) return rc;
-  CU_TRY(c, cudaStreamSynchronize(c->stream));   // pinned scratch reuse
-  if ((rc = pinned_reserve(c, c->h_small, c->h_smallBytes, std::max(wBytes + idBytes, (size_t)c->maxK * 4)))) return rc;
-  memcpy(c->h_small, w, wBytes);
-  memcpy((char*)c->h_small + wBytes, ids, idBytes);
-  CU_TRY(c, cudaMemcpyAsync(c->d_mwIn.p, c->h_small, wBytes, cudaMemcpyHostToDevice, c->stream));
-  CU_TRY(c, cudaMemcpyAsync(c->d_mwIds.p, (char*)c->h_small + wBytes, idBytes, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = upload_small(c, c->d_mwIn.p, w, wBytes, ids, c->d_mwIds.p, idBytes))) return rc;
   morph_weights_kernel<<<K, 128, 0, c->stream>>>(reinterpret_cast<const float*>(c->d_mwIn.p),
                                                  reinterpret_cast<const uint32_t*>(c->d_mwIds.p),
                                                  reinterpret_cast<float*>(c->d_mwDense.p), K, Mact, c->Mpad);
@@ -1186,8 +1260,10 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
   if (feat < 0) return fail(c, RZ_ERR_INVALID_ARG, "rz_deform: feature combination 0x%x is not built", need);
   // a pipelined upload (rz_set_palettes) is consumed block by block below; feature sets with per-launch side kernels or
   // count-dependent tables take the whole upload first
-  const bool pipelined = !c->pend.empty() && !(feat & (FEAT_MORPH | FEAT_SDEF | FEAT_BOUNDS | FEAT_GPAL));
-  if (!pipelined && (rc = flush_pending(c))) return rc;
+  bool uploadInFlight = false;                                      // blocks of a pipelined rz_set_palettes upload
+  for (const auto& b : c->pend) uploadInFlight |= b.ev != nullptr;
+  const bool pipelined = uploadInFlight && !(feat & (FEAT_MORPH | FEAT_SDEF | FEAT_BOUNDS | FEAT_GPAL));
+  if (uploadInFlight && !pipelined && (rc = flush_pending(c))) return rc;
   KernelEntry ke{nullptr, 0, 0, 0, 0, 0, feat};
   size_t smem = 0;
   int occ = 0;
@@ -1201,7 +1277,7 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
     if (!e.fn) return false;
     const size_t sm = smem_needed(e.I, e.NT, feat, c->B, Mpad, e.NB);
     if (sm > smemMax) return false;
-    if (cudaFuncSetAttribute(e.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (raise_smem_limit(c->device, e.fn, sm) != cudaSuccess) { cudaGetLastError(); return false; }
     int o = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, e.fn, e.NT, sm) != cudaSuccess || o < 1) { cudaGetLastError(); return false; }
     ke = e; smem = sm; occ = o;
@@ -1250,8 +1326,7 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
     if (!ok) return fail(c, RZ_ERR_INVALID_ARG, "rz_deform: no kernel shape fits B=%u (smem limit %zu)", c->B, smemMax);
   }
   if (c->tuneCtas && (int)c->tuneCtas < occ) occ = (int)c->tuneCtas;
-  // (another context may have lowered the limit on the same kernel function: always re-assert it, it is cheap)
-  CU_TRY(c, cudaFuncSetAttribute(ke.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CU_TRY(c, raise_smem_limit(c->device, ke.fn, smem));      // (a no-op unless another device / a first use needs it)
   if (!cached) {
     c->shapeKe = ke; c->shapeSmem = smem; c->shapeOcc = occ;
     c->shapeKey.feat = feat; c->shapeKey.B = c->B; c->shapeKey.Mpad = Mpad; c->shapeKey.countClass = countClass;
@@ -1283,44 +1358,59 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
   prm.posStride = c->layoutMode ? 16u : 48u;
   prm.rowStride = c->layoutMode ? c->B * 16u : 16u;
   uint32_t gridUsed = 0;
-  // one launch over the instance range [f, f+n)
-  auto launch_range = [&](uint32_t f, uint32_t n) -> int {
-  prm.K0 = f; prm.Kcount = n;
-  prm.nGroups = (n + ke.I - 1) / ke.I;
-  const uint32_t tilesPerPass = ke.NT / kTile;
-  const uint32_t nPasses = (c->nTiles + tilesPerPass - 1) / tilesPerPass;
-  uint32_t grid = (uint32_t)(c->numSM * occ);
-  uint32_t nChunks = c->tuneChunks ? c->tuneChunks : (grid * 8 + prm.nGroups - 1) / prm.nGroups;
-  nChunks = std::max(1u, std::min(nChunks, nPasses));
-  const uint32_t passesPerChunk = (nPasses + nChunks - 1) / nChunks;
-  prm.tilesPerChunk = passesPerChunk * tilesPerPass;
-  prm.nChunks = (c->nTiles + prm.tilesPerChunk - 1) / prm.tilesPerChunk;
-  if ((feat & FEAT_MORPH) && c->morphNnz && nChunks > 1) {
-    // Morph passes are latency chains (record -> entries -> weights: one L2 round trip per kMorphBatch entries of the
-    // deepest vertex), several times longer than a plain pass, and PMX morphs cluster on the face: uniform chunks would
-    // leave a few very long items (measured: +70 % on config 3).  Chunk boundaries are placed so that every item carries
-    // the same estimated time instead; the table only depends on the launch shape and is cached.
-    if (c->chunkKey.tilesPerPass != tilesPerPass || c->chunkKey.target != nChunks || !c->d_chunkTab.p) {
-      static const float tripCost = getenv("RZ_MORPH_TRIP_COST") ? (float)atof(getenv("RZ_MORPH_TRIP_COST")) : 0.5f;
-      std::vector<uint32_t> tab;
-      build_chunk_table(c->tileMorphMax.data(), c->nTiles, tilesPerPass, nChunks, tripCost, kMorphPF, kMorphBatch, tab);
-      if ((rc = dev_reserve(c, c->d_chunkTab, tab.size() * 4))) return rc;
-      CU_TRY(c, cudaMemcpyAsync(c->d_chunkTab.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, c->stream));
-      CU_TRY(c, cudaStreamSynchronize(c->stream));                  // once per launch shape; `tab` goes out of scope
-      c->chunkKey.tilesPerPass = tilesPerPass; c->chunkKey.target = nChunks;
-      c->chunkCount = (uint32_t)tab.size() - 1;
+  // ---- one launch over the instance range [f, f+n): plan (host work, may synchronise once per launch shape) ...
+  struct RangeLaunch { DeformParams prm; uint32_t grid; };
+  auto plan_range = [&](uint32_t f, uint32_t n, RangeLaunch& out) -> int {
+    prm.K0 = f; prm.Kcount = n;
+    prm.nGroups = (n + ke.I - 1) / ke.I;
+    const uint32_t tilesPerPass = ke.NT / kTile;
+    const uint32_t nPasses = (c->nTiles + tilesPerPass - 1) / tilesPerPass;
+    uint32_t grid = (uint32_t)(c->numSM * occ);
+    uint32_t nChunks = c->tuneChunks ? c->tuneChunks : (grid * 8 + prm.nGroups - 1) / prm.nGroups;
+    nChunks = std::max(1u, std::min(nChunks, nPasses));
+    const uint32_t passesPerChunk = (nPasses + nChunks - 1) / nChunks;
+    prm.tilesPerChunk = passesPerChunk * tilesPerPass;
+    prm.nChunks = (c->nTiles + prm.tilesPerChunk - 1) / prm.tilesPerChunk;
+    prm.chunkTab = nullptr;
+    if ((feat & FEAT_MORPH) && c->morphNnz && nChunks > 1) {
+      // Morph passes are latency chains (record -> entries -> weights: one L2 round trip per kMorphBatch entries of the
+      // deepest vertex), several times longer than a plain pass, and PMX morphs cluster on the face: uniform chunks would
+      // leave a few very long items (measured: +70 % on config 3).  Chunk boundaries are placed so that every item carries
+      // the same estimated time instead; the table only depends on the launch shape and is cached.
+      if (c->chunkKey.tilesPerPass != tilesPerPass || c->chunkKey.target != nChunks || !c->d_chunkTab.p) {
+        static const float tripCost = getenv("RZ_MORPH_TRIP_COST") ? (float)atof(getenv("RZ_MORPH_TRIP_COST")) : 0.5f;
+        std::vector<uint32_t> tab;
+        build_chunk_table(c->tileMorphMax.data(), c->nTiles, tilesPerPass, nChunks, tripCost, kMorphPF, kMorphBatch, tab);
+        int rcc;
+        if ((rcc = dev_reserve(c, c->d_chunkTab, tab.size() * 4))) return rcc;
+        CU_TRY(c, cudaMemcpyAsync(c->d_chunkTab.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        CU_TRY(c, cudaStreamSynchronize(c->stream));                  // once per launch shape; `tab` goes out of scope
+        c->chunkKey.tilesPerPass = tilesPerPass; c->chunkKey.target = nChunks;
+        c->chunkCount = (uint32_t)tab.size() - 1;
+      }
+      prm.chunkTab = reinterpret_cast<const uint32_t*>(c->d_chunkTab.p);
+      prm.nChunks = c->chunkCount;
     }
-    prm.chunkTab = reinterpret_cast<const uint32_t*>(c->d_chunkTab.p);
-    prm.nChunks = c->chunkCount;
-  }
-  const uint32_t nItems = prm.nGroups * prm.nChunks;
-  grid = std::min(grid, nItems);
-  gridUsed = std::max(gridUsed, grid);
-  CU_TRY(c, cudaMemsetAsync(c->d_counter.p, 0, 4, c->stream));
-  void* args[] = {&prm};
-  CU_TRY(c, cudaLaunchKernel(ke.fn, dim3(grid), dim3(ke.NT), args, smem, c->stream));
-  c->launches++;
-  return RZ_OK;
+    const uint32_t nItems = prm.nGroups * prm.nChunks;
+    grid = std::min(grid, nItems);
+    gridUsed = std::max(gridUsed, grid);
+    out.prm = prm;
+    out.grid = grid;
+    return RZ_OK;
+  };
+  // ... and issue (stream operations only: also runs under stream capture)
+  auto issue_range = [&](RangeLaunch& r) -> int {
+    CU_TRY(c, cudaMemsetAsync(c->d_counter.p, 0, 4, c->stream));
+    void* args[] = {&r.prm};
+    CU_TRY(c, cudaLaunchKernel(ke.fn, dim3(r.grid), dim3(ke.NT), args, smem, c->stream));
+    c->launches++;
+    return RZ_OK;
+  };
+  auto launch_range = [&](uint32_t f, uint32_t n) -> int {
+    RangeLaunch r;
+    int rcl;
+    if ((rcl = plan_range(f, n, r))) return rcl;
+    return issue_range(r);
   };
 
   if (feat & FEAT_SDEF) {
@@ -1335,19 +1425,23 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
   }
   // an asynchronous read-back still copying from the buffer this frame writes (with two buffers: the read of two frames ago)
   if (c->readPending[c->cur]) CU_TRY(c, cudaStreamWaitEvent(c->stream, c->evReadDone[c->cur], 0));
-  CU_TRY(c, cudaEventRecord(c->evStart, c->stream));
-  if (feat & FEAT_SDEF) {
-    // rotation of every skin matrix as a quaternion, once per (palette, bone) instead of once per SDEF vertex-instance
-    const uint32_t n = c->P * c->B;
-    skin_quats_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(reinterpret_cast<const float4*>(c->d_skin.p),
-                                                               reinterpret_cast<float4*>(c->d_quat.p), c->P, c->B, c->layoutMode ? 1u : 0u);
-    c->launches++;
-  }
-  if (feat & FEAT_BOUNDS) {
-    bounds_reset_kernel<<<(count * 6 + 127) / 128, 128, 0, c->stream>>>(reinterpret_cast<int*>(c->d_bounds.p) + (size_t)first * 6, count * 6);
-    c->launches++;
-  }
+  // the side kernels of a frame, ahead of the deform launch (stream operations only)
+  auto issue_side = [&]() {
+    if (feat & FEAT_SDEF) {
+      // rotation of every skin matrix as a quaternion, once per (palette, bone) instead of once per SDEF vertex-instance
+      const uint32_t n = c->P * c->B;
+      skin_quats_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(reinterpret_cast<const float4*>(c->d_skin.p),
+                                                                 reinterpret_cast<float4*>(c->d_quat.p), c->P, c->B, c->layoutMode ? 1u : 0u);
+      c->launches++;
+    }
+    if (feat & FEAT_BOUNDS) {
+      bounds_reset_kernel<<<(count * 6 + 127) / 128, 128, 0, c->stream>>>(reinterpret_cast<int*>(c->d_bounds.p) + (size_t)first * 6, count * 6);
+      c->launches++;
+    }
+  };
   if (pipelined) {
+    CU_TRY(c, cudaEventRecord(c->evStart, c->stream));
+    issue_side();
     // identity mapping: instance k reads palette k.  Blocks that do not touch [first, first+count) stay pending; parts of
     // the range whose blocks were consumed by an earlier call are launched as they are.
     std::vector<rz_ctx_impl::PendBlock> keep;
@@ -1357,8 +1451,8 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
       const uint32_t lo = std::max(first, b.pal0), hi = std::min(end, b.pal0 + b.n);
       if (lo >= hi) { keep.push_back(b); continue; }
       if (lo > cursor && (rc = launch_range(cursor, lo - cursor))) return rc;
-      CU_TRY(c, cudaStreamWaitEvent(c->stream, b.ev, 0));
-      launch_skin_block(c, reinterpret_cast<const float*>(c->d_world.p), b.pal0, b.n);
+      if (b.ev) CU_TRY(c, cudaStreamWaitEvent(c->stream, b.ev, 0));
+      launch_skin_block(c, b.src, b.pal0, b.n);
       CU_TRY(c, cudaEventRecord(c->evWorldFree, c->stream));
       c->worldFreeValid = true;
       if ((rc = launch_range(lo, hi - lo))) return rc;
@@ -1367,7 +1461,65 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
     if (cursor < end && (rc = launch_range(cursor, end - cursor))) return rc;
     c->pend.swap(keep);
   } else {
-    if ((rc = launch_range(first, count))) return rc;
+    // ---- the frame as ONE CUDA graph: [lazy skin-matrix passes] [skin quaternions] [AABB reset] counter reset, deform.
+    // Recorded once per distinct frame description (every pointer, size and launch dimension below is part of the key)
+    // and replayed with a single cudaGraphLaunch afterwards: a steady-state frame costs one driver call, whatever the
+    // feature set ("launches pre-recorded in a CUDA graph").
+    RangeLaunch r;
+    if ((rc = plan_range(first, count, r))) return rc;
+    rz_ctx_impl::GraphKey key;
+    memset(&key, 0, sizeof key);
+    key.fn = ke.fn; key.grid = r.grid; key.nt = (uint32_t)ke.NT; key.smem = smem; key.prm = r.prm; key.feat = feat;
+    key.first = first; key.count = count; key.P = c->P;
+    key.invBind = c->d_invBind.p; key.bonePos = c->d_bonePos.p; key.layoutMode = c->layoutMode;
+    key.nPend = (uint32_t)std::min<size_t>(c->pend.size(), 4);
+    bool readsWorld = false;
+    for (uint32_t i = 0; i < key.nPend; ++i) { key.pendSrc[i] = c->pend[i].src; key.pendPal0[i] = c->pend[i].pal0; key.pendN[i] = c->pend[i].n; }
+    for (const auto& b : c->pend) readsWorld |= b.src == c->d_world.p;
+    const bool useGraph = c->useGraphs && c->pend.size() <= 4;
+    auto issue_frame = [&]() -> int {
+      for (const auto& b : c->pend) launch_skin_block(c, b.src, b.pal0, b.n);
+      issue_side();
+      return issue_range(r);
+    };
+    CU_TRY(c, cudaEventRecord(c->evStart, c->stream));
+    if (!useGraph) {
+      if ((rc = issue_frame())) return rc;
+    } else {
+      rz_ctx_impl::GraphEntry* hit = nullptr;
+      for (auto& g : c->graphs)
+        if (memcmp(&g.key, &key, sizeof key) == 0) { hit = &g; break; }
+      if (!hit) {
+        const uint64_t launches0 = c->launches;
+        cudaGraph_t graph = nullptr;
+        CU_TRY(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        const int rci = issue_frame();
+        const cudaError_t ee = cudaStreamEndCapture(c->stream, &graph);
+        if (rci) { if (graph) cudaGraphDestroy(graph); return rci; }
+        if (ee != cudaSuccess) return fail(c, RZ_ERR_CUDA, "rz_deform: stream capture failed: %s", cudaGetErrorString(ee));
+        rz_ctx_impl::GraphEntry ge;
+        ge.key = key;
+        ge.nodes = (uint32_t)(c->launches - launches0);
+        const cudaError_t ei = cudaGraphInstantiate(&ge.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ei != cudaSuccess) return fail(c, RZ_ERR_CUDA, "rz_deform: cudaGraphInstantiate: %s", cudaGetErrorString(ei));
+        c->launches = launches0;
+        if (c->graphs.size() >= 8) {                                  // small cache, oldest out
+          cudaGraphExecDestroy(c->graphs.front().exec);
+          c->graphs.erase(c->graphs.begin());
+        }
+        c->graphs.push_back(ge);
+        hit = &c->graphs.back();
+      }
+      CU_TRY(c, cudaGraphLaunch(hit->exec, c->stream));
+      c->launches += hit->nodes;
+      c->graphLaunches++;
+    }
+    c->pend.clear();
+    if (readsWorld) {
+      CU_TRY(c, cudaEventRecord(c->evWorldFree, c->stream));
+      c->worldFreeValid = true;
+    }
   }
   CU_TRY(c, cudaEventRecord(c->evStop, c->stream));
   c->evPending = true;
@@ -1390,6 +1542,8 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
 int32_t rz_sync(rz_ctx* c) {
   if (!c) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_sync: null ctx");
   CU_TRY(c, cudaSetDevice(c->device));
+  int rc;
+  if (c->V && c->palettesSet && (rc = flush_pending(c))) return rc;   // "everything issued so far" includes a lazy skin-matrix pass
   CU_TRY(c, cudaStreamSynchronize(c->stream));
   return RZ_OK;
 }
@@ -1681,41 +1835,38 @@ int32_t rz_read_skinning(rz_ctx* c, uint16_t* joints, uint8_t* weights) {
   if (!c) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_read_skinning: null ctx");
   if (c->V == 0) return fail(c, RZ_ERR_STATE, "rz_read_skinning before rz_load_mesh");
   CU_TRY(c, cudaSetDevice(c->device));
-  std::vector<float4> rec2(c->Vp);
-  std::vector<uint32_t> wb(c->Vp);
+  // Everything below is derived from the records the KERNEL reads (rec0.w, rec1.w, rec2 = w2, w3, palette rows): the
+  // pre-normalised f32 weights are re-quantised to UNORM8 and the palette rows mapped back to bone ids; the only host-side
+  // knowledge used is the permutation the library itself applied (lane, influence slot, palette row).
+  std::vector<float4> rec0(c->Vp), rec1(c->Vp), rec2(c->Vp);
+  CU_TRY(c, cudaMemcpyAsync(rec0.data(), c->d_rec0.p, (size_t)c->Vp * 16, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(rec1.data(), c->d_rec1.p, (size_t)c->Vp * 16, cudaMemcpyDeviceToHost, c->stream));
   CU_TRY(c, cudaMemcpyAsync(rec2.data(), c->d_rec2.p, (size_t)c->Vp * 16, cudaMemcpyDeviceToHost, c->stream));
-  CU_TRY(c, cudaMemcpyAsync(wb.data(), c->d_wbits.p, (size_t)c->Vp * 4, cudaMemcpyDeviceToHost, c->stream));
   CU_TRY(c, cudaStreamSynchronize(c->stream));
   for (uint32_t p = 0; p < c->Vp; ++p) {
     const uint32_t sv = c->procToVertex[p];
     if (sv == ~0u) continue;
     const uint32_t v = c->vorder[sv];                     // stored position -> caller vertex id
-    if (joints) {
-      uint32_t j01, j23;
-      memcpy(&j01, &rec2[p].z, 4);
-      memcpy(&j23, &rec2[p].w, 4);
-      if (c->packedMeta) {
-        j01 = (j01 & 0xFFFu) | (((j01 >> 12) & 0xFFFu) << 16);
-        j23 = (j23 & 0xFFFu) | (((j23 >> 12) & 0xFFFu) << 16);
-      }
-      // the device stores palette rows; map them back to the caller's bone ids
-      uint16_t dj[4] = {(uint16_t)c->boneAt[j01 & 0xFFFF], (uint16_t)c->boneAt[j01 >> 16], (uint16_t)c->boneAt[j23 & 0xFFFF],
-                        (uint16_t)c->boneAt[j23 >> 16]};
-      // slots beyond the vertex' last non-zero weight hold a borrowed joint on the device (gather coalescing, see
-      // rebuild_tables); they never influence the result, report the caller's value there
-      // zero-weight slots hold a borrowed joint on the device and the packer may have moved an influence to another slot
-      // (rebuild_tables); undo both: active influences come from the device table, the rest is the caller's value
-      const uint8_t* w8 = reinterpret_cast<const uint8_t*>(&wb[p]);
-      const bool zeroSum = (uint32_t)w8[0] + w8[1] + w8[2] + w8[3] == 0;
-      const bool packed = c->permMode >= 2;
-      uint32_t n = 1;
-      if (!zeroSum) for (uint32_t k = 0; k < 4; ++k) if (w8[k]) n = k + 1;
-      for (uint32_t k = 0; k < 4; ++k) {
-        const bool fromDevice = packed ? (w8[k] != 0 || (zeroSum && k == 0)) && k < n : k < n;
-        joints[(size_t)v * 4 + k] = fromDevice ? dj[c->procSlotMap[(size_t)p * 4 + k]] : c->h_joints[(size_t)v * 4 + k];
-      }
+    uint32_t j01, j23;
+    memcpy(&j01, &rec2[p].z, 4);
+    memcpy(&j23, &rec2[p].w, 4);
+    if (c->packedMeta) {
+      j01 = (j01 & 0xFFFu) | (((j01 >> 12) & 0xFFFu) << 16);
+      j23 = (j23 & 0xFFFu) | (((j23 >> 12) & 0xFFFu) << 16);
     }
-    if (weights) memcpy(&weights[(size_t)v * 4], &wb[p], 4);
+    const uint16_t dj[4] = {(uint16_t)c->boneAt[j01 & 0xFFFF], (uint16_t)c->boneAt[j01 >> 16], (uint16_t)c->boneAt[j23 & 0xFFFF],
+                            (uint16_t)c->boneAt[j23 >> 16]};
+    const float dw[4] = {rec0[p].w, rec1[p].w, rec2[p].x, rec2[p].y};
+    for (uint32_t k = 0; k < 4; ++k) {
+      // device slot that holds the caller's influence k (kNoSlot: its weight is zero, no slot was spent on it)
+      const uint8_t s = c->procSlotMap[(size_t)p * 4 + k];
+      const long q = s == kNoSlot ? 0 : lrintf(dw[s] * 255.0f);
+      if (weights) weights[(size_t)v * 4 + k] = (uint8_t)std::max(0l, std::min(255l, q));
+      // a zero-weight slot gathers a BORROWED palette row on the device (lane_plan.h: the row of a neighbouring lane, so
+      // that the unconditional gather costs no extra shared-memory wavefront); it never influences the result and the
+      // caller's own index is reported there
+      if (joints) joints[(size_t)v * 4 + k] = (s != kNoSlot && q != 0) ? dj[s] : c->h_joints[(size_t)v * 4 + k];
+    }
   }
   return RZ_OK;
 }

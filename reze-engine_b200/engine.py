@@ -167,7 +167,6 @@ class Engine:
             self.ctx.load_sdef(model.sdef.vertexIndex, model.sdef.c_r0_r1)
         if self._flags & capi.RZ_FLAG_OUTLINE:
             self.ctx.load_edge_size(self.vertexEdgeSizes(model))
-        self._world_stage = self.ctx.palette_staging(self.instances)
         if self.gpu_pose:
             self.ctx.load_skeleton(model.getSkeleton().bones)
             self._rot_stage = np.zeros((self.instances, len(model.getSkeleton().bones), 4), np.float32)
@@ -376,10 +375,13 @@ class Engine:
                 self._rot_stage[k] = m.localRotations.reshape(B, 4)
             self.ctx.set_local_rotations(self._rot_stage, K=self.instances)
         else:
+            # rz_palette_staging hands out two pinned buffers alternately and waits until the upload that last read the
+            # one it returns has completed: ask before EVERY refill (the previous frame's copy may still be in flight)
+            stage = self.ctx.palette_staging(self.instances)
             for k, m in enumerate(self.models):
                 m.evaluatePose()
-                self._world_stage[k] = m.getBoneWorldMatrices().reshape(B, 16)
-            self.ctx.set_palettes(self._world_stage, K=self.instances)
+                stage[k] = m.getBoneWorldMatrices().reshape(B, 16)
+            self.ctx.set_palettes(stage, K=self.instances)
         self.ctx.deform()
 
     def runRenderLoop(self, callback: Optional[Callable[[], None]] = None, frames: Optional[int] = None,
