@@ -278,6 +278,12 @@ int32_t rz_read_skinning(rz_ctx* ctx, uint16_t* joints /* 4V */, uint8_t* weight
 /* device-computed skin matrices of palette p as 3x4 row-major (12 floats per bone) */
 int32_t rz_read_skin_matrices(rz_ctx* ctx, uint32_t palette, float* skin3x4 /* 12*B */);
 
+/* Bone WORLD matrices of palette p (16 floats per bone, column-major, exactly the layout of Model.getBoneWorldMatrices(),
+ * model.ts:317-319) recovered from the device's skin matrices: world = skin * invBind^-1.  For hosts whose pose is
+ * evaluated on the device (rz_set_local_rotations / rz_set_instance_clocks) but that need the matrices back — the kinematic
+ * half of Physics.step moves bodies to their bones from exactly these (syncFromBones, physics.ts:649-703). */
+int32_t rz_read_world_matrices(rz_ctx* ctx, uint32_t palette, float* world16 /* 16*B */);
+
 /* ---- stats: replaces Engine.getStats() (engine.ts:1664-1666) ---- */
 int32_t rz_get_stats(rz_ctx* ctx, rz_stats* out);
 

@@ -35,6 +35,7 @@ EXPORTS = [
     "rz_load_edge_size", "rz_get_output_layout", "rz_read_outline", "rz_read_interleaved",
     "rz_plan_morph_rows", "rz_plan_chunks", "rz_read_instance_async", "rz_read_wait",
     "rz_load_rigid_bodies", "rz_apply_body_transforms", "rz_plan_sdef", "rz_plan_palette_rows", "rz_plan_lanes2",
+    "rz_read_world_matrices",
 ]
 
 
@@ -123,6 +124,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.rz_plan_sdef.argtypes = [vp, u32, vp, vp, u32, u32, vp, vp, u32, vp, vp, P(u32)]
     lib.rz_read_bounds.argtypes = [vp, u32, u32, vp]
     lib.rz_read_skinning.argtypes = [vp, vp, vp]
+    lib.rz_read_world_matrices.argtypes = [vp, C.c_uint32, vp]
     lib.rz_read_skin_matrices.argtypes = [vp, u32, vp]
     lib.rz_get_stats.argtypes = [vp, P(RzStats)]
     lib.rz_last_error.argtypes = [vp]
@@ -492,6 +494,12 @@ class DeformContext:
     def read_skin_matrices(self, palette: int) -> np.ndarray:
         out = np.empty((self.B, 12), dtype=np.float32)
         self._check(self.lib.rz_read_skin_matrices(self.h, palette, _ptr(out)))
+        return out
+
+    def read_world_matrices(self, palette: int) -> np.ndarray:
+        """[B,16] column-major bone world matrices of a palette (the layout of Model.getBoneWorldMatrices())."""
+        out = np.empty((self.B, 16), np.float32)
+        self._check(self.lib.rz_read_world_matrices(self.h, palette, _ptr(out)))
         return out
 
     def stats(self) -> dict:

@@ -1896,6 +1896,39 @@ int32_t rz_read_skin_matrices(rz_ctx* c, uint32_t palette, float* skin3x4) {
   return RZ_OK;
 }
 
+int32_t rz_read_world_matrices(rz_ctx* c, uint32_t palette, float* world16) {
+  if (!c || !world16) return fail(c, RZ_ERR_INVALID_ARG, "rz_read_world_matrices: null argument");
+  if (!c->palettesSet) return fail(c, RZ_ERR_STATE, "rz_read_world_matrices before this frame's palettes were set");
+  if (palette >= c->P) return fail(c, RZ_ERR_INVALID_ARG, "rz_read_world_matrices: palette %u >= P=%u", palette, c->P);
+  // The device keeps skin = world * invBind (rows 0-2); world = skin * invBind^-1.  invBind is affine (the reference's is a
+  // pure translation, pmx-loader.ts:791-824), so its inverse is closed-form; evaluated in f64 on the host, B small products.
+  std::vector<float> skin((size_t)c->B * 12);
+  int rc = rz_read_skin_matrices(c, palette, skin.data());
+  if (rc) return rc;
+  for (uint32_t b = 0; b < c->B; ++b) {
+    const float* ib = &c->h_invBind[(size_t)b * 16];            // column-major
+    double A[3][3], t[3];
+    for (int r = 0; r < 3; ++r) { for (int col = 0; col < 3; ++col) A[r][col] = ib[col * 4 + r]; t[r] = ib[12 + r]; }
+    const double det = A[0][0] * (A[1][1] * A[2][2] - A[1][2] * A[2][1]) - A[0][1] * (A[1][0] * A[2][2] - A[1][2] * A[2][0]) +
+                       A[0][2] * (A[1][0] * A[2][1] - A[1][1] * A[2][0]);
+    if (det == 0.0) return fail(c, RZ_ERR_INVALID_ARG, "rz_read_world_matrices: inverse bind matrix of bone %u is singular", b);
+    double Ai[3][3];
+    Ai[0][0] = (A[1][1] * A[2][2] - A[1][2] * A[2][1]) / det; Ai[0][1] = (A[0][2] * A[2][1] - A[0][1] * A[2][2]) / det; Ai[0][2] = (A[0][1] * A[1][2] - A[0][2] * A[1][1]) / det;
+    Ai[1][0] = (A[1][2] * A[2][0] - A[1][0] * A[2][2]) / det; Ai[1][1] = (A[0][0] * A[2][2] - A[0][2] * A[2][0]) / det; Ai[1][2] = (A[0][2] * A[1][0] - A[0][0] * A[1][2]) / det;
+    Ai[2][0] = (A[1][0] * A[2][1] - A[1][1] * A[2][0]) / det; Ai[2][1] = (A[0][1] * A[2][0] - A[0][0] * A[2][1]) / det; Ai[2][2] = (A[0][0] * A[1][1] - A[0][1] * A[1][0]) / det;
+    double ti[3];
+    for (int r = 0; r < 3; ++r) ti[r] = -(Ai[r][0] * t[0] + Ai[r][1] * t[1] + Ai[r][2] * t[2]);
+    const float* s = &skin[(size_t)b * 12];                     // 3x4 row-major
+    float* o = world16 + (size_t)b * 16;
+    for (int r = 0; r < 3; ++r) {
+      for (int col = 0; col < 3; ++col) o[col * 4 + r] = (float)(s[r * 4] * Ai[0][col] + s[r * 4 + 1] * Ai[1][col] + s[r * 4 + 2] * Ai[2][col]);
+      o[12 + r] = (float)(s[r * 4] * ti[0] + s[r * 4 + 1] * ti[1] + s[r * 4 + 2] * ti[2] + s[r * 4 + 3]);
+    }
+    o[3] = o[7] = o[11] = 0.f; o[15] = 1.f;
+  }
+  return RZ_OK;
+}
+
 int32_t rz_get_stats(rz_ctx* c, rz_stats* out) {
   if (!c || !out) return fail(c, RZ_ERR_INVALID_ARG, "rz_get_stats: null argument");
   CU_TRY(c, cudaSetDevice(c->device));

@@ -12,6 +12,7 @@ extern "C" {
 typedef struct napi_env__* napi_env;
 typedef struct napi_value__* napi_value;
 typedef struct napi_callback_info__* napi_callback_info;
+typedef struct napi_ref__* napi_ref;
 typedef enum { napi_ok, napi_invalid_arg, napi_generic_failure } napi_status;
 typedef enum { napi_undefined, napi_null, napi_boolean, napi_number, napi_string, napi_symbol, napi_object, napi_function,
                napi_external, napi_bigint } napi_valuetype;
@@ -35,6 +36,9 @@ napi_status napi_typeof(napi_env env, napi_value value, napi_valuetype* result);
 napi_status napi_set_named_property(napi_env env, napi_value object, const char* utf8name, napi_value value);
 napi_status napi_throw_error(napi_env env, const char* code, const char* msg);
 napi_status napi_throw_type_error(napi_env env, const char* code, const char* msg);
+napi_status napi_throw_range_error(napi_env env, const char* code, const char* msg);
+napi_status napi_create_reference(napi_env env, napi_value value, uint32_t initial_refcount, napi_ref* result);
+napi_status napi_delete_reference(napi_env env, napi_ref ref);
 napi_status napi_create_object(napi_env env, napi_value* result);
 napi_status napi_create_double(napi_env env, double value, napi_value* result);
 napi_status napi_create_bigint_uint64(napi_env env, uint64_t value, napi_value* result);
