@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RZE_B200_ABI_VERSION 2
+#define RZE_B200_ABI_VERSION 3
 
 typedef struct rz_ctx rz_ctx;
 
@@ -70,11 +70,14 @@ typedef struct rz_config {
   void*    stream;         /* optional cudaStream_t to launch on (e.g. the caller's current stream);
                               NULL = the context creates its own non-blocking stream */
   uint32_t tune_instances_per_group; /* 0 = auto; kernel tuning knob (instances sharing one vertex pass) */
-  uint32_t tune_store_mode;          /* reserved (ignored): results always leave through smem-staged TMA bulk stores */
+  uint32_t tune_store_mode;          /* 0 = auto; sub-batch size of the two-vertices-per-lane kernel (instances whose gathers are in
+                                        flight together and whose stores form one commit group); ignored by the other kernels */
   uint32_t tune_threads;             /* 0 = auto; threads per CTA: 256, 512, 768 or 1024 (must be a compiled launch shape) */
   uint32_t tune_chunks;              /* 0 = auto; vertex chunks per instance group (work-item granularity) */
   uint32_t tune_ctas_per_sm;         /* 0 = auto; persistent CTAs per SM */
-  uint32_t tune_reserved[3];
+  uint32_t tune_vertices_per_lane;   /* 0 = auto (two on the plain planar path, one wherever morphs / SDEF / a fused consumer
+                                        run); 1 = always the one-vertex-per-lane kernel; 2 = insist on the two-vertex kernel */
+  uint32_t tune_reserved[2];
 } rz_config;
 
 typedef struct rz_stats {
@@ -93,6 +96,7 @@ typedef struct rz_stats {
   uint32_t morphCount, morphNnz, sdefCount, activeMorphs;
   uint32_t instancesPerGroup, storeMode, ctas, threads; /* launch shape actually used */
   uint32_t smemBytes;
+  uint32_t verticesPerLane;    /* 2: the last rz_deform ran the two-vertices-per-lane kernel (deform2_kernel.cuh), else 1 */
   uint32_t fastGatherPermille; /* share of the warp-level palette-row gathers whose lane pairs were packed onto the
                                 * shared-memory broadcast fast path at load time (pair packing) */
 } rz_stats;
@@ -243,15 +247,18 @@ int32_t rz_plan_morph_rows(const uint32_t* laneVertex /* Vp */, uint32_t Vp, uin
                            const uint32_t* vertIdx, const float* delta3, uint32_t M, uint32_t* rowFirst /* Vp/32 */,
                            uint32_t* rowDepth /* Vp/32 */, uint8_t* morphMajor /* Vp/32 */, float* rows, uint64_t rowsCapacity,
                            uint64_t* rowsNeeded);
-/* GROUNDWORK, not used by this round's kernel: the lane plan for TWO vertices per lane.  Windows of 64
- * consecutive vertices become one group of 32 lanes x 2 vertices sharing one list of <= 4 palette rows per lane (groupPaired = 1)
- * or, where no such pairing exists, two ordinary groups of 32 lanes x 1 vertex.  Per group: first output vertex, vertex count;
- * per lane (group*32 + lane): the two vertices (0xFFFFFFFF = none), the four rows it gathers, the shader-normalised weight of
- * every row for vertex A and for vertex B (0 where the row is not that vertex' bone).  stats[4]: gather instructions on the
- * fast path, all gather instructions, paired windows, fallback windows.  Call with every output NULL to learn *nGroups. */
+/* The lane plan of the two-vertices-per-lane kernel (deform2_kernel.cuh), device-free like rz_plan_lanes.
+ * Windows of 64 consecutive vertices become one group of 32 lanes x 2 vertices sharing one list of <= 4 palette rows per lane
+ * (groupPaired = 1) or, where no such pairing exists, two ordinary groups of 32 lanes x 1 vertex.  Per group: first output vertex,
+ * vertex count; per lane (group*32 + lane): the two vertices (0xFFFFFFFF = none), the four rows it gathers, the shader-normalised
+ * weight of every row for vertex A and for vertex B (0 where the row is not that vertex' bone), the staging slot (0..63) each
+ * side writes — A-slots of a group are distinct modulo 32, likewise B-slots (bank-conflict-free staging) — and the number of
+ * rows the lane uses.  stats[4]: gather instructions on the fast path, all gather instructions, paired windows, fallback
+ * windows.  Call with every output NULL to learn *nGroups.  Any output may be NULL. */
 int32_t rz_plan_lanes2(const uint16_t* joints, const uint8_t* weights, uint32_t V, uint32_t B, uint32_t groupCapacity,
                        uint32_t* groupFirst, uint32_t* groupCount, uint8_t* groupPaired, uint32_t* laneVertA, uint32_t* laneVertB,
-                       uint16_t* laneJoints, float* laneWeightsA, float* laneWeightsB, uint64_t* stats, uint32_t* nGroups);
+                       uint16_t* laneJoints, float* laneWeightsA, float* laneWeightsB, uint64_t* stats, uint32_t* nGroups,
+                       uint8_t* laneSlotA, uint8_t* laneSlotB, uint8_t* laneSlots);
 /* The bank-aware palette permutation rz_load_mesh applies: bonePos[b] = palette row of bone b, chosen so
  * that bones gathered by the same warp instruction sit in different 16-byte bank groups.  laneJoints as returned by
  * rz_plan_lanes. */

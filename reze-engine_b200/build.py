@@ -49,7 +49,7 @@ def _run(cmd, log):
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJDIR, exist_ok=True)
     nvcc = _nvcc()
-    hdrs = [os.path.join(CSRC, h) for h in ("deform_kernel.cuh", "kernel_table.h", "aux_kernels.cuh", "lane_plan.h", "lane_plan2.h", "mesh_tables.h")]
+    hdrs = [os.path.join(CSRC, h) for h in ("deform_kernel.cuh", "deform2_kernel.cuh", "kernel_table.h", "aux_kernels.cuh", "lane_plan.h", "lane_plan2.h", "mesh_tables.h")]
     hdrs.append(os.path.join(os.path.dirname(HERE), "include", "rze_b200.h"))
     jobs = []
     objs = []
@@ -64,6 +64,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs.append(o)
         if force or not _newer(o, [inst_src] + hdrs):
             jobs.append(([nvcc, *ARCH, *COMMON, f"-DRZ_FEAT={f}", "-c", inst_src, "-o", o], o + ".log"))
+    v2_src, v2_obj = os.path.join(CSRC, "deform2_inst.cu"), os.path.join(OBJDIR, "deform2.o")
+    objs.append(v2_obj)
+    if force or not _newer(v2_obj, [v2_src] + hdrs):
+        jobs.append(([nvcc, *ARCH, *COMMON, "-c", v2_src, "-o", v2_obj], v2_obj + ".log"))
     if jobs:
         with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
             outs = list(ex.map(lambda j: _run(*j), jobs))

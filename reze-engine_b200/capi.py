@@ -50,7 +50,8 @@ class RzConfig(C.Structure):
         ("struct_size", C.c_uint32), ("device", C.c_int32), ("max_instances", C.c_uint32), ("flags", C.c_uint32),
         ("stream", C.c_void_p),
         ("tune_instances_per_group", C.c_uint32), ("tune_store_mode", C.c_uint32), ("tune_threads", C.c_uint32),
-        ("tune_chunks", C.c_uint32), ("tune_ctas_per_sm", C.c_uint32), ("tune_reserved", C.c_uint32 * 3),
+        ("tune_chunks", C.c_uint32), ("tune_ctas_per_sm", C.c_uint32), ("tune_vertices_per_lane", C.c_uint32),
+        ("tune_reserved", C.c_uint32 * 2),
     ]
 
 
@@ -62,7 +63,7 @@ class RzStats(C.Structure):
         ("vertexCount", C.c_uint32), ("boneCount", C.c_uint32), ("instanceCount", C.c_uint32), ("paletteCount", C.c_uint32),
         ("morphCount", C.c_uint32), ("morphNnz", C.c_uint32), ("sdefCount", C.c_uint32), ("activeMorphs", C.c_uint32),
         ("instancesPerGroup", C.c_uint32), ("storeMode", C.c_uint32), ("ctas", C.c_uint32), ("threads", C.c_uint32),
-        ("smemBytes", C.c_uint32), ("fastGatherPermille", C.c_uint32),
+        ("smemBytes", C.c_uint32), ("verticesPerLane", C.c_uint32), ("fastGatherPermille", C.c_uint32),
     ]
 
     def asdict(self):
@@ -120,7 +121,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.rz_plan_morph_rows.argtypes = [vp, u32, u32, vp, vp, vp, u32, vp, vp, vp, vp, C.c_uint64, P(C.c_uint64)]
     lib.rz_plan_chunks.argtypes = [vp, u32, u32, u32, vp, P(u32)]
     lib.rz_plan_palette_rows.argtypes = [vp, u32, u32, vp]
-    lib.rz_plan_lanes2.argtypes = [vp, vp, u32, u32, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, P(u32)]
+    lib.rz_plan_lanes2.argtypes = [vp, vp, u32, u32, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, P(u32), vp, vp, vp]
     lib.rz_plan_sdef.argtypes = [vp, u32, vp, vp, u32, u32, vp, vp, u32, vp, vp, P(u32)]
     lib.rz_read_bounds.argtypes = [vp, u32, u32, vp]
     lib.rz_read_skinning.argtypes = [vp, vp, vp]
@@ -186,22 +187,23 @@ def plan_morph_rows(lane_vertex, V: int, offsets, vert_idx, delta3, lib: Optiona
 
 
 def plan_lanes2(joints, weights, B: int, lib: Optional[C.CDLL] = None) -> dict:
-    """rz_plan_lanes2 (groundwork for two vertices per lane, device-free): groups of 32 lanes covering up to 64 vertices."""
+    """rz_plan_lanes2 (the two-vertices-per-lane kernel's lane plan, device-free): groups of 32 lanes covering up to 64 vertices."""
     lib = lib or load_library()
     j, w = _arr(joints, np.uint16).reshape(-1, 4), _arr(weights, np.uint8).reshape(-1, 4)
     V = j.shape[0]
     n = C.c_uint32(0)
     stats = np.zeros(4, np.uint64)
-    st = lib.rz_plan_lanes2(_ptr(j), _ptr(w), V, B, 0, None, None, None, None, None, None, None, None, _ptr(stats), C.byref(n))
+    st = lib.rz_plan_lanes2(_ptr(j), _ptr(w), V, B, 0, None, None, None, None, None, None, None, None, _ptr(stats), C.byref(n), None, None, None)
     if st != 0:
         raise RzError(st, (lib.rz_last_error(None) or b"").decode())
     G = n.value
     out = dict(groupFirst=np.zeros(G, np.uint32), groupCount=np.zeros(G, np.uint32), groupPaired=np.zeros(G, np.uint8),
                vertA=np.zeros(G * 32, np.uint32), vertB=np.zeros(G * 32, np.uint32), laneJoints=np.zeros((G * 32, 4), np.uint16),
-               wA=np.zeros((G * 32, 4), np.float32), wB=np.zeros((G * 32, 4), np.float32))
+               wA=np.zeros((G * 32, 4), np.float32), wB=np.zeros((G * 32, 4), np.float32),
+               slotA=np.zeros(G * 32, np.uint8), slotB=np.zeros(G * 32, np.uint8), laneSlots=np.zeros(G * 32, np.uint8))
     st = lib.rz_plan_lanes2(_ptr(j), _ptr(w), V, B, G, _ptr(out["groupFirst"]), _ptr(out["groupCount"]), _ptr(out["groupPaired"]),
                             _ptr(out["vertA"]), _ptr(out["vertB"]), _ptr(out["laneJoints"]), _ptr(out["wA"]), _ptr(out["wB"]), _ptr(stats),
-                            C.byref(n))
+                            C.byref(n), _ptr(out["slotA"]), _ptr(out["slotB"]), _ptr(out["laneSlots"]))
     if st != 0:
         raise RzError(st, (lib.rz_last_error(None) or b"").decode())
     out.update(fast=int(stats[0]), total=int(stats[1]), pairedWindows=int(stats[2]), fallbackWindows=int(stats[3]))
@@ -251,7 +253,8 @@ class DeformContext:
     """One rz_ctx: one GPU, one mesh, K instances."""
 
     def __init__(self, max_instances: int = 1, device: int = 0, flags: int = 0, stream: int = 0,
-                 instances_per_group: int = 0, store_mode: int = 0, threads: int = 0, chunks: int = 0, ctas_per_sm: int = 0):
+                 instances_per_group: int = 0, store_mode: int = 0, threads: int = 0, chunks: int = 0, ctas_per_sm: int = 0,
+                 vertices_per_lane: int = 0):
         self.lib = load_library()
         cfg = RzConfig()
         cfg.struct_size = C.sizeof(RzConfig)
@@ -264,6 +267,7 @@ class DeformContext:
         cfg.tune_threads = threads
         cfg.tune_chunks = chunks
         cfg.tune_ctas_per_sm = ctas_per_sm
+        cfg.tune_vertices_per_lane = vertices_per_lane
         h = C.c_void_p()
         st = self.lib.rz_create(C.byref(cfg), C.byref(h))
         if st != 0:

@@ -67,7 +67,9 @@ struct DeformParams {
   unsigned long long nrmOffF;          // floats from pos plane to normal plane
   unsigned long long hullOffF;         // floats from pos plane to outline-hull plane (FEAT_HULL)
   uint32_t V, B, nTiles, K0, Kcount, Mpad;
-  uint32_t nGroups, nChunks, tilesPerChunk;
+  uint32_t nGroups, nChunks, tilesPerChunk;   // instance groups; chunks per (fine) instance group; tiles per chunk
+  uint32_t nCoarse, nItems;                   // the first nCoarse instance groups are ONE item each (long items first, short ones
+                                              // level the tail: rze_b200.cu pick_items); nItems = nCoarse + (nGroups - nCoarse) * nChunks
   uint32_t packedMeta;                 // 1: meta lives in the spare bits of the joint words (B <= 4096), no separate load
   uint32_t posStride, rowStride;       // palette addressing: chunk r of palette row `pos` sits at pos*posStride + r*rowStride bytes
   const uint32_t* __restrict__ chunkTab; // [nChunks+1] tile boundaries of cost-balanced chunks, or nullptr (uniform tilesPerChunk)
@@ -319,13 +321,16 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
     if (tid == 0) ctrl->item = atomicAdd(prm.counter, 1u);
     __syncthreads();
     const uint32_t item = *reinterpret_cast<volatile uint32_t*>(&ctrl->item);
-    if (item >= prm.nGroups * prm.nChunks) break;
-    const uint32_t g = item / prm.nChunks;
-    const uint32_t chunk = item - g * prm.nChunks;
+    if (item >= prm.nItems) break;
+    uint32_t g = item, tile0 = 0, tile1 = prm.nTiles;
+    if (item >= prm.nCoarse) {
+      const uint32_t r = item - prm.nCoarse, gq = r / prm.nChunks, chunk = r - gq * prm.nChunks;
+      g = prm.nCoarse + gq;
+      tile0 = prm.chunkTab ? __ldg(prm.chunkTab + chunk) : chunk * prm.tilesPerChunk;
+      tile1 = prm.chunkTab ? __ldg(prm.chunkTab + chunk + 1) : min(prm.nTiles, tile0 + prm.tilesPerChunk);
+    }
     const uint32_t kBase = prm.K0 + g * I;                       // first instance of this group
     const uint32_t nInst = min((uint32_t)I, prm.K0 + prm.Kcount - kBase);
-    const uint32_t tile0 = prm.chunkTab ? __ldg(prm.chunkTab + chunk) : chunk * prm.tilesPerChunk;
-    const uint32_t tile1 = prm.chunkTab ? __ldg(prm.chunkTab + chunk + 1) : min(prm.nTiles, tile0 + prm.tilesPerChunk);
     float* const outItem = prm.out + (size_t)kBase * prm.instStrideF;   // pos plane of the group's first instance
 
     // ---- stage the palettes (+ morph weights) of the I instances: TMA bulk copies on one mbarrier

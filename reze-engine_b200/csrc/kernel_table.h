@@ -24,6 +24,12 @@ struct KernelEntry {
 // {shared, global 8} there is the bare set and the "everything" set (morph 1 + SDEF 2 + bounds 4), plus the common ones.
 #define RZ_FEAT_LIST(X) X(0) X(1) X(3) X(4) X(7) X(16) X(19) X(20) X(23) X(8) X(11) X(15) X(24) X(31) X(32) X(39) X(40) X(47) \
   X(64) X(71) X(72) X(79)
+// two-vertices-per-lane plain path (deform2_kernel.cuh): X(I, NT, MINB, SB, NBUF)
+#define RZ_SHAPES_V2(X) \
+  X(6, 384, 1, 2, 2) X(6, 512, 1, 1, 2) X(6, 512, 1, 1, 3) X(6, 256, 1, 3, 2) X(6, 256, 1, 2, 2) X(5, 512, 1, 1, 2) \
+  X(4, 384, 1, 2, 2) X(4, 512, 1, 2, 2) X(4, 512, 1, 1, 2) X(4, 256, 1, 2, 2) X(4, 256, 1, 4, 1) \
+  X(3, 256, 2, 3, 1) X(3, 256, 1, 3, 2) X(3, 512, 1, 1, 2) X(2, 256, 2, 2, 1) X(2, 256, 1, 2, 2) X(2, 512, 1, 1, 2) X(1, 256, 2, 1, 2)
+KernelEntry lookup_v2(int I, int NT, int MINB, int SB);
 #define RZ_DECL(f) KernelEntry lookup_feat_##f(int I, int NT, int MINB);
 RZ_FEAT_LIST(RZ_DECL)
 #undef RZ_DECL

@@ -1,6 +1,5 @@
-// lane_plan2.h — load-time planning for TWO vertices per lane (groundwork for the next kernel generation; DESIGN.md
-// section 10).  Pure host C++, no CUDA.  NOT used by the deform kernel of this round: reachable only through the
-// device-free diagnostic entry rz_plan_lanes2 and its CPU tests.
+// lane_plan2.h — load-time planning for TWO vertices per lane: the table deform2_kernel (deform2_kernel.cuh) runs on.
+// Pure host C++, no CUDA; also reachable through the device-free diagnostic entry rz_plan_lanes2 (CPU tests).
 //
 // Why: the deform kernel is bound by the shared-memory pipe, and 20 of its ~32 shared-memory cycles per warp-instance
 // are palette gathers -- one gather instruction per influence slot per warp of 32 vertices.  If a lane evaluates two
@@ -36,6 +35,12 @@ struct LanePlan2 {
   std::vector<float> wA, wB;          // [4] shader-normalised weight of slot s for vertex A / B (0 where not its bone)
   uint64_t slots = 0, fastSlots = 0;  // gather instructions (group x slot) of packed groups / of those on the fast path
   uint32_t pairedWindows = 0, fallbackWindows = 0;
+  // staging slots: where in the group's 64-vertex staging area the lane writes its vertex A / B.  A real vertex sits at
+  // (vertex - groupFirst); a lane without a vertex on a side gets one of the slots no vertex owns (never drained).  Sides are
+  // chosen so that the 32 A-slots of a group are distinct modulo 32, likewise the B-slots: 12-byte staging records then hit
+  // 32 distinct banks per store instruction (3 * slot mod 32 is a bijection on a residue system).
+  std::vector<uint8_t> slotA, slotB;
+  std::vector<uint8_t> laneN;         // slots the lane uses (highest slot with a non-zero weight on either side + 1, >= 1)
 };
 
 inline void plan_lanes2(const uint16_t* JT, const uint8_t* WT, uint32_t V, uint32_t B, LanePlan2& out) {
@@ -193,6 +198,79 @@ inline void plan_lanes2(const uint16_t* JT, const uint8_t* WT, uint32_t V, uint3
       for (int t = 0; t < std::min(S[v].n, 4); ++t)
         for (int k = 0; k < 4; ++k)
           if (vp.devW[(size_t)p * 4 + k] != 0.f && vp.gatherJ[(size_t)p * 4 + k] == S[v].b[t]) { w[k] = S[v].w[t]; break; }
+    }
+  }
+
+  // ---- staging slots and sides
+  out.slotA.assign(VL, 0); out.slotB.assign(VL, 0); out.laneN.assign(VL, 1);
+  for (uint32_t g = 0; g < out.nGroups; ++g) {
+    const uint32_t first = out.groupFirst[g], base = g * 32;
+    int owner[64];                                          // slot -> lane * 2 + side, -1: free
+    for (int s2 = 0; s2 < 64; ++s2) owner[s2] = -1;
+    int slotOf[32][2];
+    for (uint32_t l = 0; l < 32; ++l)
+      for (int side = 0; side < 2; ++side) {
+        const uint32_t v = side ? out.vertB[base + l] : out.vertA[base + l];
+        slotOf[l][side] = v == ~0u ? -1 : (int)(v - first);
+        if (v != ~0u) owner[v - first] = (int)l * 2 + side;
+      }
+    if (!out.groupPaired[g]) {
+      // one vertex per lane, all on side A (the kernel skips side B of such a group): real vertices own slots 0..count-1
+      // (< 32), empty lanes take the remaining low slots, the unused B sides the high half -- distinct modulo 32 as they are
+      int lowFree = 0;
+      for (uint32_t l = 0; l < 32; ++l) {
+        const uint32_t p = base + l;
+        if (slotOf[l][0] < 0) {
+          while (owner[lowFree] >= 0) ++lowFree;
+          slotOf[l][0] = lowFree;
+          owner[lowFree] = (int)l * 2;
+        }
+        out.slotA[p] = (uint8_t)slotOf[l][0];
+        out.slotB[p] = (uint8_t)(32 + l);
+        int n = 1;
+        for (int k = 0; k < 4; ++k) if (out.wA[(size_t)p * 4 + k] != 0.f) n = k + 1;
+        out.laneN[p] = (uint8_t)n;
+      }
+      continue;
+    }
+    int nextFree = 0;
+    for (uint32_t l = 0; l < 32; ++l)
+      for (int side = 0; side < 2; ++side) {
+        if (slotOf[l][side] >= 0) continue;
+        while (owner[nextFree] >= 0) ++nextFree;            // 64 slots, 32 lanes x 2: there is always one left
+        slotOf[l][side] = nextFree;
+        owner[nextFree] = (int)l * 2 + side;
+      }
+    // Every slot now has exactly one lane partner (the lane's other slot) and one residue partner (slot ^ 32): the union
+    // of the two pairings is a set of even cycles that alternate between them, so colouring alternately along each cycle
+    // gives every lane one slot of each colour AND every residue class one slot of each colour.
+    int colour[64];
+    for (int s2 = 0; s2 < 64; ++s2) colour[s2] = -1;
+    for (int s0 = 0; s0 < 64; ++s0) {
+      if (colour[s0] >= 0) continue;
+      int cur = s0, col = 0;
+      for (;;) {
+        colour[cur] = col;
+        const int ln = owner[cur] >> 1, sd = owner[cur] & 1;
+        const int mate = slotOf[ln][sd ^ 1];                // lane partner: the other colour
+        colour[mate] = col ^ 1;
+        const int nxt = mate ^ 32;                          // its residue partner: back to `col`
+        if (nxt == s0 || colour[nxt] >= 0) break;
+        cur = nxt;
+      }
+    }
+    for (uint32_t l = 0; l < 32; ++l) {
+      const uint32_t p = base + l;
+      if (colour[slotOf[l][0]] == 1) {                      // swap the lane's sides
+        std::swap(out.vertA[p], out.vertB[p]);
+        for (int k = 0; k < 4; ++k) std::swap(out.wA[(size_t)p * 4 + k], out.wB[(size_t)p * 4 + k]);
+        std::swap(slotOf[l][0], slotOf[l][1]);
+      }
+      out.slotA[p] = (uint8_t)slotOf[l][0];
+      out.slotB[p] = (uint8_t)slotOf[l][1];
+      int n = 1;
+      for (int k = 0; k < 4; ++k) if (out.wA[(size_t)p * 4 + k] != 0.f || out.wB[(size_t)p * 4 + k] != 0.f) n = k + 1;
+      out.laneN[p] = (uint8_t)n;
     }
   }
 }

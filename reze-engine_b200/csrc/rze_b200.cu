@@ -7,6 +7,7 @@
 // sm_100a image, rz_create fails with RZ_ERR_NO_DEVICE.
 #include "../../include/rze_b200.h"
 #include "deform_kernel.cuh"
+#include "deform2_kernel.cuh"
 #include "aux_kernels.cuh"
 #include "kernel_table.h"
 #include "lane_plan.h"
@@ -29,7 +30,7 @@ using namespace rz;
 
 // the ctypes / N-API mirrors of these structs rely on the layout
 static_assert(sizeof(rz_config) == 56, "rz_config layout changed: update capi.py / napi shim");
-static_assert(sizeof(rz_stats) == 128, "rz_stats layout changed: update capi.py / napi shim");
+static_assert(sizeof(rz_stats) == 136, "rz_stats layout changed: update capi.py / napi shim");
 
 namespace {
 
@@ -45,7 +46,7 @@ struct rz_ctx_impl {
   cudaStream_t stream = nullptr;
   bool ownStream = false;
   uint32_t flags = 0, maxK = 1;
-  uint32_t tuneI = 0, tuneStore = 0, tuneThreads = 0, tuneChunks = 0, tuneCtas = 0;
+  uint32_t tuneI = 0, tuneStore = 0, tuneThreads = 0, tuneChunks = 0, tuneCtas = 0, tuneVpl = 0;
   int numSM = 0, maxSmemOptin = 0;
   std::string err;
 
@@ -80,6 +81,14 @@ struct rz_ctx_impl {
   //   layoutMode 0: palette rows of 48 B ([B][3] float4); 1: [3][B] float4 + co-occurrence clustering (measured slower)
   int permMode = 2, colorMode = 1, layoutMode = 0;       // vertex ordering inside a tile / bank-aware palette permutation
   DevBuf d_rec0, d_rec1, d_rec2, d_meta, d_mrange, d_ments, d_sdefIdx, d_sdefTab, d_invBind;
+  // two-vertices-per-lane table of the plain path (lane_plan2.h / deform2_kernel.cuh); built when the output layout is the
+  // plain planar one (no fused consumer flags); vplMode: RZ_VPL=0 disables it (A/B measurements)
+  DevBuf d_rec2v;
+  uint32_t vgCount = 0;                   // vertex groups (32 lanes each)
+  bool vpl2Ready = false;
+  int vplMode = 1;
+  std::vector<uint32_t> p2VertA, p2VertB; // stored vertex evaluated on side A / B of lane L (~0u: none)
+  uint64_t p2FastSlots = 0, p2Slots = 0;
   uint32_t morphNnz = 0, sdefActive = 0;
   std::vector<uint32_t> tileMorphMax;     // [nTiles] most morph entries on one vertex of the tile (chunk balancing)
   DevBuf d_chunkTab;
@@ -141,7 +150,7 @@ struct rz_ctx_impl {
 
   // CUDA graphs of recorded frames (rz_deform)
   struct GraphKey {
-    const void* fn; uint32_t grid, nt; size_t smem; DeformParams prm; int feat; uint32_t first, count, P;
+    const void* fn; uint32_t grid, nt; size_t smem; DeformParams prm; Deform2Params prm2; int feat; uint32_t first, count, P;
     const void* invBind; const void* bonePos; int layoutMode;
     uint32_t nPend; const void* pendSrc[4]; uint32_t pendPal0[4], pendN[4];
   };
@@ -159,9 +168,10 @@ struct rz_ctx_impl {
   std::vector<double> frameStamps;
   uint64_t frames = 0, launches = 0;
   size_t devBytes = 0;
-  uint32_t usedI = 0, usedStore = 0, usedCtas = 0, usedThreads = 0, usedSmem = 0;
+  uint32_t usedI = 0, usedStore = 0, usedCtas = 0, usedThreads = 0, usedSmem = 0, usedVpl = 1;
   // launch-shape cache: the selection below (lookup + occupancy query) only depends on these
-  struct ShapeKey { int feat = -1; uint32_t B = 0, Mpad = 0, countClass = 0; } shapeKey;
+  struct ShapeKey { int feat = -1; uint32_t B = 0, Mpad = 0, countClass = 0; bool v2Allowed = false; } shapeKey;
+  bool shapeV2 = false;
   KernelEntry shapeKe{nullptr, 0, 0, 0, 0, 0, 0};
   size_t shapeSmem = 0;
   int shapeOcc = 0;
@@ -323,6 +333,35 @@ size_t smem_needed(int I, int NT, int feat, uint32_t B, uint32_t Mpad, int nbuf 
   return s;
 }
 
+size_t smem_needed2(int I, int NT, uint32_t B, int SB, int NBUF) {   // deform2_kernel: control block, I palettes, per warp NBUF sub-batch buffers
+  return kCtrlBytes + (size_t)I * B * 48 + (size_t)(NT / 32) * NBUF * SB * 1536;   // (2 planes x 64 vertices x 12 B per instance)
+}
+
+// How to cut a launch into work items.  Items are pulled from an atomic queue by `grid` persistent CTAs, so the launch ends
+// when the last CTA finishes.  Few, long items leave a tail (683 instance groups on 148 CTAs: 5 rounds for 4.6 rounds of
+// work); many short ones pay the fixed cost of an item (palette staging + two CTA-wide barriers, o ~ 2.5 us) over and over.
+// So: the first `coarse` instance groups are one item each, the rest are cut into `chunks` pieces that level the tail
+// ("long items first").  Both are chosen by the estimate  rounds1 * (T + o) + ceil(rest * c / grid) * (T / c + o),
+// T = one whole instance group on one CTA (measured on B200: within ~1 % of an exhaustive sweep, profiles/r02_chunk_sweep.txt).
+struct ItemPlan { uint32_t coarse, chunks; };
+ItemPlan pick_items(uint32_t nGroups, uint32_t grid, uint32_t V, int I, uint32_t maxChunks) {
+  const double T = (double)V * I * 0.6e-9, o = 2.5e-6 / std::max(T, 1e-9);
+  ItemPlan best{0, 1};
+  double bestCost = 1e300;
+  static const uint32_t cs[] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16};
+  const uint32_t fullRounds = nGroups / std::max(grid, 1u);
+  for (uint32_t r1 = 0; r1 <= fullRounds; ++r1) {
+    const uint32_t rest = nGroups - r1 * grid;
+    for (uint32_t c : cs) {
+      if (c > std::max(1u, maxChunks)) break;
+      if (rest == 0 && c > 1) break;
+      const double cost = r1 * (1.0 + o) + std::ceil((double)rest * c / grid) * (1.0 / c + o);
+      if (cost < bestCost * 0.9995) { bestCost = cost; best = ItemPlan{r1 * grid, c}; }
+    }
+  }
+  return best;
+}
+
 // ---- table preprocessing ------------------------------------------------------------------------
 // Tile = 256 consecutive vertices (work-item granularity).  A warp owns 32 consecutive vertices; which LANE evaluates
 // which of them is chosen at load time (see below).  Staging writes of a warp always hit 32 distinct banks
@@ -428,8 +467,18 @@ int rebuild_tables(rz_ctx_impl* c) {
   c->packFastSlots = plan.fastSlots;
   c->packTotalSlots = plan.totalSlots;
 
-  // ---- bank-aware palette permutation (mesh_tables.h)
-  plan_palette_rows(gatherJ.data(), Vp, B, c->colorMode, c->layoutMode, c->bonePos);
+  // ---- two vertices per lane (lane_plan2.h): the plain path's own table, when this context can run the plain path at all
+  LanePlan2 plan2;
+  const bool vpl2 = c->vplMode != 0 && c->layoutMode == 0 &&
+                    !(c->flags & (RZ_FLAG_NO_NORMALS | RZ_FLAG_OUTLINE | RZ_FLAG_INTERLEAVED | RZ_FLAG_BOUNDS));
+  if (vpl2) plan_lanes2(JT, WT, V, B, plan2);
+  c->vpl2Ready = false;
+
+  // ---- bank-aware palette permutation (mesh_tables.h): one permutation serves both tables; it follows the gather pattern
+  // of the kernel that will run most (the two-vertex plain path unless morphs / SDEF send every launch to the feature kernel)
+  const bool colourByV2 = vpl2 && c->M == 0 && !((c->flags & RZ_FLAG_SDEF) && !c->h_sdefVert.empty());
+  if (colourByV2) plan_palette_rows(plan2.gatherJ.data(), plan2.nGroups * 32, B, c->colorMode, c->layoutMode, c->bonePos);
+  else plan_palette_rows(gatherJ.data(), Vp, B, c->colorMode, c->layoutMode, c->bonePos);
   c->boneAt.assign(B, 0);
   for (uint32_t b = 0; b < B; ++b) c->boneAt[c->bonePos[b]] = b;
 
@@ -477,6 +526,35 @@ int rebuild_tables(rz_ctx_impl* c) {
     metaArr[p] = meta;
   }
 
+  // ---- records of the two-vertex table: 6 float4 planes, SoA over lanes (deform2_kernel.cuh kRec2Planes)
+  std::vector<float4> rec2v;
+  if (vpl2) {
+    const uint32_t L = plan2.nGroups * 32;
+    rec2v.assign((size_t)kRec2Planes * L, make_float4(0.f, 0.f, 0.f, 0.f));
+    for (uint32_t p = 0; p < L; ++p) {
+      const uint32_t g = p / 32, vA = plan2.vertA[p], vB = plan2.vertB[p];
+      const uint16_t* j = &plan2.gatherJ[(size_t)p * 4];
+      const float* wa = &plan2.wA[(size_t)p * 4];
+      const float* wb = &plan2.wB[(size_t)p * 4];
+      const uint32_t r01 = c->bonePos[j[0]] | (c->bonePos[j[1]] << 16), r23 = c->bonePos[j[2]] | (c->bonePos[j[3]] << 16);
+      const uint32_t meta = (uint32_t)plan2.slotA[p] | ((uint32_t)plan2.slotB[p] << kM2SlotB) | ((uint32_t)plan2.laneN[p] << kM2N) |
+                            (vA != ~0u ? kM2HasA : 0u) | (vB != ~0u ? kM2HasB : 0u) | (plan2.groupCount[g] << kM2Cnt);
+      const uint32_t first = plan2.groupFirst[g];
+      float4 q0 = make_float4(0.f, 0.f, 0.f, wa[0]), q1 = make_float4(0.f, 0.f, 0.f, wa[1]);
+      float4 q2 = make_float4(0.f, 0.f, 0.f, wb[0]), q3 = make_float4(0.f, 0.f, 0.f, wb[1]);
+      if (vA != ~0u) { const float* x = &VT[(size_t)vA * 8]; q0.x = x[0]; q0.y = x[1]; q0.z = x[2]; q1.x = x[3]; q1.y = x[4]; q1.z = x[5]; }
+      if (vB != ~0u) { const float* x = &VT[(size_t)vB * 8]; q2.x = x[0]; q2.y = x[1]; q2.z = x[2]; q3.x = x[3]; q3.y = x[4]; q3.z = x[5]; }
+      float4 q5;
+      memcpy(&q5.x, &r01, 4); memcpy(&q5.y, &r23, 4); memcpy(&q5.z, &meta, 4); memcpy(&q5.w, &first, 4);
+      rec2v[p] = q0; rec2v[(size_t)L + p] = q1; rec2v[2 * (size_t)L + p] = q2; rec2v[3 * (size_t)L + p] = q3;
+      rec2v[4 * (size_t)L + p] = make_float4(wa[2], wa[3], wb[2], wb[3]);
+      rec2v[5 * (size_t)L + p] = q5;
+    }
+    c->vgCount = plan2.nGroups;
+    c->p2VertA = plan2.vertA; c->p2VertB = plan2.vertB;
+    c->p2FastSlots = plan2.fastSlots; c->p2Slots = plan2.slots;
+  }
+
   // ---- morph rows, lane-interleaved per warp (mesh_tables.h)
   MorphRows mrows;
   build_morph_rows(procVertex.data(), Vp, mcount, mstart, ments, mrows);
@@ -520,6 +598,11 @@ int rebuild_tables(rz_ctx_impl* c) {
   if (!uvArr.empty()) {
     if ((rc = dev_reserve(c, c->d_uv, (size_t)Vp * 8))) return rc;
     CU_TRY(c, cudaMemcpyAsync(c->d_uv.p, uvArr.data(), (size_t)Vp * 8, cudaMemcpyHostToDevice, c->stream));
+  }
+  if (vpl2) {
+    if ((rc = dev_reserve(c, c->d_rec2v, rec2v.size() * 16))) return rc;
+    CU_TRY(c, cudaMemcpyAsync(c->d_rec2v.p, rec2v.data(), rec2v.size() * 16, cudaMemcpyHostToDevice, c->stream));
+    c->vpl2Ready = true;
   }
   CU_TRY(c, cudaStreamSynchronize(c->stream));   // the std::vectors above go out of scope
 
@@ -638,6 +721,7 @@ int32_t rz_create(const rz_config* cfg, rz_ctx** out) {
     c->tuneThreads = cfg->tune_threads;
     c->tuneChunks = cfg->tune_chunks;
     c->tuneCtas = cfg->tune_ctas_per_sm;
+    c->tuneVpl = cfg->tune_vertices_per_lane;
   }
   if (cfg->stream) {
     c->stream = reinterpret_cast<cudaStream_t>(cfg->stream);
@@ -649,6 +733,7 @@ int32_t rz_create(const rz_config* cfg, rz_ctx** out) {
   if (const char* e1 = getenv("RZ_PERM")) c->permMode = atoi(e1);        // experiment knobs (tuning)
   if (const char* e2 = getenv("RZ_COLOR")) c->colorMode = atoi(e2);
   if (const char* e3 = getenv("RZ_LAYOUT")) c->layoutMode = atoi(e3);
+  if (const char* e4 = getenv("RZ_VPL")) c->vplMode = atoi(e4);
   c->noPipeline = getenv("RZ_NO_PIPELINE") != nullptr;
   c->useGraphs = getenv("RZ_NO_GRAPH") == nullptr;
   if (const char* eb = getenv("RZ_PIPELINE_BLOCK")) c->pipelineBlock = (uint32_t)std::max(1, atoi(eb));
@@ -681,7 +766,7 @@ int32_t rz_destroy(rz_ctx* c) {
   for (cudaEvent_t e : c->evPool) cudaEventDestroy(e);
   if (c->evWorldFree) cudaEventDestroy(c->evWorldFree);
   if (c->copyStream) cudaStreamDestroy(c->copyStream);
-  DevBuf* bufs[] = {&c->d_rec0, &c->d_rec1, &c->d_rec2, &c->d_meta, &c->d_mrange, &c->d_ments, &c->d_sdefIdx, &c->d_sdefTab,
+  DevBuf* bufs[] = {&c->d_rec0, &c->d_rec1, &c->d_rec2, &c->d_rec2v, &c->d_meta, &c->d_mrange, &c->d_ments, &c->d_sdefIdx, &c->d_sdefTab,
                     &c->d_invBind, &c->d_bonePos, &c->d_world, &c->d_skin, &c->d_inst2pal, &c->d_mwIn, &c->d_mwIds, &c->d_mwDense,
                     &c->d_out, &c->d_out2, &c->d_bounds, &c->d_counter, &c->d_skParent, &c->d_skBindT, &c->d_skAppendParent, &c->d_skAppendRatio,
                     &c->d_skLevelBones, &c->d_skLevelStart, &c->d_skChainStart, &c->d_skChainBones, &c->d_twStart, &c->d_twTarget, &c->d_twRest, &c->d_twStartMs, &c->d_twDurMs,
@@ -1268,11 +1353,15 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
   size_t smem = 0;
   int occ = 0;
   const uint32_t countClass = std::min<uint32_t>(count, 8u);        // shapes are only restricted by count when count < I <= 8
+  // the plain planar path runs the two-vertices-per-lane kernel (deform2_kernel.cuh) whenever its table exists
+  const bool v2Allowed = feat == 0 && c->vpl2Ready && c->tuneVpl != 1;
+  bool v2 = false;
   const bool cached = c->shapeKe.fn && c->shapeKey.feat == feat && c->shapeKey.B == c->B && c->shapeKey.Mpad == Mpad &&
-                      c->shapeKey.countClass == countClass;
-  if (cached) { ke = c->shapeKe; smem = c->shapeSmem; occ = c->shapeOcc; }
+                      c->shapeKey.countClass == countClass && c->shapeKey.v2Allowed == v2Allowed;
+  if (cached) { ke = c->shapeKe; smem = c->shapeSmem; occ = c->shapeOcc; v2 = c->shapeV2; }
+  const bool tuned = c->tuneI || c->tuneThreads;                    // an explicitly requested shape is taken as it is
   auto try_shape = [&](int I, int NT, int MINB) -> bool {
-    if ((uint32_t)I > count && I > 1) return false;                 // never wider than the instance range
+    if (!tuned && (uint32_t)I > count && I > 1) return false;       // never wider than the instance range
     KernelEntry e = lookup_kernel(feat, I, NT, MINB);
     if (!e.fn) return false;
     const size_t sm = smem_needed(e.I, e.NT, feat, c->B, Mpad, e.NB);
@@ -1280,14 +1369,32 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
     if (raise_smem_limit(c->device, e.fn, sm) != cudaSuccess) { cudaGetLastError(); return false; }
     int o = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, e.fn, e.NT, sm) != cudaSuccess || o < 1) { cudaGetLastError(); return false; }
-    ke = e; smem = sm; occ = o;
+    ke = e; smem = sm; occ = o; v2 = false;
+    return true;
+  };
+  auto try_shape2 = [&](int I, int NT, int MINB, int SB) -> bool {
+    if (!v2Allowed || (!tuned && (uint32_t)I > count && I > 1)) return false;
+    KernelEntry e = lookup_v2(I, NT, MINB, SB);
+    if (!e.fn) return false;
+    const size_t sm = smem_needed2(e.I, e.NT, c->B, e.SB, e.NB);
+    if (sm > smemMax) return false;
+    if (raise_smem_limit(c->device, e.fn, sm) != cudaSuccess) { cudaGetLastError(); return false; }
+    int o = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, e.fn, e.NT, sm) != cudaSuccess || o < 1) { cudaGetLastError(); return false; }
+    ke = e; smem = sm; occ = o; v2 = true;
     return true;
   };
   if (cached) {
     // nothing to do
-  } else if (c->tuneI || c->tuneThreads) {
+  } else if (tuned) {
     const int I = c->tuneI ? (int)c->tuneI : 2, NT = c->tuneThreads ? (int)c->tuneThreads : 256;
-    if (!try_shape(I, NT, (int)c->tuneCtas) && !try_shape(I, NT, 0))
+    // (tune_store_mode doubles as the sub-batch size of the two-vertex kernel; 0 = first compiled)
+    if (try_shape2(I, NT, (int)c->tuneCtas, (int)c->tuneStore) || try_shape2(I, NT, 0, (int)c->tuneStore)) {
+      // the requested shape exists for the two-vertex kernel
+    } else if (c->tuneVpl == 2) {
+      return fail(c, RZ_ERR_INVALID_ARG, "rz_deform: two-vertices-per-lane shape I=%d threads=%d ctas/SM=%u sub-batch=%u is not built, does not fit (B=%u) or "
+                  "the context's flags rule the plain path out", I, NT, c->tuneCtas, c->tuneStore, c->B);
+    } else if (!try_shape(I, NT, (int)c->tuneCtas) && !try_shape(I, NT, 0))
       return fail(c, RZ_ERR_INVALID_ARG, "rz_deform: requested launch shape I=%d threads=%d ctas/SM=%u is not built or does not fit (B=%u)",
                   I, NT, c->tuneCtas, c->B);
   } else {
@@ -1309,7 +1416,13 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
     else if (feat & FEAT_ILV) prefLite = prefIlv;
     else if (feat == FEAT_NONRM) prefLite = prefWide6;
     bool ok = false;
-    if (feat != 0) {
+    if (v2Allowed) {
+      // two-vertex kernel: 8 warps x 64 vertices with the widest palette stage first (measured on B200, profiles/r02_*)
+      static const int pref2[][4] = {{4, 512, 1, 2}, {4, 384, 1, 2}, {3, 512, 1, 1}, {2, 256, 2, 2}, {2, 512, 1, 1}, {3, 256, 1, 3},
+                                     {2, 256, 1, 2}, {1, 256, 2, 1}};
+      for (const auto& p : pref2) if (try_shape2(p[0], p[1], p[2], p[3])) { ok = true; break; }
+    }
+    if (!ok && feat != 0) {
       for (int q = 0; q < 5 && !ok; ++q) ok = try_shape(prefLite[q][0], prefLite[q][1], prefLite[q][2]);
     }
     if (!ok) {
@@ -1328,7 +1441,8 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
   if (c->tuneCtas && (int)c->tuneCtas < occ) occ = (int)c->tuneCtas;
   CU_TRY(c, raise_smem_limit(c->device, ke.fn, smem));      // (a no-op unless another device / a first use needs it)
   if (!cached) {
-    c->shapeKe = ke; c->shapeSmem = smem; c->shapeOcc = occ;
+    c->shapeKe = ke; c->shapeSmem = smem; c->shapeOcc = occ; c->shapeV2 = v2;
+    c->shapeKey.v2Allowed = v2Allowed;
     c->shapeKey.feat = feat; c->shapeKey.B = c->B; c->shapeKey.Mpad = Mpad; c->shapeKey.countClass = countClass;
   }
   DeformParams prm;
@@ -1357,17 +1471,48 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
   prm.packedMeta = c->packedMeta ? 1u : 0u;
   prm.posStride = c->layoutMode ? 16u : 48u;
   prm.rowStride = c->layoutMode ? c->B * 16u : 16u;
+  Deform2Params prm2;
+  memset(&prm2, 0, sizeof prm2);
+  if (v2) {
+    prm2.rec = reinterpret_cast<const float4*>(c->d_rec2v.p);
+    prm2.skin = prm.skin; prm2.inst2pal = prm.inst2pal; prm2.out = prm.out;
+    prm2.instStrideF = c->instStrideF; prm2.nrmOffF = c->nrmOffF;
+    prm2.lanes = c->vgCount * 32; prm2.nVG = c->vgCount; prm2.V = c->V; prm2.B = c->B;
+    prm2.counter = prm.counter;
+  }
   uint32_t gridUsed = 0;
   // ---- one launch over the instance range [f, f+n): plan (host work, may synchronise once per launch shape) ...
-  struct RangeLaunch { DeformParams prm; uint32_t grid; };
+  struct RangeLaunch { DeformParams prm; Deform2Params prm2; uint32_t grid; };
   auto plan_range = [&](uint32_t f, uint32_t n, RangeLaunch& out) -> int {
+    if (v2) {
+      prm2.K0 = f; prm2.Kcount = n;
+      prm2.nGroups = (n + ke.I - 1) / ke.I;
+      const uint32_t vgPerPass = ke.NT / 32;                        // one vertex group (64 vertices) per warp per pass
+      const uint32_t nPasses = (c->vgCount + vgPerPass - 1) / vgPerPass;
+      uint32_t grid = (uint32_t)(c->numSM * occ);
+      ItemPlan ip = c->tuneChunks ? ItemPlan{0, c->tuneChunks} : pick_items(prm2.nGroups, grid, c->V, ke.I, nPasses);
+      const uint32_t nChunks = std::max(1u, std::min(ip.chunks, nPasses));
+      prm2.vgPerChunk = (nPasses + nChunks - 1) / nChunks * vgPerPass;
+      prm2.nChunks = (c->vgCount + prm2.vgPerChunk - 1) / prm2.vgPerChunk;
+      prm2.nCoarse = std::min(ip.coarse, prm2.nGroups);
+      prm2.nItems = prm2.nCoarse + (prm2.nGroups - prm2.nCoarse) * prm2.nChunks;
+      grid = std::min(grid, prm2.nItems);
+      gridUsed = std::max(gridUsed, grid);
+      memset(&out.prm, 0, sizeof out.prm);
+      out.prm2 = prm2;
+      out.grid = grid;
+      return RZ_OK;
+    }
     prm.K0 = f; prm.Kcount = n;
     prm.nGroups = (n + ke.I - 1) / ke.I;
     const uint32_t tilesPerPass = ke.NT / kTile;
     const uint32_t nPasses = (c->nTiles + tilesPerPass - 1) / tilesPerPass;
     uint32_t grid = (uint32_t)(c->numSM * occ);
-    uint32_t nChunks = c->tuneChunks ? c->tuneChunks : (grid * 8 + prm.nGroups - 1) / prm.nGroups;
-    nChunks = std::max(1u, std::min(nChunks, nPasses));
+    const bool morphTab = (feat & FEAT_MORPH) && c->morphNnz;       // cost-balanced chunk table below: uniform, finer items
+    ItemPlan ip = c->tuneChunks ? ItemPlan{0, c->tuneChunks}
+                : morphTab ? ItemPlan{0, (grid * 8 + prm.nGroups - 1) / prm.nGroups}
+                           : pick_items(prm.nGroups, grid, c->V, ke.I, nPasses);
+    uint32_t nChunks = std::max(1u, std::min(ip.chunks, nPasses));
     const uint32_t passesPerChunk = (nPasses + nChunks - 1) / nChunks;
     prm.tilesPerChunk = passesPerChunk * tilesPerPass;
     prm.nChunks = (c->nTiles + prm.tilesPerChunk - 1) / prm.tilesPerChunk;
@@ -1391,17 +1536,19 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
       prm.chunkTab = reinterpret_cast<const uint32_t*>(c->d_chunkTab.p);
       prm.nChunks = c->chunkCount;
     }
-    const uint32_t nItems = prm.nGroups * prm.nChunks;
-    grid = std::min(grid, nItems);
+    prm.nCoarse = std::min(ip.coarse, prm.nGroups);
+    prm.nItems = prm.nCoarse + (prm.nGroups - prm.nCoarse) * prm.nChunks;
+    grid = std::min(grid, prm.nItems);
     gridUsed = std::max(gridUsed, grid);
     out.prm = prm;
+    memset(&out.prm2, 0, sizeof out.prm2);
     out.grid = grid;
     return RZ_OK;
   };
   // ... and issue (stream operations only: also runs under stream capture)
   auto issue_range = [&](RangeLaunch& r) -> int {
     CU_TRY(c, cudaMemsetAsync(c->d_counter.p, 0, 4, c->stream));
-    void* args[] = {&r.prm};
+    void* args[] = {v2 ? (void*)&r.prm2 : (void*)&r.prm};
     CU_TRY(c, cudaLaunchKernel(ke.fn, dim3(r.grid), dim3(ke.NT), args, smem, c->stream));
     c->launches++;
     return RZ_OK;
@@ -1469,7 +1616,7 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
     if ((rc = plan_range(first, count, r))) return rc;
     rz_ctx_impl::GraphKey key;
     memset(&key, 0, sizeof key);
-    key.fn = ke.fn; key.grid = r.grid; key.nt = (uint32_t)ke.NT; key.smem = smem; key.prm = r.prm; key.feat = feat;
+    key.fn = ke.fn; key.grid = r.grid; key.nt = (uint32_t)ke.NT; key.smem = smem; key.prm = r.prm; key.prm2 = r.prm2; key.feat = feat;
     key.first = first; key.count = count; key.P = c->P;
     key.invBind = c->d_invBind.p; key.bonePos = c->d_bonePos.p; key.layoutMode = c->layoutMode;
     key.nPend = (uint32_t)std::min<size_t>(c->pend.size(), 4);
@@ -1524,7 +1671,7 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
   CU_TRY(c, cudaEventRecord(c->evStop, c->stream));
   c->evPending = true;
   c->frames++;
-  c->usedI = ke.I; c->usedStore = 2; c->usedCtas = gridUsed; c->usedThreads = ke.NT; c->usedSmem = (uint32_t)smem;
+  c->usedI = ke.I; c->usedStore = v2 ? 3 : 2; c->usedVpl = v2 ? 2 : 1; c->usedCtas = gridUsed; c->usedThreads = ke.NT; c->usedSmem = (uint32_t)smem;
   c->lastVerts = (uint64_t)count * c->V;
   // compulsory DRAM bytes: outputs + mesh + palettes + invBind + morph entries/weights + sdef records
   // (fused consumers add their own compulsory bytes: +12 B per vertex-instance for the hull plane, 32 B instead of 24 B
@@ -1742,7 +1889,8 @@ int32_t rz_plan_morph_rows(const uint32_t* laneVertex, uint32_t Vp, uint32_t V, 
 
 int32_t rz_plan_lanes2(const uint16_t* joints, const uint8_t* weights, uint32_t V, uint32_t B, uint32_t groupCapacity, uint32_t* groupFirst,
                        uint32_t* groupCount, uint8_t* groupPaired, uint32_t* laneVertA, uint32_t* laneVertB, uint16_t* laneJoints,
-                       float* laneWeightsA, float* laneWeightsB, uint64_t* stats, uint32_t* nGroups) {
+                       float* laneWeightsA, float* laneWeightsB, uint64_t* stats, uint32_t* nGroups, uint8_t* laneSlotA, uint8_t* laneSlotB,
+                       uint8_t* laneSlots) {
   if (!joints || !weights || V == 0 || B == 0 || !nGroups) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_plan_lanes2: null or empty tables");
   for (size_t i = 0; i < (size_t)V * 4; ++i)
     if (joints[i] >= B) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_plan_lanes2: joint %u >= B=%u", (unsigned)joints[i], B);
@@ -1761,6 +1909,9 @@ int32_t rz_plan_lanes2(const uint16_t* joints, const uint8_t* weights, uint32_t 
   if (laneJoints) memcpy(laneJoints, plan.gatherJ.data(), L * 8);
   if (laneWeightsA) memcpy(laneWeightsA, plan.wA.data(), L * 16);
   if (laneWeightsB) memcpy(laneWeightsB, plan.wB.data(), L * 16);
+  if (laneSlotA) memcpy(laneSlotA, plan.slotA.data(), L);
+  if (laneSlotB) memcpy(laneSlotB, plan.slotB.data(), L);
+  if (laneSlots) memcpy(laneSlots, plan.laneN.data(), L);
   return RZ_OK;
 }
 
@@ -1831,43 +1982,110 @@ int32_t rz_read_bounds(rz_ctx* c, uint32_t first, uint32_t count, float* minmax6
   return RZ_OK;
 }
 
+// One vertex' (bone, weight) terms as the device holds them -> the caller's four slots.  Term order on the device is the
+// planner's; the caller's order is recovered by matching bone ids against the caller's joint list (the permutation the
+// library applied), every device term being consumed exactly once.  Returns false when a device term matches no slot.
+static bool terms_to_caller_slots(const uint16_t* callerJ, const uint16_t* bone, const float* w, int nTerms, uint16_t* outJ, uint8_t* outW) {
+  bool used[8] = {false, false, false, false, false, false, false, false};
+  int left = 0;
+  for (int t = 0; t < nTerms; ++t) left += w[t] != 0.f;
+  for (int k = 0; k < 4; ++k) {
+    outJ[k] = callerJ[k];                                   // zero-weight slot: the device spends nothing on it
+    outW[k] = 0;
+  }
+  // pass 1: caller slots whose bone matches an unused device term
+  for (int k = 0; k < 4 && left; ++k)
+    for (int t = 0; t < nTerms; ++t) {
+      if (used[t] || w[t] == 0.f || bone[t] != callerJ[k]) continue;
+      const long q = lrintf(w[t] * 255.0f);
+      outJ[k] = bone[t];
+      outW[k] = (uint8_t)std::max(0l, std::min(255l, q));
+      used[t] = true;
+      --left;
+      break;
+    }
+  return left == 0;
+}
+
 int32_t rz_read_skinning(rz_ctx* c, uint16_t* joints, uint8_t* weights) {
   if (!c) return fail(nullptr, RZ_ERR_INVALID_ARG, "rz_read_skinning: null ctx");
   if (c->V == 0) return fail(c, RZ_ERR_STATE, "rz_read_skinning before rz_load_mesh");
   CU_TRY(c, cudaSetDevice(c->device));
-  // Everything below is derived from the records the KERNEL reads (rec0.w, rec1.w, rec2 = w2, w3, palette rows): the
-  // pre-normalised f32 weights are re-quantised to UNORM8 and the palette rows mapped back to bone ids; the only host-side
-  // knowledge used is the permutation the library itself applied (lane, influence slot, palette row).
-  std::vector<float4> rec0(c->Vp), rec1(c->Vp), rec2(c->Vp);
-  CU_TRY(c, cudaMemcpyAsync(rec0.data(), c->d_rec0.p, (size_t)c->Vp * 16, cudaMemcpyDeviceToHost, c->stream));
-  CU_TRY(c, cudaMemcpyAsync(rec1.data(), c->d_rec1.p, (size_t)c->Vp * 16, cudaMemcpyDeviceToHost, c->stream));
-  CU_TRY(c, cudaMemcpyAsync(rec2.data(), c->d_rec2.p, (size_t)c->Vp * 16, cudaMemcpyDeviceToHost, c->stream));
-  CU_TRY(c, cudaStreamSynchronize(c->stream));
-  for (uint32_t p = 0; p < c->Vp; ++p) {
-    const uint32_t sv = c->procToVertex[p];
-    if (sv == ~0u) continue;
-    const uint32_t v = c->vorder[sv];                     // stored position -> caller vertex id
-    uint32_t j01, j23;
-    memcpy(&j01, &rec2[p].z, 4);
-    memcpy(&j23, &rec2[p].w, 4);
-    if (c->packedMeta) {
-      j01 = (j01 & 0xFFFu) | (((j01 >> 12) & 0xFFFu) << 16);
-      j23 = (j23 & 0xFFFu) | (((j23 >> 12) & 0xFFFu) << 16);
-    }
-    const uint16_t dj[4] = {(uint16_t)c->boneAt[j01 & 0xFFFF], (uint16_t)c->boneAt[j01 >> 16], (uint16_t)c->boneAt[j23 & 0xFFFF],
-                            (uint16_t)c->boneAt[j23 >> 16]};
-    const float dw[4] = {rec0[p].w, rec1[p].w, rec2[p].x, rec2[p].y};
-    for (uint32_t k = 0; k < 4; ++k) {
-      // device slot that holds the caller's influence k (kNoSlot: its weight is zero, no slot was spent on it)
-      const uint8_t s = c->procSlotMap[(size_t)p * 4 + k];
-      const long q = s == kNoSlot ? 0 : lrintf(dw[s] * 255.0f);
-      if (weights) weights[(size_t)v * 4 + k] = (uint8_t)std::max(0l, std::min(255l, q));
-      // a zero-weight slot gathers a BORROWED palette row on the device (lane_plan.h: the row of a neighbouring lane, so
-      // that the unconditional gather costs no extra shared-memory wavefront); it never influences the result and the
-      // caller's own index is reported there
-      if (joints) joints[(size_t)v * 4 + k] = (s != kNoSlot && q != 0) ? dj[s] : c->h_joints[(size_t)v * 4 + k];
+  // Everything below is derived from the records the KERNELS read: the pre-normalised f32 weights are re-quantised to UNORM8
+  // and the palette rows mapped back to bone ids; the only host-side knowledge used is the permutation the library itself
+  // applied (lane, influence slot, palette row).  Both device tables are decoded -- the one-vertex-per-lane records every
+  // feature kernel runs on and, when present, the two-vertices-per-lane records of the plain path -- and must agree.
+  const uint32_t V = c->V;
+  std::vector<uint16_t> J1((size_t)V * 4), J2;
+  std::vector<uint8_t> W1((size_t)V * 4), W2;
+  {
+    std::vector<float4> rec0(c->Vp), rec1(c->Vp), rec2(c->Vp);
+    CU_TRY(c, cudaMemcpyAsync(rec0.data(), c->d_rec0.p, (size_t)c->Vp * 16, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(rec1.data(), c->d_rec1.p, (size_t)c->Vp * 16, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(rec2.data(), c->d_rec2.p, (size_t)c->Vp * 16, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    for (uint32_t p = 0; p < c->Vp; ++p) {
+      const uint32_t sv = c->procToVertex[p];
+      if (sv == ~0u) continue;
+      const uint32_t v = c->vorder[sv];                     // stored position -> caller vertex id
+      uint32_t j01, j23;
+      memcpy(&j01, &rec2[p].z, 4);
+      memcpy(&j23, &rec2[p].w, 4);
+      if (c->packedMeta) {
+        j01 = (j01 & 0xFFFu) | (((j01 >> 12) & 0xFFFu) << 16);
+        j23 = (j23 & 0xFFFu) | (((j23 >> 12) & 0xFFFu) << 16);
+      }
+      const uint16_t dj[4] = {(uint16_t)c->boneAt[j01 & 0xFFFF], (uint16_t)c->boneAt[j01 >> 16], (uint16_t)c->boneAt[j23 & 0xFFFF],
+                              (uint16_t)c->boneAt[j23 >> 16]};
+      const float dw[4] = {rec0[p].w, rec1[p].w, rec2[p].x, rec2[p].y};
+      for (uint32_t k = 0; k < 4; ++k) {
+        // device slot that holds the caller's influence k (kNoSlot: its weight is zero, no slot was spent on it)
+        const uint8_t sl = c->procSlotMap[(size_t)p * 4 + k];
+        const long q = sl == kNoSlot ? 0 : lrintf(dw[sl] * 255.0f);
+        W1[(size_t)v * 4 + k] = (uint8_t)std::max(0l, std::min(255l, q));
+        // a zero-weight slot gathers a BORROWED palette row on the device (lane_plan.h: the row of a neighbouring lane, so
+        // that the unconditional gather costs no extra shared-memory wavefront); it never influences the result and the
+        // caller's own index is reported there
+        J1[(size_t)v * 4 + k] = (sl != kNoSlot && q != 0) ? dj[sl] : c->h_joints[(size_t)v * 4 + k];
+      }
     }
   }
+  if (c->vpl2Ready) {
+    const size_t L = (size_t)c->vgCount * 32;
+    std::vector<float4> rec((size_t)kRec2Planes * L);
+    CU_TRY(c, cudaMemcpyAsync(rec.data(), c->d_rec2v.p, rec.size() * 16, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    J2.assign((size_t)V * 4, 0);
+    W2.assign((size_t)V * 4, 0);
+    std::vector<uint8_t> seen(V, 0);
+    for (size_t p = 0; p < L; ++p) {
+      uint32_t r01, r23, meta;
+      memcpy(&r01, &rec[5 * L + p].x, 4); memcpy(&r23, &rec[5 * L + p].y, 4); memcpy(&meta, &rec[5 * L + p].z, 4);
+      const uint16_t bone[4] = {(uint16_t)c->boneAt[r01 & 0xFFFF], (uint16_t)c->boneAt[r01 >> 16], (uint16_t)c->boneAt[r23 & 0xFFFF],
+                                (uint16_t)c->boneAt[r23 >> 16]};
+      for (int side = 0; side < 2; ++side) {
+        const uint32_t sv = side ? c->p2VertB[p] : c->p2VertA[p];
+        if (((meta & (side ? kM2HasB : kM2HasA)) != 0) != (sv != ~0u))
+          return fail(c, RZ_ERR_STATE, "rz_read_skinning: two-vertex record %zu disagrees with the lane plan about side %d", p, side);
+        if (sv == ~0u) continue;
+        const uint32_t v = c->vorder[sv];
+        const float w[4] = {side ? rec[2 * L + p].w : rec[p].w, side ? rec[3 * L + p].w : rec[L + p].w,
+                            side ? rec[4 * L + p].z : rec[4 * L + p].x, side ? rec[4 * L + p].w : rec[4 * L + p].y};
+        if (!terms_to_caller_slots(&c->h_joints[(size_t)v * 4], bone, w, 4, &J2[(size_t)v * 4], &W2[(size_t)v * 4]))
+          return fail(c, RZ_ERR_STATE, "rz_read_skinning: vertex %u carries a device term for a bone it does not list", v);
+        seen[v]++;
+      }
+    }
+    for (uint32_t v = 0; v < V; ++v)
+      if (seen[v] != 1) return fail(c, RZ_ERR_STATE, "rz_read_skinning: vertex %u is evaluated %u times by the two-vertex table", v, (unsigned)seen[v]);
+    if (J1 != J2 || W1 != W2) {
+      for (uint32_t v = 0; v < V; ++v)
+        if (memcmp(&J1[(size_t)v * 4], &J2[(size_t)v * 4], 8) || memcmp(&W1[(size_t)v * 4], &W2[(size_t)v * 4], 4))
+          return fail(c, RZ_ERR_STATE, "rz_read_skinning: the one-vertex and two-vertex device tables disagree at vertex %u", v);
+    }
+  }
+  if (joints) memcpy(joints, J1.data(), (size_t)V * 8);
+  if (weights) memcpy(weights, W1.data(), (size_t)V * 4);
   return RZ_OK;
 }
 
@@ -1960,6 +2178,8 @@ int32_t rz_get_stats(rz_ctx* c, rz_stats* out) {
   out->instancesPerGroup = c->usedI; out->storeMode = c->usedStore; out->ctas = c->usedCtas; out->threads = c->usedThreads;
   out->smemBytes = c->usedSmem;
   out->fastGatherPermille = c->packTotalSlots ? (uint32_t)(c->packFastSlots * 1000 / c->packTotalSlots) : 0u;
+  if (c->usedVpl == 2 && c->p2Slots) out->fastGatherPermille = (uint32_t)(c->p2FastSlots * 1000 / c->p2Slots);
+  out->verticesPerLane = c->usedVpl;
   return RZ_OK;
 }
 

@@ -49,19 +49,62 @@ def test_every_launch_shape_matches_oracle(rzlib, orc, wl_small, I, nt, mb):
     K, P = 11, 4                                    # partial last group for every I; shared palettes
     world = synth.make_palettes(wl.bones, P, np.random.default_rng(1))
     i2p = (np.arange(K) * 3) % P
-    with capi.DeformContext(max_instances=K, instances_per_group=I, threads=nt, ctas_per_sm=mb) as ctx:
+    with capi.DeformContext(max_instances=K, instances_per_group=I, threads=nt, ctas_per_sm=mb, vertices_per_lane=1) as ctx:
         ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
         ctx.set_palettes(world, i2p)
         ctx.deform()
         s = ctx.stats()
-        assert (s["instancesPerGroup"], s["threads"]) == (I, nt)
+        assert (s["instancesPerGroup"], s["threads"], s["verticesPerLane"]) == (I, nt, 1)
         check_all(orc, ctx, wl, world, i2p, K)
         # instances that share a palette are bit-identical
         a, b = ctx.read_instance(0), ctx.read_instance(4)
         assert i2p[0] == i2p[4] and np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
 
 
-@pytest.mark.parametrize("V", [1, 31, 255, 256, 257, 1001, 1022])
+SHAPES_V2 = [(6, 384, 1, 2), (6, 512, 1, 1), (6, 256, 1, 3), (6, 256, 1, 2), (5, 512, 1, 1), (4, 384, 1, 2), (4, 512, 1, 2), (4, 512, 1, 1),
+             (4, 256, 1, 2), (4, 256, 1, 4), (3, 256, 2, 3), (3, 256, 1, 3), (3, 512, 1, 1), (2, 256, 2, 2), (2, 256, 1, 2), (2, 512, 1, 1),
+             (1, 256, 2, 1)]                                                                                    # csrc/kernel_table.h RZ_SHAPES_V2
+
+
+@pytest.mark.parametrize("I,nt,mb,sb", SHAPES_V2)
+def test_every_two_vertex_launch_shape_matches_oracle(rzlib, orc, wl_small, I, nt, mb, sb):
+    """The plain path's default kernel (two vertices per lane, deform2_kernel.cuh) in every compiled shape: partial last
+    instance group, shared palettes, sub-range launches, and bit-identical to itself across instances sharing a palette.
+    Against the one-vertex kernel the results differ at most by the order of the <= 4 blend terms."""
+    wl = wl_small
+    K, P = 11, 4
+    world = synth.make_palettes(wl.bones, P, np.random.default_rng(1))
+    i2p = (np.arange(K) * 3) % P
+    with capi.DeformContext(max_instances=K, instances_per_group=I, threads=nt, ctas_per_sm=mb, store_mode=sb, vertices_per_lane=2) as ctx:
+        ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
+        j, w = ctx.read_skinning()                   # decodes BOTH device tables and insists that they agree
+        assert np.array_equal(j, wl.joints.reshape(-1)) and np.array_equal(w, wl.weights.reshape(-1))
+        ctx.set_palettes(world, i2p)
+        ctx.deform()
+        s = ctx.stats()
+        assert (s["instancesPerGroup"], s["threads"], s["verticesPerLane"]) == (I, nt, 2)
+        check_all(orc, ctx, wl, world, i2p, K)
+        a, b = ctx.read_instance(0), ctx.read_instance(4)
+        assert i2p[0] == i2p[4] and np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        ref = [ctx.read_instance(k) for k in range(K)]
+        ctx.set_palettes(world[::-1].copy(), i2p)     # other poses, then only a sub-range is re-deformed with the first ones
+        ctx.deform()
+        ctx.set_palettes(world, i2p)
+        ctx.deform(3, 5)
+        for k in range(3, 8):
+            got = ctx.read_instance(k)
+            assert np.array_equal(got[0], ref[k][0]) and np.array_equal(got[1], ref[k][1])
+    with capi.DeformContext(max_instances=K, vertices_per_lane=1) as one:
+        one.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
+        one.set_palettes(world, i2p)
+        one.deform()
+        assert one.stats()["verticesPerLane"] == 1
+        for k in (0, 10):
+            g1 = one.read_instance(k)
+            assert rel_err(ref[k][0], g1[0]) <= 2e-6 and rel_err(ref[k][1], g1[1]) <= 2e-6
+
+
+@pytest.mark.parametrize("V", [1, 3, 31, 33, 63, 64, 65, 127, 129, 255, 256, 257, 1001, 1022])
 def test_ragged_vertex_counts(rzlib, orc, V):
     wl = synth.make_workload(V, 16, seed=100 + V)
     world = synth.make_palettes(wl.bones, 3, np.random.default_rng(2))
@@ -331,7 +374,7 @@ def test_interleaved_vertex_stream(rzlib, orc, wl_small, full):
         extra = (capi.RZ_FLAG_SDEF | capi.RZ_FLAG_BOUNDS) if full else 0
         outs = {}
         for flags in (0, capi.RZ_FLAG_INTERLEAVED):
-            with capi.DeformContext(max_instances=K, flags=flags | extra, instances_per_group=2, threads=256) as ctx:
+            with capi.DeformContext(max_instances=K, flags=flags | extra, instances_per_group=2, threads=256, vertices_per_lane=1) as ctx:   # same one-vertex kernel arithmetic in both layouts: comparable bit for bit
                 ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
                 if full:
                     ctx.load_morphs(wl.morphs.offsets, wl.morphs.vertexIndex, wl.morphs.delta)

@@ -300,7 +300,7 @@ int main(void) {
     assert nums[7:10] == [capi.RzOutputLayout.vertexStride.offset, capi.RzOutputLayout.hullOffset.offset, capi.RzOutputLayout.uvOffset.offset]
     assert nums[10:17] == [capi.RZ_FLAG_SDEF, capi.RZ_FLAG_NO_NORMALS, capi.RZ_FLAG_BOUNDS, capi.RZ_FLAG_REORDER_VERTICES, capi.RZ_FLAG_OUTLINE,
                            capi.RZ_FLAG_INTERLEAVED, capi.RZ_FLAG_DOUBLE_BUFFER]
-    assert nums[17] == 2
+    assert nums[17] == 3
 
 
 def test_napi_shim_type_checks_against_the_c_abi(rzlib, tmp_path):
@@ -325,9 +325,9 @@ def test_capi_exports_every_declared_symbol(rzlib):
     assert declared == set(capi.EXPORTS)
     for name in declared:
         assert hasattr(rzlib, name), name
-    assert rzlib.rz_abi_version() == 2
+    assert rzlib.rz_abi_version() == 3
     import ctypes as C
-    assert C.sizeof(capi.RzConfig) == 56 and C.sizeof(capi.RzStats) == 128
+    assert C.sizeof(capi.RzConfig) == 56 and C.sizeof(capi.RzStats) == 136
 
 
 @pytest.mark.parametrize("mode", [0, 1, 2])
@@ -402,8 +402,22 @@ def _check_plan2(J, W, B, r):
             got = sorted((int(lj[p, k]), float(ww[p, k])) for k in range(4) if ww[p, k] != 0)
             assert want == got, (v, want, got)
     assert (seen == 1).all()
-    none = (r["vertA"] == 0xFFFFFFFF)
-    assert (r["vertB"][none] == 0xFFFFFFFF).all() and not r["wA"][none].any() and not r["wB"][none].any()
+    assert not r["wA"][r["vertA"] == 0xFFFFFFFF].any() and not r["wB"][r["vertB"] == 0xFFFFFFFF].any()   # a missing side blends nothing
+    # staging slots (deform2_kernel.cuh): a real vertex sits at (vertex - groupFirst); the 64 slots of a group are used exactly
+    # once; A-slots are distinct modulo 32 and so are B-slots (12-byte records: 3*slot mod 32 is then a bijection on the banks)
+    sa, sb, ln = r["slotA"].astype(np.int64), r["slotB"].astype(np.int64), r["laneSlots"]
+    for g in range(len(gf)):
+        a, b = sa[g * 32:(g + 1) * 32], sb[g * 32:(g + 1) * 32]
+        assert sorted(np.concatenate([a, b]).tolist()) == list(range(64))
+        assert len(set((a % 32).tolist())) == 32 and len(set((b % 32).tolist())) == 32
+    for side, skey in (("vertA", sa), ("vertB", sb)):
+        vv = r[side]
+        real = vv != 0xFFFFFFFF
+        assert np.array_equal(skey[real], vv[real].astype(np.int64) - gf[np.nonzero(real)[0] // 32])
+        assert (skey[~real] >= gc[np.nonzero(~real)[0] // 32]).all()                                  # dummies are never drained
+    used = np.maximum((r["wA"] != 0), (r["wB"] != 0))
+    want_n = np.where(used.any(axis=1), 4 - np.argmax(used[:, ::-1], axis=1), 1)
+    assert np.array_equal(ln.astype(np.int64), want_n)
 
 
 def test_two_vertices_per_lane_plan(rzlib):

@@ -19,7 +19,9 @@ world = synth.make_palettes(wl.bones, K, np.random.default_rng(1))
 stream = torch.cuda.Stream()
 torch.cuda.set_stream(stream)
 dw = torch.from_numpy(world).cuda()
-ctx = capi.DeformContext(max_instances=K, stream=stream.cuda_stream)
+E = lambda k, d=0: int(os.environ.get(k, d))
+ctx = capi.DeformContext(max_instances=K, stream=stream.cuda_stream, vertices_per_lane=E("VPL"), instances_per_group=E("IPG"), threads=E("NT"),
+                         store_mode=E("SB"), chunks=E("CHUNKS"))
 ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
 ctx.set_palettes_device(dw.data_ptr(), K)
 
@@ -54,9 +56,12 @@ stop = True
 th.join()
 ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(N)]
 inside = [s for s in samples if t_begin <= s[0] <= t_end]
+st = ctx.stats()
+print(json.dumps({"vpl": st["verticesPerLane"], "I": st["instancesPerGroup"], "threads": st["threads"], "chunks": E("CHUNKS"),
+                  "sm_mhz_last": [s_[1] for s_ in inside[-5:]], "power_last": [round(s_[3]) for s_ in inside[-5:]]}))
 print(json.dumps({"ms_first10": ms[:10], "ms_20_30": ms[20:30], "ms_50_60": ms[50:60], "ms_100_110": ms[100:110], "ms_last10": ms[-10:],
                   "mean_first20": float(np.mean(ms[:20])), "mean_last100": float(np.mean(ms[-100:]))}))
-step = max(1, len(inside) // 30)
+step = max(1, len(inside) // int(os.environ.get("ROWS", "8")))
 for s in inside[::step]:
     print("t=%.3f sm=%d mem=%d power=%.0fW temp=%d reasons=0x%x" % (s[0] - t_begin, s[1], s[2], s[3], s[4], s[5]))
 idle = [s for s in samples if s[0] < t_begin][-3:]

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--pair-coherent", type=int, default=0, help="experiment: make groups of N consecutive vertices share joints (upper bound of lane packing)")
     ap.add_argument("--flags", type=lambda x: int(x, 0), default=0, help="rz_config.flags, e.g. 0x8 = RZ_FLAG_REORDER_VERTICES")
     ap.add_argument("--npz", default="", help="real model dumped by tests/golden/make_fixtures.py (e.g. tests/golden/_local/serqet2.npz) instead of the synthetic mesh")
+    ap.add_argument("--own-palettes", action="store_true", help="one palette per instance (the headline) instead of 1024 shared ones")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.jsonl"))
     a = ap.parse_args()
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
@@ -42,7 +43,7 @@ def main():
         Wt = wl.weights[:n].reshape(-1, g, 4)
         J[:, 1:, :] = J[:, :1, :]
         Wt[:, 1:, :] = Wt[:, :1, :]
-    P = min(K, 1024)
+    P = K if a.own_palettes else min(K, 1024)
     world = synth.make_palettes(wl.bones, P, np.random.default_rng(1))
     dw = torch.from_numpy(world).cuda()
     i2p = torch.arange(K, dtype=torch.int32, device="cuda") % P
@@ -51,11 +52,13 @@ def main():
     rows = []
     L = lambda s: [int(x) for x in s.split(",")]
     shapes = [tuple(int(x) for x in sh.split(":")) for sh in a.shapes.split(",")]
-    for (I, nt, ctas), chunks in itertools.product(shapes, L(a.chunks)):
-        st = 2
+    for shape, chunks in itertools.product(shapes, L(a.chunks)):
+        I, nt, ctas = shape[:3]
+        st = shape[3] if len(shape) > 3 else 0               # sub-batch of the two-vertex kernel
+        vpl = shape[4] if len(shape) > 4 else 0               # 0 auto, 1 one vertex per lane, 2 two
         try:
             ctx = capi.DeformContext(max_instances=K, stream=stream.cuda_stream, instances_per_group=I, threads=nt,
-                                     ctas_per_sm=ctas, chunks=chunks, flags=a.flags)
+                                     ctas_per_sm=ctas, chunks=chunks, flags=a.flags, store_mode=st, vertices_per_lane=vpl)
             ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
             ctx.set_palettes_device(dw.data_ptr(), P, i2p.data_ptr(), K)
             for _ in range(2):
@@ -70,7 +73,7 @@ def main():
             s = ctx.stats()
             ctx.close()
             med = float(np.median(ms))
-            row = dict(I=s["instancesPerGroup"], threads=s["threads"], store=s["storeMode"], ctas=s["ctas"], smem=s["smemBytes"], req=[I, nt, st, ctas, chunks],
+            row = dict(vpl=s["verticesPerLane"], I=s["instancesPerGroup"], threads=s["threads"], store=s["storeMode"], ctas=s["ctas"], smem=s["smemBytes"], req=[I, nt, st, ctas, chunks],
                        ms=med, ms_min=float(min(ms)), flags=a.flags, fast_gathers=s["fastGatherPermille"] / 1000, perm=os.environ.get("RZ_PERM", "default"), gverts=K * V / med / 1e6, gbs=s["algorithmicBytes"] / med / 1e6)
         except Exception as e:  # noqa: BLE001
             row = dict(req=[I, nt, st, ctas, chunks], error=str(e))
