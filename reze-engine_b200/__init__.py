@@ -8,6 +8,6 @@ from .math3d import Vec3, Quat, Mat4, easeInOut            # noqa: F401  (refere
 from .model import Model, Bone, Skeleton, Skinning, VertexMorphs, SdefTable  # noqa: F401
 from .pmx import PmxLoader                                  # noqa: F401
 from .vmd import VMDLoader, VMDKeyFrame, BoneFrame          # noqa: F401
-from .engine import Engine, EngineStats                     # noqa: F401
+from .engine import Engine, EngineStats, MultiDeviceEngine  # noqa: F401
 
-__all__ = ["Engine", "EngineStats", "Vec3", "Quat", "Mat4", "easeInOut", "Model", "PmxLoader", "VMDLoader"]
+__all__ = ["Engine", "EngineStats", "MultiDeviceEngine", "Vec3", "Quat", "Mat4", "easeInOut", "Model", "PmxLoader", "VMDLoader"]

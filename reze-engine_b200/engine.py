@@ -458,3 +458,96 @@ class Engine:
     def readSkinned(self, instance: int = 0):
         """Skinned positions and normals of one instance, [V,3] float32 each."""
         return self.ctx.read_instance(instance)
+
+
+class MultiDeviceEngine:
+    """A crowd over several GPUs from ONE process (SURVEY 8b row 1 "device list", 8e): one Engine — one rz_ctx, one CUDA
+    stream — per entry of `devices`, the K instances split into contiguous ranges by `sharding.instance_range` (the same
+    rule the one-process-per-GPU bench uses).  Every entry point of the C ABI is asynchronous on its device, so one host
+    thread launches the frame on all devices before it waits for any; no data crosses between devices, results stay where
+    they were produced (`readSkinned` routes to the owning shard).  The reference is one process with one GPUDevice
+    (engine.ts:158-163): this is what its `Engine` becomes when the device is a list.  `devices` may name a device more
+    than once (logical shards on one GPU: how the sharding is tested on a single-GPU box).
+
+    Mirrors ts/engine.ts MultiDeviceEngine; the per-shard keyword arguments are Engine's."""
+
+    def __init__(self, canvas=None, options: Optional[dict] = None, *, devices: Sequence[int], instances: int = 1, **engine_kwargs):
+        from . import sharding
+        if not devices:
+            raise ValueError("devices must name at least one CUDA device")
+        self.instances = int(instances)
+        self.shards: List[tuple] = []                       # (engine, first, count)
+        for g, dev in enumerate(devices):
+            first, last = sharding.instance_range(self.instances, len(devices), g)
+            if last > first:
+                self.shards.append((Engine(canvas, options, instances=last - first, device=int(dev), **engine_kwargs), first, last - first))
+
+    def _each(self):
+        return (e for e, _, _ in self.shards)
+
+    def init(self):
+        for e in self._each():
+            e.init()
+        return self
+
+    def dispose(self):
+        for e in self._each():
+            e.dispose()
+
+    def loadModel(self, path):
+        model = None
+        for e in self._each():
+            model = e.loadModel(path)
+        return model
+
+    def loadAnimation(self, url: str):
+        for e in self._each():
+            e.loadAnimation(url)
+
+    def setInstanceOffsets(self, offsets_ms):
+        off = np.ascontiguousarray(offsets_ms, dtype=np.float64).reshape(self.instances)
+        for e, first, count in self.shards:
+            e.setInstanceOffsets(off[first:first + count])
+
+    def setMorphWeights(self, weights, morph_names_or_ids):
+        w = np.ascontiguousarray(weights, dtype=np.float32).reshape(self.instances, -1)
+        for e, first, count in self.shards:
+            e.setMorphWeights(w[first:first + count], morph_names_or_ids)
+
+    def playAnimation(self, options: Optional[dict] = None):
+        for e in self._each():
+            e.playAnimation(options, instance=None)
+
+    def stopAnimation(self):
+        for e in self._each():
+            e.stopAnimation()
+
+    def shardOf(self, instance: int):
+        for e, first, count in self.shards:
+            if first <= instance < first + count:
+                return e, instance - first
+        raise IndexError(instance)
+
+    def rotateBones(self, bones, rotations, durationMs=None, instance: Optional[int] = None):
+        """instance=None addresses every instance of every shard (the default here: a crowd call)."""
+        if instance is None:
+            for e in self._each():
+                e.rotateBones(bones, rotations, durationMs, instance=None)
+        else:
+            e, local = self.shardOf(instance)
+            e.rotateBones(bones, rotations, durationMs, instance=0 if e.crowd else local)
+
+    def render(self):
+        for e in self._each():                                # every device is launched before any is waited for
+            e.render()
+
+    def sync(self):
+        for e in self._each():
+            e.ctx.sync()
+
+    def readSkinned(self, instance: int = 0):
+        e, local = self.shardOf(instance)
+        return e.readSkinned(local)
+
+    def getStats(self) -> List[EngineStats]:
+        return [e.getStats() for e in self._each()]

@@ -255,3 +255,99 @@ def test_headline_shape_partial_groups_and_full_palette_set(rzlib, orc):
         ctx.deform()
         assert crc == [zlib.crc32(ctx.read_instance(k)[0].tobytes()) for k in range(0, K, 41)]
         assert len(set(crc)) == len(crc)                              # every instance has its own pose
+
+
+def test_multi_device_engine_two_logical_shards_equal_the_unsharded_crowd(rzlib, tmp_path):
+    """Single-process multi-device (SURVEY 8b row 1 'device list', 8e): MultiDeviceEngine(devices=[0, 0]) — two contexts with
+    their own streams, instance ranges from sharding.instance_range — plays the same staggered-phase crowd as one Engine
+    with all K instances and must reproduce it BIT FOR BIT, instance by instance (instances are independent; no collective).
+    Also through the raw C ABI: two contexts deforming the two halves of a palette set vs one context deforming all."""
+    from helpers import random_pmx, write_vmd
+    from reze_engine_b200 import Engine, MultiDeviceEngine, sharding
+    rng = np.random.default_rng(52)
+    data, *_ = random_pmx(rng, V=1500, B=20, n_morph=0, with_sdef=False)
+    (tmp_path / "m.pmx").write_bytes(data)
+    qs = [Quat(*rng.normal(size=4)).normalize() for _ in range(4)]
+    (tmp_path / "a.vmd").write_bytes(write_vmd([("骨1", 0, qs[0].toArray()), ("骨1", 20, qs[1].toArray()), ("骨4", 10, qs[2].toArray()),
+                                                ("骨7", 30, qs[3].toArray())]))
+    K = 21
+    offsets = (np.arange(K) * 61.8) % 1000.0
+    outs = []
+    for devices in (None, [0, 0], [0, 0, 0]):
+        clock = ManualClock()
+        eng = (Engine(None, None, instances=K, clock=clock, crowd=True) if devices is None
+               else MultiDeviceEngine(None, None, devices=devices, instances=K, clock=clock, crowd=True)).init()
+        eng.loadModel(str(tmp_path / "m.pmx"))
+        eng.loadAnimation(str(tmp_path / "a.vmd"))
+        eng.setInstanceOffsets(offsets)
+        eng.playAnimation()
+        frames = []
+        for f in range(3):
+            clock.now_ms = 400.0 * f + 150.0
+            eng.render()
+            frames.append([eng.readSkinned(k) for k in range(K)])
+        if devices is not None:
+            assert [(first, count) for _, first, count in eng.shards] == [
+                (sharding.instance_range(K, len(devices), g)[0], sharding.instance_range(K, len(devices), g)[1] - sharding.instance_range(K, len(devices), g)[0])
+                for g in range(len(devices))]
+            assert len({id(e.ctx) for e, _, _ in eng.shards}) == len(devices)
+        outs.append(frames)
+        eng.dispose()
+    for sharded in outs[1:]:
+        for fa, fb in zip(outs[0], sharded):
+            for (pa, na), (pb, nb) in zip(fa, fb):
+                assert np.array_equal(pa, pb) and np.array_equal(na, nb)
+    assert rel_err(outs[0][0][0][0], outs[0][2][0][0]) > 1e-3            # the clip moves the mesh between the sampled frames
+
+    wl = synth.make_workload(20_000, 128)
+    K = 40
+    world = synth.make_palettes(wl.bones, K, np.random.default_rng(8))
+    with capi.DeformContext(max_instances=K) as whole:
+        whole.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
+        whole.set_palettes(world)
+        whole.deform()
+        ctxs = []
+        for g in range(2):
+            first, last = sharding.instance_range(K, 2, g)
+            c = capi.DeformContext(max_instances=last - first)
+            c.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
+            c.set_palettes(world[first:last])
+            ctxs.append((c, first, last))
+        for c, _, _ in ctxs:                                            # both launched before either is read
+            c.deform()
+        for c, first, last in ctxs:
+            for k in range(first, last, 7):
+                a, b = whole.read_instance(k), c.read_instance(k - first)
+                assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+            c.close()
+
+
+def test_world_matrices_come_back_from_a_device_evaluated_pose(rzlib):
+    """rz_read_world_matrices: the bone world matrices of a pose evaluated ON THE DEVICE (local rotations in, hierarchy +
+    append on the GPU) equal what Model.evaluatePose leaves in getBoneWorldMatrices() (model.ts:317-319, 330-420) — the input
+    the kinematic half of Physics.step needs back on the host (syncFromBones, physics.ts:649-703)."""
+    z = _local("serqet2.npz")
+    bones = _bones(z)
+    B = len(bones)
+    clock = ManualClock()
+    model = Model(z["vtx8"], np.zeros(0, np.uint32), [], [], Skeleton(bones, z["invBind"]), Skinning(z["joints"], z["weights"]), clock=clock)
+    rng = np.random.default_rng(9)
+    names = [b.name for b in bones]
+    pick = rng.choice(B, 60, replace=False)
+    model.rotateBones([names[i] for i in pick], [Quat(*rng.normal(size=4)).normalize() for _ in pick], 0)
+    model.evaluatePose()
+    ref = model.getBoneWorldMatrices().reshape(B, 16).copy()
+    with capi.DeformContext(max_instances=2) as ctx:
+        ctx.load_mesh(z["vtx8"], z["joints"], z["weights"], z["invBind"])
+        ctx.load_skeleton(bones)
+        rot = np.stack([model.localRotations.reshape(B, 4), np.tile(np.array([0, 0, 0, 1], np.float32), (B, 1))])
+        ctx.set_local_rotations(rot)
+        got = ctx.read_world_matrices(0)
+        assert rel_err(got, ref) <= 2e-6, rel_err(got, ref)
+        rest = ctx.read_world_matrices(1)                                # identity pose: world = bind translation chain
+        model.rotateBones(names, [Quat(0, 0, 0, 1)] * B, 0)
+        model.evaluatePose()
+        assert rel_err(rest, model.getBoneWorldMatrices().reshape(B, 16)) <= 2e-6
+        # and from host-uploaded world matrices it is the identity map
+        ctx.set_palettes(np.stack([ref, ref]))
+        assert rel_err(ctx.read_world_matrices(1), ref) <= 2e-6

@@ -318,6 +318,51 @@ def test_napi_shim_type_checks_against_the_c_abi(rzlib, tmp_path):
     assert "napi_register_module_v1" in defined
 
 
+def test_typescript_facade_matches_the_shim_and_the_reference_api():
+    """ts/engine.ts cannot be compiled here (no tsc / Node.js).  What can be checked statically: every `rz.<name>(` call it
+    makes is a function the N-API shim registers under that name (and with that many arguments), every public method of the
+    reference's Engine that belongs to the replaced path exists with the reference's name (engine/src/engine.ts:157, 1419,
+    1425, 1593, 1664, 1668, 1684, 1692, 1704, 1723, 2124), and dispose() releases the context."""
+    ts = open(os.path.join(ROOT, "ts", "engine.ts")).read()
+    ts = re.sub(r"//[^\n]*", "", ts)                                          # (comments quote calls in short form)
+    shim = open(os.path.join(ROOT, "napi", "rze_b200_napi.cc")).read()
+    registered = dict(re.findall(r'RZ_FN\("(\w+)",\s*(\w+)\)', shim))
+    assert len(registered) >= 27
+    arity = {}
+    for js_name, fn in registered.items():
+        m = re.search(r"napi_value %s\(napi_env env, napi_callback_info info\)\s*\{(?:\s*return palette_feed\(|\s*ARGS\((\d+)\))" % fn, shim)
+        assert m, fn
+        arity[js_name] = int(m.group(1)) if m.group(1) else 5               # the three palette feeds share a 5-argument helper
+    calls = re.findall(r"\brz\.(\w+)\(", ts)
+    assert calls and set(calls) <= set(registered), set(calls) - set(registered)
+    for need in ("create", "destroy", "loadMesh", "loadMorphs", "loadSdef", "loadEdgeSize", "loadSkeleton", "setPalettes", "setLocalRotations", "setTweens",
+                 "setInstanceClocks", "loadAnimation", "setMorphWeights", "deform", "sync", "readInstance", "readInstanceAsync", "readWait", "getStats",
+                 "loadRigidBodies", "applyBodyTransforms", "readWorldMatrices"):
+        assert need in calls, need
+    # argument counts of the calls (top-level commas inside the parentheses)
+    for m in re.finditer(r"\brz\.(\w+)\(", ts):
+        depth, i, nargs, seen = 1, m.end(), 0, False
+        while depth:
+            ch = ts[i]
+            if ch in "([{":
+                depth += 1
+            elif ch in ")]}":
+                depth -= 1
+            elif ch == "," and depth == 1:
+                nargs += 1
+            if depth and not ch.isspace():
+                seen = True
+            i += 1
+        nargs = nargs + 1 if seen else 0
+        assert nargs == arity[m.group(1)], (m.group(1), nargs, arity[m.group(1)])
+    for method in ("async init()", "async loadModel(path: string)", "async loadAnimation(url: string)", "playAnimation(", "stopAnimation()", "rotateBones(",
+                   "render()", "runRenderLoop(", "stopRenderLoop()", "getStats()", "dispose()"):
+        assert "public " + method in ts, method
+    body = ts[ts.index("public dispose()"):]
+    assert "rz.destroy(this.ctx)" in body[:body.index("\n  }")]
+    assert "class MultiDeviceEngine" in ts
+
+
 def test_capi_exports_every_declared_symbol(rzlib):
     from reze_engine_b200 import capi
     hdr = open(os.path.join(ROOT, "include", "rze_b200.h")).read()
