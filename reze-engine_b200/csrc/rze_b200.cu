@@ -344,12 +344,13 @@ size_t smem_needed2(int I, int NT, uint32_t B, int SB, int NBUF) {   // deform2_
 // ("long items first").  Both are chosen by the estimate  rounds1 * (T + o) + ceil(rest * c / grid) * (T / c + o),
 // T = one whole instance group on one CTA (measured on B200: within ~1 % of an exhaustive sweep, profiles/r02_chunk_sweep.txt).
 struct ItemPlan { uint32_t coarse, chunks; };
-ItemPlan pick_items(uint32_t nGroups, uint32_t grid, uint32_t V, int I, uint32_t maxChunks) {
+ItemPlan pick_items(uint32_t nGroups, uint32_t grid, uint32_t V, int I, uint32_t maxChunks, bool twoLevel = true) {
   const double T = (double)V * I * 0.6e-9, o = 2.5e-6 / std::max(T, 1e-9);
   ItemPlan best{0, 1};
   double bestCost = 1e300;
   static const uint32_t cs[] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16};
-  const uint32_t fullRounds = nGroups / std::max(grid, 1u);
+  // (one-vertex-per-lane kernels: uniform items only -- the two-level plan measured slower there, profiles/r02_chunk_sweep.txt)
+  const uint32_t fullRounds = twoLevel ? nGroups / std::max(grid, 1u) : 0u;
   for (uint32_t r1 = 0; r1 <= fullRounds; ++r1) {
     const uint32_t rest = nGroups - r1 * grid;
     for (uint32_t c : cs) {
@@ -1511,7 +1512,7 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
     const bool morphTab = (feat & FEAT_MORPH) && c->morphNnz;       // cost-balanced chunk table below: uniform, finer items
     ItemPlan ip = c->tuneChunks ? ItemPlan{0, c->tuneChunks}
                 : morphTab ? ItemPlan{0, (grid * 8 + prm.nGroups - 1) / prm.nGroups}
-                           : pick_items(prm.nGroups, grid, c->V, ke.I, nPasses);
+                           : pick_items(prm.nGroups, grid, c->V, ke.I, nPasses, false);
     uint32_t nChunks = std::max(1u, std::min(ip.chunks, nPasses));
     const uint32_t passesPerChunk = (nPasses + nChunks - 1) / nChunks;
     prm.tilesPerChunk = passesPerChunk * tilesPerPass;
