@@ -397,6 +397,38 @@ def main():
     pose_value = world_size * K * V / (pose_ms * 1e-3)
     pose_h2d = P * 4 + (K * 4 if i2p is not None else 0)
 
+    # ---- e2e_local_rotations: the host evaluates the tweens only (model.ts:158-194) and ships local rotations, 16 B per bone
+    # instead of a 64 B world matrix; hierarchy + append + skin matrices run on the device.  The upload travels on the copy
+    # stream into the rotation buffer the previous frame did not use, so it overlaps that frame's deform.
+    from reze_engine_b200 import crowd as _crowd
+    lrot = _crowd.tween_pose_batch(qa, qb, phase).astype(np.float32)            # [P, B, 4]
+    for _ in range(2):
+        rs = ctx.rotation_staging(P)
+        rs[:] = lrot
+    def step_rot(s):
+        rs = ctx.rotation_staging(P)
+        rs[s % P] = lrot[s % P]
+        ctx.set_local_rotations(rs, i2p, K=K)
+        ctx.deform()
+    for s in range(2):
+        step_rot(s)
+        ctx.read_instance(0, out_pos=h_pos, out_nrm=h_nrm)
+    time.sleep(1.0)
+    barrier()
+    wall0 = time.perf_counter()
+    r0_, r1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0_.record()
+    for s in range(esteps):
+        step_rot(s)
+        read_back(s)
+    ctx.read_wait()
+    r1_.record()
+    barrier()
+    rot_ms_rank = max(r0_.elapsed_time(r1_), (time.perf_counter() - wall0) * 1e3) / esteps
+    rot_ms = sharding.max_over_ranks(rot_ms_rank)
+    rot_value = world_size * K * V / (rot_ms * 1e-3)
+    rot_h2d = P * B * 16 + (K * 4 if i2p is not None else 0)
+
     # ---- one-off: the WHOLE result of a frame copied to the host (what a host-side consumer of every instance would pay;
     # the per-step legs above read ONE instance back because the stream is meant to stay on the device, engine.ts:270-274)
     full = None
@@ -495,7 +527,7 @@ def main():
 
     # trivial result gather (the only collective): one small record per GPU
     if world_size > 1:
-        per_gpu = sharding.gather_records([float(K * V), kernel_ms, float(launches), K * V / (kernel_ms * 1e-3), my_total_ms, e2e_ms_rank, pose_ms_rank])
+        per_gpu = sharding.gather_records([float(K * V), kernel_ms, float(launches), K * V / (kernel_ms * 1e-3), my_total_ms, e2e_ms_rank, pose_ms_rank, rot_ms_rank])
         launches = int(sum(r[2] for r in per_gpu))
     else:
         per_gpu = None
@@ -536,6 +568,9 @@ def main():
                     "path": "rz_set_instance_clocks(one host clock value per instance, 16 KB; tween + bone hierarchy + skin matrices evaluated on the device) + rz_deform + " + readback_path},
             "e2e_world_upload": {"value": e2e_value, "unit": "verts/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                                  "path": "rz_palette_staging + rz_set_palettes(pinned host world matrices exactly as getBoneWorldMatrices() returns them, the reference's feed; uploaded in blocks pipelined against the deform) + rz_deform + " + readback_path},
+            "e2e_local_rotations": {"value": rot_value, "unit": "verts/s", "ms_per_step": rot_ms, "h2d_bytes_per_step": rot_h2d, "d2h_bytes_per_step": d2h,
+                                    "path": "rz_palette_staging + rz_set_local_rotations(pinned host local rotations, 16 B per bone: the host evaluates the tweens, "
+                                            "the device walks the hierarchy; upload on the copy stream, overlapping the previous frame) + rz_deform + " + readback_path},
             "e2e_full_readback": full,
             "sustained": sustained,
             "gpu_launches": launches,
@@ -552,7 +587,7 @@ def main():
             out[label] = row
         if per_gpu:
             out["per_gpu"] = [{"verts_per_step": r[0], "deform_kernel_ms": r[1], "launches": r[2], "verts_per_s_kernel": r[3],
-                               "total_ms": r[4], "e2e_world_upload_ms_per_step": r[5], "e2e_ms_per_step": r[6]} for r in per_gpu]
+                               "total_ms": r[4], "e2e_world_upload_ms_per_step": r[5], "e2e_ms_per_step": r[6], "e2e_local_rotations_ms_per_step": r[7]} for r in per_gpu]
         if not args.no_cpu and world_size == 1:
             threads = os.cpu_count() or 1
             rate, Ks, dt = cpu_reference_rate(wl, world, K, args.cpu_seconds, threads)

@@ -336,6 +336,15 @@ class DeformContext:
         buf = (C.c_float * (P * self.B * 16)).from_address(p.value)
         return np.frombuffer(buf, dtype=np.float32).reshape(P, self.B, 16)
 
+    def rotation_staging(self, P: int) -> np.ndarray:
+        """Pinned host buffer shaped [P, B, 4] (xyzw per bone) for set_local_rotations; same two-buffer protocol as
+        palette_staging: ask before every refill."""
+        nbytes = P * self.B * 16
+        p = C.c_void_p()
+        self._check(self.lib.rz_palette_staging(self.h, nbytes, C.byref(p)))
+        buf = (C.c_float * (P * self.B * 4)).from_address(p.value)
+        return np.frombuffer(buf, dtype=np.float32).reshape(P, self.B, 4)
+
     def set_palettes(self, world, inst_to_palette=None, K: Optional[int] = None):
         world = np.asarray(world)
         if world.dtype != np.float32 or not world.flags.c_contiguous:

@@ -394,7 +394,9 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
     // first kMorphPF morph entries of a record's vertex; fetched one pass ahead so that the dependent chain
     // record -> entries -> weights costs one L2 round trip less per pass
     float4 pf[MORPH ? kMorphPF : 1];
+    // (warps without morph rows -- ~90 % of a PMX mesh -- skip the prefetch altogether: mr.y is warp-uniform)
     auto load_pf = [&](const VRec& r) {
+      if (r.mr.y == 0u) return;
 #pragma unroll
       for (int u = 0; u < kMorphPF; ++u)
         pf[u] = ((uint32_t)u < r.mr.y) ? ldg_el(prm.ments + r.mr.x + (uint32_t)u * 32u + (uint32_t)lane, polLast) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -406,11 +408,6 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
 
     for (uint32_t t = tile0; t < tile1; t += NT / kTile) {
       const VRec v = cur;
-      float4 pfv[MORPH ? kMorphPF : 1];
-      if (MORPH) {
-#pragma unroll
-        for (int u = 0; u < kMorphPF; ++u) pfv[u] = pf[u];
-      }
       if (t + NT / kTile < tile1) cur = load_rec(t + NT / kTile);
       if (t + (uint32_t)warp / (kTile / 32) >= tile1) continue;       // warp-uniform: this warp has no tile in the pass
 
@@ -455,7 +452,7 @@ __global__ void __launch_bounds__(NT, MINB) deform_kernel(const DeformParams prm
             }
           };
 #pragma unroll
-          for (int u = 0; u < kMorphPF; ++u) apply(pfv[u]);
+          for (int u = 0; u < kMorphPF; ++u) apply(pf[u]);      // (pf is only rewritten at the end of this pass, for the next one)
           // the rest kMorphBatch depth steps at a time so their L2 latencies overlap; the bound is warp-uniform
           const float4* ep = prm.ments + mr.x + (uint32_t)lane;
           for (uint32_t u0 = kMorphPF; u0 < mr.y; u0 += kMorphBatch) {

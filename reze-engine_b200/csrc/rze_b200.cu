@@ -105,7 +105,12 @@ struct rz_ctx_impl {
   // physics -> bone feedback (rz_load_rigid_bodies / rz_apply_body_transforms)
   DevBuf d_rbBones, d_rbStart, d_rbIds, d_rbOffInv, d_rbPosQuat;
   uint32_t rbBones = 0, rbBodies = 0;
-  DevBuf d_twStart, d_twTarget, d_twRest, d_twStartMs, d_twDurMs, d_twActive, d_localRot, d_nowMs, d_twAux, d_invBindSoA;
+  DevBuf d_twStart, d_twTarget, d_twRest, d_twStartMs, d_twDurMs, d_twActive, d_localRot, d_localRot2, d_nowMs, d_twAux, d_invBindSoA;
+  // local-rotation uploads alternate between two device buffers on the copy stream, so frame n+1's rotations travel while
+  // frame n is still being deformed; evRotFree[x]: the pose kernel that last read buffer x has been issued
+  uint32_t rotCur = 0;
+  cudaEvent_t evRotFree[2] = {nullptr, nullptr}, evRotCopied = nullptr;
+  bool rotFreeValid[2] = {false, false};
 
   // per-frame
   uint32_t P = 0, K = 0;
@@ -746,6 +751,9 @@ int32_t rz_create(const rz_config* cfg, rz_ctx** out) {
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->evReadDone[0], cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->evReadDone[1], cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->evWorldFree, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->evRotFree[0], cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->evRotFree[1], cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->evRotCopied, cudaEventDisableTiming);
   if (e != cudaSuccess) {
     const int code = fail(nullptr, e == cudaErrorMemoryAllocation ? RZ_ERR_OOM : RZ_ERR_CUDA, "rz_create: stream / event creation failed: %s", cudaGetErrorString(e));
     rz_destroy(c);
@@ -766,12 +774,14 @@ int32_t rz_destroy(rz_ctx* c) {
   for (auto& g : c->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   for (cudaEvent_t e : c->evPool) cudaEventDestroy(e);
   if (c->evWorldFree) cudaEventDestroy(c->evWorldFree);
+  for (cudaEvent_t e : c->evRotFree) if (e) cudaEventDestroy(e);
+  if (c->evRotCopied) cudaEventDestroy(c->evRotCopied);
   if (c->copyStream) cudaStreamDestroy(c->copyStream);
   DevBuf* bufs[] = {&c->d_rec0, &c->d_rec1, &c->d_rec2, &c->d_rec2v, &c->d_meta, &c->d_mrange, &c->d_ments, &c->d_sdefIdx, &c->d_sdefTab,
                     &c->d_invBind, &c->d_bonePos, &c->d_world, &c->d_skin, &c->d_inst2pal, &c->d_mwIn, &c->d_mwIds, &c->d_mwDense,
                     &c->d_out, &c->d_out2, &c->d_bounds, &c->d_counter, &c->d_skParent, &c->d_skBindT, &c->d_skAppendParent, &c->d_skAppendRatio,
                     &c->d_skLevelBones, &c->d_skLevelStart, &c->d_skChainStart, &c->d_skChainBones, &c->d_twStart, &c->d_twTarget, &c->d_twRest, &c->d_twStartMs, &c->d_twDurMs,
-                    &c->d_twActive, &c->d_localRot, &c->d_nowMs, &c->d_twAux, &c->d_invBindSoA, &c->d_rbBones, &c->d_rbStart, &c->d_rbIds, &c->d_rbOffInv, &c->d_rbPosQuat, &c->d_trStart, &c->d_trMs, &c->d_trQ, &c->d_trRest, &c->d_quat, &c->d_chunkTab, &c->d_edge, &c->d_uv};
+                    &c->d_twActive, &c->d_localRot, &c->d_localRot2, &c->d_nowMs, &c->d_twAux, &c->d_invBindSoA, &c->d_rbBones, &c->d_rbStart, &c->d_rbIds, &c->d_rbOffInv, &c->d_rbPosQuat, &c->d_trStart, &c->d_trMs, &c->d_trQ, &c->d_trRest, &c->d_quat, &c->d_chunkTab, &c->d_edge, &c->d_uv};
   for (DevBuf* b : bufs) dev_free(c, *b);
   for (auto& b : c->stage) pinned_free(b);
   for (auto& b : c->scratch) pinned_free(b);
@@ -1073,7 +1083,7 @@ static int launch_pose(rz_ctx* c, uint32_t P) {
     CU_TRY(c, raise_smem_limit(c->device, reinterpret_cast<const void*>(&pose_jump_kernel<MODE>), smemJump));
     const int threads = c->B <= 1024 ? (int)std::max<uint32_t>(64u, (c->B + 31u) / 32u * 32u) : 512;   // one bone per thread when possible
     pose_jump_kernel<MODE><<<P, threads, smemJump, c->stream>>>(sk, tw, tr, reinterpret_cast<const float4*>(c->d_twAux.p),
-                                                                reinterpret_cast<const float4*>(c->d_localRot.p),
+                                                                reinterpret_cast<const float4*>(c->rotCur ? c->d_localRot2.p : c->d_localRot.p),
                                                                 reinterpret_cast<const float*>(c->d_nowMs.p),
                                                                 reinterpret_cast<const float4*>(c->d_invBind.p),
                                                                 reinterpret_cast<const float4*>(c->d_invBindSoA.p),
@@ -1087,7 +1097,7 @@ static int launch_pose(rz_ctx* c, uint32_t P) {
     CU_TRY(c, raise_smem_limit(c->device, reinterpret_cast<const void*>(&pose_chain_kernel<MODE>), smem));
     pose_chain_kernel<MODE><<<P, 256, smem, c->stream>>>(sk, tw, tr, reinterpret_cast<const uint32_t*>(c->d_skChainStart.p),
                                                          reinterpret_cast<const uint32_t*>(c->d_skChainBones.p),
-                                                         reinterpret_cast<const float4*>(c->d_localRot.p),
+                                                         reinterpret_cast<const float4*>(c->rotCur ? c->d_localRot2.p : c->d_localRot.p),
                                                          reinterpret_cast<const float*>(c->d_nowMs.p),
                                                          reinterpret_cast<const float4*>(c->d_invBind.p),
                                                          reinterpret_cast<const uint32_t*>(c->d_bonePos.p),
@@ -1097,7 +1107,7 @@ static int launch_pose(rz_ctx* c, uint32_t P) {
     return RZ_OK;
   }
   CU_TRY(c, raise_smem_limit(c->device, reinterpret_cast<const void*>(&pose_kernel<MODE>), smem));
-  pose_kernel<MODE><<<P, 128, smem, c->stream>>>(sk, tw, tr, reinterpret_cast<const float4*>(c->d_localRot.p),
+  pose_kernel<MODE><<<P, 128, smem, c->stream>>>(sk, tw, tr, reinterpret_cast<const float4*>(c->rotCur ? c->d_localRot2.p : c->d_localRot.p),
                                                  reinterpret_cast<const float*>(c->d_nowMs.p),
                                                  reinterpret_cast<const float4*>(c->d_invBind.p),
                                                  reinterpret_cast<const uint32_t*>(c->d_bonePos.p),
@@ -1131,7 +1141,16 @@ int32_t rz_set_local_rotations(rz_ctx* c, const float* quats, uint32_t P, const 
   int rc;
   if ((rc = set_mapping(c, inst2pal, P, K, "rz_set_local_rotations"))) return rc;
   const size_t bytes = (size_t)P * c->B * 16;
-  if ((rc = dev_reserve(c, c->d_localRot, bytes))) return rc;
+  // the rotations go to the device buffer the previous frame did NOT use, on the copy stream: the transfer overlaps the
+  // previous frame's deform instead of queueing behind it; the pose kernel waits for the copy, the copy for the pose
+  // kernel that last read this buffer (two frames ago)
+  c->rotCur ^= 1u;
+  DevBuf& rot = c->rotCur ? c->d_localRot2 : c->d_localRot;
+  if (bytes > rot.bytes || !rot.p) {
+    CU_TRY(c, cudaStreamSynchronize(c->stream));             // growing: nothing may still read the old allocation
+    c->rotFreeValid[c->rotCur] = false;
+  }
+  if ((rc = dev_reserve(c, rot, bytes))) return rc;
   const char* src = reinterpret_cast<const char*>(quats);
   rz_ctx_impl::PinnedBuf* srcBuf = staging_of(c, quats, bytes);
   if (!srcBuf) {
@@ -1140,9 +1159,14 @@ int32_t rz_set_local_rotations(rz_ctx* c, const float* quats, uint32_t P, const 
     src = reinterpret_cast<const char*>(c->big.p);
     srcBuf = &c->big;
   }
-  CU_TRY(c, cudaMemcpyAsync(c->d_localRot.p, src, bytes, cudaMemcpyHostToDevice, c->stream));
-  if ((rc = pinned_release(c, *srcBuf, c->stream))) return rc;
+  if (c->rotFreeValid[c->rotCur]) CU_TRY(c, cudaStreamWaitEvent(c->copyStream, c->evRotFree[c->rotCur], 0));
+  CU_TRY(c, cudaMemcpyAsync(rot.p, src, bytes, cudaMemcpyHostToDevice, c->copyStream));
+  CU_TRY(c, cudaEventRecord(c->evRotCopied, c->copyStream));
+  if ((rc = pinned_release(c, *srcBuf, c->copyStream))) return rc;
+  CU_TRY(c, cudaStreamWaitEvent(c->stream, c->evRotCopied, 0));
   if ((rc = launch_pose<0>(c, P))) return rc;
+  CU_TRY(c, cudaEventRecord(c->evRotFree[c->rotCur], c->stream));
+  c->rotFreeValid[c->rotCur] = true;
   c->P = P; c->K = K; c->palettesSet = true;
   return RZ_OK;
 }

@@ -18,6 +18,7 @@ from reze_engine_b200 import capi, synth  # noqa: E402
 TOL = 1e-5
 LITE = [(0, 0), (1, 256), (2, 256), (2, 512), (4, 512)]
 FULL = LITE + [(3, 256), (6, 512), (4, 768), (3, 768), (2, 1024), (6, 256)]
+V2 = [(0, 0, 0), (4, 512, 2), (4, 384, 2), (6, 384, 2), (6, 512, 1), (6, 256, 3), (5, 512, 1), (3, 256, 3), (2, 256, 2), (1, 256, 1), (4, 256, 4)]   # (I, threads, sub-batch)
 
 
 def rel(a, b):
@@ -65,8 +66,14 @@ def main():
         I, nt = (FULL if plain else LITE)[int(rng.integers(0, len(FULL if plain else LITE)))]
         first = int(rng.integers(0, K))
         count = int(rng.integers(1, K - first + 1))
-        if I > count:                                        # a tuned group wider than the instance range is refused
-            I, nt = 0, 0
+        # the plain planar path: half the cases on the two-vertices-per-lane kernel in one of its shapes, half on the one-vertex kernel
+        vpl, sb = 0, 0
+        if plain and B <= 4000:
+            if rng.integers(0, 2):
+                vpl = 2
+                I, nt, sb = V2[int(rng.integers(0, len(V2)))]
+            else:
+                vpl = 1
         wl = synth.make_workload(V, B, M=M, sdef=sdef, seed=int(rng.integers(1, 1 << 30)))
         P = K if rng.integers(0, 3) == 0 else int(rng.integers(1, K + 1))     # one palette per instance a third of the time
         world0 = synth.make_palettes(wl.bones, P, rng)          # a first frame that must leave no trace
@@ -79,7 +86,7 @@ def main():
         row = dict(case=case, V=V, B=B, K=K, P=P, M=M, sdef=sdef, flags=flags, I=I, nt=nt, first=first, count=count,
                    pipe_block=os.environ["RZ_PIPELINE_BLOCK"], identity=i2p is None)
         try:
-            with capi.DeformContext(max_instances=K, flags=flags, instances_per_group=I, threads=nt) as ctx:
+            with capi.DeformContext(max_instances=K, flags=flags, instances_per_group=I, threads=nt, store_mode=sb, vertices_per_lane=vpl) as ctx:
                 ctx.load_mesh(wl.vtx8, wl.joints, wl.weights, wl.invBind)
                 if M:
                     ctx.load_morphs(wl.morphs.offsets, wl.morphs.vertexIndex, wl.morphs.delta)
@@ -121,7 +128,8 @@ def main():
                 j, w = ctx.read_skinning()
                 assert np.array_equal(j, wl.joints.reshape(-1)) and np.array_equal(w, wl.weights.reshape(-1)), "integer tables"
                 s = ctx.stats()
-                row.update(err=err, usedI=s["instancesPerGroup"], usedThreads=s["threads"])
+                row.update(err=err, usedI=s["instancesPerGroup"], usedThreads=s["threads"], vpl=s["verticesPerLane"])
+                assert vpl == 0 or s["verticesPerLane"] == vpl, "kernel variant"
                 worst = max(worst, err)
                 assert err <= TOL, f"parity {err}"
         except Exception as e:  # noqa: BLE001

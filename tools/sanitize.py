@@ -36,6 +36,20 @@ for flags, I, nt in ((0, 2, 256), (capi.RZ_FLAG_SDEF | capi.RZ_FLAG_BOUNDS, 4, 5
         ctx.sync()
         print("ok", flags, ctx.stats()["instancesPerGroup"], ctx.stats()["threads"])
 
+# ---- round 2: the two-vertices-per-lane kernel of the plain path (sub-batch staging ring, two-level item plan, ragged tail),
+# launched through the frame's CUDA graph and directly
+for I, nt, sb in ((4, 512, 2), (6, 384, 2), (6, 512, 1), (3, 256, 3), (1, 256, 1)):
+    for Vx in (1500, 67):
+        wx = synth.make_workload(Vx, 40)
+        with capi.DeformContext(max_instances=K, instances_per_group=I, threads=nt, store_mode=sb, vertices_per_lane=2) as ctx:
+            ctx.load_mesh(wx.vtx8, wx.joints, wx.weights, wx.invBind)
+            ctx.set_palettes(synth.make_palettes(wx.bones, K, rng))
+            ctx.deform()
+            ctx.deform(2, 3)
+            ctx.sync()
+            assert ctx.stats()["verticesPerLane"] == 2
+    print("ok two-vertex kernel", I, nt, sb)
+
 # ---- the round's later additions: pointer-jumping / chain / level pose kernels, pipelined palette upload, double-buffered
 # results with asynchronous read-back, physics feedback, SDEF + outline on a palette that does not fit shared memory
 import torch  # noqa: E402
