@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--cases", type=int, default=60)
     ap.add_argument("--seed", type=int, default=2026)
     ap.add_argument("--seconds", type=float, default=150.0)
+    ap.add_argument("--plain-share", type=float, default=0.4, help="share of cases forced onto the plain planar path (two-vertices-per-lane kernel)")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "fuzz.jsonl"))
     a = ap.parse_args()
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
@@ -46,13 +47,16 @@ def main():
         sdef = bool(rng.integers(0, 2))
         flags = 0
         layout = int(rng.integers(0, 4))                    # 0 planar, 1 outline, 2 interleaved, 3 positions only
+        force_plain = a.plain_share > 0 and rng.random() < a.plain_share   # the plain planar path (two-vertex kernel) often enough
+        if force_plain:
+            M, sdef, layout = 0, False, 0
         if layout == 1:
             flags |= capi.RZ_FLAG_OUTLINE
         elif layout == 2:
             flags |= capi.RZ_FLAG_INTERLEAVED
         elif layout == 3:
             flags |= capi.RZ_FLAG_NO_NORMALS
-        if rng.integers(0, 2):
+        if rng.integers(0, 2) and not force_plain:
             flags |= capi.RZ_FLAG_BOUNDS
         if sdef:
             flags |= capi.RZ_FLAG_SDEF
