@@ -21,13 +21,21 @@
 
 namespace rz {
 
-constexpr int kRec2Planes = 6;   // float4 planes of the two-vertex lane record (SoA: plane q of lane L at rec[q*lanes + L])
+constexpr int kRec2Planes = 7;   // float4 planes of the two-vertex lane record (SoA: plane q of lane L at rec[q*lanes + L])
 // q0 = (pA.xyz, wA0)  q1 = (nA.xyz, wA1)  q2 = (pB.xyz, wB0)  q3 = (nB.xyz, wB1)  q4 = (wA2, wA3, wB2, wB3)
 // q5 = (row0 | row1 << 16,  row2 | row3 << 16,  meta,  first output vertex of the group)   [bit patterns]
+// q6 = (uA, vA, uB, vB) texture coordinates (interleaved output) or (edgeA, edgeB, 0, 0) outline offsets (hull output);
+//      only read by those two layouts
 // meta: bits 0-5 slotA, 6-11 slotB (output position inside the group's 64-vertex staging), 12-14 slots used by this lane,
 //       15 vertex A real, 16 vertex B real, 17-23 vertices the group covers (0..64)
 constexpr int kM2SlotB = 6, kM2N = 12, kM2Cnt = 17;
 constexpr uint32_t kM2HasA = 1u << 15, kM2HasB = 1u << 16;
+
+// output layouts of the two-vertex kernel (the feature sets without morphs / SDEF / AABB)
+enum : int { OUT2_PLANAR = 0,   // position plane + normal plane                        (engine.ts:245-276)
+             OUT2_NONRM = 1,    // positions only: the depth-only blend                 (engine.ts:692-715)
+             OUT2_HULL = 2,     // + outline hull plane pos' + n^' * edge               (engine.ts:431-463, 458-461)
+             OUT2_ILV = 3 };    // one interleaved 32-byte [pos, nrm, uv] stream        (engine.ts:340-347)
 
 struct Deform2Params {
   const float4* __restrict__ rec;        // [6][lanes]
@@ -36,6 +44,7 @@ struct Deform2Params {
   float* __restrict__ out;
   unsigned long long instStrideF;        // floats between instances
   unsigned long long nrmOffF;            // floats from the position plane to the normal plane
+  unsigned long long hullOffF;           // floats from the position plane to the outline-hull plane (OUT2_HULL)
   uint32_t lanes;                        // vertex groups * 32
   uint32_t nVG;                          // vertex groups (32 lanes each)
   uint32_t V, B, K0, Kcount;
@@ -45,19 +54,23 @@ struct Deform2Params {
   uint32_t* counter;
 };
 
-struct Rec2 { float4 q0, q1, q2, q3, q4, q5; };
+struct Rec2 { float4 q0, q1, q2, q3, q4, q5, q6; };
 
 // I: instances per palette stage; NT: threads per CTA; MINB: CTAs/SM the registers are sized for;
 // SB: instances per sub-batch (gathers in flight together, one store commit group); divides I
 // NBUF: staging buffers per warp, each holding ONE sub-batch; sub-batches rotate through them, so the stores of up to
 //       NBUF-1 sub-batches drain while the next one is computed -- and the staging footprint no longer grows with I
-template <int I, int NT, int MINB, int SB, int NBUF>
+// OUT : output layout (OUT2_*)
+template <int I, int NT, int MINB, int SB, int NBUF, int OUT = OUT2_PLANAR>
 __global__ void __launch_bounds__(NT, MINB) deform2_kernel(const Deform2Params prm) {
   static_assert(I % SB == 0, "sub-batch must divide the group");
   constexpr int W = NT / 32;
   constexpr int NSB = I / SB;                          // sub-batches = store commit groups per pass
-  constexpr uint32_t kPlaneB = 64u * 12u;              // one staging plane of a warp: 64 vertices
-  constexpr uint32_t kInstB = 2u * kPlaneB;            // position + normal plane of one instance
+  constexpr bool ILV = OUT == OUT2_ILV, HULL = OUT == OUT2_HULL, NRM = OUT != OUT2_NONRM;
+  constexpr uint32_t kVtxB = ILV ? 32u : 12u;          // bytes per vertex of a staging plane
+  constexpr uint32_t kPlaneB = 64u * kVtxB;            // one staging plane of a warp: 64 vertices
+  constexpr uint32_t kInstB = (ILV ? 1u : (NRM ? 2u : 1u) + (HULL ? 1u : 0u)) * kPlaneB;   // the planes of one instance
+  constexpr uint32_t kHullO = 2u * kPlaneB;            // hull position relative to the position (OUT2_HULL)
   constexpr uint32_t kBufB = (uint32_t)SB * kInstB;    // one staging buffer: a sub-batch
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -119,6 +132,7 @@ __global__ void __launch_bounds__(NT, MINB) deform2_kernel(const Deform2Params p
       r.q3 = ldg_el(p + 3u * (size_t)prm.lanes, polLast);
       r.q4 = ldg_el(p + 4u * (size_t)prm.lanes, polLast);
       r.q5 = ldg_el(p + 5u * (size_t)prm.lanes, polLast);
+      r.q6 = (ILV || HULL) ? ldg_el(p + 6u * (size_t)prm.lanes, polLast) : make_float4(0.f, 0.f, 0.f, 0.f);
       return r;
     };
     uint32_t vg = vg0 + (uint32_t)warp;
@@ -136,30 +150,46 @@ __global__ void __launch_bounds__(NT, MINB) deform2_kernel(const Deform2Params p
       const uint32_t first = __shfl_sync(0xffffffffu, __float_as_uint(v.q5.w), 0);     // group constants: uniform registers
       const uint32_t cnt = __shfl_sync(0xffffffffu, (meta >> kM2Cnt) & 127u, 0);
       const uint32_t j0 = (j01 & 0xFFFFu) * 48u, j1 = (j01 >> 16) * 48u, j2 = (j23 & 0xFFFFu) * 48u, j3 = (j23 >> 16) * 48u;
-      const uint32_t oA = (meta & 63u) * 12u, oB = ((meta >> kM2SlotB) & 63u) * 12u;     // the lane's two staging slots
+      const uint32_t oA = (meta & 63u) * kVtxB, oB = ((meta >> kM2SlotB) & 63u) * kVtxB;   // the lane's two staging slots
       const int nmax = __reduce_max_sync(0xffffffffu, (int)((meta >> kM2N) & 7u));
       // unit weights everywhere (rigid window): the blend is the row itself
       const bool unitW = __all_sync(0xffffffffu, (v.q0.w == 1.0f || !(meta & kM2HasA)) && (v.q2.w == 1.0f || !(meta & kM2HasB)));
       const float2 wA0 = make_float2(v.q0.w, v.q0.w), wA1 = make_float2(v.q1.w, v.q1.w), wA2 = make_float2(v.q4.x, v.q4.x), wA3 = make_float2(v.q4.y, v.q4.y);
       const float2 wB0 = make_float2(v.q2.w, v.q2.w), wB1 = make_float2(v.q3.w, v.q3.w), wB2 = make_float2(v.q4.z, v.q4.z), wB3 = make_float2(v.q4.w, v.q4.w);
-      const uint32_t nAligned = cnt & ~3u;                         // bulk sizes are multiples of 16 bytes
+      const uint32_t nAligned = ILV ? cnt : (cnt & ~3u);          // bulk sizes are multiples of 16 bytes
 
-      // mat-vec of one vertex with its blended matrix (pair layout: (x,y) out of packed FFMA2), normalise, stage
+      // mat-vec of one vertex with its blended matrix (pair layout: (x,y) out of packed FFMA2), normalise, stage.
+      // ex0 / ex1: the vertex' texture coordinates (ILV) or its outline offset (HULL)
       auto emit = [&](const float4 mA, const float4 mB, const float4 mC, const float px, const float py, const float pz,
-                      const float nxi, const float nyi, const float nzi, const uint32_t sa) {
+                      const float nxi, const float nyi, const float nzi, const float ex0, const float ex1, const uint32_t sa, const bool sw) {
         const float2 qx2 = make_float2(px, px), qy2 = make_float2(py, py), qz2 = make_float2(pz, pz);
         const float2 oxy = __ffma2_rn(make_float2(mA.x, mA.y), qx2,
                            __ffma2_rn(make_float2(mA.z, mA.w), qy2, __ffma2_rn(make_float2(mB.x, mB.y), qz2, make_float2(mB.z, mB.w))));
         const float oz = fmaf(mC.x, px, fmaf(mC.y, py, fmaf(mC.z, pz, mC.w)));
-        const float2 nx2 = make_float2(nxi, nxi), ny2 = make_float2(nyi, nyi), nz2 = make_float2(nzi, nzi);
-        const float2 nxy = __ffma2_rn(make_float2(mA.x, mA.y), nx2,
-                           __ffma2_rn(make_float2(mA.z, mA.w), ny2, __fmul2_rn(make_float2(mB.x, mB.y), nz2)));
-        float nx = nxy.x, ny = nxy.y, nz = fmaf(mC.x, nxi, fmaf(mC.y, nyi, mC.z * nzi));
-        const float l2 = fmaf(nx, nx, fmaf(ny, ny, nz * nz));
-        const float rl = l2 > 0.f ? rsqrtf(l2) : 0.f;               // normalize(0) := 0 (SURVEY 8c edge case)
-        nx *= rl; ny *= rl; nz *= rl;
-        sts3(sa, oxy.x, oxy.y, oz);
-        sts3(sa + kPlaneB, nx, ny, nz);
+        float nx = 0.f, ny = 0.f, nz = 0.f;
+        if (NRM) {
+          const float2 nx2 = make_float2(nxi, nxi), ny2 = make_float2(nyi, nyi), nz2 = make_float2(nzi, nzi);
+          const float2 nxy = __ffma2_rn(make_float2(mA.x, mA.y), nx2,
+                             __ffma2_rn(make_float2(mA.z, mA.w), ny2, __fmul2_rn(make_float2(mB.x, mB.y), nz2)));
+          nx = nxy.x; ny = nxy.y; nz = fmaf(mC.x, nxi, fmaf(mC.y, nyi, mC.z * nzi));
+          const float l2 = fmaf(nx, nx, fmaf(ny, ny, nz * nz));
+          const float rl = l2 > 0.f ? rsqrtf(l2) : 0.f;             // normalize(0) := 0 (SURVEY 8c edge case)
+          nx *= rl; ny *= rl; nz *= rl;
+        }
+        if (ILV) {
+          // 32-byte records: the two 16-byte halves of a record are written in opposite order by every second group of four
+          // slots, so the 8 lanes of a quarter-warp whose slots are distinct modulo 8 hit 8 distinct 16-byte bank groups in
+          // each of the two store instructions (in plain order slots s and s + 4 collide: 2-way conflicts on every store)
+          // (sw = bit 2 of the slot)
+          const float4 h0 = make_float4(oxy.x, oxy.y, oz, nx), h1 = make_float4(ny, nz, ex0, ex1);
+          const float4 f = sw ? h1 : h0, g = sw ? h0 : h1;
+          sts128(sa + (sw ? 16u : 0u), f.x, f.y, f.z, f.w);
+          sts128(sa + (sw ? 0u : 16u), g.x, g.y, g.z, g.w);
+        } else {
+          sts3(sa, oxy.x, oxy.y, oz);
+          if (NRM) sts3(sa + kPlaneB, nx, ny, nz);
+          if (HULL) sts3(sa + kHullO, fmaf(nx, ex0, oxy.x), fmaf(ny, ex0, oxy.y), fmaf(nz, ex0, oz));   // engine.ts:458-461
+        }
       };
 
       auto body = [&](auto NM, const int i0, const uint32_t stg) {
@@ -189,7 +219,7 @@ __global__ void __launch_bounds__(NT, MINB) deform2_kernel(const Deform2Params p
             if (NMAX > 1) { mA = f4_fma(b0[ii], wA1, mA); mB = f4_fma(b1[ii], wA1, mB); mC = f4_fma(b2[ii], wA1, mC); }
             if (NMAX > 2) { mA = f4_fma(c0, wA2, mA); mB = f4_fma(c1, wA2, mB); mC = f4_fma(c2, wA2, mC); }
             if (NMAX > 3) { mA = f4_fma(d0, wA3, mA); mB = f4_fma(d1, wA3, mB); mC = f4_fma(d2, wA3, mC); }
-            emit(mA, mB, mC, v.q0.x, v.q0.y, v.q0.z, v.q1.x, v.q1.y, v.q1.z, so + oA);
+            emit(mA, mB, mC, v.q0.x, v.q0.y, v.q0.z, v.q1.x, v.q1.y, v.q1.z, v.q6.x, ILV ? v.q6.y : 0.f, so + oA, (meta & 4u) != 0u);
           }
           {   // (a fallback group's lanes carry no second vertex: their B side blends zeros into a slot that is never drained --
               //  cheaper than a branch that would keep the two independent dependency chains from interleaving)
@@ -199,12 +229,12 @@ __global__ void __launch_bounds__(NT, MINB) deform2_kernel(const Deform2Params p
             if (NMAX > 1) { mA = f4_fma(b0[ii], wB1, mA); mB = f4_fma(b1[ii], wB1, mB); mC = f4_fma(b2[ii], wB1, mC); }
             if (NMAX > 2) { mA = f4_fma(c0, wB2, mA); mB = f4_fma(c1, wB2, mB); mC = f4_fma(c2, wB2, mC); }
             if (NMAX > 3) { mA = f4_fma(d0, wB3, mA); mB = f4_fma(d1, wB3, mB); mC = f4_fma(d2, wB3, mC); }
-            emit(mA, mB, mC, v.q2.x, v.q2.y, v.q2.z, v.q3.x, v.q3.y, v.q3.z, so + oB);
+            emit(mA, mB, mC, v.q2.x, v.q2.y, v.q2.z, v.q3.x, v.q3.y, v.q3.z, ILV ? v.q6.z : v.q6.y, ILV ? v.q6.w : 0.f, so + oB, (meta & (4u << kM2SlotB)) != 0u);
           }
         }
       };
 
-      float* const dst0 = outItem + (size_t)first * 3u;
+      float* const dst0 = outItem + (size_t)first * (kVtxB / 4u);
 #pragma unroll 1
       for (int sbi = 0; sbi < NSB; ++sbi) {                         // (not unrolled: one copy of the five bodies keeps the I-cache warm)
         const int i0 = sbi * SB;
@@ -229,8 +259,9 @@ __global__ void __launch_bounds__(NT, MINB) deform2_kernel(const Deform2Params p
               const int i = i0 + ii;
               if ((uint32_t)i < nInst) {
                 float* dst = dst0 + (size_t)i * prm.instStrideF;
-                bulk_s2g(dst, stg + (uint32_t)ii * kInstB, nAligned * 12u, polFirst);
-                bulk_s2g(dst + prm.nrmOffF, stg + (uint32_t)ii * kInstB + kPlaneB, nAligned * 12u, polFirst);
+                bulk_s2g(dst, stg + (uint32_t)ii * kInstB, nAligned * kVtxB, polFirst);
+                if (NRM && !ILV) bulk_s2g(dst + prm.nrmOffF, stg + (uint32_t)ii * kInstB + kPlaneB, nAligned * 12u, polFirst);
+                if (HULL) bulk_s2g(dst + prm.hullOffF, stg + (uint32_t)ii * kInstB + kHullO, nAligned * 12u, polFirst);
               }
             }
           }
@@ -247,7 +278,8 @@ __global__ void __launch_bounds__(NT, MINB) deform2_kernel(const Deform2Params p
               if (i >= nInst) break;
               float* dst = dst0 + (size_t)i * prm.instStrideF + o;
               st_cs(dst, lds32(stg + (uint32_t)ii * kInstB + o * 4u));
-              st_cs(dst + prm.nrmOffF, lds32(stg + (uint32_t)ii * kInstB + kPlaneB + o * 4u));
+              if (NRM) st_cs(dst + prm.nrmOffF, lds32(stg + (uint32_t)ii * kInstB + kPlaneB + o * 4u));
+              if (HULL) st_cs(dst + prm.hullOffF, lds32(stg + (uint32_t)ii * kInstB + kHullO + o * 4u));
             }
           }
           __syncwarp();

@@ -29,7 +29,14 @@ struct KernelEntry {
   X(6, 384, 1, 2, 2) X(6, 512, 1, 1, 2) X(6, 512, 1, 1, 3) X(6, 256, 1, 3, 2) X(6, 256, 1, 2, 2) X(5, 512, 1, 1, 2) \
   X(4, 384, 1, 2, 2) X(4, 512, 1, 2, 2) X(4, 512, 1, 1, 2) X(4, 256, 1, 2, 2) X(4, 256, 1, 4, 1) \
   X(3, 256, 2, 3, 1) X(3, 256, 1, 3, 2) X(3, 512, 1, 1, 2) X(2, 256, 2, 2, 1) X(2, 256, 1, 2, 2) X(2, 512, 1, 1, 2) X(1, 256, 2, 1, 2)
-KernelEntry lookup_v2(int I, int NT, int MINB, int SB);
+// the other output layouts (positions only / outline hull / interleaved): fewer shapes
+#define RZ_SHAPES_V2_LITE(X) \
+  X(6, 512, 1, 1, 2) X(4, 512, 1, 2, 2) X(4, 512, 1, 1, 2) X(4, 384, 1, 2, 2) X(4, 256, 1, 2, 2) X(3, 512, 1, 1, 2) X(2, 512, 1, 1, 2) \
+  X(2, 256, 2, 2, 1) X(2, 256, 1, 2, 2) X(1, 256, 2, 1, 2)
+KernelEntry lookup_v2_out0(int I, int NT, int MINB, int SB);   // OUT2_PLANAR
+KernelEntry lookup_v2_out1(int I, int NT, int MINB, int SB);   // OUT2_NONRM
+KernelEntry lookup_v2_out2(int I, int NT, int MINB, int SB);   // OUT2_HULL
+KernelEntry lookup_v2_out3(int I, int NT, int MINB, int SB);   // OUT2_ILV
 #define RZ_DECL(f) KernelEntry lookup_feat_##f(int I, int NT, int MINB);
 RZ_FEAT_LIST(RZ_DECL)
 #undef RZ_DECL

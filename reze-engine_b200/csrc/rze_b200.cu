@@ -338,8 +338,18 @@ size_t smem_needed(int I, int NT, int feat, uint32_t B, uint32_t Mpad, int nbuf 
   return s;
 }
 
-size_t smem_needed2(int I, int NT, uint32_t B, int SB, int NBUF) {   // deform2_kernel: control block, I palettes, per warp NBUF sub-batch buffers
-  return kCtrlBytes + (size_t)I * B * 48 + (size_t)(NT / 32) * NBUF * SB * 1536;   // (2 planes x 64 vertices x 12 B per instance)
+// deform2_kernel: control block, I palettes, per warp NBUF sub-batch buffers of 64 vertices x (bytes per vertex of the layout)
+size_t smem_needed2(int I, int NT, uint32_t B, int SB, int NBUF, int out2) {
+  static const size_t instBytes[4] = {64 * 24, 64 * 12, 64 * 36, 64 * 32};   // OUT2_PLANAR, _NONRM, _HULL, _ILV
+  return kCtrlBytes + (size_t)I * B * 48 + (size_t)(NT / 32) * NBUF * SB * instBytes[out2];
+}
+KernelEntry lookup_v2(int out2, int I, int NT, int MINB, int SB) {
+  switch (out2) {
+    case OUT2_PLANAR: return lookup_v2_out0(I, NT, MINB, SB);
+    case OUT2_NONRM: return lookup_v2_out1(I, NT, MINB, SB);
+    case OUT2_HULL: return lookup_v2_out2(I, NT, MINB, SB);
+    default: return lookup_v2_out3(I, NT, MINB, SB);
+  }
 }
 
 // How to cut a launch into work items.  Items are pulled from an atomic queue by `grid` persistent CTAs, so the launch ends
@@ -475,8 +485,7 @@ int rebuild_tables(rz_ctx_impl* c) {
 
   // ---- two vertices per lane (lane_plan2.h): the plain path's own table, when this context can run the plain path at all
   LanePlan2 plan2;
-  const bool vpl2 = c->vplMode != 0 && c->layoutMode == 0 &&
-                    !(c->flags & (RZ_FLAG_NO_NORMALS | RZ_FLAG_OUTLINE | RZ_FLAG_INTERLEAVED | RZ_FLAG_BOUNDS));
+  const bool vpl2 = c->vplMode != 0 && c->layoutMode == 0 && !(c->flags & RZ_FLAG_BOUNDS);
   if (vpl2) plan_lanes2(JT, WT, V, B, plan2);
   c->vpl2Ready = false;
 
@@ -555,6 +564,15 @@ int rebuild_tables(rz_ctx_impl* c) {
       rec2v[p] = q0; rec2v[(size_t)L + p] = q1; rec2v[2 * (size_t)L + p] = q2; rec2v[3 * (size_t)L + p] = q3;
       rec2v[4 * (size_t)L + p] = make_float4(wa[2], wa[3], wb[2], wb[3]);
       rec2v[5 * (size_t)L + p] = q5;
+      float4 q6 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c->flags & RZ_FLAG_INTERLEAVED) {                  // texture coordinates, passed through (engine.ts:273)
+        if (vA != ~0u) { q6.x = VT[(size_t)vA * 8 + 6]; q6.y = VT[(size_t)vA * 8 + 7]; }
+        if (vB != ~0u) { q6.z = VT[(size_t)vB * 8 + 6]; q6.w = VT[(size_t)vB * 8 + 7]; }
+      } else if ((c->flags & RZ_FLAG_OUTLINE) && !c->h_edgeSize.empty()) {   // engine.ts:459-460: edgeSize * 0.01
+        if (vA != ~0u) q6.x = c->h_edgeSize[c->vorder[vA]] * 0.01f;
+        if (vB != ~0u) q6.y = c->h_edgeSize[c->vorder[vB]] * 0.01f;
+      }
+      rec2v[6 * (size_t)L + p] = q6;
     }
     c->vgCount = plan2.nGroups;
     c->p2VertA = plan2.vertA; c->p2VertB = plan2.vertB;
@@ -1379,7 +1397,9 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
   int occ = 0;
   const uint32_t countClass = std::min<uint32_t>(count, 8u);        // shapes are only restricted by count when count < I <= 8
   // the plain planar path runs the two-vertices-per-lane kernel (deform2_kernel.cuh) whenever its table exists
-  const bool v2Allowed = feat == 0 && c->vpl2Ready && c->tuneVpl != 1;
+  // -- in every output layout, as long as no morph / SDEF / AABB is active
+  const bool v2Allowed = (feat & ~(FEAT_NONRM | FEAT_HULL | FEAT_ILV)) == 0 && c->vpl2Ready && c->tuneVpl != 1;
+  const int out2 = (feat & FEAT_ILV) ? OUT2_ILV : (feat & FEAT_HULL) ? OUT2_HULL : (feat & FEAT_NONRM) ? OUT2_NONRM : OUT2_PLANAR;
   bool v2 = false;
   const bool cached = c->shapeKe.fn && c->shapeKey.feat == feat && c->shapeKey.B == c->B && c->shapeKey.Mpad == Mpad &&
                       c->shapeKey.countClass == countClass && c->shapeKey.v2Allowed == v2Allowed;
@@ -1399,9 +1419,9 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
   };
   auto try_shape2 = [&](int I, int NT, int MINB, int SB) -> bool {
     if (!v2Allowed || (!tuned && (uint32_t)I > count && I > 1)) return false;
-    KernelEntry e = lookup_v2(I, NT, MINB, SB);
+    KernelEntry e = lookup_v2(out2, I, NT, MINB, SB);
     if (!e.fn) return false;
-    const size_t sm = smem_needed2(e.I, e.NT, c->B, e.SB, e.NB);
+    const size_t sm = smem_needed2(e.I, e.NT, c->B, e.SB, e.NB, out2);
     if (sm > smemMax) return false;
     if (raise_smem_limit(c->device, e.fn, sm) != cudaSuccess) { cudaGetLastError(); return false; }
     int o = 0;
@@ -1443,7 +1463,7 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
     bool ok = false;
     if (v2Allowed) {
       // two-vertex kernel: 8 warps x 64 vertices with the widest palette stage first (measured on B200, profiles/r02_*)
-      static const int pref2[][4] = {{4, 512, 1, 2}, {4, 384, 1, 2}, {3, 512, 1, 1}, {2, 256, 2, 2}, {2, 512, 1, 1}, {3, 256, 1, 3},
+      static const int pref2[][4] = {{4, 512, 1, 2}, {4, 384, 1, 2}, {4, 512, 1, 1}, {3, 512, 1, 1}, {2, 256, 2, 2}, {2, 512, 1, 1}, {3, 256, 1, 3},
                                      {2, 256, 1, 2}, {1, 256, 2, 1}};
       for (const auto& p : pref2) if (try_shape2(p[0], p[1], p[2], p[3])) { ok = true; break; }
     }
@@ -1501,7 +1521,7 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
   if (v2) {
     prm2.rec = reinterpret_cast<const float4*>(c->d_rec2v.p);
     prm2.skin = prm.skin; prm2.inst2pal = prm.inst2pal; prm2.out = prm.out;
-    prm2.instStrideF = c->instStrideF; prm2.nrmOffF = c->nrmOffF;
+    prm2.instStrideF = c->instStrideF; prm2.nrmOffF = c->nrmOffF; prm2.hullOffF = c->hullOffF;
     prm2.lanes = c->vgCount * 32; prm2.nVG = c->vgCount; prm2.V = c->V; prm2.B = c->B;
     prm2.counter = prm.counter;
   }
