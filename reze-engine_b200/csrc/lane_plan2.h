@@ -272,6 +272,72 @@ inline void plan_lanes2(const uint16_t* JT, const uint8_t* WT, uint32_t V, uint3
       for (int k = 0; k < 4; ++k) if (out.wA[(size_t)p * 4 + k] != 0.f || out.wB[(size_t)p * 4 + k] != 0.f) n = k + 1;
       out.laneN[p] = (uint8_t)n;
     }
+
+    // ---- quarter-warps.  The interleaved output stages 32-byte records with two STS.128 per vertex; the hardware serves a
+    // 128-bit store one quarter-warp (8 lanes) at a time, and with the half-swapping order of deform2_kernel.cuh the 8 stores
+    // of a quarter-warp hit 8 distinct 16-byte bank groups iff its 8 slots are distinct MODULO 8.  Aligned lane pairs must
+    // stay together (they share palette rows), but the 16 pairs may sit anywhere: hill-climb over swaps of pairs between
+    // the four quarter-warps until no swap lowers the number of colliding slots (A side + B side).
+    {
+      int pos[16];                                          // pos[i]: pair currently at pair position i
+      for (int i = 0; i < 16; ++i) pos[i] = i;
+      auto residue = [&](int pair, int lane01, int side) { return (int)((side ? out.slotB : out.slotA)[base + 2 * pair + lane01] & 7u); };
+      auto bin_cost = [&](const int* members) {             // colliding slots of one quarter-warp (4 pairs)
+        int cost = 0;
+        for (int side = 0; side < 2; ++side) {
+          int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+          for (int m = 0; m < 4; ++m) for (int h = 0; h < 2; ++h) cnt[residue(members[m], h, side)]++;
+          for (int c2 = 0; c2 < 8; ++c2) cost += cnt[c2] > 1 ? cnt[c2] - 1 : 0;
+        }
+        return cost;
+      };
+      auto total_cost = [&](const int* q) { return bin_cost(q) + bin_cost(q + 4) + bin_cost(q + 8) + bin_cost(q + 12); };
+      auto climb = [&](int* q) {
+        bool improved = true;
+        for (int sweep = 0; sweep < 12 && improved; ++sweep) {
+          improved = false;
+          for (int i = 0; i < 16; ++i)
+            for (int j = i + 1; j < 16; ++j) {
+              if (i / 4 == j / 4) continue;
+              const int before = bin_cost(&q[i / 4 * 4]) + bin_cost(&q[j / 4 * 4]);
+              if (before == 0) continue;
+              std::swap(q[i], q[j]);
+              const int after = bin_cost(&q[i / 4 * 4]) + bin_cost(&q[j / 4 * 4]);
+              if (after < before) improved = true; else std::swap(q[i], q[j]);
+            }
+        }
+        return total_cost(q);
+      };
+      int best = climb(pos);
+      uint32_t rs = 0x9E3779B9u ^ (g * 2654435761u);        // a few deterministic restarts from shuffled orders
+      for (int restart = 0; restart < 4 && best > 0; ++restart) {
+        int q[16];
+        for (int i = 0; i < 16; ++i) q[i] = i;
+        for (int i = 15; i > 0; --i) { rs = rs * 1664525u + 1013904223u; std::swap(q[i], q[(rs >> 8) % (uint32_t)(i + 1)]); }
+        const int c2 = climb(q);
+        if (c2 < best) { best = c2; for (int i = 0; i < 16; ++i) pos[i] = q[i]; }
+      }
+      bool moved = false;
+      for (int i = 0; i < 16; ++i) moved |= pos[i] != i;
+      if (moved) {
+        uint32_t vA[32], vB[32];
+        uint16_t gj[32][4];
+        float wa[32][4], wb[32][4];
+        uint8_t sA[32], sB[32], ln[32];
+        for (int l = 0; l < 32; ++l) {
+          const uint32_t p = base + l;
+          vA[l] = out.vertA[p]; vB[l] = out.vertB[p]; sA[l] = out.slotA[p]; sB[l] = out.slotB[p]; ln[l] = out.laneN[p];
+          for (int k = 0; k < 4; ++k) { gj[l][k] = out.gatherJ[(size_t)p * 4 + k]; wa[l][k] = out.wA[(size_t)p * 4 + k]; wb[l][k] = out.wB[(size_t)p * 4 + k]; }
+        }
+        for (int i = 0; i < 16; ++i)
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t p = base + 2 * i + h;
+            const int src = 2 * pos[i] + h;
+            out.vertA[p] = vA[src]; out.vertB[p] = vB[src]; out.slotA[p] = sA[src]; out.slotB[p] = sB[src]; out.laneN[p] = ln[src];
+            for (int k = 0; k < 4; ++k) { out.gatherJ[(size_t)p * 4 + k] = gj[src][k]; out.wA[(size_t)p * 4 + k] = wa[src][k]; out.wB[(size_t)p * 4 + k] = wb[src][k]; }
+          }
+      }
+    }
   }
 }
 

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--instances", type=int, default=2048)
     ap.add_argument("--iters", type=int, default=8)
     ap.add_argument("--shapes", default="0:0:0")
+    ap.add_argument("--only", default="", help="substring of the variant name to run alone (ncu captures)")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "consumers.jsonl"))
     a = ap.parse_args()
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
@@ -37,6 +38,8 @@ def main():
     variants = [("planar pos+nrm", 0), ("+ AABB", capi.RZ_FLAG_BOUNDS), ("+ outline hull plane", capi.RZ_FLAG_OUTLINE),
                 ("interleaved [pos,nrm,uv]", capi.RZ_FLAG_INTERLEAVED), ("positions only", capi.RZ_FLAG_NO_NORMALS)]
     for name, flags in variants:
+        if a.only and a.only not in name:
+            continue
         for sh in a.shapes.split(","):
             I, nt, ctas = (int(x) for x in sh.split(":"))
             row = dict(variant=name, flags=flags, req=[I, nt, ctas])
@@ -58,7 +61,7 @@ def main():
                         ms.append(e0.elapsed_time(e1))
                     s = ctx.stats()
                     med = float(np.median(ms))
-                    row.update(I=s["instancesPerGroup"], threads=s["threads"], ctas=s["ctas"], smem=s["smemBytes"], ms=med,
+                    row.update(vpl=s["verticesPerLane"], I=s["instancesPerGroup"], threads=s["threads"], ctas=s["ctas"], smem=s["smemBytes"], ms=med,
                                gverts=K * V / med / 1e6, alg_gbs=s["algorithmicBytes"] / med / 1e6,
                                bytes_per_vertex_instance=s["algorithmicBytes"] / (K * V))
             except Exception as e:  # noqa: BLE001
