@@ -49,6 +49,20 @@ for I, nt, sb in ((4, 512, 2), (6, 384, 2), (6, 512, 1), (3, 256, 3), (1, 256, 1
             ctx.sync()
             assert ctx.stats()["verticesPerLane"] == 2
     print("ok two-vertex kernel", I, nt, sb)
+# ... and in its other output layouts (positions only, outline hull, interleaved with the half-swapped store order)
+for flags in (capi.RZ_FLAG_NO_NORMALS, capi.RZ_FLAG_OUTLINE, capi.RZ_FLAG_INTERLEAVED):
+    for I, nt, sb in ((0, 0, 0), (4, 384, 2), (1, 256, 1)):
+        wx = synth.make_workload(1003, 40)
+        with capi.DeformContext(max_instances=K, flags=flags, instances_per_group=I, threads=nt, store_mode=sb, vertices_per_lane=2) as ctx:
+            ctx.load_mesh(wx.vtx8, wx.joints, wx.weights, wx.invBind)
+            if flags & capi.RZ_FLAG_OUTLINE:
+                ctx.load_edge_size(rng.uniform(0, 2, wx.V).astype(np.float32))
+            ctx.set_palettes(synth.make_palettes(wx.bones, K, rng))
+            ctx.deform()
+            ctx.deform(1, 5)
+            ctx.sync()
+            assert ctx.stats()["verticesPerLane"] == 2
+    print("ok two-vertex kernel, layout flags", flags)
 
 # ---- the round's later additions: pointer-jumping / chain / level pose kernels, pipelined palette upload, double-buffered
 # results with asynchronous read-back, physics feedback, SDEF + outline on a palette that does not fit shared memory
