@@ -65,7 +65,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if force or not _newer(o, [inst_src] + hdrs):
             jobs.append(([nvcc, *ARCH, *COMMON, f"-DRZ_FEAT={f}", "-c", inst_src, "-o", o], o + ".log"))
     v2_src = os.path.join(CSRC, "deform2_inst.cu")
-    for out2 in range(4):                                    # two-vertex kernel, one object per output layout (OUT2_*)
+    for out2 in range(5):                                    # two-vertex kernel, one object per output layout (OUT2_*)
         v2_obj = os.path.join(OBJDIR, "deform2.o" if out2 == 0 else f"deform2_out{out2}.o")
         objs.append(v2_obj)
         if force or not _newer(v2_obj, [v2_src] + hdrs):

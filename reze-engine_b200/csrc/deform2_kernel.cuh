@@ -35,13 +35,15 @@ constexpr uint32_t kM2HasA = 1u << 15, kM2HasB = 1u << 16;
 enum : int { OUT2_PLANAR = 0,   // position plane + normal plane                        (engine.ts:245-276)
              OUT2_NONRM = 1,    // positions only: the depth-only blend                 (engine.ts:692-715)
              OUT2_HULL = 2,     // + outline hull plane pos' + n^' * edge               (engine.ts:431-463, 458-461)
-             OUT2_ILV = 3 };    // one interleaved 32-byte [pos, nrm, uv] stream        (engine.ts:340-347)
+             OUT2_ILV = 3,      // one interleaved 32-byte [pos, nrm, uv] stream        (engine.ts:340-347)
+             OUT2_BOUNDS = 4 }; // planar + per-instance AABB of the skinned positions  
 
 struct Deform2Params {
   const float4* __restrict__ rec;        // [6][lanes]
   const float* __restrict__ skin;        // [P][B][12], pair layout (deform_kernel.cuh kRowF4)
   const uint32_t* __restrict__ inst2pal; // [K] or nullptr (identity)
   float* __restrict__ out;
+  float* __restrict__ bounds;            // [K][6] as ordered ints (OUT2_BOUNDS), else unused
   unsigned long long instStrideF;        // floats between instances
   unsigned long long nrmOffF;            // floats from the position plane to the normal plane
   unsigned long long hullOffF;           // floats from the position plane to the outline-hull plane (OUT2_HULL)
@@ -66,7 +68,7 @@ __global__ void __launch_bounds__(NT, MINB) deform2_kernel(const Deform2Params p
   static_assert(I % SB == 0, "sub-batch must divide the group");
   constexpr int W = NT / 32;
   constexpr int NSB = I / SB;                          // sub-batches = store commit groups per pass
-  constexpr bool ILV = OUT == OUT2_ILV, HULL = OUT == OUT2_HULL, NRM = OUT != OUT2_NONRM;
+  constexpr bool ILV = OUT == OUT2_ILV, HULL = OUT == OUT2_HULL, NRM = OUT != OUT2_NONRM, BOUNDS = OUT == OUT2_BOUNDS;
   constexpr uint32_t kVtxB = ILV ? 32u : 12u;          // bytes per vertex of a staging plane
   constexpr uint32_t kPlaneB = 64u * kVtxB;            // one staging plane of a warp: 64 vertices
   constexpr uint32_t kInstB = (ILV ? 1u : (NRM ? 2u : 1u) + (HULL ? 1u : 0u)) * kPlaneB;   // the planes of one instance
@@ -111,6 +113,15 @@ __global__ void __launch_bounds__(NT, MINB) deform2_kernel(const Deform2Params p
     const uint32_t kBase = prm.K0 + g * I;
     const uint32_t nInst = min((uint32_t)I, prm.K0 + prm.Kcount - kBase);
     float* const outItem = prm.out + (size_t)kBase * prm.instStrideF;
+    // AABB: running min / max of the lane's vertices per instance, in registers over the whole item (the sub-batch loop is
+    // unrolled for this layout so that the instance index is static)
+    float bmin[BOUNDS ? I : 1][3], bmax[BOUNDS ? I : 1][3];
+    if (BOUNDS) {
+#pragma unroll
+      for (int i = 0; i < I; ++i)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { bmin[i][c] = 3.4e38f; bmax[i][c] = -3.4e38f; }
+    }
 
     // ---- stage the I palettes: TMA bulk copies on one mbarrier (a partial group re-stages its last palette, never stored)
     if (tid == 0) {
@@ -161,11 +172,19 @@ __global__ void __launch_bounds__(NT, MINB) deform2_kernel(const Deform2Params p
       // mat-vec of one vertex with its blended matrix (pair layout: (x,y) out of packed FFMA2), normalise, stage.
       // ex0 / ex1: the vertex' texture coordinates (ILV) or its outline offset (HULL)
       auto emit = [&](const float4 mA, const float4 mB, const float4 mC, const float px, const float py, const float pz,
-                      const float nxi, const float nyi, const float nzi, const float ex0, const float ex1, const uint32_t sa, const bool sw) {
+                      const float nxi, const float nyi, const float nzi, const float ex0, const float ex1, const uint32_t sa, const bool sw,
+                      const int inst, const bool real) {
         const float2 qx2 = make_float2(px, px), qy2 = make_float2(py, py), qz2 = make_float2(pz, pz);
         const float2 oxy = __ffma2_rn(make_float2(mA.x, mA.y), qx2,
                            __ffma2_rn(make_float2(mA.z, mA.w), qy2, __ffma2_rn(make_float2(mB.x, mB.y), qz2, make_float2(mB.z, mB.w))));
         const float oz = fmaf(mC.x, px, fmaf(mC.y, py, fmaf(mC.z, pz, mC.w)));
+        if (BOUNDS) {
+          if (real) {                                             // (padding lanes and a fallback group's B side carry no vertex)
+            bmin[inst][0] = fminf(bmin[inst][0], oxy.x); bmax[inst][0] = fmaxf(bmax[inst][0], oxy.x);
+            bmin[inst][1] = fminf(bmin[inst][1], oxy.y); bmax[inst][1] = fmaxf(bmax[inst][1], oxy.y);
+            bmin[inst][2] = fminf(bmin[inst][2], oz); bmax[inst][2] = fmaxf(bmax[inst][2], oz);
+          }
+        }
         float nx = 0.f, ny = 0.f, nz = 0.f;
         if (NRM) {
           const float2 nx2 = make_float2(nxi, nxi), ny2 = make_float2(nyi, nyi), nz2 = make_float2(nzi, nzi);
@@ -219,7 +238,8 @@ __global__ void __launch_bounds__(NT, MINB) deform2_kernel(const Deform2Params p
             if (NMAX > 1) { mA = f4_fma(b0[ii], wA1, mA); mB = f4_fma(b1[ii], wA1, mB); mC = f4_fma(b2[ii], wA1, mC); }
             if (NMAX > 2) { mA = f4_fma(c0, wA2, mA); mB = f4_fma(c1, wA2, mB); mC = f4_fma(c2, wA2, mC); }
             if (NMAX > 3) { mA = f4_fma(d0, wA3, mA); mB = f4_fma(d1, wA3, mB); mC = f4_fma(d2, wA3, mC); }
-            emit(mA, mB, mC, v.q0.x, v.q0.y, v.q0.z, v.q1.x, v.q1.y, v.q1.z, v.q6.x, ILV ? v.q6.y : 0.f, so + oA, (meta & 4u) != 0u);
+            emit(mA, mB, mC, v.q0.x, v.q0.y, v.q0.z, v.q1.x, v.q1.y, v.q1.z, v.q6.x, ILV ? v.q6.y : 0.f, so + oA, (meta & 4u) != 0u,
+                 BOUNDS ? i0 + ii : 0, (meta & kM2HasA) != 0u);
           }
           {   // (a fallback group's lanes carry no second vertex: their B side blends zeros into a slot that is never drained --
               //  cheaper than a branch that would keep the two independent dependency chains from interleaving)
@@ -229,14 +249,14 @@ __global__ void __launch_bounds__(NT, MINB) deform2_kernel(const Deform2Params p
             if (NMAX > 1) { mA = f4_fma(b0[ii], wB1, mA); mB = f4_fma(b1[ii], wB1, mB); mC = f4_fma(b2[ii], wB1, mC); }
             if (NMAX > 2) { mA = f4_fma(c0, wB2, mA); mB = f4_fma(c1, wB2, mB); mC = f4_fma(c2, wB2, mC); }
             if (NMAX > 3) { mA = f4_fma(d0, wB3, mA); mB = f4_fma(d1, wB3, mB); mC = f4_fma(d2, wB3, mC); }
-            emit(mA, mB, mC, v.q2.x, v.q2.y, v.q2.z, v.q3.x, v.q3.y, v.q3.z, ILV ? v.q6.z : v.q6.y, ILV ? v.q6.w : 0.f, so + oB, (meta & (4u << kM2SlotB)) != 0u);
+            emit(mA, mB, mC, v.q2.x, v.q2.y, v.q2.z, v.q3.x, v.q3.y, v.q3.z, ILV ? v.q6.z : v.q6.y, ILV ? v.q6.w : 0.f, so + oB, (meta & (4u << kM2SlotB)) != 0u,
+                 BOUNDS ? i0 + ii : 0, (meta & kM2HasB) != 0u);
           }
         }
       };
 
       float* const dst0 = outItem + (size_t)first * (kVtxB / 4u);
-#pragma unroll 1
-      for (int sbi = 0; sbi < NSB; ++sbi) {                         // (not unrolled: one copy of the five bodies keeps the I-cache warm)
+      auto sub_batch = [&](const int sbi) {
         const int i0 = sbi * SB;
         // the stores issued from this staging buffer NBUF sub-batches ago must have finished reading it: all but the
         // NBUF-1 most recent commit groups are awaited
@@ -285,6 +305,33 @@ __global__ void __launch_bounds__(NT, MINB) deform2_kernel(const Deform2Params p
           __syncwarp();
         }
         sbuf = (sbuf + 1u == (uint32_t)NBUF) ? 0u : sbuf + 1u;
+      };
+      if (BOUNDS) {
+#pragma unroll
+        for (int sbi = 0; sbi < NSB; ++sbi) sub_batch(sbi);       // static instance indices for the register accumulators
+      } else {
+#pragma unroll 1
+        for (int sbi = 0; sbi < NSB; ++sbi) sub_batch(sbi);       // (not unrolled: one copy of the five bodies keeps the I-cache warm)
+      }
+    }
+    if (BOUNDS) {
+      // per-item reduction: warp shuffle, then one atomic per warp per bound (ordered-int encoding), as deform_kernel does
+#pragma unroll
+      for (int i = 0; i < I; ++i) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float lo = bmin[i][c], hi = bmax[i][c];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+          }
+          if (lane == 0 && (uint32_t)i < nInst) {
+            int* bp = reinterpret_cast<int*>(prm.bounds) + (size_t)(kBase + i) * 6;
+            atomicMin(bp + c, f2ord(lo));
+            atomicMax(bp + 3 + c, f2ord(hi));
+          }
+        }
       }
     }
     __syncthreads();   // everyone is done with this item's palettes before they are overwritten

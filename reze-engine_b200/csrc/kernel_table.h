@@ -37,6 +37,7 @@ KernelEntry lookup_v2_out0(int I, int NT, int MINB, int SB);   // OUT2_PLANAR
 KernelEntry lookup_v2_out1(int I, int NT, int MINB, int SB);   // OUT2_NONRM
 KernelEntry lookup_v2_out2(int I, int NT, int MINB, int SB);   // OUT2_HULL
 KernelEntry lookup_v2_out3(int I, int NT, int MINB, int SB);   // OUT2_ILV
+KernelEntry lookup_v2_out4(int I, int NT, int MINB, int SB);   // OUT2_BOUNDS
 #define RZ_DECL(f) KernelEntry lookup_feat_##f(int I, int NT, int MINB);
 RZ_FEAT_LIST(RZ_DECL)
 #undef RZ_DECL

@@ -340,7 +340,7 @@ size_t smem_needed(int I, int NT, int feat, uint32_t B, uint32_t Mpad, int nbuf 
 
 // deform2_kernel: control block, I palettes, per warp NBUF sub-batch buffers of 64 vertices x (bytes per vertex of the layout)
 size_t smem_needed2(int I, int NT, uint32_t B, int SB, int NBUF, int out2) {
-  static const size_t instBytes[4] = {64 * 24, 64 * 12, 64 * 36, 64 * 32};   // OUT2_PLANAR, _NONRM, _HULL, _ILV
+  static const size_t instBytes[5] = {64 * 24, 64 * 12, 64 * 36, 64 * 32, 64 * 24};   // OUT2_PLANAR, _NONRM, _HULL, _ILV, _BOUNDS
   return kCtrlBytes + (size_t)I * B * 48 + (size_t)(NT / 32) * NBUF * SB * instBytes[out2];
 }
 KernelEntry lookup_v2(int out2, int I, int NT, int MINB, int SB) {
@@ -348,6 +348,7 @@ KernelEntry lookup_v2(int out2, int I, int NT, int MINB, int SB) {
     case OUT2_PLANAR: return lookup_v2_out0(I, NT, MINB, SB);
     case OUT2_NONRM: return lookup_v2_out1(I, NT, MINB, SB);
     case OUT2_HULL: return lookup_v2_out2(I, NT, MINB, SB);
+    case OUT2_BOUNDS: return lookup_v2_out4(I, NT, MINB, SB);
     default: return lookup_v2_out3(I, NT, MINB, SB);
   }
 }
@@ -485,7 +486,9 @@ int rebuild_tables(rz_ctx_impl* c) {
 
   // ---- two vertices per lane (lane_plan2.h): the plain path's own table, when this context can run the plain path at all
   LanePlan2 plan2;
-  const bool vpl2 = c->vplMode != 0 && c->layoutMode == 0 && !(c->flags & RZ_FLAG_BOUNDS);
+  // (the AABB rides on the two-vertex kernel with the planar layout only: with another layout the context runs deform_kernel)
+  const bool vpl2 = c->vplMode != 0 && c->layoutMode == 0 &&
+                    !((c->flags & RZ_FLAG_BOUNDS) && (c->flags & (RZ_FLAG_NO_NORMALS | RZ_FLAG_OUTLINE | RZ_FLAG_INTERLEAVED)));
   if (vpl2) plan_lanes2(JT, WT, V, B, plan2);
   c->vpl2Ready = false;
 
@@ -1397,9 +1400,10 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
   int occ = 0;
   const uint32_t countClass = std::min<uint32_t>(count, 8u);        // shapes are only restricted by count when count < I <= 8
   // the plain planar path runs the two-vertices-per-lane kernel (deform2_kernel.cuh) whenever its table exists
-  // -- in every output layout, as long as no morph / SDEF / AABB is active
-  const bool v2Allowed = (feat & ~(FEAT_NONRM | FEAT_HULL | FEAT_ILV)) == 0 && c->vpl2Ready && c->tuneVpl != 1;
-  const int out2 = (feat & FEAT_ILV) ? OUT2_ILV : (feat & FEAT_HULL) ? OUT2_HULL : (feat & FEAT_NONRM) ? OUT2_NONRM : OUT2_PLANAR;
+  // -- in every output layout, as long as no morph / SDEF is active; the per-instance AABB with the planar layout only
+  const bool v2Allowed = ((feat & ~(FEAT_NONRM | FEAT_HULL | FEAT_ILV)) == 0 || feat == FEAT_BOUNDS) && c->vpl2Ready && c->tuneVpl != 1;
+  const int out2 = (feat & FEAT_ILV) ? OUT2_ILV : (feat & FEAT_HULL) ? OUT2_HULL : (feat & FEAT_NONRM) ? OUT2_NONRM
+                   : (feat & FEAT_BOUNDS) ? OUT2_BOUNDS : OUT2_PLANAR;
   bool v2 = false;
   const bool cached = c->shapeKe.fn && c->shapeKey.feat == feat && c->shapeKey.B == c->B && c->shapeKey.Mpad == Mpad &&
                       c->shapeKey.countClass == countClass && c->shapeKey.v2Allowed == v2Allowed;
@@ -1465,7 +1469,11 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
       // two-vertex kernel: 8 warps x 64 vertices with the widest palette stage first (measured on B200, profiles/r02_*)
       static const int pref2[][4] = {{4, 512, 1, 2}, {4, 384, 1, 2}, {4, 512, 1, 1}, {3, 512, 1, 1}, {2, 256, 2, 2}, {2, 512, 1, 1}, {3, 256, 1, 3},
                                      {2, 256, 1, 2}, {1, 256, 2, 1}};
-      for (const auto& p : pref2) if (try_shape2(p[0], p[1], p[2], p[3])) { ok = true; break; }
+      // AABB: 6 accumulator registers per instance and an unrolled sub-batch loop: the narrower group wins (0.917 ms at
+      // K = 2048 against 0.954 for 4 x 512 and 0.951 for the one-vertex kernel; profiles/r02_fused_consumers_K2048.jsonl)
+      if (out2 == OUT2_BOUNDS && try_shape2(3, 512, 1, 1)) ok = true;
+      if (!ok)
+        for (const auto& p : pref2) if (try_shape2(p[0], p[1], p[2], p[3])) { ok = true; break; }
     }
     if (!ok && feat != 0) {
       for (int q = 0; q < 5 && !ok; ++q) ok = try_shape(prefLite[q][0], prefLite[q][1], prefLite[q][2]);
@@ -1520,7 +1528,7 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
   memset(&prm2, 0, sizeof prm2);
   if (v2) {
     prm2.rec = reinterpret_cast<const float4*>(c->d_rec2v.p);
-    prm2.skin = prm.skin; prm2.inst2pal = prm.inst2pal; prm2.out = prm.out;
+    prm2.skin = prm.skin; prm2.inst2pal = prm.inst2pal; prm2.out = prm.out; prm2.bounds = prm.bounds;
     prm2.instStrideF = c->instStrideF; prm2.nrmOffF = c->nrmOffF; prm2.hullOffF = c->hullOffF;
     prm2.lanes = c->vgCount * 32; prm2.nVG = c->vgCount; prm2.V = c->V; prm2.B = c->B;
     prm2.counter = prm.counter;

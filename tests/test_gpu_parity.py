@@ -1090,18 +1090,20 @@ def test_headline_size_properties(rzlib, orc):
             assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])
 
 
-@pytest.mark.parametrize("layout", ["positions_only", "outline", "interleaved"])
+@pytest.mark.parametrize("layout", ["positions_only", "outline", "interleaved", "bounds"])
 @pytest.mark.parametrize("I,nt,sb", [(0, 0, 0), (4, 512, 2), (4, 384, 2), (6, 512, 1), (2, 256, 2), (1, 256, 1)])
 def test_two_vertex_kernel_in_every_output_layout(rzlib, orc, layout, I, nt, sb):
-    """The fused consumers without morph / SDEF / AABB run the two-vertices-per-lane kernel as well (deform2_kernel OUT2_*):
-    positions only (engine.ts:692-715), outline hull plane (engine.ts:458-461), interleaved 32-byte stream (engine.ts:340-347)
-    — ragged vertex count, partial instance group, sub-range, vs the oracle; uv bit-exact; same layout as the one-vertex kernel."""
+    """The fused consumers without morph / SDEF run the two-vertices-per-lane kernel as well (deform2_kernel OUT2_*):
+    positions only (engine.ts:692-715), outline hull plane (engine.ts:458-461), interleaved 32-byte stream (engine.ts:340-347),
+    planar + per-instance AABB — ragged vertex count, partial instance group, sub-range, vs the oracle; uv bit-exact; AABB
+    = min / max of the positions read back, bit for bit; same layout as the one-vertex kernel."""
     wl = synth.make_workload(1003, 48, seed=19)
     K = 7
     rng = np.random.default_rng(23)
     world = synth.make_palettes(wl.bones, K, rng)
     edge = np.where(rng.uniform(size=wl.V) < 0.7, rng.uniform(0.2, 2.0, wl.V), 0.0).astype(np.float32)
-    flags = {"positions_only": capi.RZ_FLAG_NO_NORMALS, "outline": capi.RZ_FLAG_OUTLINE, "interleaved": capi.RZ_FLAG_INTERLEAVED}[layout]
+    flags = {"positions_only": capi.RZ_FLAG_NO_NORMALS, "outline": capi.RZ_FLAG_OUTLINE, "interleaved": capi.RZ_FLAG_INTERLEAVED,
+             "bounds": capi.RZ_FLAG_BOUNDS}[layout]
     got = {}
     for vpl in (2, 1):
         with capi.DeformContext(max_instances=K, flags=flags, instances_per_group=I if vpl == 2 else 0, threads=nt if vpl == 2 else 0,
@@ -1124,6 +1126,9 @@ def test_two_vertex_kernel_in_every_output_layout(rzlib, orc, layout, I, nt, sb)
                     assert rel_err(gn, rn) <= TOL, (vpl, k)
                 if layout == "outline":
                     assert rel_err(ctx.read_outline(k), orc.outline_hull(rp, rn, edge)) <= TOL
+                if layout == "bounds":
+                    bb = ctx.read_bounds(k, 1)[0]
+                    assert np.array_equal(bb[:3], gp.min(axis=0)) and np.array_equal(bb[3:], gp.max(axis=0)), (vpl, k)
                 if layout == "interleaved":
                     st = ctx.read_interleaved(k)
                     assert np.array_equal(st[:, :3], gp) and np.array_equal(st[:, 3:6], gn)
