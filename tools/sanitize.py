@@ -49,8 +49,8 @@ for I, nt, sb in ((4, 512, 2), (6, 384, 2), (6, 512, 1), (3, 256, 3), (1, 256, 1
             ctx.sync()
             assert ctx.stats()["verticesPerLane"] == 2
     print("ok two-vertex kernel", I, nt, sb)
-# ... and in its other output layouts (positions only, outline hull, interleaved with the half-swapped store order)
-for flags in (capi.RZ_FLAG_NO_NORMALS, capi.RZ_FLAG_OUTLINE, capi.RZ_FLAG_INTERLEAVED):
+# ... and in its other output layouts (positions only, outline hull, interleaved with the half-swapped store order, planar + AABB)
+for flags in (capi.RZ_FLAG_NO_NORMALS, capi.RZ_FLAG_OUTLINE, capi.RZ_FLAG_INTERLEAVED, capi.RZ_FLAG_BOUNDS):
     for I, nt, sb in ((0, 0, 0), (4, 384, 2), (1, 256, 1)):
         wx = synth.make_workload(1003, 40)
         with capi.DeformContext(max_instances=K, flags=flags, instances_per_group=I, threads=nt, store_mode=sb, vertices_per_lane=2) as ctx:
