@@ -1472,6 +1472,10 @@ int32_t rz_deform(rz_ctx* c, uint32_t first, uint32_t count) {
       // AABB: 6 accumulator registers per instance and an unrolled sub-batch loop: the narrower group wins (0.917 ms at
       // K = 2048 against 0.954 for 4 x 512 and 0.951 for the one-vertex kernel; profiles/r02_fused_consumers_K2048.jsonl)
       if (out2 == OUT2_BOUNDS && try_shape2(3, 512, 1, 1)) ok = true;
+      // outline hull (36 B of staging per vertex-instance): 3 x 512 x SB 1 runs 1.179 ms at K = 2048 against 1.255 ms for 4 x 384;
+      // interleaved: 6 x 512 x SB 1 1.016 ms against 1.049 ms for 4 x 512 (same run; consumer shape sweep of the final build)
+      if (out2 == OUT2_HULL && try_shape2(3, 512, 1, 1)) ok = true;
+      if (out2 == OUT2_ILV && (try_shape2(6, 512, 1, 1) || try_shape2(4, 384, 1, 2))) ok = true;
       if (!ok)
         for (const auto& p : pref2) if (try_shape2(p[0], p[1], p[2], p[3])) { ok = true; break; }
     }
