@@ -31,7 +31,7 @@ constexpr int kRec2Planes = 7;   // float4 planes of the two-vertex lane record 
 constexpr int kM2SlotB = 6, kM2N = 12, kM2Cnt = 17;
 constexpr uint32_t kM2HasA = 1u << 15, kM2HasB = 1u << 16;
 
-// output layouts of the two-vertex kernel (the feature sets without morphs / SDEF / AABB)
+// output layouts of the two-vertex kernel (the feature sets without morphs / SDEF; the AABB with the planar layout only)
 enum : int { OUT2_PLANAR = 0,   // position plane + normal plane                        (engine.ts:245-276)
              OUT2_NONRM = 1,    // positions only: the depth-only blend                 (engine.ts:692-715)
              OUT2_HULL = 2,     // + outline hull plane pos' + n^' * edge               (engine.ts:431-463, 458-461)
