@@ -17,12 +17,32 @@
 #pragma once
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "lane_plan.h"
 
 namespace rz {
+
+// fn(begin, end) over [0, n) on a few host threads (load-time planning only; every range writes its own part of the plan, so
+// the result does not depend on the thread count; RZ_PLAN_THREADS=1 keeps it on the calling thread)
+template <class F>
+inline void plan_parallel_for(uint32_t n, uint32_t minPerThread, F fn) {
+  unsigned nt = std::thread::hardware_concurrency();
+  if (const char* e = getenv("RZ_PLAN_THREADS")) nt = (unsigned)std::max(1, atoi(e));
+  nt = std::max(1u, std::min(std::min(nt, 16u), n / std::max(1u, minPerThread)));
+  if (nt <= 1) { fn(0u, n); return; }
+  std::vector<std::thread> th;
+  const uint32_t per = (n + nt - 1) / nt;
+  for (unsigned t = 0; t < nt; ++t) {
+    const uint32_t b = t * per, e2 = std::min(n, b + per);
+    if (b >= e2) break;
+    th.emplace_back([=]() { fn(b, e2); });
+  }
+  for (auto& t : th) t.join();
+}
 
 struct LanePlan2 {
   uint32_t V = 0, nGroups = 0;
@@ -203,7 +223,9 @@ inline void plan_lanes2(const uint16_t* JT, const uint8_t* WT, uint32_t V, uint3
 
   // ---- staging slots and sides
   out.slotA.assign(VL, 0); out.slotB.assign(VL, 0); out.laneN.assign(VL, 1);
-  for (uint32_t g = 0; g < out.nGroups; ++g) {
+  // (the quarter-warp hill-climb below is 60 % of the planning time: groups are independent, a few host threads share them)
+  plan_parallel_for(out.nGroups, 64, [&](uint32_t gBegin, uint32_t gEnd) {
+  for (uint32_t g = gBegin; g < gEnd; ++g) {
     const uint32_t first = out.groupFirst[g], base = g * 32;
     int owner[64];                                          // slot -> lane * 2 + side, -1: free
     for (int s2 = 0; s2 < 64; ++s2) owner[s2] = -1;
@@ -339,6 +361,7 @@ inline void plan_lanes2(const uint16_t* JT, const uint8_t* WT, uint32_t V, uint3
       }
     }
   }
+  });
 }
 
 }  // namespace rz

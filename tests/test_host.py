@@ -465,6 +465,24 @@ def _check_plan2(J, W, B, r):
     assert np.array_equal(ln.astype(np.int64), want_n)
 
 
+def test_two_vertices_per_lane_plan_does_not_depend_on_the_thread_count(rzlib, monkeypatch):
+    """The slot / quarter-warp stage of rz_plan_lanes2 runs on a few host threads (groups are independent): the plan is the
+    same table, bit for bit, whatever RZ_PLAN_THREADS says."""
+    wl = synth.make_workload(12_000, 128, seed=9)
+    J, W = wl.joints.reshape(-1, 4).copy(), wl.weights.reshape(-1, 4).copy()
+    plans = []
+    for nt in ("1", "3", "8"):
+        monkeypatch.setenv("RZ_PLAN_THREADS", nt)
+        plans.append(capi.plan_lanes2(J, W, wl.B, rzlib))
+    for other in plans[1:]:
+        assert other.keys() == plans[0].keys()
+        for k, v in plans[0].items():
+            if isinstance(v, np.ndarray):
+                assert np.array_equal(v, other[k]), k
+            else:
+                assert v == other[k], k
+
+
 def test_two_vertices_per_lane_plan(rzlib):
     """rz_plan_lanes2 (groundwork for the next kernel generation): every vertex evaluated exactly once, by a lane of the group
     that owns its 64-vertex window; both vertices of a lane find all their (bone, weight) pairs among the lane's four rows;
